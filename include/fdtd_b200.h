@@ -1,0 +1,146 @@
+/*
+ * fdtd_b200.h — C ABI of the B200-native FDTD time-stepping engine (libfdtd_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of rithulkamesh/prismo: the FDTD time step
+ *   Simulation.step            /root/reference/src/prismo/core/simulation.py:147-164
+ *   -> FDTDSolver.step         core/solver.py:664-678
+ *   -> MaxwellUpdater.step     core/solver.py:535-552  (H pass :167-253/:311-397, E pass :255-309/:399-456)
+ *   -> Source.update_fields    sources/{point,plane_wave,tfsf,gaussian,mode}.py
+ *   -> Monitor.update          monitors/{field,dft,flux,mode_monitor}.py
+ * The reference is pure Python, so its "FFI" for this path is ctypes: INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain C types only; all host pointers are caller-owned; no callbacks.
+ *   - every entry point returns 0 on success, a negative FDTD_E* code on failure;
+ *     fdtd_last_error() returns a message for the last failure on this thread.
+ *   - component ids: 0 Ex, 1 Ey, 2 Ez, 3 Hx, 4 Hy, 5 Hz   (core/fields.py:61-70 order)
+ *   - host field arrays are C-order with the reference's staggered shapes (core/grid.py:157-168),
+ *     e.g. Ex is (nx, ny-1, nz-1); 2-D arrays drop the z axis.
+ *   - index boxes are half-open [lo, hi) in the component's own array index space
+ *     (what np.ix_ of core/grid.py:383-513 enumerates).
+ *   - a handle is not thread-safe; one handle drives one GPU (one x-slab in multi-GPU runs).
+ */
+#ifndef FDTD_B200_H
+#define FDTD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDTD_B200_ABI_VERSION 1
+
+enum { FDTD_OK = 0, FDTD_EINVAL = -1, FDTD_ECUDA = -2, FDTD_ENOMEM = -3, FDTD_ESTATE = -4 };
+enum { FDTD_F32 = 0, FDTD_F64 = 1 };
+enum { FDTD_EX = 0, FDTD_EY = 1, FDTD_EZ = 2, FDTD_HX = 3, FDTD_HY = 4, FDTD_HZ = 5 };
+
+/* flags for fdtd_config.flags */
+enum {
+    FDTD_FLAG_NO_GRAPH = 1,     /* never replay the step loop from a CUDA graph            */
+    FDTD_FLAG_TWO_PASS = 2      /* force the two-pass (H kernel, E kernel) 3-D step        */
+};
+
+typedef struct fdtd_engine fdtd_engine; /* opaque */
+
+/* Replaces YeeGrid + MaxwellUpdater construction (core/grid.py:78-120, core/solver.py:41-77). */
+typedef struct fdtd_config {
+    int32_t ndim;          /* 2 or 3 (2 <=> reference Lz == 0, core/grid.py:92)                   */
+    int32_t nx, ny, nz;    /* LOCAL total grid incl. PML cells (YeeGrid.dimensions); nz = 1 in 2-D */
+    double  dx, dy, dz;    /* spacing (dz ignored in 2-D)                                          */
+    double  dt;            /* time step                                                            */
+    int32_t dtype;         /* FDTD_F32 | FDTD_F64: storage + arithmetic type on the device         */
+    int32_t device;        /* CUDA device ordinal                                                  */
+    int32_t nx_global;     /* x-slab decomposition: global nx (== nx on one GPU)                   */
+    int32_t x_offset;      /* global index of local plane 0                                        */
+    int32_t flags;         /* FDTD_FLAG_*                                                          */
+    int32_t reserved;
+} fdtd_config;
+
+/* One additive injection  F[box] += amp(step) [* profile(cell)] [/ divisor]
+ * (sources/point.py:64-73, plane_wave.py:202-221, tfsf.py:314-411, gaussian.py:256-298, mode.py:255-361) */
+typedef struct fdtd_source_op {
+    int32_t component;
+    int32_t lo[3], hi[3];   /* box in the component's index space (LOCAL x); z = [0,1) in 2-D */
+    int32_t table;          /* column of the amplitude table (see fdtd_set_tables)             */
+    const double* profile;  /* NULL, or box-shaped C-order host array (copied)                 */
+    double  divisor;        /* applied only when profile != NULL; 1.0 = none                   */
+    int32_t group;          /* ops sharing a group touch disjoint cells and may run concurrently;
+                               groups run in ascending order (source list order, simulation.py:159) */
+    int32_t reserved;
+} fdtd_source_op;
+
+/* One sampled box (monitors/field.py:124-143, dft.py:121-160, flux.py:194-215). */
+typedef struct fdtd_monitor_op {
+    int32_t component;
+    int32_t lo[3], hi[3];
+    int32_t record;         /* !=0: keep the box for every step (FieldMonitor time_domain)     */
+    int32_t n_freq;         /* >0: running DFT  acc[f] += F * phasor[step][f] * dt  (complex128) */
+    int32_t phasor_col;     /* first column of this op's phasors in the phasor table            */
+    int32_t reserved;
+} fdtd_monitor_op;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int  fdtd_abi_version(void);
+int  fdtd_struct_size(int32_t which);   /* sizeof: 0 fdtd_config, 1 fdtd_source_op, 2 fdtd_monitor_op (binding check) */
+const char* fdtd_last_error(void);
+int  fdtd_create(const fdtd_config* cfg, fdtd_engine** out);
+int  fdtd_destroy(fdtd_engine* e);
+
+/* ---- coefficients (core/solver.py:113-133): cell-centred Ca,Cb,Da,Db ---------------------- */
+int  fdtd_set_uniform_coeffs(fdtd_engine* e, double ca, double cb, double da, double db);
+/* host fp64 arrays of shape (nx[+1], ny, nz) C-order; planes = nx, or nx+1 when a right
+ * neighbour slab exists (the extra plane is the neighbour's first plane).                      */
+int  fdtd_set_coeffs(fdtd_engine* e, const double* ca, const double* cb, const double* da,
+                     const double* db, int32_t planes);
+
+/* ---- fields (core/fields.py:64-114) --------------------------------------------------------- */
+int  fdtd_upload_field(fdtd_engine* e, int32_t component, const void* host, int32_t host_dtype);
+int  fdtd_download_field(fdtd_engine* e, int32_t component, void* host, int32_t host_dtype);
+int  fdtd_zero_fields(fdtd_engine* e);
+/* device address / geometry of a component's padded array, for zero-copy interop (torch, NCCL) */
+int  fdtd_field_device_ptr(fdtd_engine* e, int32_t component, void** ptr, int64_t* plane_stride,
+                           int64_t* row_stride, int64_t* planes_allocated);
+
+/* ---- sources / monitors ---------------------------------------------------------------------- */
+int  fdtd_clear_ops(fdtd_engine* e);
+int  fdtd_add_source_op(fdtd_engine* e, const fdtd_source_op* op);
+int  fdtd_add_monitor_op(fdtd_engine* e, const fdtd_monitor_op* op, int32_t* id);
+/* Per-step host-evaluated tables for steps [0, n_steps) of the NEXT fdtd_run calls:
+ *   amp     [n_steps][n_amp]        fp64  source amplitudes  (waveform(t_n), sign, /377 baked in)
+ *   phasors [n_steps][n_phasor][2]  fp64  exp(-j*2*pi*f*t_n) as (re, im)
+ * Resets the engine's table cursor to 0 and sizes the record buffers for n_steps.             */
+int  fdtd_set_tables(fdtd_engine* e, int32_t n_steps, int32_t n_amp, const double* amp,
+                     int32_t n_phasor, const double* phasors);
+
+/* ---- stepping ---------------------------------------------------------------------------------- */
+int  fdtd_run(fdtd_engine* e, int32_t n_steps);   /* H pass, E pass, sources, monitors, n times     */
+int  fdtd_update_h(fdtd_engine* e);               /* MaxwellUpdater.update_magnetic_fields :135-149 */
+int  fdtd_update_e(fdtd_engine* e);               /* MaxwellUpdater.update_electric_fields :151-165 */
+int  fdtd_sync(fdtd_engine* e);
+
+/* multi-GPU x-slabs: split entry points so the host can interleave the halo exchange.
+ * phase 0 = H pass, 1 = E pass; part 0 = all planes but the last local one, 1 = last plane
+ * (the only one that reads the right neighbour's ghost plane), 2 = everything.
+ * stream = a cudaStream_t (0 = the engine's own stream).                                        */
+int  fdtd_pass(fdtd_engine* e, int32_t phase, int32_t part, void* stream);
+int  fdtd_post_step(fdtd_engine* e, void* stream);   /* sources + monitors + cursor advance       */
+/* first local plane (send side) / ghost plane (receive side) of a component */
+int  fdtd_halo_ptrs(fdtd_engine* e, int32_t component, void** first_plane, void** ghost_plane,
+                    int64_t* plane_bytes);
+
+/* ---- monitor read-out ---------------------------------------------------------------------------- */
+/* records: host fp64 [steps_run][cells]; dft: host complex128 [n_freq][cells] */
+int  fdtd_download_records(fdtd_engine* e, int32_t monitor_id, double* host, int32_t max_steps);
+int  fdtd_download_dft(fdtd_engine* e, int32_t monitor_id, double* host);
+int  fdtd_upload_dft(fdtd_engine* e, int32_t monitor_id, const double* host);
+
+/* ---- introspection ----------------------------------------------------------------------------------- */
+int  fdtd_steps_done(fdtd_engine* e, int64_t* steps);
+int  fdtd_kernel_launches(fdtd_engine* e, int64_t* launches); /* kernels launched by this handle  */
+int  fdtd_mem_info(fdtd_engine* e, int64_t* free_bytes, int64_t* total_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDTD_B200_H */

@@ -1,0 +1,803 @@
+// fdtd_engine.cu — host side of libfdtd_b200.so: the C ABI declared in include/fdtd_b200.h.
+//
+// Owns the device state of one FDTD engine (one GPU / one x-slab): six padded SoA field arrays,
+// optional cell-centred coefficient arrays, source / monitor op tables, per-step amplitude and
+// phasor tables, record and DFT pools, and the stream / CUDA graph that replays the step loop.
+// No torch, no Python: plain CUDA runtime.
+#include "../../include/fdtd_b200.h"
+#include "fdtd_kernels.cuh"
+#include "fdtd_fused.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace fdtd;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? FDTD_ENOMEM : FDTD_ECUDA, "%s: %s",     \
+                        #call, cudaGetErrorString(e_));                                           \
+    } while (0)
+
+static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+struct HostSrc { SrcOp op; int group; };
+
+struct fdtd_engine {
+    fdtd_config cfg{};
+    Geom g{};
+    Strides3 st{};
+    size_t esz = 4;                 // element size of T
+    long long plane_elems = 0;      // sx
+    long long planes_alloc = 0;     // nx + 2
+    long long array_elems = 0;
+    void* fld[6] = {};              // set A
+    void* fldB[6] = {};             // set B (fused ping-pong), allocated lazily
+    int cur = 0;                    // which set holds the current fields (fused path)
+    void* coef[4] = {};             // Ca Cb Da Db arrays (T) or null
+    bool het = false;
+    double uni[4] = {1, 0, 1, 0};
+    cudaStream_t stream = nullptr;
+    // ops
+    std::vector<HostSrc> src;
+    std::vector<MonOp> mon;
+    std::vector<double> prof_host;
+    bool ops_dirty = true;
+    SrcOp* d_src = nullptr;         // all source ops, ordered by group
+    std::vector<int> grp_first, grp_count; std::vector<long long> grp_threads;
+    MonOp* d_mon = nullptr; long long mon_threads = 0;
+    double* d_prof = nullptr;
+    void** d_comp_ptr[2] = {nullptr, nullptr};   // device arrays of 6 component pointers (set A / B)
+    // tables
+    int n_steps_tab = 0, n_amp = 0, n_phasor = 0;
+    double *d_amp = nullptr, *d_phasor = nullptr;
+    void* d_rec = nullptr; long long rec_elems_per_step = 0;
+    double2* d_dft = nullptr; long long dft_elems = 0;
+    int* d_step = nullptr;          // table cursor (device)
+    int cursor = 0;                 // host mirror of the cursor
+    int* d_cnt = nullptr;           // 2 x 6 gate counters (2-D)
+    long long steps_done = 0, launches = 0;
+    // graph
+    cudaGraphExec_t gexec = nullptr; int graph_steps = 0; int graph_cur = 0;
+    // staging
+    void* d_stage = nullptr; size_t stage_bytes = 0;
+    FusedPlan fused{};
+};
+
+// ---------------------------------------------------------------------------------------------------
+static void comp_shape(const fdtd_engine* e, int comp, int shp[3])
+{
+    // staggered shapes, core/grid.py:157-168 (LOCAL nx; the global trim of the last plane is applied
+    // by the caller through x_offset/nx_global)
+    const int nx = e->g.nx, ny = e->g.ny, nz = e->g.nz;
+    const bool last = (e->g.x0 + nx == e->g.nxg);
+    const int nxm = last ? nx - 1 : nx;
+    static const int shortx[6] = {0, 1, 1, 1, 0, 0}, shorty[6] = {1, 0, 1, 0, 1, 0}, shortz[6] = {1, 1, 0, 0, 0, 1};
+    shp[0] = shortx[comp] ? nxm : nx;
+    shp[1] = shorty[comp] ? ny - 1 : ny;
+    if (e->cfg.ndim == 3) shp[2] = shortz[comp] ? nz - 1 : nz;
+    else shp[2] = 1;
+}
+
+template <typename T> static Fields<T> fields_of(void* const* p)
+{
+    Fields<T> f;
+    f.ex = (T*)p[0]; f.ey = (T*)p[1]; f.ez = (T*)p[2]; f.hx = (T*)p[3]; f.hy = (T*)p[4]; f.hz = (T*)p[5];
+    return f;
+}
+template <typename T> static Coefs<T> coefs_of(const fdtd_engine* e)
+{
+    Coefs<T> c;
+    c.ca = (const T*)e->coef[0]; c.cb = (const T*)e->coef[1];
+    c.da = (const T*)e->coef[2]; c.db = (const T*)e->coef[3];
+    c.uca = (T)e->uni[0]; c.ucb = (T)e->uni[1]; c.uda = (T)e->uni[2]; c.udb = (T)e->uni[3];
+    return c;
+}
+static void** cur_fields(fdtd_engine* e) { return e->cur ? e->fldB : e->fld; }
+
+static int ensure_stage(fdtd_engine* e, size_t bytes)
+{
+    if (e->stage_bytes >= bytes) return 0;
+    if (e->d_stage) cudaFree(e->d_stage);
+    e->d_stage = nullptr; e->stage_bytes = 0;
+    CU(cudaMalloc(&e->d_stage, bytes));
+    e->stage_bytes = bytes;
+    return 0;
+}
+
+static void drop_graph(fdtd_engine* e)
+{
+    if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+    e->graph_steps = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" int fdtd_abi_version(void) { return FDTD_B200_ABI_VERSION; }
+extern "C" const char* fdtd_last_error(void) { return g_err.c_str(); }
+extern "C" int fdtd_struct_size(int32_t which)
+{
+    switch (which) {
+    case 0: return (int)sizeof(fdtd_config);
+    case 1: return (int)sizeof(fdtd_source_op);
+    case 2: return (int)sizeof(fdtd_monitor_op);
+    default: return -1;
+    }
+}
+
+extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
+{
+    if (!cfg || !out) return fail(FDTD_EINVAL, "fdtd_create: null argument");
+    if (cfg->ndim != 2 && cfg->ndim != 3) return fail(FDTD_EINVAL, "ndim must be 2 or 3, got %d", cfg->ndim);
+    if (cfg->nx < 3 || cfg->ny < 3 || (cfg->ndim == 3 && cfg->nz < 3))
+        return fail(FDTD_EINVAL, "grid %dx%dx%d too small (need >= 3 cells per axis)", cfg->nx, cfg->ny, cfg->nz);
+    if (cfg->dtype != FDTD_F32 && cfg->dtype != FDTD_F64) return fail(FDTD_EINVAL, "bad dtype %d", cfg->dtype);
+    if (!(cfg->dx > 0) || !(cfg->dy > 0) || (cfg->ndim == 3 && !(cfg->dz > 0)) || !(cfg->dt > 0))
+        return fail(FDTD_EINVAL, "spacings and dt must be positive");
+    const int nxg = cfg->nx_global > 0 ? cfg->nx_global : cfg->nx;
+    if (cfg->x_offset < 0 || cfg->x_offset + cfg->nx > nxg)
+        return fail(FDTD_EINVAL, "slab [%d,%d) outside global nx=%d", cfg->x_offset, cfg->x_offset + cfg->nx, nxg);
+    if (cfg->ndim == 2 && nxg != cfg->nx) return fail(FDTD_EINVAL, "2-D grids are not slab-decomposed");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FDTD_EINVAL, "device %d not in [0,%d)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+
+    fdtd_engine* e = new fdtd_engine();
+    e->cfg = *cfg;
+    e->cfg.nx_global = nxg;
+    Geom& g = e->g;
+    g.nx = cfg->nx; g.ny = cfg->ny; g.nz = cfg->ndim == 3 ? cfg->nz : 1;
+    g.nxg = nxg; g.x0 = cfg->x_offset;
+    g.dx = cfg->dx; g.dy = cfg->dy; g.dz = cfg->ndim == 3 ? cfg->dz : 0.0;
+    g.rdx = (float)(1.0 / g.dx); g.rdy = (float)(1.0 / g.dy); g.rdz = cfg->ndim == 3 ? (float)(1.0 / g.dz) : 0.f;
+    if (cfg->ndim == 3) {
+        g.pz = (int)round_up(g.nz, 32);
+        g.sy = g.pz; g.sx = (long long)g.ny * g.pz;
+        e->st.s[0] = g.sx; e->st.s[1] = g.sy; e->st.s[2] = 1;
+    } else {
+        g.pz = (int)round_up(g.ny, 32);
+        g.sy = 1; g.sx = g.pz;
+        e->st.s[0] = g.sx; e->st.s[1] = 1; e->st.s[2] = 0;
+    }
+    e->esz = cfg->dtype == FDTD_F64 ? 8 : 4;
+    e->plane_elems = g.sx;
+    e->planes_alloc = g.nx + 2;
+    e->array_elems = e->plane_elems * e->planes_alloc;
+
+    cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { delete e; return fail(FDTD_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce)); }
+    for (int c = 0; c < 6; ++c) {
+        ce = cudaMalloc(&e->fld[c], e->array_elems * e->esz);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(e->fld[c], 0, e->array_elems * e->esz, e->stream);
+        if (ce != cudaSuccess) {
+            fdtd_destroy(e);
+            return fail(ce == cudaErrorMemoryAllocation ? FDTD_ENOMEM : FDTD_ECUDA,
+                        "allocating field %d (%lld bytes): %s", c, (long long)(e->array_elems * e->esz),
+                        cudaGetErrorString(ce));
+        }
+    }
+    ce = cudaMalloc(&e->d_step, sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(e->d_step, 0, sizeof(int), e->stream);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_cnt, 12 * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(e->d_cnt, 0, 12 * sizeof(int), e->stream);
+    for (int s = 0; s < 2 && ce == cudaSuccess; ++s) ce = cudaMalloc((void**)&e->d_comp_ptr[s], 6 * sizeof(void*));
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->d_comp_ptr[0], e->fld, 6 * sizeof(void*), cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) { fdtd_destroy(e); return fail(FDTD_ECUDA, "engine setup: %s", cudaGetErrorString(ce)); }
+    // vacuum defaults (solver.py:84-97, :113-133): Ca = Da = 1, Cb = dt/eps0, Db = dt/mu0
+    const double eps0 = 8.854187817e-12, mu0 = 4 * M_PI * 1e-7;
+    e->uni[0] = 1.0; e->uni[1] = cfg->dt / eps0; e->uni[2] = 1.0; e->uni[3] = cfg->dt / mu0;
+    *out = e;
+    return 0;
+}
+
+extern "C" int fdtd_destroy(fdtd_engine* e)
+{
+    if (!e) return 0;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    drop_graph(e);
+    for (int c = 0; c < 6; ++c) { cudaFree(e->fld[c]); cudaFree(e->fldB[c]); }
+    for (int c = 0; c < 4; ++c) cudaFree(e->coef[c]);
+    cudaFree(e->d_src); cudaFree(e->d_mon); cudaFree(e->d_prof);
+    cudaFree(e->d_comp_ptr[0]); cudaFree(e->d_comp_ptr[1]);
+    cudaFree(e->d_amp); cudaFree(e->d_phasor); cudaFree(e->d_rec); cudaFree(e->d_dft);
+    cudaFree(e->d_step); cudaFree(e->d_cnt); cudaFree(e->d_stage);
+    fused_release(e->fused);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return 0;
+}
+
+// ---- coefficients -----------------------------------------------------------------------------------
+extern "C" int fdtd_set_uniform_coeffs(fdtd_engine* e, double ca, double cb, double da, double db)
+{
+    if (!e) return fail(FDTD_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    for (int c = 0; c < 4; ++c) { cudaFree(e->coef[c]); e->coef[c] = nullptr; }
+    e->het = false;
+    e->uni[0] = ca; e->uni[1] = cb; e->uni[2] = da; e->uni[3] = db;
+    drop_graph(e);
+    return 0;
+}
+
+template <typename TD, typename TH>
+static int scatter_host(fdtd_engine* e, TD* dst, const TH* host, long long c0, int c1, int c2)
+{
+    const long long total = c0 * c1 * c2;
+    const long long chunk = std::min<long long>(total, (64ll << 20) / sizeof(TH));
+    if (total == 0) return 0;
+    if (int rc = ensure_stage(e, chunk * sizeof(TH))) return rc;
+    for (long long first = 0; first < total; first += chunk) {
+        const long long n = std::min(chunk, total - first);
+        CU(cudaMemcpyAsync(e->d_stage, host + first, n * sizeof(TH), cudaMemcpyHostToDevice, e->stream));
+        const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+        k_scatter<TD, TH><<<blocks, 256, 0, e->stream>>>(dst, (const TH*)e->d_stage, first, n, c1, c2, e->st);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(e->stream));   // staging buffer is reused
+    }
+    return 0;
+}
+template <typename TD, typename TH>
+static int gather_host(fdtd_engine* e, TH* host, const TD* src, long long c0, int c1, int c2)
+{
+    const long long total = c0 * c1 * c2;
+    const long long chunk = std::min<long long>(total, (64ll << 20) / sizeof(TH));
+    if (total == 0) return 0;
+    if (int rc = ensure_stage(e, chunk * sizeof(TH))) return rc;
+    for (long long first = 0; first < total; first += chunk) {
+        const long long n = std::min(chunk, total - first);
+        const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+        k_gather<TD, TH><<<blocks, 256, 0, e->stream>>>((TH*)e->d_stage, src, first, n, c1, c2, e->st);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(host + first, e->d_stage, n * sizeof(TH), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return 0;
+}
+
+extern "C" int fdtd_set_coeffs(fdtd_engine* e, const double* ca, const double* cb, const double* da,
+                               const double* db, int32_t planes)
+{
+    if (!e || !ca || !cb || !da || !db) return fail(FDTD_EINVAL, "fdtd_set_coeffs: null argument");
+    if (planes != e->g.nx && planes != e->g.nx + 1)
+        return fail(FDTD_EINVAL, "coefficient arrays must have nx=%d (or nx+1) planes, got %d", e->g.nx, planes);
+    CU(cudaSetDevice(e->cfg.device));
+    const double* src[4] = {ca, cb, da, db};
+    for (int c = 0; c < 4; ++c) {
+        if (!e->coef[c]) CU(cudaMalloc(&e->coef[c], e->array_elems * e->esz));
+        CU(cudaMemsetAsync(e->coef[c], 0, e->array_elems * e->esz, e->stream));
+        int rc;
+        const int c1 = e->g.ny, c2 = e->cfg.ndim == 3 ? e->g.nz : 1;
+        if (e->cfg.dtype == FDTD_F64) rc = scatter_host<double, double>(e, (double*)e->coef[c], src[c], planes, c1, c2);
+        else rc = scatter_host<float, double>(e, (float*)e->coef[c], src[c], planes, c1, c2);
+        if (rc) return rc;
+    }
+    e->het = true;
+    drop_graph(e);
+    return 0;
+}
+
+// ---- fields ---------------------------------------------------------------------------------------------
+extern "C" int fdtd_upload_field(fdtd_engine* e, int32_t comp, const void* host, int32_t host_dtype)
+{
+    if (!e || !host || comp < 0 || comp > 5) return fail(FDTD_EINVAL, "fdtd_upload_field: bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    int s[3]; comp_shape(e, comp, s);
+    void* dst = cur_fields(e)[comp];
+    CU(cudaMemsetAsync(dst, 0, e->array_elems * e->esz, e->stream));
+    const bool d64 = e->cfg.dtype == FDTD_F64, h64 = host_dtype == FDTD_F64;
+    if (host_dtype != FDTD_F32 && host_dtype != FDTD_F64) return fail(FDTD_EINVAL, "bad host dtype %d", host_dtype);
+    if (d64 && h64) return scatter_host<double, double>(e, (double*)dst, (const double*)host, s[0], s[1], s[2]);
+    if (d64 && !h64) return scatter_host<double, float>(e, (double*)dst, (const float*)host, s[0], s[1], s[2]);
+    if (!d64 && h64) return scatter_host<float, double>(e, (float*)dst, (const double*)host, s[0], s[1], s[2]);
+    return scatter_host<float, float>(e, (float*)dst, (const float*)host, s[0], s[1], s[2]);
+}
+
+extern "C" int fdtd_download_field(fdtd_engine* e, int32_t comp, void* host, int32_t host_dtype)
+{
+    if (!e || !host || comp < 0 || comp > 5) return fail(FDTD_EINVAL, "fdtd_download_field: bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    int s[3]; comp_shape(e, comp, s);
+    const void* src = cur_fields(e)[comp];
+    const bool d64 = e->cfg.dtype == FDTD_F64, h64 = host_dtype == FDTD_F64;
+    if (host_dtype != FDTD_F32 && host_dtype != FDTD_F64) return fail(FDTD_EINVAL, "bad host dtype %d", host_dtype);
+    if (d64 && h64) return gather_host<double, double>(e, (double*)host, (const double*)src, s[0], s[1], s[2]);
+    if (d64 && !h64) return gather_host<double, float>(e, (float*)host, (const double*)src, s[0], s[1], s[2]);
+    if (!d64 && h64) return gather_host<float, double>(e, (double*)host, (const float*)src, s[0], s[1], s[2]);
+    return gather_host<float, float>(e, (float*)host, (const float*)src, s[0], s[1], s[2]);
+}
+
+extern "C" int fdtd_zero_fields(fdtd_engine* e)
+{
+    if (!e) return fail(FDTD_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    for (int c = 0; c < 6; ++c) CU(cudaMemsetAsync(cur_fields(e)[c], 0, e->array_elems * e->esz, e->stream));
+    return 0;
+}
+
+extern "C" int fdtd_field_device_ptr(fdtd_engine* e, int32_t comp, void** ptr, int64_t* plane_stride,
+                                     int64_t* row_stride, int64_t* planes_allocated)
+{
+    if (!e || comp < 0 || comp > 5) return fail(FDTD_EINVAL, "fdtd_field_device_ptr: bad argument");
+    if (ptr) *ptr = cur_fields(e)[comp];
+    if (plane_stride) *plane_stride = e->g.sx;
+    if (row_stride) *row_stride = e->cfg.ndim == 3 ? e->g.sy : 1;
+    if (planes_allocated) *planes_allocated = e->planes_alloc;
+    return 0;
+}
+
+// ---- ops ------------------------------------------------------------------------------------------------
+static int check_box(const fdtd_engine* e, int comp, const int32_t* lo, const int32_t* hi, int n[3])
+{
+    if (comp < 0 || comp > 5) return fail(FDTD_EINVAL, "component %d out of range", comp);
+    int s[3]; comp_shape(e, comp, s);
+    for (int a = 0; a < 3; ++a) {
+        if (lo[a] < 0 || hi[a] > s[a] || hi[a] < lo[a])
+            return fail(FDTD_EINVAL, "box [%d,%d) outside axis %d extent %d of component %d", lo[a], hi[a], a, s[a], comp);
+        n[a] = hi[a] - lo[a];
+    }
+    return 0;
+}
+
+extern "C" int fdtd_clear_ops(fdtd_engine* e)
+{
+    if (!e) return fail(FDTD_EINVAL, "null engine");
+    e->src.clear(); e->mon.clear(); e->prof_host.clear();
+    e->ops_dirty = true;
+    drop_graph(e);
+    return 0;
+}
+
+extern "C" int fdtd_add_source_op(fdtd_engine* e, const fdtd_source_op* op)
+{
+    if (!e || !op) return fail(FDTD_EINVAL, "fdtd_add_source_op: null argument");
+    HostSrc h{};
+    if (int rc = check_box(e, op->component, op->lo, op->hi, h.op.n)) return rc;
+    if (op->table < 0) return fail(FDTD_EINVAL, "negative table index");
+    h.op.comp = op->component;
+    for (int a = 0; a < 3; ++a) h.op.lo[a] = op->lo[a];
+    h.op.table = op->table;
+    h.op.divisor = op->divisor;
+    h.op.prof_off = -1;
+    const long long cells = (long long)h.op.n[0] * h.op.n[1] * h.op.n[2];
+    if (op->profile && cells > 0) {
+        h.op.prof_off = (long long)e->prof_host.size();
+        e->prof_host.insert(e->prof_host.end(), op->profile, op->profile + cells);
+    }
+    h.group = op->group;
+    if (cells > 0) e->src.push_back(h);
+    e->ops_dirty = true;
+    drop_graph(e);
+    return 0;
+}
+
+extern "C" int fdtd_add_monitor_op(fdtd_engine* e, const fdtd_monitor_op* op, int32_t* id)
+{
+    if (!e || !op) return fail(FDTD_EINVAL, "fdtd_add_monitor_op: null argument");
+    MonOp m{};
+    if (int rc = check_box(e, op->component, op->lo, op->hi, m.n)) return rc;
+    if (op->n_freq < 0 || (op->n_freq > 0 && op->phasor_col < 0)) return fail(FDTD_EINVAL, "bad n_freq/phasor_col");
+    m.comp = op->component;
+    for (int a = 0; a < 3; ++a) m.lo[a] = op->lo[a];
+    m.record = op->record; m.n_freq = op->n_freq; m.phasor_col = op->phasor_col;
+    m.cells = (long long)m.n[0] * m.n[1] * m.n[2];
+    if (id) *id = (int32_t)e->mon.size();
+    e->mon.push_back(m);
+    e->ops_dirty = true;
+    drop_graph(e);
+    return 0;
+}
+
+// upload op tables, (re)allocate the dft pool; keeps existing DFT sums when the layout is unchanged
+static int finalize_ops(fdtd_engine* e)
+{
+    if (!e->ops_dirty) return 0;
+    CU(cudaStreamSynchronize(e->stream));
+    std::stable_sort(e->src.begin(), e->src.end(), [](const HostSrc& a, const HostSrc& b) { return a.group < b.group; });
+    e->grp_first.clear(); e->grp_count.clear(); e->grp_threads.clear();
+    std::vector<SrcOp> flat;
+    for (size_t i = 0; i < e->src.size();) {
+        size_t j = i; long long t = 0;
+        while (j < e->src.size() && e->src[j].group == e->src[i].group) {
+            e->src[j].op.first_thread = t;
+            t += (long long)e->src[j].op.n[0] * e->src[j].op.n[1] * e->src[j].op.n[2];
+            flat.push_back(e->src[j].op);
+            ++j;
+        }
+        e->grp_first.push_back((int)i); e->grp_count.push_back((int)(j - i)); e->grp_threads.push_back(t);
+        i = j;
+    }
+    cudaFree(e->d_src); e->d_src = nullptr;
+    if (!flat.empty()) {
+        CU(cudaMalloc(&e->d_src, flat.size() * sizeof(SrcOp)));
+        CU(cudaMemcpy(e->d_src, flat.data(), flat.size() * sizeof(SrcOp), cudaMemcpyHostToDevice));
+    }
+    cudaFree(e->d_prof); e->d_prof = nullptr;
+    if (!e->prof_host.empty()) {
+        CU(cudaMalloc(&e->d_prof, e->prof_host.size() * sizeof(double)));
+        CU(cudaMemcpy(e->d_prof, e->prof_host.data(), e->prof_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    long long t = 0, rec = 0, dft = 0;
+    for (auto& m : e->mon) {
+        m.first_thread = t; t += m.cells;
+        m.rec_off = rec;      // per-step offset; the kernel adds step * cells
+        if (m.record) rec += m.cells;
+        m.dft_off = dft; dft += (long long)m.n_freq * m.cells;
+    }
+    e->mon_threads = t;
+    e->rec_elems_per_step = rec;
+    cudaFree(e->d_mon); e->d_mon = nullptr;
+    if (dft != e->dft_elems || !e->d_dft) {
+        cudaFree(e->d_dft); e->d_dft = nullptr;
+        if (dft > 0) {
+            CU(cudaMalloc(&e->d_dft, dft * sizeof(double2)));
+            CU(cudaMemset(e->d_dft, 0, dft * sizeof(double2)));
+        }
+        e->dft_elems = dft;
+    }
+    e->ops_dirty = false;
+    return 0;
+}
+
+// record offsets depend on the number of tabled steps: op.rec_off = base(op) * n_steps
+static int upload_mon_ops(fdtd_engine* e)
+{
+    cudaFree(e->d_mon); e->d_mon = nullptr;
+    if (e->mon.empty()) return 0;
+    std::vector<MonOp> ops = e->mon;
+    for (auto& m : ops) m.rec_off = m.rec_off * (long long)std::max(e->n_steps_tab, 1);
+    CU(cudaMalloc(&e->d_mon, ops.size() * sizeof(MonOp)));
+    CU(cudaMemcpy(e->d_mon, ops.data(), ops.size() * sizeof(MonOp), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int fdtd_set_tables(fdtd_engine* e, int32_t n_steps, int32_t n_amp, const double* amp,
+                               int32_t n_phasor, const double* phasors)
+{
+    if (!e || n_steps < 0 || n_amp < 0 || n_phasor < 0) return fail(FDTD_EINVAL, "fdtd_set_tables: bad argument");
+    if ((n_amp > 0 && n_steps > 0 && !amp) || (n_phasor > 0 && n_steps > 0 && !phasors))
+        return fail(FDTD_EINVAL, "fdtd_set_tables: null table");
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = finalize_ops(e)) return rc;
+    for (auto& h : e->src)
+        if (h.op.table >= n_amp) return fail(FDTD_EINVAL, "source op uses table %d but n_amp = %d", h.op.table, n_amp);
+    for (auto& m : e->mon)
+        if (m.n_freq > 0 && m.phasor_col + m.n_freq > n_phasor)
+            return fail(FDTD_EINVAL, "monitor op uses phasors [%d,%d) but n_phasor = %d", m.phasor_col, m.phasor_col + m.n_freq, n_phasor);
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_amp); cudaFree(e->d_phasor); cudaFree(e->d_rec);
+    e->d_amp = e->d_phasor = nullptr; e->d_rec = nullptr;
+    e->n_steps_tab = n_steps; e->n_amp = n_amp; e->n_phasor = n_phasor;
+    if (n_steps > 0 && n_amp > 0) {
+        CU(cudaMalloc(&e->d_amp, (size_t)n_steps * n_amp * sizeof(double)));
+        CU(cudaMemcpy(e->d_amp, amp, (size_t)n_steps * n_amp * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (n_steps > 0 && n_phasor > 0) {
+        CU(cudaMalloc(&e->d_phasor, (size_t)n_steps * n_phasor * 2 * sizeof(double)));
+        CU(cudaMemcpy(e->d_phasor, phasors, (size_t)n_steps * n_phasor * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (n_steps > 0 && e->rec_elems_per_step > 0)
+        CU(cudaMalloc(&e->d_rec, (size_t)n_steps * e->rec_elems_per_step * e->esz));
+    if (int rc = upload_mon_ops(e)) return rc;
+    e->cursor = 0;
+    CU(cudaMemset(e->d_step, 0, sizeof(int)));
+    drop_graph(e);
+    return 0;
+}
+
+// ---- kernels launch helpers --------------------------------------------------------------------------------
+template <typename T> static int launch_pass3d(fdtd_engine* e, int phase, int i_begin, int i_end, cudaStream_t s)
+{
+    if (i_end <= i_begin) return 0;
+    constexpr int V = VecOf<T>::V;
+    const Geom& g = e->g;
+    const int vec_per_row = g.pz / V;
+    dim3 block(std::min(vec_per_row, 64), 1, 1);
+    block.y = std::max(1, 256 / (int)block.x);
+    dim3 grid((vec_per_row + block.x - 1) / block.x, (g.ny + block.y - 1) / block.y, i_end - i_begin);
+    Fields<T> f = fields_of<T>(cur_fields(e));
+    Coefs<T> c = coefs_of<T>(e);
+    if (phase == 0) {
+        if (e->het) k_h3d<T, true><<<grid, block, 0, s>>>(f, c, g, i_begin);
+        else k_h3d<T, false><<<grid, block, 0, s>>>(f, c, g, i_begin);
+    } else {
+        if (e->het) k_e3d<T, true><<<grid, block, 0, s>>>(f, c, g, i_begin);
+        else k_e3d<T, false><<<grid, block, 0, s>>>(f, c, g, i_begin);
+    }
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T> static int launch_pass2d(fdtd_engine* e, int phase, int parity, cudaStream_t s)
+{
+    const Geom& g = e->g;
+    dim3 block(128, 1, 1), grid((g.ny + 127) / 128, g.nx, 1);
+    Fields<T> f = fields_of<T>(cur_fields(e));
+    Coefs<T> c = coefs_of<T>(e);
+    int* cur = e->d_cnt + 6 * (parity & 1);
+    int* nxt = e->d_cnt + 6 * ((parity + 1) & 1);
+    if (phase == 0) {
+        if (e->het) k_h2d<T, true><<<grid, block, 0, s>>>(f, c, g, cur, nxt);
+        else k_h2d<T, false><<<grid, block, 0, s>>>(f, c, g, cur, nxt);
+    } else {
+        if (e->het) k_e2d<T, true><<<grid, block, 0, s>>>(f, c, g, nxt);
+        else k_e2d<T, false><<<grid, block, 0, s>>>(f, c, g, nxt);
+    }
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <typename T> static int launch_count2d(fdtd_engine* e, int parity, cudaStream_t s)
+{
+    int* cur = e->d_cnt + 6 * (parity & 1);
+    CU(cudaMemsetAsync(cur, 0, 6 * sizeof(int), s));
+    void** p = cur_fields(e);
+    CFields<T> f; f.ex = (const T*)p[0]; f.ey = (const T*)p[1]; f.ez = (const T*)p[2];
+    f.hx = f.hy = f.hz = nullptr;
+    const long long n = e->plane_elems * e->g.nx;
+    k_count2d<T><<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, s>>>(f, n, cur);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// sources (group by group, list order) then monitors, for table row (*d_step + step_off)
+template <typename T> static int launch_post(fdtd_engine* e, int step_off, int parity, cudaStream_t s)
+{
+    void** comp = e->d_comp_ptr[e->cur];
+    int* cnt_next = e->cfg.ndim == 2 ? e->d_cnt + 6 * ((parity + 1) & 1) : nullptr;
+    for (size_t gidx = 0; gidx < e->grp_first.size(); ++gidx) {
+        const long long total = e->grp_threads[gidx];
+        if (total == 0) continue;
+        k_sources<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+            (T* const*)comp, e->d_src + e->grp_first[gidx], e->grp_count[gidx], total, e->st, e->d_amp, e->n_amp,
+            e->d_step, step_off, e->d_prof, cnt_next);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    if (e->mon_threads > 0) {
+        k_monitors<T><<<(unsigned)((e->mon_threads + 255) / 256), 256, 0, s>>>(
+            (const T* const*)comp, e->d_mon, (int)e->mon.size(), e->mon_threads, e->st, e->d_phasor, e->n_phasor,
+            e->d_step, step_off, e->cfg.dt, (T*)e->d_rec, e->d_dft);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+template <typename T> static int one_step(fdtd_engine* e, int step_off, int parity, cudaStream_t s)
+{
+    if (e->cfg.ndim == 3) {
+        if (int rc = launch_pass3d<T>(e, 0, 0, e->g.nx, s)) return rc;
+        if (int rc = launch_pass3d<T>(e, 1, 0, e->g.nx, s)) return rc;
+    } else {
+        if (int rc = launch_pass2d<T>(e, 0, parity, s)) return rc;
+        if (int rc = launch_pass2d<T>(e, 1, parity, s)) return rc;
+    }
+    return launch_post<T>(e, step_off, parity, s);
+}
+
+static bool has_post(const fdtd_engine* e) { return !e->src.empty() || !e->mon.empty(); }
+
+template <typename T> static int run_steps(fdtd_engine* e, int n)
+{
+    cudaStream_t s = e->stream;
+    if (e->cfg.ndim == 2) if (int rc = launch_count2d<T>(e, 0, s)) return rc;
+    const bool use_graph = !(e->cfg.flags & FDTD_FLAG_NO_GRAPH) && n >= 32;
+    int done = 0;
+    if (use_graph) {
+        const int G = 16;
+        if (!e->gexec) {
+            cudaGraph_t graph = nullptr;
+            const long long l0 = e->launches;
+            CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            int rc = 0;
+            for (int q = 0; q < G && !rc; ++q) rc = one_step<T>(e, q, q, s);
+            if (!rc) { k_bump<<<1, 1, 0, s>>>(e->d_step, G); e->launches++; }
+            cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(FDTD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&e->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { e->gexec = nullptr; return fail(FDTD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce)); }
+            e->graph_steps = G;
+            e->graph_cur = (int)(e->launches - l0);   // kernels per replay
+            e->launches = l0;
+        }
+        while (n - done >= e->graph_steps) {
+            CU(cudaGraphLaunch(e->gexec, s));
+            e->launches += e->graph_cur;
+            done += e->graph_steps;
+        }
+    }
+    const int rest = n - done;
+    for (int q = 0; q < rest; ++q)
+        if (int rc = one_step<T>(e, q, done + q, s)) return rc;
+    if (rest > 0) { k_bump<<<1, 1, 0, s>>>(e->d_step, rest); e->launches++; CU(cudaGetLastError()); }
+    return 0;
+}
+
+extern "C" int fdtd_run(fdtd_engine* e, int32_t n_steps)
+{
+    if (!e || n_steps < 0) return fail(FDTD_EINVAL, "fdtd_run: bad argument");
+    if (n_steps == 0) return 0;
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = finalize_ops(e)) return rc;
+    if (has_post(e)) {
+        if (e->cursor + n_steps > e->n_steps_tab)
+            return fail(FDTD_ESTATE, "fdtd_run(%d): only %d tabled steps left (call fdtd_set_tables)", n_steps,
+                        e->n_steps_tab - e->cursor);
+        if (!e->d_mon && !e->mon.empty()) if (int rc = upload_mon_ops(e)) return rc;
+    }
+    int rc = e->cfg.dtype == FDTD_F64 ? run_steps<double>(e, n_steps) : run_steps<float>(e, n_steps);
+    if (rc) return rc;
+    e->cursor += n_steps;
+    e->steps_done += n_steps;
+    return 0;
+}
+
+static int single_pass(fdtd_engine* e, int phase)
+{
+    CU(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = e->stream;
+    const bool d64 = e->cfg.dtype == FDTD_F64;
+    if (e->cfg.ndim == 3)
+        return d64 ? launch_pass3d<double>(e, phase, 0, e->g.nx, s) : launch_pass3d<float>(e, phase, 0, e->g.nx, s);
+    if (phase == 0) {
+        if (int rc = d64 ? launch_count2d<double>(e, 0, s) : launch_count2d<float>(e, 0, s)) return rc;
+    }
+    return d64 ? launch_pass2d<double>(e, phase, 0, s) : launch_pass2d<float>(e, phase, 0, s);
+}
+extern "C" int fdtd_update_h(fdtd_engine* e) { return e ? single_pass(e, 0) : fail(FDTD_EINVAL, "null engine"); }
+extern "C" int fdtd_update_e(fdtd_engine* e) { return e ? single_pass(e, 1) : fail(FDTD_EINVAL, "null engine"); }
+
+extern "C" int fdtd_sync(fdtd_engine* e)
+{
+    if (!e) return fail(FDTD_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// ---- multi-GPU split entry points ------------------------------------------------------------------------------
+extern "C" int fdtd_pass(fdtd_engine* e, int32_t phase, int32_t part, void* stream)
+{
+    if (!e || phase < 0 || phase > 1 || part < 0 || part > 2) return fail(FDTD_EINVAL, "fdtd_pass: bad argument");
+    if (e->cfg.ndim != 3) return fail(FDTD_EINVAL, "fdtd_pass is 3-D only");
+    CU(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    const int nx = e->g.nx;
+    int b = 0, t = nx;
+    if (part == 0) t = nx - 1;
+    if (part == 1) b = nx - 1;
+    return e->cfg.dtype == FDTD_F64 ? launch_pass3d<double>(e, phase, b, t, s) : launch_pass3d<float>(e, phase, b, t, s);
+}
+
+extern "C" int fdtd_post_step(fdtd_engine* e, void* stream)
+{
+    if (!e) return fail(FDTD_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = finalize_ops(e)) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    if (has_post(e)) {
+        if (e->cursor + 1 > e->n_steps_tab) return fail(FDTD_ESTATE, "fdtd_post_step: no tabled steps left");
+        if (!e->d_mon && !e->mon.empty()) if (int rc = upload_mon_ops(e)) return rc;
+        int rc = e->cfg.dtype == FDTD_F64 ? launch_post<double>(e, 0, 0, s) : launch_post<float>(e, 0, 0, s);
+        if (rc) return rc;
+    }
+    k_bump<<<1, 1, 0, s>>>(e->d_step, 1); e->launches++;
+    CU(cudaGetLastError());
+    e->cursor += 1; e->steps_done += 1;
+    return 0;
+}
+
+extern "C" int fdtd_halo_ptrs(fdtd_engine* e, int32_t comp, void** first_plane, void** ghost_plane, int64_t* plane_bytes)
+{
+    if (!e || comp < 0 || comp > 5) return fail(FDTD_EINVAL, "fdtd_halo_ptrs: bad argument");
+    char* base = (char*)cur_fields(e)[comp];
+    if (first_plane) *first_plane = base;
+    if (ghost_plane) *ghost_plane = base + (size_t)e->g.nx * e->plane_elems * e->esz;
+    if (plane_bytes) *plane_bytes = (int64_t)(e->plane_elems * e->esz);
+    return 0;
+}
+
+// ---- monitor read-out ---------------------------------------------------------------------------------------------
+extern "C" int fdtd_download_records(fdtd_engine* e, int32_t id, double* host, int32_t max_steps)
+{
+    if (!e || !host || id < 0 || id >= (int)e->mon.size()) return fail(FDTD_EINVAL, "fdtd_download_records: bad argument");
+    const MonOp& m = e->mon[id];
+    if (!m.record) return fail(FDTD_EINVAL, "monitor op %d does not record", id);
+    CU(cudaSetDevice(e->cfg.device));
+    const int steps = std::min<int>(max_steps, e->cursor);
+    const long long n = (long long)steps * m.cells;
+    if (n == 0) return 0;
+    const long long off = m.rec_off * (long long)std::max(e->n_steps_tab, 1);
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->cfg.dtype == FDTD_F64) {
+        CU(cudaMemcpy(host, (const double*)e->d_rec + off, n * sizeof(double), cudaMemcpyDeviceToHost));
+    } else {
+        const long long chunk = std::min<long long>(n, (64ll << 20) / sizeof(double));
+        if (int rc = ensure_stage(e, chunk * sizeof(double))) return rc;
+        for (long long first = 0; first < n; first += chunk) {
+            const long long c = std::min(chunk, n - first);
+            k_convert<float, double><<<(int)std::min<long long>((c + 255) / 256, 148 * 16), 256, 0, e->stream>>>(
+                (double*)e->d_stage, (const float*)e->d_rec + off + first, c);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(host + first, e->d_stage, c * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaStreamSynchronize(e->stream));
+        }
+    }
+    return 0;
+}
+
+extern "C" int fdtd_download_dft(fdtd_engine* e, int32_t id, double* host)
+{
+    if (!e || !host || id < 0 || id >= (int)e->mon.size()) return fail(FDTD_EINVAL, "fdtd_download_dft: bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = finalize_ops(e)) return rc;
+    const MonOp& m = e->mon[id];
+    const long long n = (long long)m.n_freq * m.cells;
+    if (n == 0) return 0;
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(host, e->d_dft + m.dft_off, n * sizeof(double2), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int fdtd_upload_dft(fdtd_engine* e, int32_t id, const double* host)
+{
+    if (!e || !host || id < 0 || id >= (int)e->mon.size()) return fail(FDTD_EINVAL, "fdtd_upload_dft: bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = finalize_ops(e)) return rc;
+    const MonOp& m = e->mon[id];
+    const long long n = (long long)m.n_freq * m.cells;
+    if (n == 0) return 0;
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(e->d_dft + m.dft_off, host, n * sizeof(double2), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ---- introspection ---------------------------------------------------------------------------------------------------
+extern "C" int fdtd_steps_done(fdtd_engine* e, int64_t* steps)
+{
+    if (!e || !steps) return fail(FDTD_EINVAL, "bad argument");
+    *steps = e->steps_done;
+    return 0;
+}
+extern "C" int fdtd_kernel_launches(fdtd_engine* e, int64_t* launches)
+{
+    if (!e || !launches) return fail(FDTD_EINVAL, "bad argument");
+    *launches = e->launches;
+    return 0;
+}
+extern "C" int fdtd_mem_info(fdtd_engine* e, int64_t* free_bytes, int64_t* total_bytes)
+{
+    if (!e) return fail(FDTD_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return 0;
+}

@@ -1,0 +1,480 @@
+// fdtd_kernels.cuh — sm_100a device code of the B200 FDTD engine (two-pass kernels, 2-D kernels,
+// source / monitor / layout kernels).  The fused single-sweep kernel lives in fdtd_fused.cuh.
+//
+// Reference semantics (bug-compatible): /root/reference/src/prismo/core/solver.py
+//   3-D H pass :167-253, E pass :255-309, 2-D H pass :311-397, E pass :399-456, averaging :458-533.
+//
+// Layout: six SoA arrays with IDENTICAL strides.  3-D: element (i,j,k) at i*sx + j*sy + k with
+// sy = pz = round_up(nz,32), sx = ny*pz; 2-D: (i,j) at i*sx + j with sx = round_up(ny,32).
+// Each array owns nx+2 planes: [0,nx) data, plane nx = right-neighbour ghost (multi-GPU) or zeros,
+// plane nx+1 = guard, so "+1" neighbour loads never leave the allocation.  Cells outside a
+// component's staggered shape are padding: always zero, never stored with anything else.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fdtd {
+
+template <typename T> struct Fields { T *ex, *ey, *ez, *hx, *hy, *hz; };
+template <typename T> struct CFields { const T *ex, *ey, *ez, *hx, *hy, *hz; };
+
+template <typename T> struct Coefs {
+    const T *ca, *cb, *da, *db;   // cell-centred arrays (field layout) when het != 0
+    T uca, ucb, uda, udb;         // uniform values otherwise
+};
+
+struct Geom {
+    int nx, ny, nz;        // local logical dims
+    int nxg, x0;           // global nx, global index of local plane 0
+    int pz;                // padded length of the contiguous axis
+    long long sx, sy;      // strides (elements); 2-D: sy = 1
+    double dx, dy, dz;     // spacings
+    float rdx, rdy, rdz;   // fp32 reciprocals
+};
+
+// ---- arithmetic policies ---------------------------------------------------------------------
+// fp64 reproduces NumPy bit for bit: every operation rounded separately (no FMA contraction),
+// "/ d" is a true division.  fp32 is free to contract and multiplies by 1/d.
+template <typename T> struct Ar;
+template <> struct Ar<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double diff(double a1, double a0, double d, float) {
+        return __ddiv_rn(__dsub_rn(a1, a0), d);
+    }
+    static __device__ __forceinline__ double quarter() { return 0.25; }
+};
+template <> struct Ar<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float diff(float a1, float a0, double, float rd) {
+        return (a1 - a0) * rd;
+    }
+};
+
+// H: da*h - db*(c1 - c2)     E: ca*e + cb*(c1 - c2)      (solver.py:201-205, :275)
+template <typename T> __device__ __forceinline__ T upd_h(T da, T h, T db, T c1, T c2) {
+    return Ar<T>::sub(Ar<T>::mul(da, h), Ar<T>::mul(db, Ar<T>::sub(c1, c2)));
+}
+template <typename T> __device__ __forceinline__ T upd_e(T ca, T e, T cb, T c1, T c2) {
+    return Ar<T>::add(Ar<T>::mul(ca, e), Ar<T>::mul(cb, Ar<T>::sub(c1, c2)));
+}
+// 0.5*(a+b) and 0.25*(((a+b)+c)+d) in the reference's summation order (solver.py:458-501)
+template <typename T> __device__ __forceinline__ T mean2(T a, T b) {
+    return Ar<T>::mul((T)0.5, Ar<T>::add(a, b));
+}
+template <typename T> __device__ __forceinline__ T mean4(T a, T b, T c, T d) {
+    return Ar<T>::mul((T)0.25, Ar<T>::add(Ar<T>::add(Ar<T>::add(a, b), c), d));
+}
+
+// ---- vector helpers: V consecutive elements along the contiguous axis, 16 bytes ---------------
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { typedef float4 type; static const int V = 4; };
+template <> struct VecOf<double> { typedef double2 type; static const int V = 2; };
+
+template <typename T, int V> struct Pack { T v[V]; };
+
+template <typename T> __device__ __forceinline__ Pack<T, VecOf<T>::V> ldv(const T* p) {
+    typedef typename VecOf<T>::type VT;
+    union { VT q; Pack<T, VecOf<T>::V> r; } u;
+    u.q = *reinterpret_cast<const VT*>(p);
+    return u.r;
+}
+template <typename T> __device__ __forceinline__ void stv(T* p, const Pack<T, VecOf<T>::V>& r) {
+    typedef typename VecOf<T>::type VT;
+    union { VT q; Pack<T, VecOf<T>::V> r; } u;
+    u.r = r;
+    *reinterpret_cast<VT*>(p) = u.q;
+}
+// V+1 elements: the vector plus the first element of the next one (the k+1 neighbour of lane V-1)
+template <typename T> struct PackP { T v[VecOf<T>::V + 1]; };
+template <typename T> __device__ __forceinline__ PackP<T> ldvp(const T* p) {
+    PackP<T> r;
+    Pack<T, VecOf<T>::V> a = ldv<T>(p);
+#pragma unroll
+    for (int e = 0; e < VecOf<T>::V; ++e) r.v[e] = a.v[e];
+    r.v[VecOf<T>::V] = p[VecOf<T>::V];
+    return r;
+}
+
+// =================================================================================================
+// 3-D two-pass kernels.  One thread owns V consecutive k of one (i,j) row.
+// grid: x = ceil(pz/V / bx), y = ceil(ny / by), z = planes in [i_begin, i_end)
+// =================================================================================================
+template <typename T, bool HET>
+__global__ void __launch_bounds__(256)
+k_h3d(Fields<T> f, Coefs<T> c, Geom g, int i_begin)
+{
+    constexpr int V = VecOf<T>::V;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = i_begin + blockIdx.z;
+    if (k >= g.pz || j >= g.ny) return;
+    const long long o = (long long)i * g.sx + (long long)j * g.sy + k;
+
+    const PackP<T> ex = ldvp<T>(f.ex + o), ey = ldvp<T>(f.ey + o);
+    const Pack<T, V> ez = ldv<T>(f.ez + o);
+    const Pack<T, V> ez_j = ldv<T>(f.ez + o + g.sy), ex_j = ldv<T>(f.ex + o + g.sy);
+    const Pack<T, V> ez_i = ldv<T>(f.ez + o + g.sx), ey_i = ldv<T>(f.ey + o + g.sx);
+    Pack<T, V> hx = ldv<T>(f.hx + o), hy = ldv<T>(f.hy + o), hz = ldv<T>(f.hz + o);
+
+    PackP<T> da, db;
+    Pack<T, V> da_i, db_i, da_j, db_j;
+    if (HET) {
+        da = ldvp<T>(c.da + o); db = ldvp<T>(c.db + o);
+        da_i = ldv<T>(c.da + o + g.sx); db_i = ldv<T>(c.db + o + g.sx);
+        da_j = ldv<T>(c.da + o + g.sy); db_j = ldv<T>(c.db + o + g.sy);
+    }
+    const int gi = g.x0 + i;
+    const bool ix1 = gi < g.nxg - 1, ix2 = gi < g.nxg - 2;
+    const bool jy1 = j < g.ny - 1, jy2 = j < g.ny - 2;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const bool kz1 = (k + e) < g.nz - 1, kz2 = (k + e) < g.nz - 2;
+        T a, b;
+        // Hx (solver.py:178-205): j < ny-2, k < nz-2, every plane of the (nx-1)-plane array
+        if (HET) { a = mean2<T>(da.v[e], da_i.v[e]); b = mean2<T>(db.v[e], db_i.v[e]); }
+        else { a = c.uda; b = c.udb; }
+        T n = upd_h<T>(a, hx.v[e], b, Ar<T>::diff(ez_j.v[e], ez.v[e], g.dy, g.rdy),
+                       Ar<T>::diff(ey.v[e + 1], ey.v[e], g.dz, g.rdz));
+        if (ix1 && jy2 && kz2) hx.v[e] = n;
+        // Hy (:212-229): i < nx-2, k < nz-2
+        if (HET) { a = mean2<T>(da.v[e], da_j.v[e]); b = mean2<T>(db.v[e], db_j.v[e]); }
+        n = upd_h<T>(a, hy.v[e], b, Ar<T>::diff(ex.v[e + 1], ex.v[e], g.dz, g.rdz),
+                     Ar<T>::diff(ez_i.v[e], ez.v[e], g.dx, g.rdx));
+        if (ix2 && jy1 && kz2) hy.v[e] = n;
+        // Hz (:236-253): i < nx-2, j < ny-2
+        if (HET) { a = mean2<T>(da.v[e], da.v[e + 1]); b = mean2<T>(db.v[e], db.v[e + 1]); }
+        n = upd_h<T>(a, hz.v[e], b, Ar<T>::diff(ey_i.v[e], ey.v[e], g.dx, g.rdx),
+                     Ar<T>::diff(ex_j.v[e], ex.v[e], g.dy, g.rdy));
+        if (ix2 && jy2 && kz1) hz.v[e] = n;
+    }
+    stv<T>(f.hx + o, hx); stv<T>(f.hy + o, hy); stv<T>(f.hz + o, hz);
+}
+
+template <typename T, bool HET>
+__global__ void __launch_bounds__(256)
+k_e3d(Fields<T> f, Coefs<T> c, Geom g, int i_begin)
+{
+    constexpr int V = VecOf<T>::V;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = i_begin + blockIdx.z;
+    if (k >= g.pz || j >= g.ny) return;
+    const long long o = (long long)i * g.sx + (long long)j * g.sy + k;
+
+    const PackP<T> hx = ldvp<T>(f.hx + o), hy = ldvp<T>(f.hy + o);
+    const Pack<T, V> hz = ldv<T>(f.hz + o);
+    const Pack<T, V> hz_j = ldv<T>(f.hz + o + g.sy), hx_j = ldv<T>(f.hx + o + g.sy);
+    const Pack<T, V> hz_i = ldv<T>(f.hz + o + g.sx), hy_i = ldv<T>(f.hy + o + g.sx);
+    Pack<T, V> ex = ldv<T>(f.ex + o), ey = ldv<T>(f.ey + o), ez = ldv<T>(f.ez + o);
+
+    PackP<T> ca, cb, ca_j, cb_j, ca_i, cb_i;
+    Pack<T, V> ca_ij, cb_ij;
+    if (HET) {
+        ca = ldvp<T>(c.ca + o); cb = ldvp<T>(c.cb + o);
+        ca_j = ldvp<T>(c.ca + o + g.sy); cb_j = ldvp<T>(c.cb + o + g.sy);
+        ca_i = ldvp<T>(c.ca + o + g.sx); cb_i = ldvp<T>(c.cb + o + g.sx);
+        ca_ij = ldv<T>(c.ca + o + g.sx + g.sy); cb_ij = ldv<T>(c.cb + o + g.sx + g.sy);
+    }
+    const int gi = g.x0 + i;
+    const bool ix0 = gi < g.nxg, ix1 = gi < g.nxg - 1;
+    const bool jy0 = j < g.ny, jy1 = j < g.ny - 1;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;
+        T a, b;
+        // Ex (solver.py:265-275): averaged over y and z
+        if (HET) {
+            a = mean4<T>(ca.v[e], ca_j.v[e], ca.v[e + 1], ca_j.v[e + 1]);
+            b = mean4<T>(cb.v[e], cb_j.v[e], cb.v[e + 1], cb_j.v[e + 1]);
+        } else { a = c.uca; b = c.ucb; }
+        T n = upd_e<T>(a, ex.v[e], b, Ar<T>::diff(hz_j.v[e], hz.v[e], g.dy, g.rdy),
+                       Ar<T>::diff(hy.v[e + 1], hy.v[e], g.dz, g.rdz));
+        if (ix0 && jy1 && kz1) ex.v[e] = n;
+        // Ey (:282-292): averaged over x and z
+        if (HET) {
+            a = mean4<T>(ca.v[e], ca_i.v[e], ca.v[e + 1], ca_i.v[e + 1]);
+            b = mean4<T>(cb.v[e], cb_i.v[e], cb.v[e + 1], cb_i.v[e + 1]);
+        }
+        n = upd_e<T>(a, ey.v[e], b, Ar<T>::diff(hx.v[e + 1], hx.v[e], g.dz, g.rdz),
+                     Ar<T>::diff(hz_i.v[e], hz.v[e], g.dx, g.rdx));
+        if (ix1 && jy0 && kz1) ey.v[e] = n;
+        // Ez (:299-309): averaged over x and y
+        if (HET) {
+            a = mean4<T>(ca.v[e], ca_i.v[e], ca_j.v[e], ca_ij.v[e]);
+            b = mean4<T>(cb.v[e], cb_i.v[e], cb_j.v[e], cb_ij.v[e]);
+        }
+        n = upd_e<T>(a, ez.v[e], b, Ar<T>::diff(hy_i.v[e], hy.v[e], g.dx, g.rdx),
+                     Ar<T>::diff(hx_j.v[e], hx.v[e], g.dy, g.rdy));
+        if (ix1 && jy1 && kz0) ez.v[e] = n;
+    }
+    stv<T>(f.ex + o, ex); stv<T>(f.ey + o, ey); stv<T>(f.ez + o, ez);
+}
+
+// =================================================================================================
+// 2-D kernels (y contiguous).  One thread per (i,j).  Gates (solver.py:321,367) come from exact
+// device-side counts of non-zero / NaN cells per E component: cnt[0..2] = #(|F|>0), cnt[3..5] = #NaN.
+// =================================================================================================
+__device__ __forceinline__ bool gate_on(const int* cnt, int comp) {
+    // np.max(np.abs(F)) > 0  <=>  no NaN anywhere (max would be NaN) and some |F| > 0
+    return cnt[3 + comp] == 0 && cnt[comp] > 0;
+}
+
+template <typename T, bool HET>
+__global__ void __launch_bounds__(256)
+k_h2d(Fields<T> f, Coefs<T> c, Geom g, const int* __restrict__ cnt_cur, int* __restrict__ cnt_next)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 6 && cnt_next) cnt_next[threadIdx.x] = 0;
+    if (j >= g.ny) return;
+    const bool g1 = gate_on(cnt_cur, 2);
+    const bool g2 = gate_on(cnt_cur, 0) || gate_on(cnt_cur, 1);
+    const long long o = (long long)i * g.sx + j;
+    const bool ix1 = i < g.nx - 1, ix2 = i < g.nx - 2;
+    const bool jy1 = j < g.ny - 1, jy2 = j < g.ny - 2;
+    T da = c.uda, db = c.udb, da_i = c.uda, db_i = c.udb, da_j = c.uda, db_j = c.udb;
+    if (HET) {
+        da = c.da[o]; db = c.db[o];
+        da_i = c.da[o + g.sx]; db_i = c.db[o + g.sx];
+        da_j = c.da[o + 1]; db_j = c.db[o + 1];
+    }
+    if (g1) {
+        const T ez = f.ez[o];
+        if (ix1 && jy2) {   // Hx[:, :ny-2] = da*Hx + db*dEz/dy   (sign kept, solver.py:338-341)
+            const T a = HET ? mean2<T>(da, da_i) : da, b = HET ? mean2<T>(db, db_i) : db;
+            f.hx[o] = Ar<T>::add(Ar<T>::mul(a, f.hx[o]),
+                                 Ar<T>::mul(b, Ar<T>::diff(f.ez[o + 1], ez, g.dy, g.rdy)));
+        }
+        if (ix2 && jy1) {   // Hy[:nx-2, :] = da*Hy - db*dEz/dx     (:358-361)
+            const T a = HET ? mean2<T>(da, da_j) : da, b = HET ? mean2<T>(db, db_j) : db;
+            f.hy[o] = Ar<T>::sub(Ar<T>::mul(a, f.hy[o]),
+                                 Ar<T>::mul(b, Ar<T>::diff(f.ez[o + g.sx], ez, g.dx, g.rdx)));
+        }
+    }
+    if (g2) {               // whole Hz array, curls zero-padded, coefficients not averaged (:371-397)
+        const T cey = ix2 ? Ar<T>::diff(f.ey[o + g.sx], f.ey[o], g.dx, g.rdx) : (T)0;
+        const T cex = jy2 ? Ar<T>::diff(f.ex[o + 1], f.ex[o], g.dy, g.rdy) : (T)0;
+        f.hz[o] = upd_h<T>(da, f.hz[o], db, cey, cex);
+    }
+}
+
+template <typename T> __device__ __forceinline__ void count_cell(T v, int& nz, int& nn) {
+    nz += (fabs((double)v) > 0.0) ? 1 : 0;
+    nn += (v != v) ? 1 : 0;
+}
+
+__device__ __forceinline__ void block_count_flush(int* cnt, int comp, int nz, int nn) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        nz += __shfl_xor_sync(0xffffffffu, nz, s);
+        nn += __shfl_xor_sync(0xffffffffu, nn, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nz) atomicAdd(cnt + comp, nz);
+        if (nn) atomicAdd(cnt + 3 + comp, nn);
+    }
+}
+
+template <typename T, bool HET>
+__global__ void __launch_bounds__(256)
+k_e2d(Fields<T> f, Coefs<T> c, Geom g, int* __restrict__ cnt_next)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    int nz0 = 0, nn0 = 0, nz1 = 0, nn1 = 0, nz2 = 0, nn2 = 0;
+    if (j < g.ny) {
+        const long long o = (long long)i * g.sx + j;
+        const bool ix1 = i < g.nx - 1, jy1 = j < g.ny - 1;
+        T ca = c.uca, cb = c.ucb, ca_i = c.uca, cb_i = c.ucb, ca_j = c.uca, cb_j = c.ucb,
+          ca_ij = c.uca, cb_ij = c.ucb;
+        if (HET) {
+            ca = c.ca[o]; cb = c.cb[o];
+            ca_i = c.ca[o + g.sx]; cb_i = c.cb[o + g.sx];
+            ca_j = c.ca[o + 1]; cb_j = c.cb[o + 1];
+            ca_ij = c.ca[o + g.sx + 1]; cb_ij = c.cb[o + g.sx + 1];
+        }
+        const T hz = f.hz[o];
+        if (ix1 && jy1) {   // Ez (solver.py:409-423)
+            const T a = HET ? mean4<T>(ca, ca_i, ca_j, ca_ij) : ca;
+            const T b = HET ? mean4<T>(cb, cb_i, cb_j, cb_ij) : cb;
+            const T hy = f.hy[o], hx = f.hx[o];
+            const T n = upd_e<T>(a, f.ez[o], b, Ar<T>::diff(f.hy[o + g.sx], hy, g.dx, g.rdx),
+                                 Ar<T>::diff(f.hx[o + 1], hx, g.dy, g.rdy));
+            f.ez[o] = n; count_cell<T>(n, nz2, nn2);
+        }
+        if (jy1) {          // Ex = ca*Ex + cb*dHz/dy (:433-442)
+            const T a = HET ? mean2<T>(ca, ca_j) : ca, b = HET ? mean2<T>(cb, cb_j) : cb;
+            const T n = Ar<T>::add(Ar<T>::mul(a, f.ex[o]),
+                                   Ar<T>::mul(b, Ar<T>::diff(f.hz[o + 1], hz, g.dy, g.rdy)));
+            f.ex[o] = n; count_cell<T>(n, nz0, nn0);
+        }
+        if (ix1) {          // Ey = ca*Ey - cb*dHz/dx (:447-456)
+            const T a = HET ? mean2<T>(ca, ca_i) : ca, b = HET ? mean2<T>(cb, cb_i) : cb;
+            const T n = Ar<T>::sub(Ar<T>::mul(a, f.ey[o]),
+                                   Ar<T>::mul(b, Ar<T>::diff(f.hz[o + g.sx], hz, g.dx, g.rdx)));
+            f.ey[o] = n; count_cell<T>(n, nz1, nn1);
+        }
+    }
+    if (cnt_next) {
+        block_count_flush(cnt_next, 0, nz0, nn0);
+        block_count_flush(cnt_next, 1, nz1, nn1);
+        block_count_flush(cnt_next, 2, nz2, nn2);
+    }
+}
+
+// count non-zero / NaN cells of the three E arrays (2-D gates), whole padded array (padding is 0)
+template <typename T>
+__global__ void k_count2d(CFields<T> f, long long n, int* __restrict__ cnt)
+{
+    int nz0 = 0, nn0 = 0, nz1 = 0, nn1 = 0, nz2 = 0, nn2 = 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x) {
+        count_cell<T>(f.ex[t], nz0, nn0);
+        count_cell<T>(f.ey[t], nz1, nn1);
+        count_cell<T>(f.ez[t], nz2, nn2);
+    }
+    block_count_flush(cnt, 0, nz0, nn0);
+    block_count_flush(cnt, 1, nz1, nn1);
+    block_count_flush(cnt, 2, nz2, nn2);
+}
+
+// =================================================================================================
+// sources and monitors
+// =================================================================================================
+struct SrcOp {
+    int comp;
+    int lo[3], n[3];          // box origin and extent (n[2] = 1 in 2-D)
+    int table;
+    long long prof_off;       // offset into the profile pool, -1 = uniform
+    double divisor;
+    long long first_thread;   // prefix of cells over the ops of one launch
+};
+struct MonOp {
+    int comp;
+    int lo[3], n[3];
+    int record, n_freq, phasor_col;
+    long long rec_off;        // offset into the record pool (elements of T) of step 0
+    long long dft_off;        // offset into the dft pool (complex = 2 doubles)
+    long long cells;
+    long long first_thread;
+};
+
+struct Strides3 { long long s[3]; };   // 3-D: (sx, sy, 1); 2-D: (sx, 1, 0)
+
+// F[box] += amp[step][table] (* profile / divisor).  Arithmetic in fp64, rounded once to T on store
+// (what NumPy does for "f32_array += python_float").  Keeps the 2-D gate counters exact.
+template <typename T>
+__global__ void k_sources(T* const* __restrict__ comp_ptr, const SrcOp* __restrict__ ops, int n_ops,
+                          long long total, Strides3 st, const double* __restrict__ amp, int n_amp,
+                          const int* __restrict__ step_ptr, int step_off,
+                          const double* __restrict__ prof, int* __restrict__ cnt)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int q = 0;
+    while (q + 1 < n_ops && ops[q + 1].first_thread <= t) ++q;
+    const SrcOp op = ops[q];
+    const long long cell = t - op.first_thread;
+    const int c2 = (int)(cell % op.n[2]);
+    const long long r = cell / op.n[2];
+    const int c1 = (int)(r % op.n[1]);
+    const int c0 = (int)(r / op.n[1]);
+    const long long o = (op.lo[0] + c0) * st.s[0] + (op.lo[1] + c1) * st.s[1] + (op.lo[2] + c2) * st.s[2];
+    const int step = *step_ptr + step_off;
+    double a = amp[(long long)step * n_amp + op.table];
+    if (op.prof_off >= 0) {
+        a = __dmul_rn(a, prof[op.prof_off + cell]);
+        if (op.divisor != 1.0) a = __ddiv_rn(a, op.divisor);
+    }
+    T* p = comp_ptr[op.comp] + o;
+    const T old = *p;
+    const T nv = (T)__dadd_rn((double)old, a);
+    *p = nv;
+    if (cnt && op.comp < 3) {
+        const int dz = ((fabs((double)nv) > 0.0) ? 1 : 0) - ((fabs((double)old) > 0.0) ? 1 : 0);
+        const int dn = ((nv != nv) ? 1 : 0) - ((old != old) ? 1 : 0);
+        if (dz) atomicAdd(cnt + op.comp, dz);
+        if (dn) atomicAdd(cnt + 3 + op.comp, dn);
+    }
+}
+
+// record the box and / or accumulate the running DFT  acc[f] += (F*ph)*dt  (monitors/field.py:139-143)
+template <typename T>
+__global__ void k_monitors(const T* const* __restrict__ comp_ptr, const MonOp* __restrict__ ops,
+                           int n_ops, long long total, Strides3 st, const double* __restrict__ phasors,
+                           int n_phasor, const int* __restrict__ step_ptr, int step_off, double dt,
+                           T* __restrict__ rec, double2* __restrict__ dft)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int q = 0;
+    while (q + 1 < n_ops && ops[q + 1].first_thread <= t) ++q;
+    const MonOp op = ops[q];
+    const long long cell = t - op.first_thread;
+    const int c2 = (int)(cell % op.n[2]);
+    const long long r = cell / op.n[2];
+    const int c1 = (int)(r % op.n[1]);
+    const int c0 = (int)(r / op.n[1]);
+    const long long o = (op.lo[0] + c0) * st.s[0] + (op.lo[1] + c1) * st.s[1] + (op.lo[2] + c2) * st.s[2];
+    const int step = *step_ptr + step_off;
+    const T v = comp_ptr[op.comp][o];
+    if (op.record) rec[op.rec_off + (long long)step * op.cells + cell] = v;
+    if (op.n_freq > 0) {
+        const double d = (double)v;
+        const double* ph = phasors + ((long long)step * n_phasor + op.phasor_col) * 2;
+        for (int fq = 0; fq < op.n_freq; ++fq) {
+            double2* a = dft + op.dft_off + (long long)fq * op.cells + cell;
+            double2 acc = *a;
+            acc.x = __dadd_rn(acc.x, __dmul_rn(__dmul_rn(d, ph[2 * fq]), dt));
+            acc.y = __dadd_rn(acc.y, __dmul_rn(__dmul_rn(d, ph[2 * fq + 1]), dt));
+            *a = acc;
+        }
+    }
+}
+
+__global__ void k_bump(int* step_ptr, int n) { *step_ptr += n; }
+
+// =================================================================================================
+// layout: compact host-order chunk <-> padded device array (with dtype conversion)
+// =================================================================================================
+template <typename TD, typename TH>
+__global__ void k_scatter(TD* __restrict__ dst, const TH* __restrict__ src, long long first, long long count,
+                          int c1, int c2, Strides3 st)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long lin = first + t;
+        const int k = (int)(lin % c2);
+        const long long r = lin / c2;
+        const int j = (int)(r % c1);
+        const long long i = r / c1;
+        dst[i * st.s[0] + j * st.s[1] + k * st.s[2]] = (TD)src[t];
+    }
+}
+template <typename TD, typename TH>
+__global__ void k_gather(TH* __restrict__ dst, const TD* __restrict__ src, long long first, long long count,
+                         int c1, int c2, Strides3 st)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long lin = first + t;
+        const int k = (int)(lin % c2);
+        const long long r = lin / c2;
+        const int j = (int)(r % c1);
+        const long long i = r / c1;
+        dst[t] = (TH)src[i * st.s[0] + j * st.s[1] + k * st.s[2]];
+    }
+}
+template <typename TD, typename TH>
+__global__ void k_convert(TH* __restrict__ dst, const TD* __restrict__ src, long long n)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x)
+        dst[t] = (TH)src[t];
+}
+
+}  // namespace fdtd

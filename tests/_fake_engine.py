@@ -1,0 +1,129 @@
+"""NumPy test double for prismo_b200.engine.Engine — interprets the device op descriptors on the CPU.
+
+TEST INFRASTRUCTURE.  It exists so that the host logic (lowering of sources/monitors to ops, tables,
+chunking, write-back into monitor objects, the prismo plugin) can be verified without a GPU against the
+real reference.  It implements exactly the op semantics documented in include/fdtd_b200.h, with the oracle
+kernels standing in for the CUDA field update.  The product never imports this.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import kernels
+from prismo_b200.grid import SHORT_AXES
+
+COMPONENTS = ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")
+
+
+class FakeEngine:
+    instances = []
+
+    def __init__(self, ndim, dims, spacing, dt, dtype="float64", device=0, nx_global=None, x_offset=0, flags=0):
+        self.ndim, self.dims, self.spacing, self.dt = ndim, tuple(dims), tuple(spacing), dt
+        self.dtype = np.dtype(dtype)
+        self.F = {c: np.zeros(self.field_shape(c), dtype=np.float64) for c in COMPONENTS}
+        full = self.dims if ndim == 3 else (self.dims[0], self.dims[1], 1)
+        eps0, mu0 = 8.854187817e-12, 4 * np.pi * 1e-7
+        self.coeffs = [np.full(full, v) for v in (1.0, dt / eps0, 1.0, dt / mu0)]
+        self.src, self.mon = [], []
+        self.cursor, self.n_tab = 0, 0
+        self.kernel_launches = 0
+        self.uploads = 0
+        FakeEngine.instances.append(self)
+
+    def close(self):
+        pass
+
+    def field_shape(self, comp):
+        n = list(self.dims[: self.ndim])
+        for ax in SHORT_AXES[comp]:
+            if ax < self.ndim:
+                n[ax] -= 1
+        return tuple(n)
+
+    def set_uniform_coeffs(self, ca, cb, da, db):
+        full = self.dims if self.ndim == 3 else (self.dims[0], self.dims[1], 1)
+        self.coeffs = [np.full(full, float(v)) for v in (ca, cb, da, db)]
+
+    def set_coeffs(self, Ca, Cb, Da, Db):
+        self.coeffs = [np.array(a, dtype=np.float64).reshape(self.dims if self.ndim == 3 else self.dims[:2] + (1,))
+                       for a in (Ca, Cb, Da, Db)]
+
+    def upload(self, comp, a):
+        a = np.asarray(a)
+        if a.shape != self.field_shape(comp):
+            raise ValueError("shape")
+        self.F[comp][...] = a
+        self.uploads += 1
+
+    def download(self, comp, out=None):
+        if out is None:
+            return self.F[comp].copy()
+        out[...] = self.F[comp]
+        return out
+
+    def clear_ops(self):
+        self.src, self.mon = [], []
+
+    def add_source_op(self, op):
+        self.src.append(op)
+
+    def add_monitor_op(self, op):
+        op.shape = tuple(h - l for l, h in zip(op.lo, op.hi))
+        self.mon.append(dict(op=op, rec=[], dft=np.zeros((op.n_freq,) + op.shape, dtype=np.complex128)))
+        return len(self.mon) - 1
+
+    def set_tables(self, n_steps, amp=None, phasors=None):
+        self.amp = None if amp is None else np.asarray(amp).reshape(n_steps, -1)
+        self.ph = None if phasors is None else np.asarray(phasors).reshape(n_steps, -1)
+        self.n_tab, self.cursor = n_steps, 0
+        for m in self.mon:
+            m["rec"] = []
+
+    def _sl(self, op):
+        return tuple(slice(l, h) for l, h in zip(op.lo, op.hi))
+
+    def run(self, n):
+        if (self.src or self.mon) and self.cursor + n > self.n_tab:
+            raise RuntimeError("no tabled steps left")
+        Ca, Cb, Da, Db = self.coeffs
+        for _ in range(n):
+            kernels.step(self.F, (Ca, Cb, Da, Db), self.spacing + ((0.0,) if len(self.spacing) == 2 else ()), self.ndim == 2)
+            s = self.cursor
+            for g in sorted({o.group for o in self.src}):
+                for o in (o for o in self.src if o.group == g):
+                    a = self.amp[s, o.table]
+                    if o.profile is not None:
+                        a = a * np.asarray(o.profile)
+                        if o.divisor != 1.0:
+                            a = a / o.divisor
+                    self.F[o.component][self._sl(o)] += a
+            for m in self.mon:
+                o = m["op"]
+                d = self.F[o.component][self._sl(o)].copy()
+                if o.record:
+                    m["rec"].append(d)
+                for k in range(o.n_freq):
+                    ph = self.ph[s, o.phasor_col + k]
+                    m["dft"][k] += (d * ph.real) * self.dt + 1j * ((d * ph.imag) * self.dt)
+            self.cursor += 1
+            self.kernel_launches += 2
+
+    def update_h(self):
+        kernels.update_h(self.F, self.coeffs[2], self.coeffs[3], self.spacing, self.ndim == 2)
+
+    def update_e(self):
+        kernels.update_e(self.F, self.coeffs[0], self.coeffs[1], self.spacing, self.ndim == 2)
+
+    def sync(self):
+        pass
+
+    def records(self, i, steps):
+        m = self.mon[i]
+        return np.array(m["rec"][:steps]).reshape((steps,) + m["op"].shape)
+
+    def dft(self, i):
+        return self.mon[i]["dft"].copy()
+
+    def set_dft(self, i, v):
+        self.mon[i]["dft"][...] = v

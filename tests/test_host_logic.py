@@ -1,0 +1,166 @@
+"""Host-side logic without a GPU: lowering, tables, chunking, write-back and the prismo plugin, run on a
+NumPy test double of the engine (tests/_fake_engine.py) and compared with golden / live reference results."""
+import os
+
+import numpy as np
+import pytest
+
+import prismo_b200 as pb
+import prismo_b200.session as session
+from tests import scenarios as S
+from tests._fake_engine import FakeEngine
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+# scipy.ndimage.zoom(a*P) vs a*zoom(P): the one place the lowering is not bitwise (a few ulp)
+TOL = {"src3d_mode": 1e-14}
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    monkeypatch.setattr(session, "Engine", FakeEngine)
+    FakeEngine.instances.clear()
+    return FakeEngine
+
+
+def _compare(name, res, gold):
+    assert sorted(res) == sorted(gold)
+    for k in gold:
+        if name in TOL:
+            assert S.rel_l2(res[k], gold[k]) <= TOL[name], f"{name}:{k}"
+        else:
+            assert res[k].shape == gold[k].shape and np.array_equal(res[k], gold[k], equal_nan=True), \
+                f"{name}:{k} rel-L2 {S.rel_l2(res[k], gold[k]):.3e}"
+
+
+@pytest.mark.parametrize("name", sorted(S.SCENARIOS))
+def test_mirror_classes_lower_like_reference(name, fake):
+    spec = S.SCENARIOS[name]
+    gold = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    sim = S.build_mirror(spec, pb)
+    sim.run_steps(3)                              # two submissions: DFT sums and records must carry over
+    sim.run_steps(spec["steps"] - 3)
+    _compare(name, S.results_mirror(sim), gold)
+    assert sim.step_count == spec["steps"] and sim.solver.step_count == spec["steps"]
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("name", sorted(S.SCENARIOS))
+def test_plugin_runs_reference_objects(name, fake, ref):
+    """prismo.set_backend('b200') + unchanged reference Simulation/sources/monitors."""
+    pb.register()
+    spec = S.SCENARIOS[name]
+    gold = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    try:
+        sim = S.build_reference(spec, ref, backend="b200")
+        assert sim.solver.updater.backend.name == "b200" and sim.fields.backend.is_gpu
+        sim.step()
+        sim.run((spec["steps"] - 1 - 0.5) * sim.dt)        # ceil -> steps-1 more
+        assert len(fake.instances) == 1                    # one engine per simulation, reused
+        _compare(name, S.results_reference(sim), gold)
+    finally:
+        ref.set_backend("numpy")
+
+
+@pytest.mark.reference
+def test_plugin_leaves_other_backends_alone(fake, ref):
+    pb.register()
+    assert "b200" in ref.list_available_backends() and "numpy" in ref.list_available_backends()
+    with pytest.raises(ValueError, match="Unknown backend"):
+        ref.set_backend("nope")
+    ref.set_backend("numpy")
+    sim = S.build_reference(S.SCENARIOS["upd3d_vac"], ref)
+    sim.step()
+    assert not fake.instances                              # stock NumPy path, no engine created
+    assert ref.get_backend().name == "numpy"
+    b = ref.get_backend("b200")
+    assert b.name == "b200" and b.is_gpu and isinstance(b.zeros((2, 2)), np.ndarray)
+    ref.set_backend("numpy")
+
+
+@pytest.mark.reference
+def test_plugin_progress_callback_and_solver_entry_points(fake, ref):
+    pb.register()
+    try:
+        spec = S.SCENARIOS["src3d_plane"]
+        ref.set_backend("numpy")
+        a = S.build_reference(spec, ref)
+        calls_a = []
+        a.run(25.5 * a.dt, progress_callback=lambda i, n, t, el: calls_a.append((i, n, t)), progress_interval=7)
+        b = S.build_reference(spec, ref, backend="b200")
+        calls_b = []
+        b.run(25.5 * b.dt, progress_callback=lambda i, n, t, el: calls_b.append((i, n, t)), progress_interval=7)
+        assert calls_a == calls_b and len(calls_a) == 5
+        for c in S.COMPONENTS:
+            assert np.array_equal(a.fields[c], b.fields[c], equal_nan=True)
+        # FDTDSolver.run_steps with a per-step callback, MaxwellUpdater half steps
+        seen = []
+        b.solver.run_steps(3, callback=lambda s, k: seen.append((k, s.step_count)))
+        a.solver.fields = a.fields
+        assert [k for k, _ in seen] == [0, 1, 2]
+        b.solver.updater.update_magnetic_fields(b.fields)
+        b.solver.updater.update_electric_fields(b.fields)
+    finally:
+        ref.set_backend("numpy")
+
+
+def test_tables_follow_accumulated_time(fake):
+    t = session.Session.step_times(0.0, 0.1, 5)
+    acc = 0.0
+    for k in range(5):
+        acc += 0.1
+        assert t[k] == acc                               # repeated adds, not (k+1)*dt
+    assert session.Session.step_times(0.0, 0.1, 10)[-1] != 10 * 0.1     # 0.9999999999999999
+
+
+def test_record_pool_chunking(fake, monkeypatch):
+    """A tiny record pool forces many chunks; results must not change."""
+    spec = S.SCENARIOS["mon3d_field"]
+    gold = dict(np.load(os.path.join(GOLD, "mon3d_field.npz")))
+    monkeypatch.setattr(session, "_RECORD_POOL_BYTES", 3 * 8 * 6 * 200)
+    sim = S.build_mirror(spec, pb)
+    sim.run_steps(spec["steps"])
+    _compare("mon3d_field", S.results_mirror(sim), gold)
+
+
+def test_unknown_source_is_rejected(fake):
+    class Weird:
+        enabled = True
+
+    sim = pb.Simulation((0.5e-6, 0.5e-6, 0.5e-6), 20e6, pml_layers=2)
+    sim.sources.append(Weird())
+    with pytest.raises(NotImplementedError, match="no CPU fallback"):
+        sim.step()
+
+
+def test_reference_error_behaviour(fake):
+    g = pb.YeeGrid(pb.GridSpec((0.5e-6, 0.5e-6, 0.5e-6), 20e6, 2))
+    with pytest.raises(ValueError, match="Courant"):
+        pb.MaxwellUpdater(g, dt=1.0)                               # solver.py:67-71
+    f = pb.ElectromagneticFields(g)
+    with pytest.raises(KeyError):
+        f["Bx"]                                                    # fields.py:86-87
+    with pytest.raises(ValueError, match="Shape mismatch"):
+        f["Ex"] = np.zeros((2, 2, 2))
+    with pytest.raises(ValueError):
+        pb.PlaneWaveSource((0, 0, 0), (0, 0, 0), "x", "x", 1e14, pulse=False)
+    with pytest.raises(ValueError, match="pulse_width"):
+        pb.ElectricDipole((0, 0, 0), "x", 1e14)
+    sim2 = pb.Simulation((1e-6, 0.8e-6, 0.0), 20e6, pml_layers=3)
+    sim3 = pb.Simulation((0.5e-6, 0.5e-6, 0.5e-6), 20e6, pml_layers=2)
+    sim3.add_monitor(pb.DFTMonitor((0, 0, 0), (0, 0, 0), [1e14]))
+    with pytest.raises(ValueError, match="2-D only"):              # reference raises in 3-D too (F8)
+        sim3.step()
+    sim2.add_source(pb.ModeSource((0, 0, 0), (0, 0.2e-6, 0), None, "+x", None))
+    with pytest.raises(IndexError):
+        sim2.step()
+
+
+def test_grid_matches_reference_quirks():
+    g = pb.YeeGrid(pb.GridSpec((10e-6, 5e-6, 0.0), 50e6, 10))
+    assert g.dimensions == (521, 271, 1) and g.is_2d            # float ceil: 10e-6*50e6 -> 501 (+20)
+    assert g.get_field_shape("Ex") == (521, 270) and g.get_field_shape("Hz") == (521, 271)
+    assert g.point_to_index((-1.0, 1.0, 0.0)) == (0, g.Ny - 1, 0)   # clamps to the PHYSICAL count
+    g3 = pb.YeeGrid(pb.GridSpec((1e-6, 1e-6, 1e-6), 20e6, 5))
+    assert g3.get_field_shape("Ey") == (29, 30, 29)
+    ix = g3.get_component_indices("Ez", 0, 100, 3, 4, 0, 100)
+    assert ix[0].shape == (20, 1, 1) and ix[1].ravel().tolist() == [3] and ix[2].shape == (1, 1, 20)
