@@ -130,8 +130,13 @@ int  fdtd_run_profiled(fdtd_engine* e, int32_t n_steps, double* out_ms);
  * (the only one that reads the right neighbour's ghost plane), 2 = everything.
  * stream = a cudaStream_t (0 = the engine's own stream).                                        */
 int  fdtd_pass(fdtd_engine* e, int32_t phase, int32_t part, void* stream);
+/* fused single-sweep step over local planes [i_begin, i_end): current set -> other set; flip != 0 makes the
+ * other set current (last piece of a step).  Slabs: planes nx, nx+1 of the current set are ghosts that must
+ * hold the right neighbour's planes 0, 1 before the piece containing plane nx-1 is launched.                */
+int  fdtd_sweep(fdtd_engine* e, int32_t i_begin, int32_t i_end, int32_t flip, void* stream);
 int  fdtd_post_step(fdtd_engine* e, void* stream);   /* sources + monitors + cursor advance       */
-/* first local plane (send side) / ghost plane (receive side) of a component */
+/* first local plane (send side) / first ghost plane (receive side) of a component IN THE CURRENT SET;
+ * plane 1 / the second ghost plane follow contiguously at +plane_bytes                                    */
 int  fdtd_halo_ptrs(fdtd_engine* e, int32_t component, void** first_plane, void** ghost_plane,
                     int64_t* plane_bytes);
 

@@ -71,6 +71,7 @@ _PROTOS = {
     "fdtd_timer_stop": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "fdtd_run_profiled": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double)]),
     "fdtd_pass": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "fdtd_sweep": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "fdtd_post_step": (C.c_int, [_P, _P]),
     "fdtd_halo_ptrs": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "fdtd_download_records": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),

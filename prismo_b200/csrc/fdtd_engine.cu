@@ -79,6 +79,7 @@ struct fdtd_engine {
     // graph
     cudaGraphExec_t gexec[2] = {nullptr, nullptr}; int graph_steps = 0; int graph_kernels[2] = {0, 0};
     int fused_lx = 0;               // planes per fused segment (0 = auto)
+    int fused_pol = 0;              // bit0: streaming (evict-first) stores (measured 1.4% slower: off)
     // staging
     void* d_stage = nullptr; size_t stage_bytes = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -210,6 +211,7 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     const double eps0 = 8.854187817e-12, mu0 = 4 * M_PI * 1e-7;
     e->uni[0] = 1.0; e->uni[1] = cfg->dt / eps0; e->uni[2] = 1.0; e->uni[3] = cfg->dt / mu0;
     if (const char* lx = getenv("FDTD_B200_FUSED_LX")) e->fused_lx = atoi(lx);    // tuning / tests
+    if (const char* pol = getenv("FDTD_B200_FUSED_POL")) e->fused_pol = atoi(pol) & 1;
     *out = e;
     return 0;
 }
@@ -621,7 +623,8 @@ template <typename T> static int launch_post(fdtd_engine* e, int step_off, int p
 
 static bool use_fused(const fdtd_engine* e)
 {
-    return e->cfg.ndim == 3 && !e->het && !(e->cfg.flags & FDTD_FLAG_TWO_PASS) && e->g.nxg == e->g.nx;
+    // slabs (nxg != nx) use the fused sweep too, but through fdtd_sweep: the host interleaves the halo exchange
+    return e->cfg.ndim == 3 && !e->het && !(e->cfg.flags & FDTD_FLAG_TWO_PASS);
 }
 
 static int ensure_set_b(fdtd_engine* e)
@@ -659,22 +662,25 @@ template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i
     const int planes = i_end - i_begin;
     int lx = e->fused_lx;
     if (lx <= 0) {
-        // enough items for >= ~8 waves of 148 CTAs, but segments of >= 32 planes (1 prologue plane each)
+        // >= ~40 waves of 148 CTAs so the ragged last wave costs ~1%, with segments of >= 32 planes
+        // (each segment re-reads one plane of H and two of E as its prologue); short segments also keep
+        // co-resident CTAs on nearby planes, so tile rims are re-read from L2 instead of DRAM
         const long long tiles = (long long)t.ntj * t.ntk;
-        long long want = (148ll * 8 + tiles - 1) / tiles;
+        long long want = (148ll * 40 + tiles - 1) / tiles;
         lx = (int)std::max<long long>(32, (planes + want - 1) / std::max<long long>(want, 1));
     }
     t.lx = std::min(lx, planes);
     t.nseg = (planes + t.lx - 1) / t.lx;
     const size_t smem = fused_smem_bytes<T, TJ>();
-    const int which = sizeof(T) == 8;
+    const int which = (sizeof(T) == 8) * 2 + (e->fused_pol & 1);
+    auto kern = (e->fused_pol & 1) ? k_fused3d<T, TJ, 1> : k_fused3d<T, TJ, 0>;
     if (!e->fused.attr_set[which]) {
-        CU(cudaFuncSetAttribute(k_fused3d<T, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         e->fused.attr_set[which] = true;
     }
     dim3 block(32, TJ + 1, 1);
     const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
-    k_fused3d<T, TJ><<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t);
+    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -752,6 +758,9 @@ extern "C" int fdtd_run(fdtd_engine* e, int32_t n_steps)
 {
     if (!e || n_steps < 0) return fail(FDTD_EINVAL, "fdtd_run: bad argument");
     if (n_steps == 0) return 0;
+    if (e->g.nxg != e->g.nx)
+        return fail(FDTD_ESTATE, "fdtd_run on an x-slab: drive slabs with fdtd_sweep / fdtd_pass + fdtd_post_step "
+                                 "and exchange the halo planes in between");
     CU(cudaSetDevice(e->cfg.device));
     if (int rc = finalize_ops(e)) return rc;
     if (has_post(e)) {
@@ -876,6 +885,25 @@ extern "C" int fdtd_pass(fdtd_engine* e, int32_t phase, int32_t part, void* stre
     if (part == 0) t = nx - 1;
     if (part == 1) b = nx - 1;
     return e->cfg.dtype == FDTD_F64 ? launch_pass3d<double>(e, phase, b, t, s) : launch_pass3d<float>(e, phase, b, t, s);
+}
+
+// Fused sweep over local planes [i_begin, i_end) of the CURRENT set into the other set; flip != 0 makes the
+// other set current afterwards (pass it on the last piece of a step).  For x-slabs: planes nx and nx+1 of the
+// current set must hold the right neighbour's planes 0 and 1 (Ex,Ey,Ez,Hy,Hz / Ey,Ez) before the piece that
+// contains plane nx-1 runs; H+ of the ghost plane is recomputed locally (fused-sweep variant).
+extern "C" int fdtd_sweep(fdtd_engine* e, int32_t i_begin, int32_t i_end, int32_t flip, void* stream)
+{
+    if (!e || i_begin < 0 || i_end > e->g.nx || i_end < i_begin) return fail(FDTD_EINVAL, "fdtd_sweep: bad plane range");
+    if (!use_fused(e)) return fail(FDTD_ESTATE, "fdtd_sweep needs a 3-D engine with uniform coefficients (fused path)");
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = ensure_set_b(e)) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    if (i_end > i_begin) {
+        int rc = e->cfg.dtype == FDTD_F64 ? launch_fused<double>(e, i_begin, i_end, s) : launch_fused<float>(e, i_begin, i_end, s);
+        if (rc) return rc;
+    }
+    if (flip) e->cur ^= 1;
+    return 0;
 }
 
 extern "C" int fdtd_post_step(fdtd_engine* e, void* stream)

@@ -28,7 +28,7 @@ struct FusedTiling {
     int own_lanes;          // lanes per row that own (store) cells; lanes >= own_lanes are rim providers
 };
 
-struct FusedPlan { bool attr_set[2] = {false, false}; };
+struct FusedPlan { bool attr_set[4] = {false, false, false, false}; };
 static inline void fused_release(FusedPlan&) {}
 constexpr int kFusedTJ = 15;        // 15 owner rows + 1 rim row = 16 warps, one CTA per SM
 
@@ -53,8 +53,19 @@ template <typename T> __device__ __forceinline__ T shfl_next(T v)
     return __shfl_down_sync(0xffffffffu, v, 1);
 }
 
-// TJ owner rows per CTA; blockDim = (32, TJ + 1)
-template <typename T, int TJ>
+// store with an L2 evict-first hint: the output set is not read again until the next step (>> L2 away),
+// so it should not push the rim lines that neighbouring CTAs are about to re-read out of L2
+template <typename T, int POL> __device__ __forceinline__ void stv_pol(T* p, const Pack<T, VecOf<T>::V>& r)
+{
+    typedef typename VecOf<T>::type VT;
+    union { VT q; Pack<T, VecOf<T>::V> r; } u;
+    u.r = r;
+    if (POL & 1) __stcs(reinterpret_cast<VT*>(p), u.q);
+    else *reinterpret_cast<VT*>(p) = u.q;
+}
+
+// TJ owner rows per CTA; blockDim = (32, TJ + 1);  POL bit0: streaming stores
+template <typename T, int TJ, int POL>
 __global__ void __launch_bounds__(32 * (TJ + 1), 1)
 k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
 {
@@ -149,7 +160,7 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
             if (ix2 && jy2 && kz1[e]) hnz.v[e] = n;
         }
         if (owner && i + 1 < i1) {
-            stv<T>(out.hx + o + po, hnx); stv<T>(out.hy + o + po, hny); stv<T>(out.hz + o + po, hnz);
+            stv_pol<T, POL>(out.hx + o + po, hnx); stv_pol<T, POL>(out.hy + o + po, hny); stv_pol<T, POL>(out.hz + o + po, hnz);
         }
         // ---- E+[i] ---------------------------------------------------------------------------------------------
         if (i >= i0) {
@@ -172,7 +183,7 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
             }
             if (owner) {
                 const long long pe = (long long)i * g.sx;
-                stv<T>(out.ex + o + pe, nx_); stv<T>(out.ey + o + pe, ny_); stv<T>(out.ez + o + pe, nz_);
+                stv_pol<T, POL>(out.ex + o + pe, nx_); stv_pol<T, POL>(out.ey + o + pe, ny_); stv_pol<T, POL>(out.ez + o + pe, nz_);
             }
         }
         // ---- rotate the window --------------------------------------------------------------------------------------

@@ -226,6 +226,10 @@ class Engine:
     def run_pass(self, phase: int, part: int = 2, stream: int = 0):
         _lib.check(self._lib.fdtd_pass(self._h, int(phase), int(part), C.c_void_p(stream)))
 
+    def sweep(self, i_begin: int, i_end: int, flip: bool, stream: int = 0):
+        """Fused step over local planes [i_begin, i_end) (see fdtd_sweep in include/fdtd_b200.h)."""
+        _lib.check(self._lib.fdtd_sweep(self._h, int(i_begin), int(i_end), int(bool(flip)), C.c_void_p(stream)))
+
     def post_step(self, stream: int = 0):
         _lib.check(self._lib.fdtd_post_step(self._h, C.c_void_p(stream)))
 

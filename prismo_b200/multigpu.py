@@ -1,0 +1,134 @@
+"""x-slab domain decomposition of the fused FDTD step across the GPUs of one box.
+
+One process per GPU (``torchrun``); ``torch.distributed`` is only the plumbing (rendezvous + NCCL
+send/recv of halo planes); every field update runs in libfdtd_b200.so on this rank's engine.
+
+Decomposition: rank r owns total-grid planes [x0_r, x0_r + nx_r).  Both curls of the
+reference scheme are forward differences (core/solver.py:178-300), so data only ever flows from rank r+1
+to rank r.  For the fused single sweep the step-n inputs a rank needs from its right neighbour are the
+neighbour's planes 0 and 1 at time n:   Ex, Ey, Ez, Hy, Hz of plane 0   and   Ey, Ez of plane 1
+(7 planes; H+ of the ghost plane is recomputed locally).  They land in planes nx_r and nx_r + 1 of the
+local arrays, which every array owns anyway (ghost + guard, see fdtd_kernels.cuh).
+
+Overlap: the ghosts are consumed only by the sweep's LAST x-segment, while the planes a rank must send
+are final as soon as its own post-step (sources) is done.  So each step is
+    post halo send/recv (comm stream)  ||  sweep planes [0, nx_r - tail)        (compute stream)
+    wait for the halo                  ->  sweep planes [nx_r - tail, nx_r), flip sets, sources + monitors
+Results are bitwise identical to the single-GPU run: same kernel, same per-cell operation order.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+
+def slab_range(nx: int, rank: int, world: int):
+    """Planes [x0, x0 + n) of rank: contiguous, sizes differ by at most one."""
+    base, rem = divmod(nx, world)
+    n = base + (1 if rank < rem else 0)
+    return rank * base + min(rank, rem), n
+
+
+# (component, planes to ship): plane 0 of everything the ghost-plane H+ recompute reads, plane 1 of Ey/Ez
+HALO_SPEC = (("Ex", 1), ("Ey", 2), ("Ez", 2), ("Hy", 1), ("Hz", 1))
+
+
+class _CudaAlias:
+    """Expose a raw device range to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class SlabStepper:
+    """Drives one engine (one x-slab) and its halo exchange.  ``engine`` is a prismo_b200.Engine created
+    with nx_global / x_offset, or any object with the same sweep / post_step / halo_tensors surface."""
+
+    def __init__(self, engine, rank: int, world: int, tail_planes: int = 32, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.eng, self.rank, self.world, self.group = engine, rank, world, group
+        self.nx = engine.dims[0]
+        if world > 1 and self.nx < 3:
+            raise ValueError("each slab needs at least 3 planes")
+        self.tail = max(2, min(tail_planes, self.nx))     # >= 2: the head sweep reads up to plane head + 1
+        self.cuda = hasattr(engine, "halo_ptrs")
+        if self.cuda:
+            self.compute = torch.cuda.Stream()
+            self.comm = torch.cuda.Stream()
+        self._alias_cache = {}
+
+    # ---- halo buffers as torch tensors ------------------------------------------------------------------
+    def _halo_tensors(self):
+        """[(send tensor, recv tensor)] for the CURRENT buffer set."""
+        if not self.cuda:
+            return self.eng.halo_tensors(HALO_SPEC)
+        torch = self.torch
+        out = []
+        esz = self.eng.dtype.itemsize
+        typestr = "<f4" if esz == 4 else "<f8"
+        for comp, planes in HALO_SPEC:
+            first, ghost, plane_bytes = self.eng.halo_ptrs(comp)
+            n = planes * plane_bytes // esz
+            key = (first, ghost, n)
+            if key not in self._alias_cache:
+                self._alias_cache[key] = (torch.as_tensor(_CudaAlias(first, n, typestr), device="cuda"),
+                                          torch.as_tensor(_CudaAlias(ghost, n, typestr), device="cuda"))
+            out.append(self._alias_cache[key])
+        return out
+
+    def _post_exchange(self):
+        """Send my planes 0/1 to rank-1, receive rank+1's into my ghost planes.  Returns the work handles."""
+        dist = self.dist
+        ops = []
+        for send, recv in self._halo_tensors():
+            if self.rank > 0:
+                ops.append(dist.P2POp(dist.isend, send, self.rank - 1, self.group))
+            if self.rank < self.world - 1:
+                ops.append(dist.P2POp(dist.irecv, recv, self.rank + 1, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    # ---- stepping ---------------------------------------------------------------------------------------------
+    def step(self):
+        eng, torch = self.eng, self.torch
+        if self.world == 1:
+            eng.sweep(0, self.nx, True, self._s(self.compute) if self.cuda else 0)
+            eng.post_step(self._s(self.compute) if self.cuda else 0)
+            return
+        if self.cuda:
+            # the planes we send were finished by the previous post_step on the compute stream
+            self.comm.wait_stream(self.compute)
+            with torch.cuda.stream(self.comm):
+                works = self._post_exchange()
+            head = self.nx - self.tail
+            eng.sweep(0, head, False, self._s(self.compute))
+            with torch.cuda.stream(self.comm):
+                for w in works:
+                    w.wait()
+            self.compute.wait_stream(self.comm)
+            eng.sweep(head, self.nx, True, self._s(self.compute))
+            eng.post_step(self._s(self.compute))
+        else:
+            works = self._post_exchange()
+            head = self.nx - self.tail
+            eng.sweep(0, head, False)
+            for w in works:
+                w.wait()
+            eng.sweep(head, self.nx, True)
+            eng.post_step()
+
+    def run(self, n: int):
+        for _ in range(n):
+            self.step()
+
+    def synchronize(self):
+        if self.cuda:
+            self.compute.synchronize()
+            self.comm.synchronize()
+
+    @staticmethod
+    def _s(stream) -> int:
+        return int(stream.cuda_stream)

@@ -127,3 +127,69 @@ class FakeEngine:
 
     def set_dft(self, i, v):
         self.mon[i]["dft"][...] = v
+
+
+class FakeSlabEngine(FakeEngine):
+    """One x-slab of a 3-D grid on the CPU, with the ghost planes and the split sweep / post_step surface of
+    the real engine, so SlabStepper's orchestration (halo exchange order, overlap split) can run under gloo.
+
+    Non-last slabs keep an extended oracle domain of nx+3 planes: local planes, the neighbour's planes 0 and 1
+    (ghosts), and a dummy; the oracle's own edge rules then only ever corrupt ghost planes, which the next
+    exchange overwrites."""
+
+    def __init__(self, ndim, dims, spacing, dt, dtype="float64", device=0, nx_global=None, x_offset=0, flags=0):
+        assert ndim == 3
+        self.nx_global = nx_global or dims[0]
+        self.x_offset = x_offset
+        self.last = x_offset + dims[0] == self.nx_global
+        super().__init__(ndim, dims, spacing, dt, dtype)
+        self.ext = dims[0] + (0 if self.last else 3)
+        ed = (self.ext, dims[1], dims[2])
+        self.G = {c: np.zeros(self._shape(ed, c)) for c in COMPONENTS}
+        eps0, mu0 = 8.854187817e-12, 4 * np.pi * 1e-7
+        self.coeffs = [np.full(ed, v) for v in (1.0, dt / eps0, 1.0, dt / mu0)]
+        self.F = {c: self.G[c][: self.field_shape(c)[0]] for c in COMPONENTS}     # local views
+        self.pending = []
+
+    @staticmethod
+    def _shape(d, comp):
+        n = list(d)
+        for ax in SHORT_AXES[comp]:
+            n[ax] -= 1
+        return tuple(n)
+
+    def field_shape(self, comp):
+        n = list(self.dims)
+        for ax in SHORT_AXES[comp]:
+            if ax == 0 and not self.last:
+                continue
+            n[ax] -= 1
+        return tuple(n)
+
+    def halo_tensors(self, spec):
+        import torch
+
+        nx = self.dims[0]
+        return [(torch.from_numpy(self.G[c][0:p]), torch.from_numpy(self.G[c][nx:nx + p])) for c, p in spec]
+
+    def sweep(self, i_begin, i_end, flip, stream=0):
+        self.pending.append((i_begin, i_end))
+        if not flip:
+            return
+        assert self.pending[0][0] == 0 and self.pending[-1][1] == self.dims[0]
+        assert all(a[1] == b[0] for a, b in zip(self.pending, self.pending[1:]))
+        self.pending = []
+        kernels.step(self.G, self.coeffs, self.spacing, False)
+
+    def post_step(self, stream=0):
+        s = self.cursor
+        for g in sorted({o.group for o in self.src}):
+            for o in (o for o in self.src if o.group == g):
+                self.F[o.component][self._sl(o)] += self.amp[s, o.table]
+        for m in self.mon:
+            o = m["op"]
+            d = self.F[o.component][self._sl(o)].copy()
+            for k in range(o.n_freq):
+                ph = self.ph[s, o.phasor_col + k]
+                m["dft"][k] += (d * ph.real) * self.dt + 1j * ((d * ph.imag) * self.dt)
+        self.cursor += 1

@@ -231,21 +231,22 @@ def test_cropped_subdomain_matches_oracle():
     for c in S.COMPONENTS:
         eng.upload(c, F[c])
     eng.run(n)
+    # both curls are forward differences, so a cell depends only on cells at +0..+2n along every axis:
+    # crop [lo, lo + size + 2n + 2) and compare the first `size` cells
     lo, size = (40, 30, 20), (24, 20, 16)
-    sub = {}
     sdims = tuple(s + 2 * n + 2 for s in size)
+    sub = {}
     for c in S.COMPONENTS:
         shp = list(sdims)
         for ax in {"Ex": (1, 2), "Ey": (0, 2), "Ez": (0, 1), "Hx": (0,), "Hy": (1,), "Hz": (2,)}[c]:
             shp[ax] -= 1
-        sl = tuple(slice(l - n, l - n + s) for l, s in zip(lo, shp))
-        sub[c] = F[c][sl].copy()
+        sub[c] = F[c][tuple(slice(l, l + s) for l, s in zip(lo, shp))].copy()
     coeffs = kernels.vacuum_coefficients(sdims, dt)
     for _ in range(n):
         kernels.step(sub, coeffs, (2e-8,) * 3, False)
     for c in S.COMPONENTS:
         got = eng.download(c)[tuple(slice(l, l + s) for l, s in zip(lo, size))]
-        want = sub[c][tuple(slice(n, n + s) for s in size)]
+        want = sub[c][tuple(slice(0, s) for s in size)]
         assert np.array_equal(got, want), c
     eng.close()
 

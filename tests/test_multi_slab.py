@@ -1,0 +1,183 @@
+"""x-slab decomposition.  CPU: world_size-2 and -3 gloo runs of SlabStepper on a NumPy slab engine, compared
+bitwise with the undecomposed oracle.  GPU (1 device): two real engines as two slabs of one grid with the halo
+copied device-to-device, compared bitwise with a single engine — the kernel-side slab semantics."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from tests import scenarios as S
+
+DIMS = (23, 12, 14)
+SPACING = (2e-8, 2.5e-8, 3e-8)
+DT = 0.5 / (299792458.0 * np.sqrt(sum((1 / s) ** 2 for s in SPACING)))
+STEPS = 6
+F0 = 193.4e12
+
+
+def _initial(dims):
+    rng = np.random.default_rng(11)
+    out = {}
+    for c in S.COMPONENTS:
+        n = list(dims)
+        for ax in {"Ex": (1, 2), "Ey": (0, 2), "Ez": (0, 1), "Hx": (0,), "Hy": (1,), "Hz": (2,)}[c]:
+            n[ax] -= 1
+        out[c] = rng.standard_normal(n) * (1.0 if c[0] == "E" else 1 / 377.0)
+    return out
+
+
+def _tables(n):
+    t, amp, ph = 0.0, np.zeros((n, 2)), np.zeros((n, 2), dtype=np.complex128)
+    for s in range(n):
+        t += DT
+        amp[s] = (-np.sin(2 * np.pi * F0 * t), 0.5 * np.cos(2 * np.pi * F0 * t))
+        ph[s] = np.exp(-1j * 2 * np.pi * np.array([F0, 1.1 * F0]) * t)
+    return amp, ph
+
+
+def _global_ops(pb):
+    """A whole-plane source on global plane 7 (Ey) and 15 (Hz), a DFT plane at global plane 11 (Ez)."""
+    nx, ny, nz = DIMS
+    src = [("Ey", 7, (ny, nz - 1), 0), ("Hz", 15, (ny, nz - 1), 1)]
+    mon = [("Ez", 11, (ny - 1, nz))]
+    return src, mon
+
+
+def _local_ops(pb, x0, nxl):
+    src, mon = _global_ops(pb)
+    s_ops = [pb.SourceOp(c, (p - x0, 0, 0), (p - x0 + 1,) + shp, tab) for c, p, shp, tab in src if x0 <= p < x0 + nxl]
+    m_ops = [pb.MonitorOp(c, (p - x0, 0, 0), (p - x0 + 1,) + shp, False, 2, 0) for c, p, shp in mon if x0 <= p < x0 + nxl]
+    return s_ops, m_ops
+
+
+def _reference_run():
+    """Undecomposed oracle run with the same ops."""
+    from oracle import kernels
+
+    F = _initial(DIMS)
+    coeffs = kernels.vacuum_coefficients(DIMS, DT)
+    amp, ph = _tables(STEPS)
+    dft = np.zeros((2, DIMS[1] - 1, DIMS[2]), dtype=np.complex128)
+    for s in range(STEPS):
+        kernels.step(F, coeffs, SPACING, False)
+        F["Ey"][7] += amp[s, 0]
+        F["Hz"][15] += amp[s, 1]
+        d = F["Ez"][11].copy()
+        for k in range(2):
+            dft[k] += (d * ph[s, k].real) * DT + 1j * ((d * ph[s, k].imag) * DT)
+    return F, dft
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    import prismo_b200 as pb
+    from prismo_b200.multigpu import SlabStepper, slab_range
+    from tests._fake_engine import FakeSlabEngine
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x0, nxl = slab_range(DIMS[0], rank, world)
+    eng = FakeSlabEngine(3, (nxl, DIMS[1], DIMS[2]), SPACING, DT, nx_global=DIMS[0], x_offset=x0)
+    init = _initial(DIMS)
+    for c in S.COMPONENTS:
+        eng.upload(c, init[c][x0:x0 + eng.field_shape(c)[0]])
+    s_ops, m_ops = _local_ops(pb, x0, nxl)
+    for o in s_ops:
+        eng.add_source_op(o)
+    ids = [eng.add_monitor_op(o) for o in m_ops]
+    amp, ph = _tables(STEPS)
+    eng.set_tables(STEPS, amp, ph)
+    st = SlabStepper(eng, rank, world, tail_planes=3)
+    st.run(STEPS)
+    res = {c: eng.download(c) for c in S.COMPONENTS}
+    for i in ids:
+        res["dft"] = eng.dft(i)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x0=x0, **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_stepper_gloo_bitwise(world, tmp_path):
+    import torch.multiprocessing as mp
+
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    F, dft = _reference_run()
+    seen_dft = False
+    for r in range(world):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        x0 = int(z["x0"])
+        for c in S.COMPONENTS:
+            got = z[c]
+            assert np.array_equal(got, F[c][x0:x0 + got.shape[0]]), f"rank {r} {c}"
+        if "dft" in z.files:
+            assert np.array_equal(z["dft"][:, 0], dft)
+            seen_dft = True
+    assert seen_dft
+
+
+def test_slab_ranges_cover_the_grid():
+    from prismo_b200.multigpu import slab_range
+
+    for nx in (8, 23, 1024):
+        for world in (1, 2, 3, 8):
+            spans = [slab_range(nx, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(n for _, n in spans) == nx
+            assert all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(n for _, n in spans) - min(n for _, n in spans) <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_two_slabs_on_one_gpu_match_single_engine(dtype):
+    """Kernel-side slab semantics (x_offset / nx_global masks, ghost planes, H+ recompute on the ghost plane):
+    two engines on one device, halo copied device-to-device each step, bitwise equal to one engine."""
+    import torch
+
+    import prismo_b200 as pb
+    from prismo_b200.multigpu import HALO_SPEC, SlabStepper, _CudaAlias, slab_range
+
+    dims = (37, 33, 70)
+    rng = np.random.default_rng(2)
+    whole = pb.Engine(3, dims, SPACING, DT, dtype=dtype)
+    init = {c: rng.standard_normal(whole.field_shape(c)) * (1.0 if c[0] == "E" else 1 / 377.0) for c in S.COMPONENTS}
+    for c in S.COMPONENTS:
+        whole.upload(c, init[c])
+    whole.run(5)
+    slabs = []
+    for r in range(2):
+        x0, nxl = slab_range(dims[0], r, 2)
+        e = pb.Engine(3, (nxl, dims[1], dims[2]), SPACING, DT, dtype=dtype, nx_global=dims[0], x_offset=x0)
+        for c in S.COMPONENTS:
+            e.upload(c, init[c][x0:x0 + e.field_shape(c)[0]])
+        slabs.append((e, x0, nxl))
+    esz = np.dtype(dtype).itemsize
+    ts = "<f4" if esz == 4 else "<f8"
+    for _ in range(5):
+        left, right = slabs[0][0], slabs[1][0]
+        left.sync(); right.sync()
+        for comp, planes in HALO_SPEC:
+            first, _, pbytes = right.halo_ptrs(comp)
+            _, ghost, _ = left.halo_ptrs(comp)
+            n = planes * pbytes // esz
+            torch.as_tensor(_CudaAlias(ghost, n, ts), device="cuda").copy_(torch.as_tensor(_CudaAlias(first, n, ts), device="cuda"))
+        torch.cuda.synchronize()
+        for e, _, nxl in slabs:
+            e.sweep(0, nxl - 4, False)
+            e.sweep(nxl - 4, nxl, True)
+            e.post_step()
+            e.sync()
+    for e, x0, nxl in slabs:
+        for c in S.COMPONENTS:
+            got = e.download(c)
+            assert np.array_equal(got, whole.download(c)[x0:x0 + got.shape[0]]), (x0, c)
+        e.close()
+    whole.close()
