@@ -15,7 +15,7 @@ def run_multi(args, rank, world, local):
     import torch.distributed as dist
 
     import bench as B
-    from prismo_b200.multigpu import SlabStepper
+    from prismo_b200.multigpu import PeerSlabRunner, SlabStepper
 
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -31,7 +31,11 @@ def run_multi(args, rank, world, local):
     eng.set_tables(total, amp, ph)
     B.seed_fields(eng, seed=rank)
     eng.sync()
-    stepper = SlabStepper(eng, rank, world, tail_planes=int(os.environ.get("FDTD_B200_TAIL", "32")))
+    halo = os.environ.get("FDTD_B200_HALO", "p2p")
+    if halo == "nccl":
+        stepper = SlabStepper(eng, rank, world, tail_planes=int(os.environ.get("FDTD_B200_TAIL", "32")))
+    else:
+        stepper = PeerSlabRunner(eng, rank, world)
 
     def fence():
         stepper.synchronize()
@@ -44,11 +48,18 @@ def run_multi(args, rank, world, local):
     l0 = eng.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with B.ClockSampler(local) as clk:
-        ev0.record(stepper.compute)
-        stepper.run(args.steps)
-        ev1.record(stepper.compute)
-        fence()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+        if halo == "nccl":
+            ev0.record(stepper.compute)
+            stepper.run(args.steps)
+            ev1.record(stepper.compute)
+            fence()
+            my_ms = ev0.elapsed_time(ev1)
+        else:                                   # the engine's own stream: events through the C ABI
+            eng.timer_start()
+            stepper.run(args.steps)
+            my_ms = eng.timer_stop()
+            fence()
+    ms = torch.tensor([my_ms], device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = torch.tensor([eng.kernel_launches - l0], device="cuda", dtype=torch.int64)
@@ -64,7 +75,7 @@ def run_multi(args, rank, world, local):
         peak, peak_src = B.peaks()
         value = cells * args.steps / (ms * 1e-3)
         achieved = bpc * cells * args.steps / (ms * 1e-3) / 1e9 / world
-        halo = 7 * dims[1] * dims[2] * (4 if args.dtype == "float32" else 8)
+        halo_bytes = 7 * dims[1] * dims[2] * (4 if args.dtype == "float32" else 8)
         line = {"metric": "fdtd_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64",
@@ -73,7 +84,10 @@ def run_multi(args, rank, world, local):
                                        f"plane source, FieldMonitor DFT plane (Ey,Hz x 5 freq)",
                            "l2": "per-rank working set >> 126 MB L2 (no flush needed)",
                            "parallelism": f"x-slabs over {world} GPUs, {dims[0] // world} planes each, "
-                                          f"{halo / 1e6:.1f} MB halo per interface per step over NCCL send/recv",
+                                          f"{halo_bytes / 1e6:.1f} MB halo per interface per step, "
+                                          + ("NCCL send/recv" if halo == "nccl" else
+                                             "DMA push into the neighbour's ghost planes over NVLink (CUDA IPC) + "
+                                             "release/acquire flags, in-kernel wait"),
                            "kernel_path": "fused single sweep, ping-pong"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src,

@@ -134,7 +134,16 @@ int  fdtd_pass(fdtd_engine* e, int32_t phase, int32_t part, void* stream);
  * other set current (last piece of a step).  Slabs: planes nx, nx+1 of the current set are ghosts that must
  * hold the right neighbour's planes 0, 1 before the piece containing plane nx-1 is launched.                */
 int  fdtd_sweep(fdtd_engine* e, int32_t i_begin, int32_t i_end, int32_t flip, void* stream);
-int  fdtd_post_step(fdtd_engine* e, void* stream);   /* sources + monitors + cursor advance       */
+int  fdtd_post_step(fdtd_engine* e, void* stream);
+/* Peer-to-peer slabs (one process per GPU).  Each rank exports a blob (CUDA IPC handles of its arrays and
+ * flag words; call with blob == NULL to get the size), the host plumbing (torch.distributed) hands every rank
+ * its LEFT neighbour's blob, and fdtd_slab_run then runs n steps with the 7 halo planes pushed by DMA into the
+ * left neighbour's ghost planes over NVLink and release/acquire flags in peer memory — no host round trips,
+ * one sweep launch per step (only the CTAs of the last x-segment wait for the halo, inside the kernel).      */
+int  fdtd_ipc_export(fdtd_engine* e, void* blob, int32_t* nbytes);
+int  fdtd_ipc_connect(fdtd_engine* e, const void* left_blob /* NULL on rank 0 */, int32_t has_right);
+int  fdtd_slab_run(fdtd_engine* e, int32_t n_steps);
+int  fdtd_slab_sync(fdtd_engine* e);   /* sources + monitors + cursor advance       */
 /* first local plane (send side) / first ghost plane (receive side) of a component IN THE CURRENT SET;
  * plane 1 / the second ghost plane follow contiguously at +plane_bytes                                    */
 int  fdtd_halo_ptrs(fdtd_engine* e, int32_t component, void** first_plane, void** ghost_plane,

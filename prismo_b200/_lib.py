@@ -73,6 +73,10 @@ _PROTOS = {
     "fdtd_pass": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "fdtd_sweep": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "fdtd_post_step": (C.c_int, [_P, _P]),
+    "fdtd_ipc_export": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
+    "fdtd_ipc_connect": (C.c_int, [_P, _P, C.c_int32]),
+    "fdtd_slab_run": (C.c_int, [_P, C.c_int32]),
+    "fdtd_slab_sync": (C.c_int, [_P]),
     "fdtd_halo_ptrs": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "fdtd_download_records": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),
     "fdtd_download_dft": (C.c_int, [_P, C.c_int32, _P]),

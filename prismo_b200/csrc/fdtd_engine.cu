@@ -83,6 +83,20 @@ struct fdtd_engine {
     // staging
     void* d_stage = nullptr; size_t stage_bytes = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // x-slab peer-to-peer halo (one process per GPU, CUDA IPC over NVLink)
+    struct Slab {
+        bool connected = false, has_left = false, has_right = false;
+        int* flags = nullptr;            // own device words: [0] halo_ready (written by the right neighbour),
+                                         // [1] ghost_consumed (written by us, read by the right neighbour), [2] error
+        void* left_fld[2][6] = {};       // left neighbour's arrays (IPC-mapped): we push into its ghost planes
+        int* left_flags = nullptr;       // left neighbour's flags (we write [0], read [1])
+        void* left_base[13] = {};        // mapped bases to close
+        cudaStream_t comm = nullptr;
+        cudaEvent_t post_done = nullptr, push_done = nullptr;
+        long long step = 0;              // steps run through fdtd_slab_run (same on every rank)
+        int left_nx = 0;
+        unsigned long long timeout_ns = 20000000000ull;
+    } slab;
     FusedPlan fused{};
 };
 
@@ -230,6 +244,10 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     cudaFree(e->d_step); cudaFree(e->d_cnt); cudaFree(e->d_stage);
     fused_release(e->fused);
     if (e->t0) { cudaEventDestroy(e->t0); cudaEventDestroy(e->t1); }
+    if (e->slab.comm) { cudaStreamSynchronize(e->slab.comm); cudaStreamDestroy(e->slab.comm); }
+    if (e->slab.post_done) { cudaEventDestroy(e->slab.post_done); cudaEventDestroy(e->slab.push_done); }
+    for (void* b : e->slab.left_base) if (b) cudaIpcCloseMemHandle(b);
+    cudaFree(e->slab.flags);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return 0;
@@ -652,6 +670,10 @@ template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i
     Fields<T> out = fields_of<T>(dst);
     FusedTiling t;
     t.i_begin = i_begin; t.i_end = i_end;
+    t.halo_flag = nullptr; t.halo_need = 0; t.error_word = nullptr; t.timeout_ns = e->slab.timeout_ns;
+    if (e->slab.connected && e->slab.has_right && i_end == g.nx) {
+        t.halo_flag = e->slab.flags; t.halo_need = (int)e->slab.step + 1; t.error_word = e->slab.flags + 2;
+    }
     const int vec_per_row = g.pz / V;
     const int ncols = (vec_per_row + 29) / 30;
     int own = (vec_per_row + ncols - 1) / ncols;
@@ -903,6 +925,151 @@ extern "C" int fdtd_sweep(fdtd_engine* e, int32_t i_begin, int32_t i_end, int32_
         if (rc) return rc;
     }
     if (flip) e->cur ^= 1;
+    return 0;
+}
+
+// ---- peer-to-peer slabs ------------------------------------------------------------------------------------------
+struct IpcBlob {
+    cudaIpcMemHandle_t fld[2][6];
+    cudaIpcMemHandle_t flags;
+    int32_t nx, ny, nz, dtype;
+    int64_t plane_elems;
+};
+
+extern "C" int fdtd_ipc_export(fdtd_engine* e, void* blob, int32_t* nbytes)
+{
+    if (!e || !nbytes) return fail(FDTD_EINVAL, "fdtd_ipc_export: bad argument");
+    if (!blob) { *nbytes = (int32_t)sizeof(IpcBlob); return 0; }
+    if (*nbytes < (int32_t)sizeof(IpcBlob)) return fail(FDTD_EINVAL, "blob too small (%d < %d)", *nbytes, (int)sizeof(IpcBlob));
+    if (!use_fused(e)) return fail(FDTD_ESTATE, "peer-to-peer slabs need the fused path (3-D, uniform coefficients)");
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = ensure_set_b(e)) return rc;
+    if (!e->slab.flags) {
+        CU(cudaMalloc(&e->slab.flags, 64));
+        CU(cudaMemset(e->slab.flags, 0, 64));
+    }
+    IpcBlob b;
+    memset(&b, 0, sizeof b);
+    for (int c = 0; c < 6; ++c) {
+        CU(cudaIpcGetMemHandle(&b.fld[0][c], e->fld[c]));
+        CU(cudaIpcGetMemHandle(&b.fld[1][c], e->fldB[c]));
+    }
+    CU(cudaIpcGetMemHandle(&b.flags, e->slab.flags));
+    b.nx = e->g.nx; b.ny = e->g.ny; b.nz = e->g.nz; b.dtype = e->cfg.dtype; b.plane_elems = e->plane_elems;
+    memcpy(blob, &b, sizeof b);
+    *nbytes = (int32_t)sizeof b;
+    return 0;
+}
+
+extern "C" int fdtd_ipc_connect(fdtd_engine* e, const void* left_blob, int32_t has_right)
+{
+    if (!e) return fail(FDTD_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    auto& sl = e->slab;
+    if (!sl.flags) return fail(FDTD_ESTATE, "call fdtd_ipc_export first");
+    if (!sl.comm) {
+        CU(cudaStreamCreateWithFlags(&sl.comm, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&sl.post_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sl.push_done, cudaEventDisableTiming));
+    }
+    sl.has_left = left_blob != nullptr;
+    sl.has_right = has_right != 0;
+    if (left_blob) {
+        IpcBlob b;
+        memcpy(&b, left_blob, sizeof b);
+        if (b.ny != e->g.ny || b.nz != e->g.nz || b.dtype != e->cfg.dtype || b.plane_elems != e->plane_elems)
+            return fail(FDTD_EINVAL, "left neighbour has a different plane geometry / dtype");
+        int n = 0;
+        for (int s = 0; s < 2; ++s)
+            for (int c = 0; c < 6; ++c) {
+                CU(cudaIpcOpenMemHandle(&sl.left_fld[s][c], b.fld[s][c], cudaIpcMemLazyEnablePeerAccess));
+                sl.left_base[n++] = sl.left_fld[s][c];
+            }
+        void* f = nullptr;
+        CU(cudaIpcOpenMemHandle(&f, b.flags, cudaIpcMemLazyEnablePeerAccess));
+        sl.left_flags = (int*)f;
+        sl.left_base[n++] = f;
+        sl.left_nx = b.nx;
+    }
+    if (const char* t = getenv("FDTD_B200_HALO_TIMEOUT_MS")) sl.timeout_ns = 1000000ull * (unsigned long long)atoll(t);
+    if (e->cur != 0) return fail(FDTD_ESTATE, "connect slabs before stepping (buffer-set parity must agree across ranks)");
+    sl.connected = true;
+    sl.step = 0;
+    CU(cudaMemset(sl.flags, 0, 64));
+    return 0;
+}
+
+// n full steps of this slab, everything enqueued asynchronously (no host synchronisation inside):
+//   comm stream    : wait until the left neighbour has consumed the ghosts of two steps ago, DMA our planes 0/1
+//                    (7 planes) into its ghost planes over NVLink, release-store its halo_ready flag
+//   compute stream : ONE fused sweep over all planes — only the CTAs of the last x-segment wait (in-kernel) for
+//                    our own halo_ready flag —, publish ghost_consumed, then sources + monitors
+template <typename T> static int slab_run(fdtd_engine* e, int n)
+{
+    auto& sl = e->slab;
+    cudaStream_t cs = e->stream, ms = sl.comm;
+    static const int comps[5] = {0, 1, 2, 4, 5};          // Ex Ey Ez Hy Hz
+    static const int planes[5] = {1, 2, 2, 1, 1};
+    const size_t pbytes = (size_t)e->plane_elems * e->esz;
+    CU(cudaEventRecord(sl.post_done, cs));
+    for (int q = 0; q < n; ++q) {
+        const long long st = sl.step;
+        if (sl.has_left) {
+            CU(cudaStreamWaitEvent(ms, sl.post_done, 0));        // our planes 0/1 of the current set are final
+            if (st >= 2) { k_wait<<<1, 1, 0, ms>>>(sl.left_flags + 1, (int)(st - 1), sl.flags + 2, sl.timeout_ns); e->launches++; }
+            void** mine = cur_fields(e);
+            void** theirs = sl.left_fld[e->cur];
+            for (int c = 0; c < 5; ++c)
+                CU(cudaMemcpyAsync((char*)theirs[comps[c]] + (size_t)sl.left_nx * pbytes, mine[comps[c]],
+                                   planes[c] * pbytes, cudaMemcpyDefault, ms));
+            k_signal<<<1, 1, 0, ms>>>(sl.left_flags, (int)(st + 1)); e->launches++;
+            CU(cudaEventRecord(sl.push_done, ms));
+        }
+        if (int rc = launch_fused<T>(e, 0, e->g.nx, cs)) return rc;   // reads the current set (+ ghosts)
+        e->cur ^= 1;
+        k_signal<<<1, 1, 0, cs>>>(sl.flags + 1, (int)(st + 1)); e->launches++;
+        // the push read the set that is now the output set of the NEXT step: it must finish before that sweep
+        if (sl.has_left) CU(cudaStreamWaitEvent(cs, sl.push_done, 0));
+        if (has_post(e)) if (int rc = launch_post<T>(e, q, 0, cs)) return rc;
+        CU(cudaEventRecord(sl.post_done, cs));
+        sl.step++;
+    }
+    k_bump<<<1, 1, 0, cs>>>(e->d_step, n); e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fdtd_slab_run(fdtd_engine* e, int32_t n_steps)
+{
+    if (!e || n_steps < 0) return fail(FDTD_EINVAL, "fdtd_slab_run: bad argument");
+    if (!e->slab.connected) return fail(FDTD_ESTATE, "fdtd_slab_run: call fdtd_ipc_export / fdtd_ipc_connect first");
+    if (n_steps == 0) return 0;
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = finalize_ops(e)) return rc;
+    if (has_post(e)) {
+        if (e->cursor + n_steps > e->n_steps_tab)
+            return fail(FDTD_ESTATE, "fdtd_slab_run(%d): only %d tabled steps left", n_steps, e->n_steps_tab - e->cursor);
+        if (!e->d_mon && !e->mon.empty()) if (int rc = upload_mon_ops(e)) return rc;
+    }
+    int rc = e->cfg.dtype == FDTD_F64 ? slab_run<double>(e, n_steps) : slab_run<float>(e, n_steps);
+    if (rc) return rc;
+    e->cursor += n_steps;
+    e->steps_done += n_steps;
+    return 0;
+}
+
+// blocks until everything enqueued by fdtd_slab_run is done; reports a halo time-out (dead peer)
+extern "C" int fdtd_slab_sync(fdtd_engine* e)
+{
+    if (!e) return fail(FDTD_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->slab.comm) CU(cudaStreamSynchronize(e->slab.comm));
+    if (e->slab.flags) {
+        int err = 0;
+        CU(cudaMemcpy(&err, e->slab.flags + 2, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return fail(FDTD_ECUDA, "halo wait timed out: a neighbouring rank stopped making progress");
+    }
     return 0;
 }
 

@@ -26,7 +26,44 @@ struct FusedTiling {
     int lx;                 // planes per segment
     int nseg, ntj, ntk;     // items = nseg * ntj * ntk
     int own_lanes;          // lanes per row that own (store) cells; lanes >= own_lanes are rim providers
+    // x-slabs: items that read the ghost planes (their segment ends at plane nx) first wait until the right
+    // neighbour has pushed them:  *halo_flag >= halo_need  (system-scope acquire; null = no wait)
+    const int* halo_flag;
+    int halo_need;
+    int* error_word;        // set to 1 if the wait times out (peer died): never hang the GPU
+    unsigned long long timeout_ns;
 };
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag >= need (or ~20 s pass: then flag the error and carry on with whatever is there)
+__device__ __forceinline__ void wait_flag_ge(const int* flag, int need, int* error_word, unsigned long long timeout_ns)
+{
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(flag) < need) {
+        __nanosleep(256);
+        if (global_ns() - t0 > timeout_ns) { if (error_word) atomicExch(error_word, 1); break; }
+    }
+}
+__global__ void k_signal(int* flag, int v) { __threadfence_system(); st_release_sys(flag, v); }
+__global__ void k_wait(const int* flag, int need, int* error_word, unsigned long long timeout_ns)
+{
+    wait_flag_ge(flag, need, error_word, timeout_ns);
+}
 
 struct FusedPlan { bool attr_set[4] = {false, false, false, false}; };
 static inline void fused_release(FusedPlan&) {}
@@ -85,6 +122,10 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
     const int k = (tk * t.own_lanes + lane) * V;
     const int i0 = t.i_begin + seg * t.lx;
     const int i1 = min(i0 + t.lx, t.i_end);
+    if (t.halo_flag && i1 == g.nx) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) wait_flag_ge(t.halo_flag, t.halo_need, t.error_word, t.timeout_ns);
+        __syncthreads();
+    }
     const bool ld_ok = (j < g.ny) && (k < g.pz);
     const bool owner = ld_ok && row < TJ && lane < t.own_lanes;
     const bool halo_row = row == TJ;

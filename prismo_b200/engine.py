@@ -230,6 +230,23 @@ class Engine:
         """Fused step over local planes [i_begin, i_end) (see fdtd_sweep in include/fdtd_b200.h)."""
         _lib.check(self._lib.fdtd_sweep(self._h, int(i_begin), int(i_end), int(bool(flip)), C.c_void_p(stream)))
 
+    def ipc_export(self) -> bytes:
+        n = C.c_int32(0)
+        _lib.check(self._lib.fdtd_ipc_export(self._h, None, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _lib.check(self._lib.fdtd_ipc_export(self._h, buf, C.byref(n)))
+        return buf.raw[: n.value]
+
+    def ipc_connect(self, left_blob: Optional[bytes], has_right: bool) -> None:
+        buf = C.create_string_buffer(left_blob, len(left_blob)) if left_blob else None
+        _lib.check(self._lib.fdtd_ipc_connect(self._h, buf, int(bool(has_right))))
+
+    def slab_run(self, n_steps: int) -> None:
+        _lib.check(self._lib.fdtd_slab_run(self._h, int(n_steps)))
+
+    def slab_sync(self) -> None:
+        _lib.check(self._lib.fdtd_slab_sync(self._h))
+
     def post_step(self, stream: int = 0):
         _lib.check(self._lib.fdtd_post_step(self._h, C.c_void_p(stream)))
 

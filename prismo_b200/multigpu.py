@@ -41,9 +41,33 @@ class _CudaAlias:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
+class PeerSlabRunner:
+    """The production path: halo planes are DMA-pushed into the left neighbour's ghost planes through CUDA IPC
+    mappings over NVLink, ordered by release/acquire flag words in peer memory; the whole step loop is enqueued
+    by libfdtd_b200.so without host round trips (fdtd_slab_run).  torch.distributed only carries the one-off
+    exchange of IPC handles."""
+
+    def __init__(self, engine, rank: int, world: int, group=None):
+        import torch.distributed as dist
+
+        self.eng, self.rank, self.world = engine, rank, world
+        blob = engine.ipc_export()
+        blobs = [None] * world
+        dist.all_gather_object(blobs, blob, group=group)
+        engine.ipc_connect(blobs[rank - 1] if rank > 0 else None, rank < world - 1)
+        dist.barrier(group=group)              # nobody steps before everybody has reset its flags
+
+    def run(self, n: int):
+        self.eng.slab_run(n)
+
+    def synchronize(self):
+        self.eng.slab_sync()
+
+
 class SlabStepper:
-    """Drives one engine (one x-slab) and its halo exchange.  ``engine`` is a prismo_b200.Engine created
-    with nx_global / x_offset, or any object with the same sweep / post_step / halo_tensors surface."""
+    """NCCL send/recv variant (and the gloo/CPU test vehicle).  Drives one engine (one x-slab) and its halo
+    exchange from Python.  ``engine`` is a prismo_b200.Engine created with nx_global / x_offset, or any object
+    with the same sweep / post_step / halo_tensors surface."""
 
     def __init__(self, engine, rank: int, world: int, tail_planes: int = 32, group=None):
         import torch

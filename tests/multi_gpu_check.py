@@ -1,0 +1,102 @@
+"""Run under torchrun on N GPUs (or N processes sharing one GPU with --same-device): the peer-to-peer slab
+path must reproduce a single-engine run bit for bit.  Prints 'MULTI_GPU_CHECK OK' on rank 0.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import prismo_b200 as pb
+    from prismo_b200.multigpu import PeerSlabRunner, SlabStepper, slab_range
+
+    same = "--same-device" in sys.argv
+    mode = "nccl" if "--nccl" in sys.argv else "p2p"
+    dtype = "float32" if "--f32" in sys.argv else "float64"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = 0 if same else int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo" if same else "nccl")
+    dims, steps = (8 * world + 5, 45, 70), 9
+    spacing = (2e-8, 2.5e-8, 3e-8)
+    dt = 0.5 / (299792458.0 * np.sqrt(sum((1 / s) ** 2 for s in spacing)))
+    comps = ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")
+    rng = np.random.default_rng(4)
+    whole_shape = {}
+    for c in comps:
+        n = list(dims)
+        for ax in pb.grid.SHORT_AXES[c]:
+            n[ax] -= 1
+        whole_shape[c] = tuple(n)
+    init = {c: rng.standard_normal(whole_shape[c]) * (1.0 if c[0] == "E" else 1 / 377.0) for c in comps}
+    amp = np.sin(np.arange(1, steps + 1)[:, None] * np.array([[0.3, 0.7]]))
+    ph = np.exp(-1j * np.arange(1, steps + 1)[:, None] * np.array([[0.2, 0.5]]))
+    src_plane, mon_plane = dims[0] // 2, dims[0] - 3
+
+    def ops(x0, nxl, shape_of):
+        s, m = [], []
+        if x0 <= src_plane < x0 + nxl:
+            i = src_plane - x0
+            s = [pb.SourceOp("Ey", (i, 0, 0), (i + 1,) + shape_of("Ey")[1:], 0), pb.SourceOp("Hz", (i, 0, 0), (i + 1,) + shape_of("Hz")[1:], 1)]
+        if x0 <= mon_plane < x0 + nxl:
+            i = mon_plane - x0
+            m = [pb.MonitorOp("Ez", (i, 0, 0), (i + 1,) + shape_of("Ez")[1:], False, 2, 0)]
+        return s, m
+
+    x0, nxl = slab_range(dims[0], rank, world)
+    eng = pb.Engine(3, (nxl, dims[1], dims[2]), spacing, dt, dtype=dtype, device=local, nx_global=dims[0], x_offset=x0)
+    for c in comps:
+        eng.upload(c, init[c][x0:x0 + eng.field_shape(c)[0]])
+    s_ops, m_ops = ops(x0, nxl, eng.field_shape)
+    for o in s_ops:
+        eng.add_source_op(o)
+    ids = [eng.add_monitor_op(o) for o in m_ops]
+    eng.set_tables(steps, amp, ph)
+    runner = PeerSlabRunner(eng, rank, world) if mode == "p2p" else SlabStepper(eng, rank, world, tail_planes=3)
+    runner.run(4)
+    runner.run(steps - 4)
+    runner.synchronize()
+    mine = {c: eng.download(c) for c in comps}
+    mine["dft"] = eng.dft(ids[0]) if ids else None
+    mine["x0"] = x0
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    ok = True
+    if rank == 0:
+        whole = pb.Engine(3, dims, spacing, dt, dtype=dtype, device=local)
+        for c in comps:
+            whole.upload(c, init[c])
+        s_ops, m_ops = ops(0, dims[0], whole.field_shape)
+        for o in s_ops:
+            whole.add_source_op(o)
+        wid = [whole.add_monitor_op(o) for o in m_ops]
+        whole.set_tables(steps, amp, ph)
+        whole.run(steps)
+        for g in gathered:
+            for c in comps:
+                want = whole.download(c)[g["x0"]:g["x0"] + g[c].shape[0]]
+                if not np.array_equal(g[c], want):
+                    ok = False
+                    print(f"MISMATCH rank x0={g['x0']} {c}: max abs diff {np.abs(g[c] - want).max():.3e}")
+            if g["dft"] is not None and not np.array_equal(g["dft"], whole.dft(wid[0])):
+                ok = False
+                print("MISMATCH dft")
+        print(f"MULTI_GPU_CHECK {'OK' if ok else 'FAILED'} world={world} mode={mode} dtype={dtype} dims={dims}", flush=True)
+        whole.close()
+    eng.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -181,3 +181,19 @@ def test_two_slabs_on_one_gpu_match_single_engine(dtype):
             assert np.array_equal(got, whole.download(c)[x0:x0 + got.shape[0]]), (x0, c)
         e.close()
     whole.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["p2p"])
+def test_peer_to_peer_slabs_two_processes_one_gpu(mode):
+    """The production halo protocol (CUDA IPC mappings, DMA push, release/acquire flags, in-kernel wait) with two
+    processes time-slicing one GPU: bitwise equal to a single engine.  Halo waits time out after 5 s."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, FDTD_B200_HALO_TIMEOUT_MS="5000")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(os.path.dirname(__file__), "multi_gpu_check.py"),
+           "--same-device"]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert "MULTI_GPU_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
