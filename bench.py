@@ -56,49 +56,62 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every 5 ms from a thread
+    (nvidia-smi -lms takes longer to start than an 8-GPU timed region lasts); nvidia-smi as a fallback."""
 
     def __init__(self, device=0):
-        self.rows, self.proc, self.device = [], None, device
+        self.device, self.rows, self.stop = device, [], threading.Event()
+        self.t = None
+
+    def _nvml(self):
+        import pynvml as N
+
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.device)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self.stop.is_set():
+            try:
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append((N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), mx, [k for k, b in bits.items() if r & b]))
+            time.sleep(0.005)
+
+    def _smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.rows.append((float(out[0]), float(out[1]), [n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")]))
+            except Exception:
+                return
+
+    def _run(self):
+        try:
+            self._nvml()
+        except Exception:
+            self._smi()
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        time.sleep(0.02)
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([v.strip() for v in line.split(",")])
-
     def __exit__(self, *exc):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-            self.t.join(timeout=2)
+        self.stop.set()
+        self.t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = sorted({r for row in self.rows for r in row[2]})
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(max(r[1] for r in self.rows)),
+                "reasons": reasons, "samples": len(self.rows)}
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -80,9 +80,21 @@ typedef struct fdtd_monitor_op {
     int32_t reserved;
 } fdtd_monitor_op;
 
+/* One auxiliary-differential-equation recursion of a dispersive medium, cell-local, driven by E[component] after
+ * every step (materials/ade.py:116-160 with the coefficients of materials/dispersion.py:189-336):
+ *   kind 0 Lorentz  P+ = c0*E + c1*E + c2*P + c3*P_prev     kind 1 Drude  J+ = c0*E + c1*J     kind 2 Debye  P+ = c0*E + c1*P
+ * mask (optional, box-shaped bytes) reproduces ADEManager.update_all's "E * mask" (ade.py:291-308).              */
+typedef struct fdtd_ade_op {
+    int32_t component;          /* 0..2 */
+    int32_t kind;
+    int32_t lo[3], hi[3];
+    double  c0, c1, c2, c3;
+    const uint8_t* mask;
+} fdtd_ade_op;
+
 /* ---- lifetime ------------------------------------------------------------------------------- */
 int  fdtd_abi_version(void);
-int  fdtd_struct_size(int32_t which);   /* sizeof: 0 fdtd_config, 1 fdtd_source_op, 2 fdtd_monitor_op (binding check) */
+int  fdtd_struct_size(int32_t which);   /* sizeof: 0 fdtd_config, 1 fdtd_source_op, 2 fdtd_monitor_op, 3 fdtd_ade_op */
 const char* fdtd_last_error(void);
 int  fdtd_create(const fdtd_config* cfg, fdtd_engine** out);
 int  fdtd_destroy(fdtd_engine* e);
@@ -106,6 +118,10 @@ int  fdtd_field_device_ptr(fdtd_engine* e, int32_t component, void** ptr, int64_
 int  fdtd_clear_ops(fdtd_engine* e);
 int  fdtd_add_source_op(fdtd_engine* e, const fdtd_source_op* op);
 int  fdtd_add_monitor_op(fdtd_engine* e, const fdtd_monitor_op* op, int32_t* id);
+int  fdtd_add_ade_op(fdtd_engine* e, const fdtd_ade_op* op, int32_t* id);
+/* ADE state, host fp64 [cells of the box]: which = 0 current (P or J), 1 previous (Lorentz only) */
+int  fdtd_download_ade(fdtd_engine* e, int32_t id, int32_t which, double* host);
+int  fdtd_upload_ade(fdtd_engine* e, int32_t id, int32_t which, const double* host);
 /* Per-step host-evaluated tables for steps [0, n_steps) of the NEXT fdtd_run calls:
  *   amp     [n_steps][n_amp]        fp64  source amplitudes  (waveform(t_n), sign, /377 baked in)
  *   phasors [n_steps][n_phasor][2]  fp64  exp(-j*2*pi*f*t_n) as (re, im)

@@ -12,4 +12,4 @@ Rules ("Oracle"):
     and ``tests/golden/*.npz`` hold outputs of the real reference (``oracle/make_golden.py``)
     that travel to the GPU box where /root/reference does not exist.
 """
-from . import kernels, grid, waveforms, sim  # noqa: F401
+from . import kernels, grid, waveforms, sim, ade  # noqa: F401

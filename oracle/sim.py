@@ -390,7 +390,7 @@ class OSimulation:
         self.dt = g.time_step(courant_factor)
         self.F = {c: np.zeros(g.shape(c), dtype=dtype) for c in COMPONENTS}
         self.set_materials(materials)
-        self.sources, self.monitors = [], []
+        self.sources, self.monitors, self.ades = [], [], []
         self.step_count, self.current_time = 0, 0.0
 
     def set_materials(self, materials=None):
@@ -417,6 +417,8 @@ class OSimulation:
             s.apply(self.F, self.current_time, self.dt)
         for m in self.monitors:
             m.update(self.F, self.current_time, self.dt)
+        for a in self.ades:                     # what a user does after sim.step(): solver.update_polarization(E)
+            a.update(self.F)
 
     def run_steps(self, n):
         for _ in range(n):

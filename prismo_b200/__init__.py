@@ -12,6 +12,7 @@ from .waveform import ContinuousWave, CustomWaveform, GaussianPulse, RickerWavel
 from .sources import (ElectricDipole, GaussianBeamSource, MagneticDipole, ModeSource, PlaneWaveSource, PointSource,
                       Source, TFSFSource)
 from .monitors import DFTMonitor, FieldMonitor, FluxMonitor, ModeExpansionMonitor, Monitor
+from .materials import (ADESolver, DebyeMaterial, DrudeMaterial, LorentzMaterial, LorentzPole, attach_ade)
 from .session import Session, configure
 from .simulation import ElectromagneticFields, FDTDSolver, MaxwellUpdater, Simulation
 from .engine import Engine, MonitorOp, SourceOp

@@ -44,6 +44,14 @@ class MonitorOp(C.Structure):
     ]
 
 
+class AdeOp(C.Structure):
+    _fields_ = [
+        ("component", C.c_int32), ("kind", C.c_int32), ("lo", C.c_int32 * 3), ("hi", C.c_int32 * 3),
+        ("c0", C.c_double), ("c1", C.c_double), ("c2", C.c_double), ("c3", C.c_double),
+        ("mask", C.POINTER(C.c_uint8)),
+    ]
+
+
 _P = C.c_void_p
 _PROTOS = {
     # name: (restype, argtypes)
@@ -62,6 +70,9 @@ _PROTOS = {
     "fdtd_clear_ops": (C.c_int, [_P]),
     "fdtd_add_source_op": (C.c_int, [_P, C.POINTER(SourceOp)]),
     "fdtd_add_monitor_op": (C.c_int, [_P, C.POINTER(MonitorOp), C.POINTER(C.c_int32)]),
+    "fdtd_add_ade_op": (C.c_int, [_P, C.POINTER(AdeOp), C.POINTER(C.c_int32)]),
+    "fdtd_download_ade": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "fdtd_upload_ade": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "fdtd_set_tables": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "fdtd_run": (C.c_int, [_P, C.c_int32]),
     "fdtd_update_h": (C.c_int, [_P]),
@@ -107,7 +118,7 @@ def load() -> C.CDLL:
     got = lib.fdtd_abi_version()
     if got != ABI_VERSION:
         raise OSError(f"{LIB_PATH}: ABI version {got}, binding expects {ABI_VERSION}")
-    for which, st in enumerate((Config, SourceOp, MonitorOp)):
+    for which, st in enumerate((Config, SourceOp, MonitorOp, AdeOp)):
         if lib.fdtd_struct_size(which) != C.sizeof(st):
             raise OSError(f"{LIB_PATH}: struct {st.__name__} is {lib.fdtd_struct_size(which)} bytes in C, "
                           f"{C.sizeof(st)} in the binding")

@@ -61,6 +61,9 @@ struct fdtd_engine {
     std::vector<HostSrc> src;
     std::vector<MonOp> mon;
     std::vector<double> prof_host;
+    std::vector<AdeOp> ade; std::vector<unsigned char> ade_mask_host;
+    AdeOp* d_ade = nullptr; void* d_aux = nullptr; unsigned char* d_ade_mask = nullptr;
+    long long aux_elems = 0, ade_threads = 0;
     bool ops_dirty = true;
     SrcOp* d_src = nullptr;         // all source ops, ordered by group
     std::vector<int> grp_first, grp_count; std::vector<long long> grp_threads;
@@ -157,6 +160,7 @@ extern "C" int fdtd_struct_size(int32_t which)
     case 0: return (int)sizeof(fdtd_config);
     case 1: return (int)sizeof(fdtd_source_op);
     case 2: return (int)sizeof(fdtd_monitor_op);
+    case 3: return (int)sizeof(fdtd_ade_op);
     default: return -1;
     }
 }
@@ -239,6 +243,7 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     for (int c = 0; c < 6; ++c) { cudaFree(e->fld[c]); cudaFree(e->fldB[c]); }
     for (int c = 0; c < 4; ++c) cudaFree(e->coef[c]);
     cudaFree(e->d_src); cudaFree(e->d_mon); cudaFree(e->d_prof);
+    cudaFree(e->d_ade); cudaFree(e->d_aux); cudaFree(e->d_ade_mask);
     cudaFree(e->d_comp_ptr[0]); cudaFree(e->d_comp_ptr[1]);
     cudaFree(e->d_amp); cudaFree(e->d_phasor); cudaFree(e->d_rec); cudaFree(e->d_dft);
     cudaFree(e->d_step); cudaFree(e->d_cnt); cudaFree(e->d_stage);
@@ -415,6 +420,7 @@ extern "C" int fdtd_clear_ops(fdtd_engine* e)
 {
     if (!e) return fail(FDTD_EINVAL, "null engine");
     e->src.clear(); e->mon.clear(); e->prof_host.clear();
+    e->ade.clear(); e->ade_mask_host.clear();
     e->ops_dirty = true;
     drop_graph(e);
     return 0;
@@ -455,6 +461,29 @@ extern "C" int fdtd_add_monitor_op(fdtd_engine* e, const fdtd_monitor_op* op, in
     m.cells = (long long)m.n[0] * m.n[1] * m.n[2];
     if (id) *id = (int32_t)e->mon.size();
     e->mon.push_back(m);
+    e->ops_dirty = true;
+    drop_graph(e);
+    return 0;
+}
+
+extern "C" int fdtd_add_ade_op(fdtd_engine* e, const fdtd_ade_op* op, int32_t* id)
+{
+    if (!e || !op) return fail(FDTD_EINVAL, "fdtd_add_ade_op: null argument");
+    if (op->component < 0 || op->component > 2) return fail(FDTD_EINVAL, "ADE ops are driven by an E component (0..2)");
+    if (op->kind < 0 || op->kind > 2) return fail(FDTD_EINVAL, "ADE kind must be 0 (Lorentz), 1 (Drude) or 2 (Debye)");
+    AdeOp a{};
+    if (int rc = check_box(e, op->component, op->lo, op->hi, a.n)) return rc;
+    a.comp = op->component; a.kind = op->kind;
+    for (int k = 0; k < 3; ++k) a.lo[k] = op->lo[k];
+    a.c0 = op->c0; a.c1 = op->c1; a.c2 = op->c2; a.c3 = op->c3;
+    a.cells = (long long)a.n[0] * a.n[1] * a.n[2];
+    a.mask_off = -1;
+    if (op->mask && a.cells > 0) {
+        a.mask_off = (long long)e->ade_mask_host.size();
+        e->ade_mask_host.insert(e->ade_mask_host.end(), op->mask, op->mask + a.cells);
+    }
+    if (id) *id = (int32_t)e->ade.size();
+    e->ade.push_back(a);
     e->ops_dirty = true;
     drop_graph(e);
     return 0;
@@ -507,9 +536,68 @@ static int finalize_ops(fdtd_engine* e)
         }
         e->dft_elems = dft;
     }
+    // ADE ops: aux pool (cur [+ prev] per op), zero-initialised when the layout changes
+    {
+        long long th = 0, aux = 0;
+        for (auto& a : e->ade) {
+            a.first_thread = th; th += a.cells;
+            a.cur_off = aux; aux += a.cells;
+            a.prev_off = -1;
+            if (a.kind == 0) { a.prev_off = aux; aux += a.cells; }
+        }
+        e->ade_threads = th;
+        cudaFree(e->d_ade); e->d_ade = nullptr;
+        cudaFree(e->d_ade_mask); e->d_ade_mask = nullptr;
+        if (!e->ade.empty()) {
+            CU(cudaMalloc(&e->d_ade, e->ade.size() * sizeof(AdeOp)));
+            CU(cudaMemcpy(e->d_ade, e->ade.data(), e->ade.size() * sizeof(AdeOp), cudaMemcpyHostToDevice));
+            if (!e->ade_mask_host.empty()) {
+                CU(cudaMalloc(&e->d_ade_mask, e->ade_mask_host.size()));
+                CU(cudaMemcpy(e->d_ade_mask, e->ade_mask_host.data(), e->ade_mask_host.size(), cudaMemcpyHostToDevice));
+            }
+        }
+        if (aux != e->aux_elems || (!e->d_aux && aux > 0)) {
+            cudaFree(e->d_aux); e->d_aux = nullptr;
+            if (aux > 0) {
+                CU(cudaMalloc(&e->d_aux, aux * e->esz));
+                CU(cudaMemset(e->d_aux, 0, aux * e->esz));
+            }
+            e->aux_elems = aux;
+        }
+    }
     e->ops_dirty = false;
     return 0;
 }
+
+// state of an ADE op: which = 0 current (P or J), 1 previous (Lorentz only); host fp64 [cells]
+static int ade_state_copy(fdtd_engine* e, int32_t id, int32_t which, double* host, bool to_device)
+{
+    if (!e || !host || id < 0 || id >= (int)e->ade.size() || which < 0 || which > 1)
+        return fail(FDTD_EINVAL, "ADE state: bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = finalize_ops(e)) return rc;
+    const AdeOp& a = e->ade[id];
+    const long long off = which == 0 ? a.cur_off : a.prev_off;
+    if (off < 0) return fail(FDTD_EINVAL, "ADE op %d has no previous-step state", id);
+    if (a.cells == 0) return 0;
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->cfg.dtype == FDTD_F64) {
+        if (to_device) CU(cudaMemcpy((double*)e->d_aux + off, host, a.cells * sizeof(double), cudaMemcpyHostToDevice));
+        else CU(cudaMemcpy(host, (double*)e->d_aux + off, a.cells * sizeof(double), cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    std::vector<float> tmp(a.cells);
+    if (to_device) {
+        for (long long i = 0; i < a.cells; ++i) tmp[i] = (float)host[i];
+        CU(cudaMemcpy((float*)e->d_aux + off, tmp.data(), a.cells * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        CU(cudaMemcpy(tmp.data(), (float*)e->d_aux + off, a.cells * sizeof(float), cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < a.cells; ++i) host[i] = tmp[i];
+    }
+    return 0;
+}
+extern "C" int fdtd_download_ade(fdtd_engine* e, int32_t id, int32_t which, double* host) { return ade_state_copy(e, id, which, host, false); }
+extern "C" int fdtd_upload_ade(fdtd_engine* e, int32_t id, int32_t which, const double* host) { return ade_state_copy(e, id, which, const_cast<double*>(host), true); }
 
 // record offsets depend on the number of tabled steps: op.rec_off = base(op) * n_steps
 static int upload_mon_ops(fdtd_engine* e)
@@ -733,7 +821,8 @@ template <typename T> static int one_step(fdtd_engine* e, int step_off, int pari
     return launch_post<T>(e, step_off, parity, s);
 }
 
-static bool has_post(const fdtd_engine* e) { return !e->src.empty() || !e->mon.empty(); }
+static bool has_tables(const fdtd_engine* e) { return !e->src.empty() || !e->mon.empty(); }
+static bool has_post(const fdtd_engine* e) { return has_tables(e) || !e->ade.empty(); }
 
 template <typename T> static int run_steps(fdtd_engine* e, int n)
 {
@@ -785,7 +874,7 @@ extern "C" int fdtd_run(fdtd_engine* e, int32_t n_steps)
                                  "and exchange the halo planes in between");
     CU(cudaSetDevice(e->cfg.device));
     if (int rc = finalize_ops(e)) return rc;
-    if (has_post(e)) {
+    if (has_tables(e)) {
         if (e->cursor + n_steps > e->n_steps_tab)
             return fail(FDTD_ESTATE, "fdtd_run(%d): only %d tabled steps left (call fdtd_set_tables)", n_steps,
                         e->n_steps_tab - e->cursor);
@@ -855,7 +944,7 @@ extern "C" int fdtd_run_profiled(fdtd_engine* e, int32_t n_steps, double* out_ms
     if (!e || n_steps <= 0 || !out_ms) return fail(FDTD_EINVAL, "fdtd_run_profiled: bad argument");
     CU(cudaSetDevice(e->cfg.device));
     if (int rc = finalize_ops(e)) return rc;
-    if (has_post(e)) {
+    if (has_tables(e)) {
         if (e->cursor + n_steps > e->n_steps_tab)
             return fail(FDTD_ESTATE, "fdtd_run_profiled(%d): only %d tabled steps left", n_steps, e->n_steps_tab - e->cursor);
         if (!e->d_mon && !e->mon.empty()) if (int rc = upload_mon_ops(e)) return rc;
@@ -1046,7 +1135,7 @@ extern "C" int fdtd_slab_run(fdtd_engine* e, int32_t n_steps)
     if (n_steps == 0) return 0;
     CU(cudaSetDevice(e->cfg.device));
     if (int rc = finalize_ops(e)) return rc;
-    if (has_post(e)) {
+    if (has_tables(e)) {
         if (e->cursor + n_steps > e->n_steps_tab)
             return fail(FDTD_ESTATE, "fdtd_slab_run(%d): only %d tabled steps left", n_steps, e->n_steps_tab - e->cursor);
         if (!e->d_mon && !e->mon.empty()) if (int rc = upload_mon_ops(e)) return rc;
@@ -1079,7 +1168,7 @@ extern "C" int fdtd_post_step(fdtd_engine* e, void* stream)
     CU(cudaSetDevice(e->cfg.device));
     if (int rc = finalize_ops(e)) return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
-    if (has_post(e)) {
+    if (has_tables(e)) {
         if (e->cursor + 1 > e->n_steps_tab) return fail(FDTD_ESTATE, "fdtd_post_step: no tabled steps left");
         if (!e->d_mon && !e->mon.empty()) if (int rc = upload_mon_ops(e)) return rc;
         int rc = e->cfg.dtype == FDTD_F64 ? launch_post<double>(e, 0, 0, s) : launch_post<float>(e, 0, 0, s);

@@ -436,6 +436,50 @@ __global__ void k_monitors(const T* const* __restrict__ comp_ptr, const MonOp* _
     }
 }
 
+// Auxiliary-differential-equation recursions of dispersive media, cell-local, driven by one E component
+// (materials/ade.py:116-160; coefficients materials/dispersion.py:189-231, 267-286, 323-336):
+//   Lorentz  P+ = C0*E + C1*E + C2*P + C3*P_prev      Drude  J+ = C0*E + C1*J      Debye  P+ = C0*E + C1*P
+// evaluated left to right like NumPy; "E" is E*mask as ADEManager.update_all forms it (ade.py:291-308).
+struct AdeOp {
+    int comp, kind;              // kind: 0 Lorentz, 1 Drude, 2 Debye
+    int lo[3], n[3];
+    double c0, c1, c2, c3;
+    long long cur_off, prev_off; // offsets (elements) into the aux pool; prev_off < 0 unless Lorentz
+    long long mask_off;          // offset into the mask pool, -1 = no mask
+    long long cells, first_thread;
+};
+
+template <typename T>
+__global__ void k_ade(const T* const* __restrict__ comp_ptr, const AdeOp* __restrict__ ops, int n_ops,
+                      long long total, Strides3 st, T* __restrict__ aux, const unsigned char* __restrict__ mask)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int q = 0;
+    while (q + 1 < n_ops && ops[q + 1].first_thread <= t) ++q;
+    const AdeOp op = ops[q];
+    const long long cell = t - op.first_thread;
+    const int c2 = (int)(cell % op.n[2]);
+    const long long r = cell / op.n[2];
+    const int c1 = (int)(r % op.n[1]);
+    const int c0 = (int)(r / op.n[1]);
+    const long long o = (op.lo[0] + c0) * st.s[0] + (op.lo[1] + c1) * st.s[1] + (op.lo[2] + c2) * st.s[2];
+    double e = (double)comp_ptr[op.comp][o];
+    if (op.mask_off >= 0) e = __dmul_rn(e, mask[op.mask_off + cell] ? 1.0 : 0.0);
+    T* cur = aux + op.cur_off + cell;
+    const double a = (double)*cur;
+    double nv;
+    if (op.kind == 0) {
+        T* prev = aux + op.prev_off + cell;
+        nv = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(op.c0, e), __dmul_rn(op.c1, e)), __dmul_rn(op.c2, a)),
+                       __dmul_rn(op.c3, (double)*prev));
+        *prev = (T)a;
+    } else {
+        nv = __dadd_rn(__dmul_rn(op.c0, e), __dmul_rn(op.c1, a));
+    }
+    *cur = (T)nv;
+}
+
 __global__ void k_bump(int* step_ptr, int n) { *step_ptr += n; }
 
 // =================================================================================================

@@ -38,6 +38,21 @@ class MonitorOp:
     shape: tuple = field(default=(), compare=False)     # box shape in the array's own rank (2 or 3 axes)
 
 
+@dataclass
+class AdeOp:
+    """Cell-local ADE recursion driven by E[component] after every step (see fdtd_ade_op)."""
+    component: str
+    kind: int                      # 0 Lorentz, 1 Drude, 2 Debye
+    lo: tuple
+    hi: tuple
+    c0: float
+    c1: float
+    c2: float = 0.0
+    c3: float = 0.0
+    mask: Optional[np.ndarray] = None
+    shape: tuple = field(default=(), compare=False)
+
+
 def _dtype_code(dt) -> int:
     dt = np.dtype(dt)
     if dt == np.float32:
@@ -69,7 +84,7 @@ class Engine:
                           x_offset=self.x_offset, flags=int(flags), reserved=0)
         _lib.check(self._lib.fdtd_create(C.byref(cfg), C.byref(self._h)))
         self._mon_ops: list = []
-        self._keep: list = []
+        self._ade_ops: list = []
 
     # ---- lifetime ---------------------------------------------------------------------------------
     def close(self):
@@ -159,6 +174,7 @@ class Engine:
     def clear_ops(self):
         _lib.check(self._lib.fdtd_clear_ops(self._h))
         self._mon_ops = []
+        self._ade_ops = []
 
     def add_source_op(self, op: SourceOp) -> None:
         c = _lib.SourceOp()
@@ -186,6 +202,37 @@ class Engine:
         op.shape = tuple(h - l for l, h in zip(op.lo, op.hi))
         self._mon_ops.append(op)
         return mid.value
+
+    def add_ade_op(self, op: AdeOp) -> int:
+        c = _lib.AdeOp()
+        c.component, c.kind = COMP_ID[op.component], int(op.kind)
+        c.lo[:] = _pad3(op.lo, 0)
+        c.hi[:] = _pad3(op.hi, 1)
+        c.c0, c.c1, c.c2, c.c3 = float(op.c0), float(op.c1), float(op.c2), float(op.c3)
+        op.shape = tuple(h - l for l, h in zip(op.lo, op.hi))
+        m = None
+        if op.mask is not None:
+            m = np.ascontiguousarray(np.asarray(op.mask) != 0, dtype=np.uint8)
+            if m.shape != op.shape:
+                raise ValueError(f"mask shape {m.shape} != box shape {op.shape}")
+            c.mask = m.ctypes.data_as(C.POINTER(C.c_uint8))
+        aid = C.c_int32()
+        _lib.check(self._lib.fdtd_add_ade_op(self._h, C.byref(c), C.byref(aid)))
+        self._ade_ops.append(op)
+        return aid.value
+
+    def ade_state(self, ade_id: int, which: int = 0) -> np.ndarray:
+        out = np.zeros(self._ade_ops[ade_id].shape, dtype=np.float64)
+        if out.size:
+            _lib.check(self._lib.fdtd_download_ade(self._h, ade_id, which, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_ade_state(self, ade_id: int, which: int, values) -> None:
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        if v.shape != self._ade_ops[ade_id].shape:
+            raise ValueError(f"ADE state shape {v.shape} != {self._ade_ops[ade_id].shape}")
+        if v.size:
+            _lib.check(self._lib.fdtd_upload_ade(self._h, ade_id, which, v.ctypes.data_as(C.c_void_p)))
 
     def set_tables(self, n_steps: int, amp: Optional[np.ndarray] = None, phasors: Optional[np.ndarray] = None):
         """amp: (n_steps, n_amp) float64; phasors: (n_steps, n_phasor) complex128."""

@@ -24,7 +24,7 @@ from typing import Callable, Optional
 
 import numpy as np
 
-from .engine import MonitorOp, SourceOp
+from .engine import AdeOp, MonitorOp, SourceOp
 from .grid import COMPONENTS, YeeGrid
 from . import postprocess
 
@@ -43,6 +43,7 @@ class Program:
     amp_fns: list = field(default_factory=list)        # (t, dt) -> float
     phasor_fns: list = field(default_factory=list)     # t -> complex
     binders: list = field(default_factory=list)
+    ade_ops: list = field(default_factory=list)
     _group: int = 0
 
     # -- building blocks ---------------------------------------------------------------------------
@@ -288,6 +289,9 @@ class _Binder:
     def collect(self, engine, times, dt, n):
         pass
 
+    def finish(self, engine):         # once, after the last chunk
+        pass
+
 
 def _patch_box(g: YeeGrid, comp, what):
     """The reference's placeholder region ``field[:10, :10]`` (monitors/dft.py:156-160)."""
@@ -424,8 +428,53 @@ _MONITORS = {"FieldMonitor": _FieldBinder, "DFTMonitor": _DFTBinder, "FluxMonito
              "ModeExpansionMonitor": _ModeExpansionBinder}
 
 
+class _AdeBinder(_Binder):
+    """One dispersive medium (materials/ade.py:16-160) attached to one E component: one device recursion per
+    Lorentz pole, or one for Drude / Debye.  State lives in the solver object between runs."""
+
+    def __init__(self, p: Program, solver, component, mask):
+        g = p.grid
+        shape = g.get_field_shape(component)
+        if tuple(solver.grid_shape) != tuple(shape):
+            raise ValueError(f"operands could not be broadcast together with shapes {tuple(solver.grid_shape)} {shape} "
+                             f"(ADESolver.grid_shape must equal the {component} array shape)")
+        self.solver = solver
+        co = solver.coeffs
+        lo, hi = (0,) * len(shape), tuple(shape)
+        m = None if mask is None else np.broadcast_to(np.asarray(mask), shape)
+        self.kind = 0 if "poles" in co else (1 if "omega_p" in co else 2)
+        self.ids = []
+        if self.kind == 0:
+            for pole in co["poles"]:
+                p.ade_ops.append(AdeOp(component, 0, lo, hi, pole["C0"], pole["C1"], pole["C2"], pole["C3"], m))
+                self.ids.append(len(p.ade_ops) - 1)
+        else:
+            p.ade_ops.append(AdeOp(component, self.kind, lo, hi, co["C0"], co["C1"], 0.0, 0.0, m))
+            self.ids.append(len(p.ade_ops) - 1)
+
+    def preload(self, engine):
+        s = self.solver
+        if self.kind == 0:
+            for n, i in enumerate(self.ids):
+                engine.set_ade_state(i, 0, s.P_current[n])
+                engine.set_ade_state(i, 1, s.P_previous[n])
+        else:
+            engine.set_ade_state(self.ids[0], 0, s.J_current if self.kind == 1 else s.P_current)
+
+    def finish(self, engine):
+        s = self.solver
+        if self.kind == 0:
+            for n, i in enumerate(self.ids):
+                s.P_current[n] = engine.ade_state(i, 0)
+                s.P_previous[n] = engine.ade_state(i, 1)
+        elif self.kind == 1:
+            s.J_current = engine.ade_state(self.ids[0], 0)
+        else:
+            s.P_current = engine.ade_state(self.ids[0], 0)
+
+
 # ======================================================================================================
-def lower(grid, sources, monitors) -> Program:
+def lower(grid, sources, monitors, ades=()) -> Program:
     """Compile source and monitor objects for ``grid`` (any object exposing the reference's YeeGrid.spec)."""
     p = Program(YeeGrid.like(grid))
     for s in sources:
@@ -444,4 +493,6 @@ def lower(grid, sources, monitors) -> Program:
                 f"monitor type {type(m).__name__} cannot be lowered to the B200 engine (no CPU fallback); "
                 f"supported: {sorted(_MONITORS)}")
         p.binders.append(_MONITORS[kind](p, m))
+    for solver, component, mask in ades:
+        p.binders.append(_AdeBinder(p, solver, component, mask))
     return p

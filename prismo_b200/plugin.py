@@ -132,7 +132,8 @@ def _advance_sim(sim, n: int) -> None:
     if n <= 0:
         return
     sess = _session_for(sim.solver.updater)
-    sim.current_time = sess.advance(sim.fields, sim.sources, sim.monitors, sim.current_time, sim.dt, n)
+    sim.current_time = sess.advance(sim.fields, sim.sources, sim.monitors, sim.current_time, sim.dt, n,
+                                    ades=getattr(sim, "_b200_ade", ()))
     sim.step_count += n
     dts = sim.solver.updater.get_time_step()
     for _ in range(n):

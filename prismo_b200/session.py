@@ -98,17 +98,19 @@ class Session:
             out.append(t)
         return out
 
-    def advance(self, fields, sources, monitors, t0: float, dt: float, n: int) -> float:
+    def advance(self, fields, sources, monitors, t0: float, dt: float, n: int, ades=()) -> float:
         """Run n full steps (H pass, E pass, sources, monitors).  Returns the new accumulated time."""
         if n <= 0:
             return t0
         eng = self.engine
-        prog = lowering.lower(self.grid, sources, monitors)
+        prog = lowering.lower(self.grid, sources, monitors, ades)
         eng.clear_ops()
         for op in prog.src_ops:
             eng.add_source_op(op)
         for op in prog.mon_ops:
             eng.add_monitor_op(op)
+        for op in prog.ade_ops:
+            eng.add_ade_op(op)
         chunk = n
         if prog.src_ops or prog.mon_ops:
             chunk = min(chunk, _MAX_TABLE_STEPS)
@@ -124,15 +126,17 @@ class Session:
             if prog.src_ops or prog.mon_ops:
                 amp, ph = prog.tables(times, dt)
                 eng.set_tables(m, amp, ph)
-                if first:
-                    for b in prog.binders:
-                        b.preload(eng)
-                    first = False
+            if first:
+                for b in prog.binders:
+                    b.preload(eng)
+                first = False
             eng.run(m)
             for b in prog.binders:
                 b.collect(eng, times, dt, m)
             t = times[-1]
             done += m
+        for b in prog.binders:
+            b.finish(eng)
         self.pull_fields(fields)
         return t
 

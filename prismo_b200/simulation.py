@@ -188,7 +188,14 @@ class Simulation:
         self.solver = FDTDSolver(self.grid, self.dt, dtype=dtype, device=device)
         self.sources: list = []
         self.monitors: list = []
+        self._b200_ade: list = []
         self.step_count, self.current_time = 0, 0.0
+
+    def add_ade(self, solver, component: str, mask=None) -> None:
+        """Attach a dispersive medium's ADE recursion (materials.ADESolver), driven by E[component] each step."""
+        from .materials import attach_ade
+
+        attach_ade(self, solver, component, mask)
 
     def add_source(self, source) -> None:
         source.initialize(self.grid)
@@ -209,7 +216,8 @@ class Simulation:
         if n <= 0:
             return
         sess = self.solver.updater.session()
-        self.current_time = sess.advance(self.fields, self.sources, self.monitors, self.current_time, self.dt, n)
+        self.current_time = sess.advance(self.fields, self.sources, self.monitors, self.current_time, self.dt, n,
+                                         ades=self._b200_ade)
         self.step_count += n
         dt_s = self.solver.updater.get_time_step()
         for _ in range(n):

@@ -25,7 +25,7 @@ class FakeEngine:
         full = self.dims if ndim == 3 else (self.dims[0], self.dims[1], 1)
         eps0, mu0 = 8.854187817e-12, 4 * np.pi * 1e-7
         self.coeffs = [np.full(full, v) for v in (1.0, dt / eps0, 1.0, dt / mu0)]
-        self.src, self.mon = [], []
+        self.src, self.mon, self.ade = [], [], []
         self.cursor, self.n_tab = 0, 0
         self.kernel_launches = 0
         self.uploads = 0
@@ -63,7 +63,7 @@ class FakeEngine:
         return out
 
     def clear_ops(self):
-        self.src, self.mon = [], []
+        self.src, self.mon, self.ade = [], [], []
 
     def add_source_op(self, op):
         self.src.append(op)
@@ -72,6 +72,30 @@ class FakeEngine:
         op.shape = tuple(h - l for l, h in zip(op.lo, op.hi))
         self.mon.append(dict(op=op, rec=[], dft=np.zeros((op.n_freq,) + op.shape, dtype=np.complex128)))
         return len(self.mon) - 1
+
+    def add_ade_op(self, op):
+        op.shape = tuple(h - l for l, h in zip(op.lo, op.hi))
+        self.ade.append(dict(op=op, cur=np.zeros(op.shape), prev=np.zeros(op.shape)))
+        return len(self.ade) - 1
+
+    def ade_state(self, i, which=0):
+        return self.ade[i]["cur" if which == 0 else "prev"].copy()
+
+    def set_ade_state(self, i, which, v):
+        self.ade[i]["cur" if which == 0 else "prev"][...] = v
+
+    def _run_ade(self):
+        for a in self.ade:
+            o = a["op"]
+            e = self.F[o.component][self._sl(o)]
+            if o.mask is not None:
+                e = e * (np.asarray(o.mask) != 0)
+            if o.kind == 0:
+                new = o.c0 * e + o.c1 * e + o.c2 * a["cur"] + o.c3 * a["prev"]
+                a["prev"] = a["cur"].copy()
+                a["cur"] = new
+            else:
+                a["cur"] = o.c0 * e + o.c1 * a["cur"]
 
     def set_tables(self, n_steps, amp=None, phasors=None):
         self.amp = None if amp is None else np.asarray(amp).reshape(n_steps, -1)
@@ -106,6 +130,7 @@ class FakeEngine:
                 for k in range(o.n_freq):
                     ph = self.ph[s, o.phasor_col + k]
                     m["dft"][k] += (d * ph.real) * self.dt + 1j * ((d * ph.imag) * self.dt)
+            self._run_ade()
             self.cursor += 1
             self.kernel_launches += 2
 

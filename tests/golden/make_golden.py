@@ -22,8 +22,7 @@ def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     for name, spec in S.SCENARIOS.items():
         sim = S.build_reference(spec, prismo)
-        for _ in range(spec["steps"]):
-            sim.step()
+        S.step_reference(sim, spec["steps"])
         res = S.results_reference(sim)
         path = os.path.join(out_dir, name + ".npz")
         np.savez_compressed(path, **res)

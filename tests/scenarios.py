@@ -99,6 +99,16 @@ SCENARIOS = {
                                 ("ModeExpansionMonitor", dict(center=(0.5e-6, 0.4e-6, 0.0), size=(0.0, 0.4e-6, 0.0),
                                                               modes=[("mode", 10, 10, 3), ("mode", 7, 5, 4)],
                                                               direction="x", frequencies=[F0]))]),
+    # ---- dispersive media: ADE recursions driven by E after every step (row a22) ---------------------------
+    "ade3d": dict(size=(0.6e-6, 0.5e-6, 0.4e-6), resolution=20e6, pml=2, courant=0.5, steps=7,
+                  sources=[("PointSource", dict(position=(0.3e-6, 0.25e-6, 0.2e-6), component="Ez",
+                                                waveform=_wf("ContinuousWave", frequency=F0)))],
+                  ade=[("lorentz", [(2 * 3.141592653589793 * 2.5e14, 1.0, 1e13), (2 * 3.141592653589793 * 4e14, 0.4, 3e13)], "Ez", "half"),
+                       ("drude", (2 * 3.141592653589793 * 2.175e15, 2 * 3.141592653589793 * 6.5e12), "Ex", None),
+                       ("debye", (2.0, 5.0, 1e-14), "Ey", "half")]),
+    "ade2d": dict(size=(1.0e-6, 0.8e-6, 0.0), resolution=20e6, pml=3, courant=0.9, steps=7,
+                  ade=[("lorentz", [(2 * 3.141592653589793 * 2.5e14, 1.0, 1e13)], "Ez", None),
+                       ("drude", (2 * 3.141592653589793 * 2.175e15, 2 * 3.141592653589793 * 6.5e12), "Ey", "half")]),
 }
 
 
@@ -127,6 +137,15 @@ def initial_fields(spec, shapes):
             a = np.zeros(shapes[c])
         out[c] = a
     return out
+
+
+def ade_mask(kind, shape):
+    if kind is None:
+        return None
+    m = np.zeros(shape, dtype=bool)
+    m[: shape[0] // 2] = True
+    m[:, ::3] = False
+    return m
 
 
 def make_mode(nx, ny, seed, ns=types.SimpleNamespace):
@@ -181,7 +200,41 @@ def build_reference(spec, prismo, backend="numpy"):
     init = initial_fields(spec, {c: sim.fields[c].shape for c in COMPONENTS})
     for c in COMPONENTS:
         sim.fields[c][...] = init[c]
+    sim._ade = []
+    if spec.get("ade"):
+        from prismo.materials import dispersion as D
+        from prismo.materials.ade import ADESolver
+
+        for kind, params, comp, mk in spec["ade"]:
+            mat = _make_material(D, kind, params)
+            solver = ADESolver(mat, sim.dt, sim.fields[comp].shape)
+            mask = ade_mask(mk, sim.fields[comp].shape)
+            sim._ade.append((solver, comp, mask))
+            if backend == "b200":
+                import prismo_b200
+
+                prismo_b200.attach_ade(sim, solver, comp, mask)
     return sim
+
+
+def _make_material(D, kind, params):
+    if kind == "lorentz":
+        return D.LorentzMaterial(1.0, [D.LorentzPole(omega_0=w, delta_epsilon=de, gamma=g) for w, de, g in params])
+    if kind == "drude":
+        return D.DrudeMaterial(9.84, *params)
+    return D.DebyeMaterial(*params)
+
+
+def step_reference(sim, n):
+    """n reference steps incl. what a user of the reference does for dispersive media: call the solver after
+    every Simulation.step() (nothing in the reference calls it — SURVEY F7)."""
+    for _ in range(n):
+        sim.step()
+        for solver, comp, mask in getattr(sim, "_ade", ()):
+            if sim.solver.updater.backend.name == "b200":
+                continue                                     # attached: runs on the device inside sim.step()
+            e = sim.fields[comp]
+            solver.update_polarization(e if mask is None else e * mask)
 
 
 def build_oracle(spec):
@@ -205,6 +258,10 @@ def build_oracle(spec):
     init = initial_fields(spec, {c: s.F[c].shape for c in COMPONENTS})
     for c in COMPONENTS:
         s.F[c][...] = init[c]
+    from oracle.ade import OAde
+
+    for kind, params, comp, mk in spec.get("ade", []):
+        s.ades.append(OAde(kind, params, s.dt, s.F[comp].shape, comp, ade_mask(mk, s.F[comp].shape)))
     return s
 
 
@@ -223,7 +280,24 @@ def build_mirror(spec, pb, dtype=None):
     init = initial_fields(spec, {c: sim.fields[c].shape for c in COMPONENTS})
     for c in COMPONENTS:
         sim.fields[c][...] = init[c]
+    sim._ade = []
+    for kind, params, comp, mk in spec.get("ade", []):
+        solver = pb.ADESolver(_make_material(pb, kind, params), sim.dt, sim.fields[comp].shape)
+        sim.add_ade(solver, comp, ade_mask(mk, sim.fields[comp].shape))
+        sim._ade.append((solver, comp, None))
     return sim
+
+
+def _ade_results(out, solvers):
+    for n, (s, _, _) in enumerate(solvers):
+        if hasattr(s, "J_current"):
+            out[f"ade{n}_J"] = np.array(s.J_current)
+        elif isinstance(s.P_current, list):
+            for i in range(len(s.P_current)):
+                out[f"ade{n}_P{i}"] = np.array(s.P_current[i])
+                out[f"ade{n}_Pp{i}"] = np.array(s.P_previous[i])
+        else:
+            out[f"ade{n}_P"] = np.array(s.P_current)
 
 
 # ---- result extraction (same keys for all three) -------------------------------------------------------------
@@ -257,6 +331,7 @@ def results_reference(sim):
                 out[f"m{n}_ct_{i}"] = np.array(m._mode_coeffs_time[i])
                 if m.frequencies is not None:
                     out[f"m{n}_cf_{i}"] = np.array(m._mode_coeffs_freq[i])
+    _ade_results(out, getattr(sim, "_ade", ()))
     return out
 
 
@@ -293,6 +368,15 @@ def results_oracle(s):
                 out[f"m{n}_ct_{i}"] = np.array(m.coeffs_time[i])
                 if m.frequencies is not None:
                     out[f"m{n}_cf_{i}"] = np.array(m.coeffs_freq[i])
+    for n, a in enumerate(s.ades):
+        if a.kind == "drude":
+            out[f"ade{n}_J"] = np.array(a.J)
+        elif a.kind == "lorentz":
+            for i in range(len(a.P)):
+                out[f"ade{n}_P{i}"] = np.array(a.P[i])
+                out[f"ade{n}_Pp{i}"] = np.array(a.Pp[i])
+        else:
+            out[f"ade{n}_P"] = np.array(a.P)
     return out
 
 

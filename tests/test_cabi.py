@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_struct_sizes():
     lib = _lib.load()
     assert lib.fdtd_abi_version() == _lib.ABI_VERSION
-    for which, st in enumerate((_lib.Config, _lib.SourceOp, _lib.MonitorOp)):
+    for which, st in enumerate((_lib.Config, _lib.SourceOp, _lib.MonitorOp, _lib.AdeOp)):
         assert lib.fdtd_struct_size(which) == ctypes.sizeof(st)
 
 

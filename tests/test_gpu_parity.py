@@ -263,3 +263,24 @@ def test_engine_error_paths():
     eng.close()
     with pytest.raises(ValueError, match="too small"):
         pb.Engine(3, (2, 8, 8), (1e-8,) * 3, 1e-17)
+
+
+def test_region_correct_dft_monitor_3d_equals_field_monitor():
+    """Extension (off by default): DFTMonitor(region_correct=True) samples its real region and works in 3-D.
+    No reference numbers exist (the reference's DFTMonitor raises in 3-D); it must agree bitwise
+    with the reference-exact FieldMonitor DFT over the same region and frequencies."""
+    spec = dict(S.SCENARIOS["mon3d_field"], monitors=[])
+    sim = S.build_mirror(spec, pb, dtype="float64")
+    freqs = [0.9 * S.F0, S.F0]
+    kw = dict(center=(0.3e-6, 0.25e-6, 0.2e-6), size=(0.0, 0.3e-6, 0.2e-6))
+    fm = pb.FieldMonitor(components=["Ey", "Hz"], time_domain=False, frequencies=freqs, **kw)
+    dm = pb.DFTMonitor(frequencies=freqs, components=["Ey", "Hz"], region_correct=True, **kw)
+    sim.add_monitor(fm)
+    sim.add_monitor(dm)
+    sim.run_steps(9)
+    for c in ("Ey", "Hz"):
+        for i, f in enumerate(freqs):
+            a, b = fm.get_frequency_data(c, f), dm.get_frequency_data(c, i)
+            assert a.shape == b.shape and a.ndim == 3 and np.abs(a).max() > 0
+            assert np.array_equal(a, b), c
+    assert dm.get_power_spectrum("Ey").shape == (2,)

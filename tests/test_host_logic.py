@@ -54,7 +54,7 @@ def test_plugin_runs_reference_objects(name, fake, ref):
         sim = S.build_reference(spec, ref, backend="b200")
         assert sim.solver.updater.backend.name == "b200" and sim.fields.backend.is_gpu
         sim.step()
-        sim.run((spec["steps"] - 1 - 0.5) * sim.dt)        # ceil -> steps-1 more
+        sim.run((spec["steps"] - 1 - 0.5) * sim.dt)        # ceil -> steps-1 more (attached ADE runs inside)
         assert len(fake.instances) == 1                    # one engine per simulation, reused
         _compare(name, S.results_reference(sim), gold)
     finally:

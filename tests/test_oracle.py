@@ -32,8 +32,7 @@ def test_oracle_matches_golden(name):
 def test_oracle_matches_live_reference(name, ref):
     spec = S.SCENARIOS[name]
     r = S.build_reference(spec, ref)
-    for _ in range(spec["steps"]):
-        r.step()
+    S.step_reference(r, spec["steps"])
     o = S.build_oracle(spec)
     o.run_steps(spec["steps"])
     rr, oo = S.results_reference(r), S.results_oracle(o)
@@ -48,8 +47,7 @@ def test_golden_is_current(name, ref):
     """The committed fixtures are what the reference produces today (guards against stale goldens)."""
     spec = S.SCENARIOS[name]
     r = S.build_reference(spec, ref)
-    for _ in range(spec["steps"]):
-        r.step()
+    S.step_reference(r, spec["steps"])
     rr = S.results_reference(r)
     gold = np.load(os.path.join(GOLD, name + ".npz"))
     assert sorted(rr) == sorted(gold.files)
