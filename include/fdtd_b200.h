@@ -38,7 +38,9 @@ enum { FDTD_EX = 0, FDTD_EY = 1, FDTD_EZ = 2, FDTD_HX = 3, FDTD_HY = 4, FDTD_HZ 
 /* flags for fdtd_config.flags */
 enum {
     FDTD_FLAG_NO_GRAPH = 1,     /* never replay the step loop from a CUDA graph            */
-    FDTD_FLAG_TWO_PASS = 2      /* force the two-pass (H kernel, E kernel) 3-D step        */
+    FDTD_FLAG_TWO_PASS = 2,     /* force the two-pass (H kernel, E kernel) 3-D step        */
+    FDTD_FLAG_YEE = 4           /* OPT-IN physics mode, not parity: stable Yee leap-frog (backward
+                                   differences in the H update) + CPML; 3-D, two-pass kernels      */
 };
 
 typedef struct fdtd_engine fdtd_engine; /* opaque */
@@ -105,6 +107,12 @@ int  fdtd_set_uniform_coeffs(fdtd_engine* e, double ca, double cb, double da, do
  * neighbour slab exists (the extra plane is the neighbour's first plane).                      */
 int  fdtd_set_coeffs(fdtd_engine* e, const double* ca, const double* cb, const double* da,
                      const double* db, int32_t planes);
+
+/* Physics mode only: working CPML (the reference's is a stub that is never applied, boundaries/pml.py:259-328).
+ * coef = host fp64, axis by axis (x, y, z), 6 vectors of length N_axis each: b, a, 1/kappa at the E-update
+ * (half-cell) positions, then at the H-update (integer) positions; identity outside the layer.
+ * thickness = 0 removes the layer.  The 12 psi arrays are allocated only over the boundary slabs.          */
+int  fdtd_set_cpml(fdtd_engine* e, int32_t thickness, const double* coef);
 
 /* ---- fields (core/fields.py:64-114) --------------------------------------------------------- */
 int  fdtd_upload_field(fdtd_engine* e, int32_t component, const void* host, int32_t host_dtype);

@@ -13,6 +13,7 @@ from .sources import (ElectricDipole, GaussianBeamSource, MagneticDipole, ModeSo
                       Source, TFSFSource)
 from .monitors import DFTMonitor, FieldMonitor, FluxMonitor, ModeExpansionMonitor, Monitor
 from .materials import (ADESolver, DebyeMaterial, DrudeMaterial, LorentzMaterial, LorentzPole, attach_ade)
+from .cpml import PMLParams
 from .session import Session, configure
 from .simulation import ElectromagneticFields, FDTDSolver, MaxwellUpdater, Simulation
 from .engine import Engine, MonitorOp, SourceOp

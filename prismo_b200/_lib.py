@@ -15,7 +15,7 @@ ABI_VERSION = 1
 F32, F64 = 0, 1
 COMPONENTS = ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")
 COMP_ID = {c: i for i, c in enumerate(COMPONENTS)}
-FLAG_NO_GRAPH, FLAG_TWO_PASS = 1, 2
+FLAG_NO_GRAPH, FLAG_TWO_PASS, FLAG_YEE = 1, 2, 4
 
 _ERR_TYPES = {-1: ValueError, -2: RuntimeError, -3: MemoryError, -4: RuntimeError}
 
@@ -62,6 +62,7 @@ _PROTOS = {
     "fdtd_destroy": (C.c_int, [_P]),
     "fdtd_set_uniform_coeffs": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double]),
     "fdtd_set_coeffs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32]),
+    "fdtd_set_cpml": (C.c_int, [_P, C.c_int32, _P]),
     "fdtd_upload_field": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),
     "fdtd_download_field": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),
     "fdtd_zero_fields": (C.c_int, [_P]),

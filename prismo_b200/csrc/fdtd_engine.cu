@@ -7,6 +7,7 @@
 #include "../../include/fdtd_b200.h"
 #include "fdtd_kernels.cuh"
 #include "fdtd_fused.cuh"
+#include "fdtd_yee.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -65,6 +66,7 @@ struct fdtd_engine {
     AdeOp* d_ade = nullptr; void* d_aux = nullptr; unsigned char* d_ade_mask = nullptr;
     long long aux_elems = 0, ade_threads = 0;
     bool ops_dirty = true;
+    Cpml cpml{}; SlabGeom slabg{}; double* d_cpml_coef = nullptr; size_t psi_bytes[12] = {};
     SrcOp* d_src = nullptr;         // all source ops, ordered by group
     std::vector<int> grp_first, grp_count; std::vector<long long> grp_threads;
     MonOp* d_mon = nullptr; long long mon_threads = 0;
@@ -82,6 +84,7 @@ struct fdtd_engine {
     // graph
     cudaGraphExec_t gexec[2] = {nullptr, nullptr}; int graph_steps = 0; int graph_kernels[2] = {0, 0};
     int fused_lx = 0;               // planes per fused segment (0 = auto)
+    int fused_tj = 15;              // owner rows per CTA (15: one 16-warp CTA/SM; 7: two 8-warp CTAs/SM)
     int fused_pol = 0;              // bit0: streaming (evict-first) stores (measured 1.4% slower: off)
     // staging
     void* d_stage = nullptr; size_t stage_bytes = 0;
@@ -229,7 +232,8 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     const double eps0 = 8.854187817e-12, mu0 = 4 * M_PI * 1e-7;
     e->uni[0] = 1.0; e->uni[1] = cfg->dt / eps0; e->uni[2] = 1.0; e->uni[3] = cfg->dt / mu0;
     if (const char* lx = getenv("FDTD_B200_FUSED_LX")) e->fused_lx = atoi(lx);    // tuning / tests
-    if (const char* pol = getenv("FDTD_B200_FUSED_POL")) e->fused_pol = atoi(pol) & 1;
+    if (const char* pol = getenv("FDTD_B200_FUSED_POL")) e->fused_pol = atoi(pol) & 3;
+    if (const char* tj = getenv("FDTD_B200_FUSED_TJ")) e->fused_tj = atoi(tj);
     *out = e;
     return 0;
 }
@@ -244,6 +248,8 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     for (int c = 0; c < 4; ++c) cudaFree(e->coef[c]);
     cudaFree(e->d_src); cudaFree(e->d_mon); cudaFree(e->d_prof);
     cudaFree(e->d_ade); cudaFree(e->d_aux); cudaFree(e->d_ade_mask);
+    cudaFree(e->d_cpml_coef);
+    for (int q = 0; q < 12; ++q) cudaFree(e->cpml.psi[q]);
     cudaFree(e->d_comp_ptr[0]); cudaFree(e->d_comp_ptr[1]);
     cudaFree(e->d_amp); cudaFree(e->d_phasor); cudaFree(e->d_rec); cudaFree(e->d_dft);
     cudaFree(e->d_step); cudaFree(e->d_cnt); cudaFree(e->d_stage);
@@ -389,6 +395,8 @@ extern "C" int fdtd_zero_fields(fdtd_engine* e)
     if (!e) return fail(FDTD_EINVAL, "null engine");
     CU(cudaSetDevice(e->cfg.device));
     for (int c = 0; c < 6; ++c) CU(cudaMemsetAsync(cur_fields(e)[c], 0, e->array_elems * e->esz, e->stream));
+    for (int q = 0; q < 12; ++q)
+        if (e->cpml.psi[q]) CU(cudaMemsetAsync(e->cpml.psi[q], 0, e->psi_bytes[q], e->stream));
     return 0;
 }
 
@@ -724,13 +732,82 @@ template <typename T> static int launch_post(fdtd_engine* e, int step_off, int p
         e->launches++;
         CU(cudaGetLastError());
     }
+    if (e->ade_threads > 0) {
+        k_ade<T><<<(unsigned)((e->ade_threads + 255) / 256), 256, 0, s>>>(
+            (const T* const*)comp, e->d_ade, (int)e->ade.size(), e->ade_threads, e->st, (T*)e->d_aux, e->d_ade_mask);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+// physics mode (opt-in): stable Yee leap-frog + CPML, see fdtd_yee.cuh
+template <typename T> static int launch_yee(fdtd_engine* e, int phase, cudaStream_t s)
+{
+    const Geom& g = e->g;
+    dim3 block(64, 4, 1), grid((g.nz + 63) / 64, (g.ny + 3) / 4, g.nx);
+    Fields<T> f = fields_of<T>(cur_fields(e));
+    Coefs<T> c = coefs_of<T>(e);
+    if (phase == 0) {
+        if (e->het) k_h3d_yee<T, true><<<grid, block, 0, s>>>(f, c, g, e->cpml, e->slabg);
+        else k_h3d_yee<T, false><<<grid, block, 0, s>>>(f, c, g, e->cpml, e->slabg);
+    } else {
+        if (e->het) k_e3d_yee<T, true><<<grid, block, 0, s>>>(f, c, g, e->cpml, e->slabg);
+        else k_e3d_yee<T, false><<<grid, block, 0, s>>>(f, c, g, e->cpml, e->slabg);
+    }
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// coef: host fp64 [3 axes][6 vectors][N_axis] concatenated axis by axis (x: 6*nx, y: 6*ny, z: 6*nz):
+// b, a, 1/kappa at E-derivative (half) positions, then at H-derivative (integer) positions
+extern "C" int fdtd_set_cpml(fdtd_engine* e, int32_t thickness, const double* coef)
+{
+    if (!e) return fail(FDTD_EINVAL, "null engine");
+    if (!(e->cfg.flags & FDTD_FLAG_YEE) || e->cfg.ndim != 3)
+        return fail(FDTD_ESTATE, "CPML belongs to the opt-in physics mode (FDTD_FLAG_YEE, 3-D)");
+    const Geom& g = e->g;
+    if (thickness < 0 || 2 * thickness + 1 > std::min(g.nx, std::min(g.ny, g.nz)))
+        return fail(FDTD_EINVAL, "CPML thickness %d does not fit the grid", thickness);
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_cpml_coef); e->d_cpml_coef = nullptr;
+    for (int q = 0; q < 12; ++q) { cudaFree(e->cpml.psi[q]); e->cpml.psi[q] = nullptr; }
+    e->cpml = Cpml{};
+    drop_graph(e);
+    if (thickness == 0) return 0;
+    if (!coef) return fail(FDTD_EINVAL, "fdtd_set_cpml: null coefficients");
+    const int N[3] = {g.nx, g.ny, g.nz};
+    const size_t total = 6 * ((size_t)g.nx + g.ny + g.nz);
+    CU(cudaMalloc(&e->d_cpml_coef, total * sizeof(double)));
+    CU(cudaMemcpy(e->d_cpml_coef, coef, total * sizeof(double), cudaMemcpyHostToDevice));
+    size_t off = 0;
+    for (int a = 0; a < 3; ++a) {
+        for (int v = 0; v < 6; ++v) e->cpml.ax[a].c[v] = e->d_cpml_coef + off + (size_t)v * N[a];
+        off += (size_t)6 * N[a];
+    }
+    e->cpml.t = thickness; e->cpml.ns = 2 * thickness + 1;
+    const long long ns = e->cpml.ns;
+    e->slabg.x_sx = g.sx;                          // x family: (ns, ny, pz)
+    e->slabg.y_sx = ns * g.sy;                     // y family: (nx, ns, pz)
+    e->slabg.z_pitch = (int)round_up(ns, 4);       // z family: (nx, ny, z_pitch)
+    const size_t bx = (size_t)ns * g.sx * e->esz, by = (size_t)g.nx * ns * g.sy * e->esz,
+                 bz = (size_t)g.nx * g.ny * e->slabg.z_pitch * e->esz;
+    static const int family[12] = {1, 2, 2, 0, 0, 1, 1, 2, 2, 0, 0, 1};     // axis of each psi array
+    for (int q = 0; q < 12; ++q) {
+        const size_t b = family[q] == 0 ? bx : (family[q] == 1 ? by : bz);
+        CU(cudaMalloc(&e->cpml.psi[q], b));
+        CU(cudaMemset(e->cpml.psi[q], 0, b));
+        e->psi_bytes[q] = b;
+    }
     return 0;
 }
 
 static bool use_fused(const fdtd_engine* e)
 {
     // slabs (nxg != nx) use the fused sweep too, but through fdtd_sweep: the host interleaves the halo exchange
-    return e->cfg.ndim == 3 && !e->het && !(e->cfg.flags & FDTD_FLAG_TWO_PASS);
+    return e->cfg.ndim == 3 && !e->het && !(e->cfg.flags & (FDTD_FLAG_TWO_PASS | FDTD_FLAG_YEE));
 }
 
 static int ensure_set_b(fdtd_engine* e)
@@ -746,9 +823,9 @@ static int ensure_set_b(fdtd_engine* e)
 }
 
 // one fused sweep over planes [i_begin, i_end): reads the current set, writes the other one
-template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i_end, cudaStream_t s)
+template <typename T, int TJ> static int launch_fused_tj(fdtd_engine* e, int i_begin, int i_end, cudaStream_t s)
 {
-    constexpr int TJ = kFusedTJ, V = VecOf<T>::V;
+    constexpr int V = VecOf<T>::V;
     const Geom& g = e->g;
     void** src = cur_fields(e);
     void** dst = e->cur ? e->fld : e->fldB;
@@ -782,18 +859,27 @@ template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i
     t.lx = std::min(lx, planes);
     t.nseg = (planes + t.lx - 1) / t.lx;
     const size_t smem = fused_smem_bytes<T, TJ>();
-    const int which = (sizeof(T) == 8) * 2 + (e->fused_pol & 1);
-    auto kern = (e->fused_pol & 1) ? k_fused3d<T, TJ, 1> : k_fused3d<T, TJ, 0>;
-    if (!e->fused.attr_set[which]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        e->fused.attr_set[which] = true;
+    auto kern = k_fused3d<T, TJ, 0>;
+    switch (e->fused_pol & 3) {
+    case 1: kern = k_fused3d<T, TJ, 1>; break;
+    case 2: kern = k_fused3d<T, TJ, 2>; break;
+    case 3: kern = k_fused3d<T, TJ, 3>; break;
+    default: break;
     }
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, TJ + 1, 1);
     const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
     kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
+}
+
+// one fused sweep over planes [i_begin, i_end): reads the current set, writes the other one
+template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i_end, cudaStream_t s)
+{
+    if (e->fused_tj == 7) return launch_fused_tj<T, 7>(e, i_begin, i_end, s);
+    return launch_fused_tj<T, kFusedTJ>(e, i_begin, i_end, s);
 }
 
 // 3-D field update of one step, in two halves: half 0 = H pass (or the whole fused sweep), half 1 = E pass
@@ -806,6 +892,7 @@ template <typename T> static int step_fields3d(fdtd_engine* e, int half, cudaStr
         e->cur ^= 1;
         return 0;
     }
+    if (e->cfg.flags & FDTD_FLAG_YEE) return launch_yee<T>(e, half, s);
     return launch_pass3d<T>(e, half, 0, e->g.nx, s);
 }
 

@@ -85,6 +85,18 @@ template <typename T> __device__ __forceinline__ Pack<T, VecOf<T>::V> ldv_if(con
 {
     return ok ? ldv<T>(p) : zero_pack<T>();
 }
+// streaming variant: ld.global.cg (L2 only) — every byte is used once per CTA, L1 allocation buys nothing
+template <typename T, int POL> __device__ __forceinline__ Pack<T, VecOf<T>::V> ldv_pol(const T* p, bool ok)
+{
+    typedef typename VecOf<T>::type VT;
+    if (!ok) return zero_pack<T>();
+    if (POL & 2) {
+        union { VT q; Pack<T, VecOf<T>::V> r; } u;
+        u.q = __ldcg(reinterpret_cast<const VT*>(p));
+        return u.r;
+    }
+    return ldv<T>(p);
+}
 template <typename T> __device__ __forceinline__ T shfl_next(T v)
 {
     return __shfl_down_sync(0xffffffffu, v, 1);
@@ -103,7 +115,7 @@ template <typename T, int POL> __device__ __forceinline__ void stv_pol(T* p, con
 
 // TJ owner rows per CTA; blockDim = (32, TJ + 1);  POL bit0: streaming stores
 template <typename T, int TJ, int POL>
-__global__ void __launch_bounds__(32 * (TJ + 1), 1)
+__global__ void __launch_bounds__(32 * (TJ + 1), (TJ <= 7 ? 2 : 1))
 k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
 {
     constexpr int V = VecOf<T>::V;
@@ -141,21 +153,21 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
     const T* pex = in.ex + o; const T* pey = in.ey + o; const T* pez = in.ez + o;
     const T* phx = in.hx + o; const T* phy = in.hy + o; const T* phz = in.hz + o;
     long long po = (long long)i0 * g.sx;                 // plane offset of E[i+1] for i = i0-1
-    P e1x = ldv_if<T>(pex + po, ld_ok), e1y = ldv_if<T>(pey + po, ld_ok), e1z = ldv_if<T>(pez + po, ld_ok);
+    P e1x = ldv_pol<T, POL>(pex + po, ld_ok), e1y = ldv_pol<T, POL>(pey + po, ld_ok), e1z = ldv_pol<T, POL>(pez + po, ld_ok);
     // prefetched: E[i+2], H[i+1]
-    P e2x = ldv_if<T>(pex + po + g.sx, ld_ok), e2y = ldv_if<T>(pey + po + g.sx, ld_ok),
-      e2z = ldv_if<T>(pez + po + g.sx, ld_ok);
-    P h1x = ldv_if<T>(phx + po, ld_ok), h1y = ldv_if<T>(phy + po, ld_ok), h1z = ldv_if<T>(phz + po, ld_ok);
+    P e2x = ldv_pol<T, POL>(pex + po + g.sx, ld_ok), e2y = ldv_pol<T, POL>(pey + po + g.sx, ld_ok),
+      e2z = ldv_pol<T, POL>(pez + po + g.sx, ld_ok);
+    P h1x = ldv_pol<T, POL>(phx + po, ld_ok), h1y = ldv_pol<T, POL>(phy + po, ld_ok), h1z = ldv_pol<T, POL>(phz + po, ld_ok);
 
     for (int i = i0 - 1; i < i1; ++i) {
         const int par = (i - i0 + 1) & 1;
         po = (long long)(i + 1) * g.sx;                  // plane i+1
         // ---- issue next iteration's loads: E[i+3], H[i+2] -----------------------------------------
         const bool more = (i + 1 < i1) && ld_ok;
-        const P n_ex = ldv_if<T>(pex + po + 2 * g.sx, more), n_ey = ldv_if<T>(pey + po + 2 * g.sx, more),
-                n_ez = ldv_if<T>(pez + po + 2 * g.sx, more);
-        const P n_hx = ldv_if<T>(phx + po + g.sx, more), n_hy = ldv_if<T>(phy + po + g.sx, more),
-                n_hz = ldv_if<T>(phz + po + g.sx, more);
+        const P n_ex = ldv_pol<T, POL>(pex + po + 2 * g.sx, more), n_ey = ldv_pol<T, POL>(pey + po + 2 * g.sx, more),
+                n_ez = ldv_pol<T, POL>(pez + po + 2 * g.sx, more);
+        const P n_hx = ldv_pol<T, POL>(phx + po + g.sx, more), n_hy = ldv_pol<T, POL>(phy + po + g.sx, more),
+                n_hz = ldv_pol<T, POL>(phz + po + g.sx, more);
         // ---- publish what the row below (j-1) needs from us -------------------------------------------
         {
             union { VT q; P r; } u;
@@ -174,8 +186,8 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
             u.q = s_h[par][row + 1][1][lane]; hx_j = u.r;
         } else {
             const bool ok = ld_ok && (j + 1 < g.ny);
-            ez_j = ldv_if<T>(pez + po + g.sy, ok);
-            ex_j = ldv_if<T>(pex + po + g.sy, ok);
+            ez_j = ldv_pol<T, POL>(pez + po + g.sy, ok);
+            ex_j = ldv_pol<T, POL>(pex + po + g.sy, ok);
             hz_j = zero_pack<T>(); hx_j = hz_j;          // the rim row produces no E+
         }
         // ---- k+1 neighbours from the next lane -----------------------------------------------------------

@@ -140,6 +140,16 @@ class Engine:
             arrs.append(a)
         _lib.check(self._lib.fdtd_set_coeffs(self._h, *[a.ctypes.data_as(C.c_void_p) for a in arrs], int(planes)))
 
+    def set_cpml(self, thickness: int, coef: Optional[np.ndarray]) -> None:
+        """Physics mode only.  coef: concatenation over x, y, z of (6, N_axis) arrays (see cpml.py)."""
+        if thickness == 0:
+            _lib.check(self._lib.fdtd_set_cpml(self._h, 0, None))
+            return
+        c = np.ascontiguousarray(coef, dtype=np.float64)
+        if c.size != 6 * sum(self.dims):
+            raise ValueError(f"CPML coefficient table has {c.size} entries, expected {6 * sum(self.dims)}")
+        _lib.check(self._lib.fdtd_set_cpml(self._h, int(thickness), c.ctypes.data_as(C.c_void_p)))
+
     # ---- fields -------------------------------------------------------------------------------------------
     def upload(self, comp: str, array) -> None:
         a = np.asarray(array)

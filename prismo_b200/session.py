@@ -44,13 +44,27 @@ def _fingerprint(arrs):
 
 
 class Session:
-    def __init__(self, grid, dt: float, dtype=None, device: Optional[int] = None, flags: Optional[int] = None):
+    def __init__(self, grid, dt: float, dtype=None, device: Optional[int] = None, flags: Optional[int] = None,
+                 physics=None):
+        """physics: None = parity mode (the reference's scheme, bug for bug).  A ``cpml.PMLParams`` (or True for
+        defaults with thickness = the grid's boundary layers) selects the OPT-IN physics mode: stable Yee
+        leap-frog + working CPML (3-D only; no reference numbers exist for it)."""
         self.grid = YeeGrid.like(grid)
         g = self.grid
         self.dt = float(dt)
+        fl = _state["flags"] if flags is None else flags
+        if physics:
+            from . import _lib, cpml
+
+            if g.is_2d:
+                raise NotImplementedError("physics mode (stable Yee + CPML) is implemented for 3-D grids")
+            fl |= _lib.FLAG_YEE
+            params = physics if isinstance(physics, cpml.PMLParams) else cpml.PMLParams(thickness=g.pml_layers)
         self.engine = Engine(3 if g.is_3d else 2, g.dimensions, g.spacing, self.dt,
                              dtype=dtype or _state["dtype"], device=_state["device"] if device is None else device,
-                             flags=_state["flags"] if flags is None else flags)
+                             flags=fl)
+        if physics and params.thickness > 0:
+            self.engine.set_cpml(params.thickness, cpml.coefficient_table(g.dimensions, g.spacing, self.dt, params))
         self._coef_sig = None
 
     def close(self):

@@ -69,7 +69,8 @@ class MaxwellUpdater:
     """Holds the cell-centred coefficients; ``step`` runs H pass + E pass on the device."""
 
     def __init__(self, grid: YeeGrid, dt: float, material_arrays: Optional[dict] = None, backend=None,
-                 dtype=None, device=None):
+                 dtype=None, device=None, physics=None):
+        self._physics = physics
         if backend is not None and not isinstance(backend, str) and not hasattr(backend, "zeros"):
             raise TypeError("backend must be a Backend instance or string name")
         self.grid, self.dt = grid, dt
@@ -106,7 +107,7 @@ class MaxwellUpdater:
 
     def session(self) -> Session:
         if self._session is None:
-            self._session = Session(self.grid, self.dt, dtype=self._dtype, device=self._device)
+            self._session = Session(self.grid, self.dt, dtype=self._dtype, device=self._device, physics=self._physics)
         self._session.set_coefficients(self.Ca, self.Cb, self.Da, self.Db)
         return self._session
 
@@ -128,12 +129,13 @@ class MaxwellUpdater:
 
 class FDTDSolver:
     def __init__(self, grid: YeeGrid, dt: Optional[float] = None, material_arrays: Optional[dict] = None,
-                 backend=None, dtype=None, device=None):
+                 backend=None, dtype=None, device=None, physics=None):
         self.grid = grid
         if dt is None:
             dt = grid.suggest_time_step(safety_factor=0.95)
         self._fields: Optional[ElectromagneticFields] = None      # allocated on first use (reference: eagerly, :611)
-        self.updater = MaxwellUpdater(grid, dt, material_arrays, backend=backend, dtype=dtype, device=device)
+        self.updater = MaxwellUpdater(grid, dt, material_arrays, backend=backend, dtype=dtype, device=device,
+                                      physics=physics)
         self.time, self.step_count = 0.0, 0
 
     @property
@@ -177,15 +179,17 @@ class FDTDSolver:
 
 class Simulation:
     def __init__(self, size, resolution: Union[float, tuple], boundary_conditions: str = "pml", pml_layers: int = 10,
-                 courant_factor: float = 0.9, dtype=None, device=None):
+                 courant_factor: float = 0.9, dtype=None, device=None, physics=None):
+        """``physics`` (our extension, default off): True or a ``PMLParams`` runs the stable Yee leap-frog with a
+        working CPML instead of the reference's scheme — see DESIGN.md "physics mode"."""
         self.grid_spec = GridSpec(size=size, resolution=resolution, boundary_layers=pml_layers)
         self.grid = YeeGrid(self.grid_spec)
         self.size, self.resolution = size, resolution
         self.boundary_conditions, self.courant_factor = boundary_conditions, courant_factor
         self.fields = ElectromagneticFields(self.grid)
         self.dt = self.grid.get_time_step(courant_factor)
-        self._dtype, self._device = dtype, device
-        self.solver = FDTDSolver(self.grid, self.dt, dtype=dtype, device=device)
+        self._dtype, self._device, self._physics = dtype, device, physics
+        self.solver = FDTDSolver(self.grid, self.dt, dtype=dtype, device=device, physics=physics)
         self.sources: list = []
         self.monitors: list = []
         self._b200_ade: list = []
@@ -208,7 +212,8 @@ class Simulation:
     def set_materials(self, material_arrays: Optional[dict]) -> None:
         """Convenience for ``sim.solver = FDTDSolver(sim.grid, sim.dt, material_arrays)`` — the only way
         materials enter the reference."""
-        self.solver = FDTDSolver(self.grid, self.dt, material_arrays, dtype=self._dtype, device=self._device)
+        self.solver = FDTDSolver(self.grid, self.dt, material_arrays, dtype=self._dtype, device=self._device,
+                                 physics=self._physics)
 
     # ---- stepping -------------------------------------------------------------------------------------
     def run_steps(self, n: int) -> None:
