@@ -8,6 +8,7 @@
 #include "fdtd_kernels.cuh"
 #include "fdtd_fused.cuh"
 #include "fdtd_yee.cuh"
+#include "fdtd_tb2.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -84,6 +85,8 @@ struct fdtd_engine {
     // graph
     cudaGraphExec_t gexec[2] = {nullptr, nullptr}; int graph_steps = 0; int graph_kernels[2] = {0, 0};
     int fused_lx = 0;               // planes per fused segment (0 = auto)
+    int tb2 = 0;                    // 1: temporally blocked sweep (two steps per pass) where applicable
+    unsigned char* d_plane_flags = nullptr;
     int fused_tj = 15;              // owner rows per CTA (15: one 16-warp CTA/SM; 7: two 8-warp CTAs/SM)
     int fused_pol = 0;              // bit0: streaming (evict-first) stores (measured 1.4% slower: off)
     // staging
@@ -234,6 +237,7 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     if (const char* lx = getenv("FDTD_B200_FUSED_LX")) e->fused_lx = atoi(lx);    // tuning / tests
     if (const char* pol = getenv("FDTD_B200_FUSED_POL")) e->fused_pol = atoi(pol) & 3;
     if (const char* tj = getenv("FDTD_B200_FUSED_TJ")) e->fused_tj = atoi(tj);
+    if (const char* tb = getenv("FDTD_B200_TB2")) e->tb2 = atoi(tb);
     *out = e;
     return 0;
 }
@@ -248,7 +252,7 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     for (int c = 0; c < 4; ++c) cudaFree(e->coef[c]);
     cudaFree(e->d_src); cudaFree(e->d_mon); cudaFree(e->d_prof);
     cudaFree(e->d_ade); cudaFree(e->d_aux); cudaFree(e->d_ade_mask);
-    cudaFree(e->d_cpml_coef);
+    cudaFree(e->d_cpml_coef); cudaFree(e->d_plane_flags);
     for (int q = 0; q < 12; ++q) cudaFree(e->cpml.psi[q]);
     cudaFree(e->d_comp_ptr[0]); cudaFree(e->d_comp_ptr[1]);
     cudaFree(e->d_amp); cudaFree(e->d_phasor); cudaFree(e->d_rec); cudaFree(e->d_dft);
@@ -573,6 +577,16 @@ static int finalize_ops(fdtd_engine* e)
             e->aux_elems = aux;
         }
     }
+    // per-plane op flags for the temporally blocked sweep (bit0: a source op covers the plane, bit1: a monitor op)
+    {
+        std::vector<unsigned char> fl(e->g.nx, 0);
+        for (auto& h : e->src)
+            for (int p = h.op.lo[0]; p < h.op.lo[0] + h.op.n[0] && p < e->g.nx; ++p) fl[p] |= 1;
+        for (auto& m : e->mon)
+            for (int p = m.lo[0]; p < m.lo[0] + m.n[0] && p < e->g.nx; ++p) fl[p] |= 2;
+        if (!e->d_plane_flags) CU(cudaMalloc(&e->d_plane_flags, e->g.nx));
+        CU(cudaMemcpy(e->d_plane_flags, fl.data(), e->g.nx, cudaMemcpyHostToDevice));
+    }
     e->ops_dirty = false;
     return 0;
 }
@@ -882,6 +896,66 @@ template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i
     return launch_fused_tj<T, kFusedTJ>(e, i_begin, i_end, s);
 }
 
+static bool use_tb2(const fdtd_engine* e)
+{
+    return e->tb2 && use_fused(e) && e->g.nxg == e->g.nx && e->ade.empty();
+}
+
+// TWO steps in one pass over planes [0, nx): reads the current set, writes the other one; the intermediate
+// step's sources / monitors (table row *d_step + step_off) are applied inside the kernel
+template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaStream_t s)
+{
+    constexpr int R = kTb2Rows, V = Vec8<T>::V;
+    const Geom& g = e->g;
+    void** src = cur_fields(e);
+    void** dst = e->cur ? e->fld : e->fldB;
+    CFields<T> in;
+    in.ex = (const T*)src[0]; in.ey = (const T*)src[1]; in.ez = (const T*)src[2];
+    in.hx = (const T*)src[3]; in.hy = (const T*)src[4]; in.hz = (const T*)src[5];
+    Fields<T> out = fields_of<T>(dst);
+    FusedTiling t;
+    t.i_begin = 0; t.i_end = g.nx;
+    t.halo_flag = nullptr; t.halo_need = 0; t.error_word = nullptr; t.timeout_ns = e->slab.timeout_ns;
+    const int vec_per_row = g.pz / V;
+    t.own_lanes = kTb2OwnLanes;
+    t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
+    t.ntj = (g.ny + (R - 4) - 1) / (R - 4);
+    int lx = e->fused_lx;
+    if (lx <= 0) {
+        const long long tiles = (long long)t.ntj * t.ntk;
+        long long want = (148ll * 24 + tiles - 1) / tiles;
+        lx = (int)std::max<long long>(64, (g.nx + want - 1) / std::max<long long>(want, 1));   // 3 prologue planes
+    }
+    t.lx = std::min(lx, g.nx);
+    t.nseg = (g.nx + t.lx - 1) / t.lx;
+    MidOps m{};
+    m.src = e->d_src; m.n_src = 0;
+    for (int c : e->grp_count) m.n_src += c;
+    m.amp = e->d_amp; m.n_amp = e->n_amp; m.prof = e->d_prof;
+    m.mon = e->d_mon; m.n_mon = (int)e->mon.size();
+    m.phasors = e->d_phasor; m.n_phasor = e->n_phasor;
+    m.rec = e->d_rec; m.dft = e->d_dft; m.dt = e->cfg.dt;
+    m.step_ptr = e->d_step; m.step_off = step_off;
+    m.plane_flags = (m.n_src || m.n_mon) ? e->d_plane_flags : nullptr;
+    const size_t smem = tb2_smem_bytes<T, R>();
+    auto kern = k_fused3d_tb2<T, R>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 block(32, R, 1);
+    const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
+    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, m, (int)e->planes_alloc);
+    e->launches++;
+    CU(cudaGetLastError());
+    e->cur ^= 1;
+    return 0;
+}
+
+// two full steps: temporally blocked sweep (step A's sources/monitors inside), then step B's sources/monitors
+template <typename T> static int two_steps(fdtd_engine* e, int step_off, cudaStream_t s)
+{
+    if (int rc = launch_tb2<T>(e, step_off, s)) return rc;
+    return launch_post<T>(e, step_off + 1, 0, s);
+}
+
 // 3-D field update of one step, in two halves: half 0 = H pass (or the whole fused sweep), half 1 = E pass
 template <typename T> static int step_fields3d(fdtd_engine* e, int half, cudaStream_t s)
 {
@@ -926,7 +1000,8 @@ template <typename T> static int run_steps(fdtd_engine* e, int n)
             const long long l0 = e->launches;
             CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             int rc = 0;
-            for (int q = 0; q < G && !rc; ++q) rc = one_step<T>(e, q, q, s);
+            if (use_tb2(e)) for (int q = 0; q < G && !rc; q += 2) rc = two_steps<T>(e, q, s);
+            else for (int q = 0; q < G && !rc; ++q) rc = one_step<T>(e, q, q, s);
             if (!rc) { k_bump<<<1, 1, 0, s>>>(e->d_step, G); e->launches++; }
             cudaError_t ce = cudaStreamEndCapture(s, &graph);
             e->cur = c0;
@@ -946,7 +1021,11 @@ template <typename T> static int run_steps(fdtd_engine* e, int n)
         }
     }
     const int rest = n - done;
-    for (int q = 0; q < rest; ++q)
+    int q = 0;
+    if (use_tb2(e))
+        for (; q + 2 <= rest; q += 2)
+            if (int rc = two_steps<T>(e, q, s)) return rc;
+    for (; q < rest; ++q)
         if (int rc = one_step<T>(e, q, done + q, s)) return rc;
     if (rest > 0) { k_bump<<<1, 1, 0, s>>>(e->d_step, rest); e->launches++; CU(cudaGetLastError()); }
     return 0;
@@ -998,7 +1077,17 @@ template <typename T> static int run_profiled(fdtd_engine* e, int n, double* out
     for (auto& x : ev) CU(cudaEventCreate(&x));
     if (e->cfg.ndim == 2) if (int rc = launch_count2d<T>(e, 0, s)) return rc;
     CU(cudaEventRecord(ev[0], s));
-    for (int q = 0; q < n; ++q) {
+    const bool tb2 = use_tb2(e) && n % 2 == 0;
+    for (int q = 0; tb2 && q < n; q += 2) {
+        // one temporally blocked sweep = two steps: its time goes to slot 0, step B's sources/monitors to slot 2
+        int rc = launch_tb2<T>(e, q, s);
+        if (rc) return rc;
+        CU(cudaEventRecord(ev[3 * q + 1], s));
+        CU(cudaEventRecord(ev[3 * q + 2], s));
+        if ((rc = launch_post<T>(e, q + 1, 0, s))) return rc;
+        for (int k = 3; k <= 6; ++k) CU(cudaEventRecord(ev[3 * q + k], s));
+    }
+    for (int q = 0; !tb2 && q < n; ++q) {
         int rc;
         if (e->cfg.ndim == 3) rc = step_fields3d<T>(e, 0, s); else rc = launch_pass2d<T>(e, 0, q, s);
         if (rc) return rc;

@@ -1,0 +1,320 @@
+// fdtd_tb2.cuh — temporally blocked fused sweep: TWO full time steps per pass over HBM.
+//
+// The single-step fused sweep (fdtd_fused.cuh) already moves the algorithmic minimum of one step, 48 B per
+// cell-update in fp32 (read 6 arrays + write 6 arrays).  The only way below that is to not write step n+1 to HBM
+// at all: this kernel carries a FOUR-stage pipeline through the register window while marching ascending in x
+//     A: H1[i+3] = f(H0[i+3], E0[i+3], E0[i+4])        B: E1[i+2] = g(E0[i+2], H1[i+2], H1[i+3])
+//     C: H2[i+1] = f(H1[i+1], E1[i+1], E1[i+2])        D: E2[i]   = g(E1[i],   H2[i],   H2[i+1])
+// (time levels 0 = input, 1 = intermediate, 2 = output), so every array is read once and written once per TWO
+// steps: 24 B per cell-update.  Each stage needs the +1 neighbours (j+1 through shared memory, k+1 through the
+// next lane) of the previous stage's result, so validity shrinks by one row and one lane per stage: of R warp
+// rows the first R-4 own cells, of 32 lanes the first 28; the rest are rim providers that store nothing.
+//
+// What the reference does BETWEEN the two steps — sources added to E1/H1, monitors sampling them
+// (core/simulation.py:158-164) — happens on the register window: E sources right after stage B (stage C must
+// see them, stage B of the neighbouring plane must not see H sources: they are added one iteration later, just
+// before stage C consumes the own-cell H1), monitors sample the post-source values exactly once per cell (owner
+// thread, own segment).  Arithmetic per cell is the same sequence of rounded operations as k_sources /
+// k_monitors / the single-step kernels, so results stay bit-identical in fp64.
+#pragma once
+#include "fdtd_fused.cuh"
+
+namespace fdtd {
+
+struct MidOps {
+    const SrcOp* src; int n_src;
+    const double* amp; int n_amp; const double* prof;
+    const MonOp* mon; int n_mon;
+    const double* phasors; int n_phasor;
+    void* rec; double2* dft; double dt;
+    const int* step_ptr; int step_off;          // table row of the intermediate step = *step_ptr + step_off
+    const unsigned char* plane_flags;           // per local plane: bit0 a source op covers it, bit1 a monitor op
+};
+
+template <typename T> struct Vec8;
+template <> struct Vec8<float> { typedef float2 type; static const int V = 2; };
+template <> struct Vec8<double> { typedef double type; static const int V = 1; };
+
+template <typename T, int V> __device__ __forceinline__ Pack<T, V> ld8(const T* p, bool ok)
+{
+    Pack<T, V> r;
+    if (!ok) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) r.v[e] = (T)0;
+        return r;
+    }
+    typedef typename Vec8<T>::type VT;
+    union { VT q; Pack<T, V> r; } u;
+    u.q = *reinterpret_cast<const VT*>(p);
+    return u.r;
+}
+template <typename T, int V> __device__ __forceinline__ void st8(T* p, const Pack<T, V>& r)
+{
+    typedef typename Vec8<T>::type VT;
+    union { VT q; Pack<T, V> r; } u;
+    u.r = r;
+    *reinterpret_cast<VT*>(p) = u.q;
+}
+
+// sources of the intermediate step on a register value (same arithmetic as k_sources)
+template <typename T, int V>
+__device__ __forceinline__ void mid_sources(const MidOps& m, int comp, int p, int j, int k0, int row, Pack<T, V>& v)
+{
+    for (int q = 0; q < m.n_src; ++q) {
+        const SrcOp& op = m.src[q];
+        if (op.comp != comp) continue;
+        const unsigned dp = (unsigned)(p - op.lo[0]), dj = (unsigned)(j - op.lo[1]);
+        if (dp >= (unsigned)op.n[0] || dj >= (unsigned)op.n[1]) continue;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const unsigned dk = (unsigned)(k0 + e - op.lo[2]);
+            if (dk >= (unsigned)op.n[2]) continue;
+            double a = m.amp[(long long)row * m.n_amp + op.table];
+            if (op.prof_off >= 0) {
+                const long long cell = ((long long)dp * op.n[1] + dj) * op.n[2] + dk;
+                a = __dmul_rn(a, m.prof[op.prof_off + cell]);
+                if (op.divisor != 1.0) a = __ddiv_rn(a, op.divisor);
+            }
+            v.v[e] = (T)__dadd_rn((double)v.v[e], a);
+        }
+    }
+}
+
+// monitors of the intermediate step (same arithmetic as k_monitors); call from the owner thread only
+template <typename T, int V>
+__device__ __forceinline__ void mid_monitors(const MidOps& m, int comp, int p, int j, int k0, int row, const Pack<T, V>& v)
+{
+    for (int q = 0; q < m.n_mon; ++q) {
+        const MonOp& op = m.mon[q];
+        if (op.comp != comp) continue;
+        const unsigned dp = (unsigned)(p - op.lo[0]), dj = (unsigned)(j - op.lo[1]);
+        if (dp >= (unsigned)op.n[0] || dj >= (unsigned)op.n[1]) continue;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const unsigned dk = (unsigned)(k0 + e - op.lo[2]);
+            if (dk >= (unsigned)op.n[2]) continue;
+            const long long cell = ((long long)dp * op.n[1] + dj) * op.n[2] + dk;
+            if (op.record) ((T*)m.rec)[op.rec_off + (long long)row * op.cells + cell] = v.v[e];
+            if (op.n_freq > 0) {
+                const double d = (double)v.v[e];
+                const double* ph = m.phasors + ((long long)row * m.n_phasor + op.phasor_col) * 2;
+                for (int fq = 0; fq < op.n_freq; ++fq) {
+                    double2* a = m.dft + op.dft_off + (long long)fq * op.cells + cell;
+                    double2 acc = *a;
+                    acc.x = __dadd_rn(acc.x, __dmul_rn(__dmul_rn(d, ph[2 * fq]), m.dt));
+                    acc.y = __dadd_rn(acc.y, __dmul_rn(__dmul_rn(d, ph[2 * fq + 1]), m.dt));
+                    *a = acc;
+                }
+            }
+        }
+    }
+}
+
+struct Masks { bool jy1, jy2; };
+
+// H stage: (hx,hy,hz) <- f(h, e (own, j+1: ez_j/ex_j, k+1: ey_n/ex_n), e_next plane (ey, ez own)); plane gi
+template <typename T, int V>
+__device__ __forceinline__ void stage_h(const Coefs<T>& c, const Geom& g, int gi, bool jy1, bool jy2, int k,
+                                        const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
+                                        const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
+                                        const Pack<T, V>& ez_j, const Pack<T, V>& ex_j, T ey_n, T ex_n,
+                                        const Pack<T, V>& ey_p, const Pack<T, V>& ez_p,
+                                        Pack<T, V>& ox, Pack<T, V>& oy, Pack<T, V>& oz)
+{
+    const bool ix1 = gi < g.nxg - 1, ix2 = gi < g.nxg - 2;
+    ox = hx; oy = hy; oz = hz;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const bool kz1 = (k + e) < g.nz - 1, kz2 = (k + e) < g.nz - 2;
+        const T ey_k = (e + 1 < V) ? ey.v[(e + 1) % V] : ey_n;
+        const T ex_k = (e + 1 < V) ? ex.v[(e + 1) % V] : ex_n;
+        T n = upd_h<T>(c.uda, hx.v[e], c.udb, Ar<T>::diff(ez_j.v[e], ez.v[e], g.dy, g.rdy),
+                       Ar<T>::diff(ey_k, ey.v[e], g.dz, g.rdz));
+        if (ix1 && jy2 && kz2) ox.v[e] = n;
+        n = upd_h<T>(c.uda, hy.v[e], c.udb, Ar<T>::diff(ex_k, ex.v[e], g.dz, g.rdz),
+                     Ar<T>::diff(ez_p.v[e], ez.v[e], g.dx, g.rdx));
+        if (ix2 && jy1 && kz2) oy.v[e] = n;
+        n = upd_h<T>(c.uda, hz.v[e], c.udb, Ar<T>::diff(ey_p.v[e], ey.v[e], g.dx, g.rdx),
+                     Ar<T>::diff(ex_j.v[e], ex.v[e], g.dy, g.rdy));
+        if (ix2 && jy2 && kz1) oz.v[e] = n;
+    }
+}
+
+// E stage: (ex,ey,ez) <- g(e, h (own, j+1: hz_j/hx_j, k+1: hy_n/hx_n), h_next plane (hy, hz own)); plane gi
+template <typename T, int V>
+__device__ __forceinline__ void stage_e(const Coefs<T>& c, const Geom& g, int gi, bool jy1, int k,
+                                        const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
+                                        const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
+                                        const Pack<T, V>& hz_j, const Pack<T, V>& hx_j, T hy_n, T hx_n,
+                                        const Pack<T, V>& hy_p, const Pack<T, V>& hz_p,
+                                        Pack<T, V>& ox, Pack<T, V>& oy, Pack<T, V>& oz)
+{
+    const bool ex0 = gi < g.nxg, ex1 = gi < g.nxg - 1;
+    ox = ex; oy = ey; oz = ez;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;
+        const T hy_k = (e + 1 < V) ? hy.v[(e + 1) % V] : hy_n;
+        const T hx_k = (e + 1 < V) ? hx.v[(e + 1) % V] : hx_n;
+        T n = upd_e<T>(c.uca, ex.v[e], c.ucb, Ar<T>::diff(hz_j.v[e], hz.v[e], g.dy, g.rdy),
+                       Ar<T>::diff(hy_k, hy.v[e], g.dz, g.rdz));
+        if (ex0 && jy1 && kz1) ox.v[e] = n;
+        n = upd_e<T>(c.uca, ey.v[e], c.ucb, Ar<T>::diff(hx_k, hx.v[e], g.dz, g.rdz),
+                     Ar<T>::diff(hz_p.v[e], hz.v[e], g.dx, g.rdx));
+        if (ex1 && kz1) oy.v[e] = n;
+        n = upd_e<T>(c.uca, ez.v[e], c.ucb, Ar<T>::diff(hy_p.v[e], hy.v[e], g.dx, g.rdx),
+                     Ar<T>::diff(hx_j.v[e], hx.v[e], g.dy, g.rdy));
+        if (ex1 && jy1 && kz0) oz.v[e] = n;
+    }
+}
+
+constexpr int kTb2Rows = 16;           // warp rows per CTA: 12 owners + 4 rim
+constexpr int kTb2OwnLanes = 28;       // owner lanes per row: 28 of 32
+
+template <typename T, int R> constexpr size_t tb2_smem_bytes() { return 2 * (size_t)R * 8 * 32 * 8; }
+
+template <typename T, int R>
+__global__ void __launch_bounds__(32 * R, 1)
+k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, MidOps m, int planes_alloc)
+{
+    constexpr int V = Vec8<T>::V;
+    typedef Pack<T, V> P;
+    typedef typename Vec8<T>::type VT;
+    extern __shared__ __align__(16) unsigned char smem_[];
+    // [parity][row][quantity 0..7][lane]: E0(z,x) of plane i+3, H1(z,x) of i+2, E1(z,x) of i+1, H2(z,x) of i
+    VT (*s_x)[R][8][32] = reinterpret_cast<VT (*)[R][8][32]>(smem_);
+
+    const int lane = threadIdx.x, row = threadIdx.y;
+    const int ntiles = t.ntj * t.ntk;
+    const int seg = blockIdx.x / ntiles, tile = blockIdx.x - seg * ntiles;
+    const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
+    const int j = tj * (R - 4) + row;
+    const int k = (tk * t.own_lanes + lane) * V;
+    const int i0 = t.i_begin + seg * t.lx;
+    const int i1 = min(i0 + t.lx, t.i_end);
+    if (t.halo_flag && i1 == g.nx) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) wait_flag_ge(t.halo_flag, t.halo_need, t.error_word, t.timeout_ns);
+        __syncthreads();
+    }
+    const bool ld_ok = (j < g.ny) && (k < g.pz);
+    const bool owner = ld_ok && row < R - 4 && lane < t.own_lanes;
+    const int rown = min(row + 1, R - 1);
+    const long long o = (long long)j * g.sy + k;
+    const bool jy1 = j < g.ny - 1, jy2 = j < g.ny - 2;
+    const int step_row = m.step_ptr ? (*m.step_ptr + m.step_off) : 0;
+
+    const T* pex = in.ex + o; const T* pey = in.ey + o; const T* pez = in.ez + o;
+    const T* phx = in.hx + o; const T* phy = in.hy + o; const T* phz = in.hz + o;
+    P z_;
+#pragma unroll
+    for (int e = 0; e < V; ++e) z_.v[e] = (T)0;
+    // window at i = i0-3
+    P e0ax = z_, e0ay = z_, e0az = z_;                                   // E0[i+2]
+    long long po = (long long)i0 * g.sx;
+    P e0bx = ld8<T, V>(pex + po, ld_ok), e0by = ld8<T, V>(pey + po, ld_ok), e0bz = ld8<T, V>(pez + po, ld_ok);   // E0[i+3]
+    P ne0x = ld8<T, V>(pex + po + g.sx, ld_ok), ne0y = ld8<T, V>(pey + po + g.sx, ld_ok),
+      ne0z = ld8<T, V>(pez + po + g.sx, ld_ok);                          // E0[i+4]
+    P nh0x = ld8<T, V>(phx + po, ld_ok), nh0y = ld8<T, V>(phy + po, ld_ok), nh0z = ld8<T, V>(phz + po, ld_ok);   // H0[i+3]
+    P h1ax = z_, h1ay = z_, h1az = z_, h1bx = z_, h1by = z_, h1bz = z_;  // H1[i+1], H1[i+2]
+    P e1ax = z_, e1ay = z_, e1az = z_, e1bx = z_, e1by = z_, e1bz = z_;  // E1[i], E1[i+1]
+    P h2ax = z_, h2ay = z_, h2az = z_;                                   // H2[i]
+
+    for (int i = i0 - 3; i < i1; ++i) {
+        const int par = (i - i0 + 3) & 1;
+        // ---- prefetch for the next iteration: E0[i+5], H0[i+4] ----------------------------------------------
+        const bool more = ld_ok && (i + 1 < i1);
+        const bool pe_ok = more && (i + 5 < planes_alloc), ph_ok = more && (i + 4 < planes_alloc);
+        const long long pp = (long long)(i + 4) * g.sx;
+        const P pe0x = ld8<T, V>(pex + pp + g.sx, pe_ok), pe0y = ld8<T, V>(pey + pp + g.sx, pe_ok),
+                pe0z = ld8<T, V>(pez + pp + g.sx, pe_ok);
+        const P ph0x = ld8<T, V>(phx + pp, ph_ok), ph0y = ld8<T, V>(phy + pp, ph_ok), ph0z = ld8<T, V>(phz + pp, ph_ok);
+
+        // ---- intermediate-step H sources / monitors on H1[i+1] (all of its pre-source uses are done) --------------
+        if (m.plane_flags && i + 1 >= i0 && i + 1 < g.nx) {
+            const unsigned char fl = m.plane_flags[i + 1];
+            if (fl & 1) {
+                mid_sources<T, V>(m, 3, i + 1, j, k, step_row, h1ax);
+                mid_sources<T, V>(m, 4, i + 1, j, k, step_row, h1ay);
+                mid_sources<T, V>(m, 5, i + 1, j, k, step_row, h1az);
+            }
+            if ((fl & 2) && owner && i + 1 < i1) {
+                mid_monitors<T, V>(m, 3, i + 1, j, k, step_row, h1ax);
+                mid_monitors<T, V>(m, 4, i + 1, j, k, step_row, h1ay);
+                mid_monitors<T, V>(m, 5, i + 1, j, k, step_row, h1az);
+            }
+        }
+        // ---- publish the j+1 inputs of all four stages ------------------------------------------------------------------
+        {
+            union { VT q; P r; } u;
+            u.r = e0bz; s_x[par][row][0][lane] = u.q;  u.r = e0bx; s_x[par][row][1][lane] = u.q;
+            u.r = h1bz; s_x[par][row][2][lane] = u.q;  u.r = h1bx; s_x[par][row][3][lane] = u.q;
+            u.r = e1bz; s_x[par][row][4][lane] = u.q;  u.r = e1bx; s_x[par][row][5][lane] = u.q;
+            u.r = h2az; s_x[par][row][6][lane] = u.q;  u.r = h2ax; s_x[par][row][7][lane] = u.q;
+        }
+        __syncthreads();
+        P e0z_j, e0x_j, h1z_j, h1x_j, e1z_j, e1x_j, h2z_j, h2x_j;
+        {
+            union { VT q; P r; } u;
+            u.q = s_x[par][rown][0][lane]; e0z_j = u.r;  u.q = s_x[par][rown][1][lane]; e0x_j = u.r;
+            u.q = s_x[par][rown][2][lane]; h1z_j = u.r;  u.q = s_x[par][rown][3][lane]; h1x_j = u.r;
+            u.q = s_x[par][rown][4][lane]; e1z_j = u.r;  u.q = s_x[par][rown][5][lane]; e1x_j = u.r;
+            u.q = s_x[par][rown][6][lane]; h2z_j = u.r;  u.q = s_x[par][rown][7][lane]; h2x_j = u.r;
+        }
+        const T e0y_n = shfl_next<T>(e0by.v[0]), e0x_n = shfl_next<T>(e0bx.v[0]);
+        const T h1y_n = shfl_next<T>(h1by.v[0]), h1x_n = shfl_next<T>(h1bx.v[0]);
+        const T e1y_n = shfl_next<T>(e1by.v[0]), e1x_n = shfl_next<T>(e1bx.v[0]);
+        const T h2y_n = shfl_next<T>(h2ay.v[0]), h2x_n = shfl_next<T>(h2ax.v[0]);
+
+        // ---- A: H1[i+3] ------------------------------------------------------------------------------------------------------
+        P h1cx, h1cy, h1cz;
+        stage_h<T, V>(c, g, g.x0 + i + 3, jy1, jy2, k, nh0x, nh0y, nh0z, e0bx, e0by, e0bz, e0z_j, e0x_j, e0y_n, e0x_n,
+                      ne0y, ne0z, h1cx, h1cy, h1cz);
+        // ---- B: E1[i+2] (+ intermediate-step E sources / monitors) ----------------------------------------------------------------
+        P e1cx, e1cy, e1cz;
+        stage_e<T, V>(c, g, g.x0 + i + 2, jy1, k, e0ax, e0ay, e0az, h1bx, h1by, h1bz, h1z_j, h1x_j, h1y_n, h1x_n,
+                      h1cy, h1cz, e1cx, e1cy, e1cz);
+        if (m.plane_flags && i + 2 >= i0 && i + 2 < g.nx) {
+            const unsigned char fl = m.plane_flags[i + 2];
+            if (fl & 1) {
+                mid_sources<T, V>(m, 0, i + 2, j, k, step_row, e1cx);
+                mid_sources<T, V>(m, 1, i + 2, j, k, step_row, e1cy);
+                mid_sources<T, V>(m, 2, i + 2, j, k, step_row, e1cz);
+            }
+            if ((fl & 2) && owner && i + 2 < i1) {
+                mid_monitors<T, V>(m, 0, i + 2, j, k, step_row, e1cx);
+                mid_monitors<T, V>(m, 1, i + 2, j, k, step_row, e1cy);
+                mid_monitors<T, V>(m, 2, i + 2, j, k, step_row, e1cz);
+            }
+        }
+        // ---- C: H2[i+1] ---------------------------------------------------------------------------------------------------------------
+        P h2bx, h2by, h2bz;
+        stage_h<T, V>(c, g, g.x0 + i + 1, jy1, jy2, k, h1ax, h1ay, h1az, e1bx, e1by, e1bz, e1z_j, e1x_j, e1y_n, e1x_n,
+                      e1cy, e1cz, h2bx, h2by, h2bz);
+        if (owner && i + 1 >= i0 && i + 1 < i1) {
+            const long long q = (long long)(i + 1) * g.sx;
+            st8<T, V>(out.hx + o + q, h2bx); st8<T, V>(out.hy + o + q, h2by); st8<T, V>(out.hz + o + q, h2bz);
+        }
+        // ---- D: E2[i] -----------------------------------------------------------------------------------------------------------------
+        if (i >= i0) {
+            P e2x, e2y, e2z;
+            stage_e<T, V>(c, g, g.x0 + i, jy1, k, e1ax, e1ay, e1az, h2ax, h2ay, h2az, h2z_j, h2x_j, h2y_n, h2x_n,
+                          h2by, h2bz, e2x, e2y, e2z);
+            if (owner) {
+                const long long q = (long long)i * g.sx;
+                st8<T, V>(out.ex + o + q, e2x); st8<T, V>(out.ey + o + q, e2y); st8<T, V>(out.ez + o + q, e2z);
+            }
+        }
+        // ---- rotate ---------------------------------------------------------------------------------------------------------------------
+        e0ax = e0bx; e0ay = e0by; e0az = e0bz;
+        e0bx = ne0x; e0by = ne0y; e0bz = ne0z;
+        ne0x = pe0x; ne0y = pe0y; ne0z = pe0z;
+        nh0x = ph0x; nh0y = ph0y; nh0z = ph0z;
+        h1ax = h1bx; h1ay = h1by; h1az = h1bz;
+        h1bx = h1cx; h1by = h1cy; h1bz = h1cz;
+        e1ax = e1bx; e1ay = e1by; e1az = e1bz;
+        e1bx = e1cx; e1by = e1cy; e1bz = e1cz;
+        h2ax = h2bx; h2ay = h2by; h2az = h2bz;
+    }
+}
+
+}  // namespace fdtd

@@ -284,3 +284,47 @@ def test_region_correct_dft_monitor_3d_equals_field_monitor():
             assert a.shape == b.shape and a.ndim == 3 and np.abs(a).max() > 0
             assert np.array_equal(a, b), c
     assert dm.get_power_spectrum("Ey").shape == (2,)
+
+
+# ---- temporally blocked sweep (two steps per pass over HBM) -------------------------------------------------
+TB2_SCENARIOS = [n for n in sorted(S.SCENARIOS) if "3d" in n and S.SCENARIOS[n].get("materials") != "random"]
+
+
+@pytest.mark.parametrize("name", TB2_SCENARIOS)
+def test_tb2_fp64_bit_exact_vs_reference_golden(name, monkeypatch):
+    """Sources and monitors of the intermediate step are applied on the register window inside the kernel;
+    everything must still equal the reference bit for bit (odd step counts end with a single-step sweep)."""
+    monkeypatch.setenv("FDTD_B200_TB2", "1")
+    spec = S.SCENARIOS[name]
+    gold = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    sim = S.build_mirror(spec, pb, dtype="float64")
+    sim.run_steps(3)                                  # pair + single
+    sim.run_steps(spec["steps"] - 3)
+    _compare_exact(name, S.results_mirror(sim), gold)
+
+
+@pytest.mark.parametrize("dims,lx,steps", [((40, 47, 130), 0, 8), ((33, 16, 121), 7, 7), ((9, 31, 250), 3, 6),
+                                           ((70, 15, 64), 1, 5), ((5, 3, 3), 2, 4), ((64, 100, 300), 16, 6)])
+def test_tb2_equals_oracle_on_ragged_grids(dims, lx, steps, monkeypatch):
+    monkeypatch.setenv("FDTD_B200_TB2", "1")
+    if lx:
+        monkeypatch.setenv("FDTD_B200_FUSED_LX", str(lx))
+    a, F, na = _engine_vs_oracle(dims, 3, 0.5, steps, "float64", False)
+    assert na <= steps // 2 + 1 + (steps % 2)          # one launch per two steps (+ bump)
+    for c in F:
+        assert np.array_equal(a[c], F[c]), f"tb2 vs oracle {c}: {S.rel_l2(a[c], F[c]):.3e}"
+    a32, F, _ = _engine_vs_oracle(dims, 3, 0.5, steps, "float32", False)
+    for c in F:
+        assert S.rel_l2(a32[c], F[c]) <= FP32_TOL, c
+
+
+def test_tb2_graph_replay_with_sources_and_monitors(monkeypatch):
+    monkeypatch.setenv("FDTD_B200_TB2", "1")
+    spec = dict(S.SCENARIOS["mon3d_field"], steps=45, courant=0.1)
+    o = S.build_oracle(spec)
+    o.run_steps(45)
+    sim = S.build_mirror(spec, pb, dtype="float64")
+    sim.run_steps(45)
+    ro, rm = S.results_oracle(o), S.results_mirror(sim)
+    for k in ro:
+        assert np.array_equal(ro[k], rm[k], equal_nan=True), k
