@@ -139,6 +139,13 @@ def workload_ops(dims, dt, spacing, x0=0, nxl=None):
         for c, tab in (("Ey", 0), ("Hz", 1)):
             s = shape(c)
             src.append(pb.SourceOp(c, (i, 0, 0), (i + 1, s[1], s[2]), tab))
+    elif x0 + nxl <= src_plane < x0 + nxl + 3:
+        # the two-step sweep recomputes the intermediate step on our ghost planes: it needs the right
+        # neighbour's injection there too (ghost op, applied inside the sweep only)
+        i = src_plane - x0
+        for c, tab in (("Ey", 0), ("Hz", 1)):
+            s = shape(c)
+            src.append(pb.SourceOp(c, (i, 0, 0), (i + 1, s[1], s[2]), tab, ghost=True))
     if x0 <= mon_plane < x0 + nxl:
         i = mon_plane - x0
         for c in ("Ey", "Hz"):

@@ -69,7 +69,8 @@ typedef struct fdtd_source_op {
     double  divisor;        /* applied only when profile != NULL; 1.0 = none                   */
     int32_t group;          /* ops sharing a group touch disjoint cells and may run concurrently;
                                groups run in ascending order (source list order, simulation.py:159) */
-    int32_t reserved;
+    int32_t reserved;       /* bit 0: GHOST op (x-slabs): the right neighbour's uniform injection on our ghost
+                               planes [nx, nx+3); only the two-step sweep applies it (intermediate step)   */
 } fdtd_source_op;
 
 /* One sampled box (monitors/field.py:124-143, dft.py:121-160, flux.py:194-215). */

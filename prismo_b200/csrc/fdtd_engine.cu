@@ -61,6 +61,7 @@ struct fdtd_engine {
     cudaStream_t stream = nullptr;
     // ops
     std::vector<HostSrc> src;
+    std::vector<SrcOp> src_ghost; SrcOp* d_src_ghost = nullptr;   // slabs: neighbour's sources on our ghost planes
     std::vector<MonOp> mon;
     std::vector<double> prof_host;
     std::vector<AdeOp> ade; std::vector<unsigned char> ade_mask_host;
@@ -208,7 +209,7 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     }
     e->esz = cfg->dtype == FDTD_F64 ? 8 : 4;
     e->plane_elems = g.sx;
-    e->planes_alloc = g.nx + 2;
+    e->planes_alloc = g.nx + 4;         // data + up to 4 ghost/guard planes (two-step sweep reads E0 up to plane nx+3)
     e->array_elems = e->plane_elems * e->planes_alloc;
 
     cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
@@ -250,7 +251,7 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     drop_graph(e);
     for (int c = 0; c < 6; ++c) { cudaFree(e->fld[c]); cudaFree(e->fldB[c]); }
     for (int c = 0; c < 4; ++c) cudaFree(e->coef[c]);
-    cudaFree(e->d_src); cudaFree(e->d_mon); cudaFree(e->d_prof);
+    cudaFree(e->d_src); cudaFree(e->d_mon); cudaFree(e->d_prof); cudaFree(e->d_src_ghost);
     cudaFree(e->d_ade); cudaFree(e->d_aux); cudaFree(e->d_ade_mask);
     cudaFree(e->d_cpml_coef); cudaFree(e->d_plane_flags);
     for (int q = 0; q < 12; ++q) cudaFree(e->cpml.psi[q]);
@@ -431,7 +432,7 @@ static int check_box(const fdtd_engine* e, int comp, const int32_t* lo, const in
 extern "C" int fdtd_clear_ops(fdtd_engine* e)
 {
     if (!e) return fail(FDTD_EINVAL, "null engine");
-    e->src.clear(); e->mon.clear(); e->prof_host.clear();
+    e->src.clear(); e->mon.clear(); e->prof_host.clear(); e->src_ghost.clear();
     e->ade.clear(); e->ade_mask_host.clear();
     e->ops_dirty = true;
     drop_graph(e);
@@ -442,6 +443,21 @@ extern "C" int fdtd_add_source_op(fdtd_engine* e, const fdtd_source_op* op)
 {
     if (!e || !op) return fail(FDTD_EINVAL, "fdtd_add_source_op: null argument");
     HostSrc h{};
+    if (op->reserved & 1) {
+        // ghost op (x-slabs, two-step sweep): the right neighbour's injection on our ghost planes [nx, nx+3),
+        // applied only to the intermediate step inside the sweep; never by the post-step kernel
+        if (op->component < 0 || op->component > 5) return fail(FDTD_EINVAL, "component %d out of range", op->component);
+        if (op->lo[0] < e->g.nx || op->hi[0] > e->g.nx + 3 || op->hi[0] < op->lo[0])
+            return fail(FDTD_EINVAL, "ghost source op must lie in planes [nx, nx+3)");
+        if (op->profile) return fail(FDTD_EINVAL, "ghost source ops are uniform (no profile)");
+        SrcOp g{};
+        g.comp = op->component; g.table = op->table; g.divisor = 1.0; g.prof_off = -1;
+        for (int a = 0; a < 3; ++a) { g.lo[a] = op->lo[a]; g.n[a] = op->hi[a] - op->lo[a]; }
+        if (g.n[0] > 0 && g.n[1] > 0 && g.n[2] > 0) e->src_ghost.push_back(g);
+        e->ops_dirty = true;
+        drop_graph(e);
+        return 0;
+    }
     if (int rc = check_box(e, op->component, op->lo, op->hi, h.op.n)) return rc;
     if (op->table < 0) return fail(FDTD_EINVAL, "negative table index");
     h.op.comp = op->component;
@@ -579,13 +595,21 @@ static int finalize_ops(fdtd_engine* e)
     }
     // per-plane op flags for the temporally blocked sweep (bit0: a source op covers the plane, bit1: a monitor op)
     {
-        std::vector<unsigned char> fl(e->g.nx, 0);
+        const int npl = e->g.nx + 4;
+        std::vector<unsigned char> fl(npl, 0);
         for (auto& h : e->src)
-            for (int p = h.op.lo[0]; p < h.op.lo[0] + h.op.n[0] && p < e->g.nx; ++p) fl[p] |= 1;
+            for (int p = h.op.lo[0]; p < h.op.lo[0] + h.op.n[0] && p < npl; ++p) fl[p] |= 1;
+        for (auto& g : e->src_ghost)
+            for (int p = g.lo[0]; p < g.lo[0] + g.n[0] && p < npl; ++p) fl[p] |= 1;
         for (auto& m : e->mon)
-            for (int p = m.lo[0]; p < m.lo[0] + m.n[0] && p < e->g.nx; ++p) fl[p] |= 2;
-        if (!e->d_plane_flags) CU(cudaMalloc(&e->d_plane_flags, e->g.nx));
-        CU(cudaMemcpy(e->d_plane_flags, fl.data(), e->g.nx, cudaMemcpyHostToDevice));
+            for (int p = m.lo[0]; p < m.lo[0] + m.n[0] && p < npl; ++p) fl[p] |= 2;
+        if (!e->d_plane_flags) CU(cudaMalloc(&e->d_plane_flags, npl));
+        CU(cudaMemcpy(e->d_plane_flags, fl.data(), npl, cudaMemcpyHostToDevice));
+        cudaFree(e->d_src_ghost); e->d_src_ghost = nullptr;
+        if (!e->src_ghost.empty()) {
+            CU(cudaMalloc(&e->d_src_ghost, e->src_ghost.size() * sizeof(SrcOp)));
+            CU(cudaMemcpy(e->d_src_ghost, e->src_ghost.data(), e->src_ghost.size() * sizeof(SrcOp), cudaMemcpyHostToDevice));
+        }
     }
     e->ops_dirty = false;
     return 0;
@@ -896,10 +920,11 @@ template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i
     return launch_fused_tj<T, kFusedTJ>(e, i_begin, i_end, s);
 }
 
-static bool use_tb2(const fdtd_engine* e)
+static bool tb2_ok(const fdtd_engine* e)
 {
-    return e->tb2 && use_fused(e) && e->g.nxg == e->g.nx && e->ade.empty();
+    return e->tb2 && use_fused(e) && e->ade.empty() && e->array_elems < (1ll << 32);
 }
+static bool use_tb2(const fdtd_engine* e) { return tb2_ok(e) && e->g.nxg == e->g.nx; }
 
 // TWO steps in one pass over planes [0, nx): reads the current set, writes the other one; the intermediate
 // step's sources / monitors (table row *d_step + step_off) are applied inside the kernel
@@ -916,6 +941,9 @@ template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaSt
     FusedTiling t;
     t.i_begin = 0; t.i_end = g.nx;
     t.halo_flag = nullptr; t.halo_need = 0; t.error_word = nullptr; t.timeout_ns = e->slab.timeout_ns;
+    if (e->slab.connected && e->slab.has_right) {
+        t.halo_flag = e->slab.flags; t.halo_need = (int)e->slab.step + 1; t.error_word = e->slab.flags + 2;
+    }
     const int vec_per_row = g.pz / V;
     t.own_lanes = kTb2OwnLanes;
     t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
@@ -936,13 +964,18 @@ template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaSt
     m.phasors = e->d_phasor; m.n_phasor = e->n_phasor;
     m.rec = e->d_rec; m.dft = e->d_dft; m.dt = e->cfg.dt;
     m.step_ptr = e->d_step; m.step_off = step_off;
-    m.plane_flags = (m.n_src || m.n_mon) ? e->d_plane_flags : nullptr;
+    m.gsrc = e->d_src_ghost; m.n_gsrc = (int)e->src_ghost.size();
+    m.n_planes = g.nx + 4;
+    m.plane_flags = (m.n_src || m.n_mon || m.n_gsrc) ? e->d_plane_flags : nullptr;
     const size_t smem = tb2_smem_bytes<T, R>();
     auto kern = k_fused3d_tb2<T, R>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, R, 1);
     const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
-    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, m, (int)e->planes_alloc);
+    Fold fo;
+    fo.hx_ = (float)(e->uni[3] / g.dx); fo.hy_ = (float)(e->uni[3] / g.dy); fo.hz_ = (float)(e->uni[3] / g.dz);
+    fo.ex_ = (float)(e->uni[1] / g.dx); fo.ey_ = (float)(e->uni[1] / g.dy); fo.ez_ = (float)(e->uni[1] / g.dz);
+    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, m, (int)e->planes_alloc, fo);
     e->launches++;
     CU(cudaGetLastError());
     e->cur ^= 1;
@@ -982,7 +1015,7 @@ template <typename T> static int one_step(fdtd_engine* e, int step_off, int pari
     return launch_post<T>(e, step_off, parity, s);
 }
 
-static bool has_tables(const fdtd_engine* e) { return !e->src.empty() || !e->mon.empty(); }
+static bool has_tables(const fdtd_engine* e) { return !e->src.empty() || !e->mon.empty() || !e->src_ghost.empty(); }
 static bool has_post(const fdtd_engine* e) { return has_tables(e) || !e->ade.empty(); }
 
 template <typename T> static int run_steps(fdtd_engine* e, int n)
@@ -1273,29 +1306,39 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
 {
     auto& sl = e->slab;
     cudaStream_t cs = e->stream, ms = sl.comm;
-    static const int comps[5] = {0, 1, 2, 4, 5};          // Ex Ey Ez Hy Hz
-    static const int planes[5] = {1, 2, 2, 1, 1};
+    // single-step sweep: plane 0 of Ex Ey Ez Hy Hz + plane 1 of Ey Ez; two-step sweep: planes 0..3 of E, 0..2 of H
+    static const int planes1[6] = {1, 2, 2, 0, 1, 1};
+    static const int planes2[6] = {4, 4, 4, 3, 3, 3};
     const size_t pbytes = (size_t)e->plane_elems * e->esz;
     CU(cudaEventRecord(sl.post_done, cs));
-    for (int q = 0; q < n; ++q) {
-        const long long st = sl.step;
+    int q = 0;
+    while (q < n) {
+        const bool pair = tb2_ok(e) && q + 2 <= n;
+        const int* planes = pair ? planes2 : planes1;
+        const long long st = sl.step;                    // exchange counter, identical on every rank
         if (sl.has_left) {
-            CU(cudaStreamWaitEvent(ms, sl.post_done, 0));        // our planes 0/1 of the current set are final
+            CU(cudaStreamWaitEvent(ms, sl.post_done, 0));        // our first planes of the current set are final
             if (st >= 2) { k_wait<<<1, 1, 0, ms>>>(sl.left_flags + 1, (int)(st - 1), sl.flags + 2, sl.timeout_ns); e->launches++; }
             void** mine = cur_fields(e);
             void** theirs = sl.left_fld[e->cur];
-            for (int c = 0; c < 5; ++c)
-                CU(cudaMemcpyAsync((char*)theirs[comps[c]] + (size_t)sl.left_nx * pbytes, mine[comps[c]],
-                                   planes[c] * pbytes, cudaMemcpyDefault, ms));
+            for (int c = 0; c < 6; ++c)
+                if (planes[c])
+                    CU(cudaMemcpyAsync((char*)theirs[c] + (size_t)sl.left_nx * pbytes, mine[c], planes[c] * pbytes,
+                                       cudaMemcpyDefault, ms));
             k_signal<<<1, 1, 0, ms>>>(sl.left_flags, (int)(st + 1)); e->launches++;
             CU(cudaEventRecord(sl.push_done, ms));
         }
-        if (int rc = launch_fused<T>(e, 0, e->g.nx, cs)) return rc;   // reads the current set (+ ghosts)
-        e->cur ^= 1;
+        if (pair) {
+            if (int rc = launch_tb2<T>(e, q, cs)) return rc;             // flips the sets itself
+        } else {
+            if (int rc = launch_fused<T>(e, 0, e->g.nx, cs)) return rc;   // reads the current set (+ ghosts)
+            e->cur ^= 1;
+        }
         k_signal<<<1, 1, 0, cs>>>(sl.flags + 1, (int)(st + 1)); e->launches++;
-        // the push read the set that is now the output set of the NEXT step: it must finish before that sweep
+        // the push read the set that is now the output set of the NEXT sweep: it must finish before that sweep
         if (sl.has_left) CU(cudaStreamWaitEvent(cs, sl.push_done, 0));
-        if (has_post(e)) if (int rc = launch_post<T>(e, q, 0, cs)) return rc;
+        q += pair ? 2 : 1;
+        if (has_post(e)) if (int rc = launch_post<T>(e, q - 1, 0, cs)) return rc;
         CU(cudaEventRecord(sl.post_done, cs));
         sl.step++;
     }

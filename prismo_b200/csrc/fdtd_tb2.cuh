@@ -23,6 +23,8 @@ namespace fdtd {
 
 struct MidOps {
     const SrcOp* src; int n_src;
+    const SrcOp* gsrc; int n_gsrc;              // x-slabs: the right neighbour's source ops on our ghost planes
+    int n_planes;                               // length of plane_flags (nx, or nx+4 with ghost planes)
     const double* amp; int n_amp; const double* prof;
     const MonOp* mon; int n_mon;
     const double* phasors; int n_phasor;
@@ -60,8 +62,9 @@ template <typename T, int V> __device__ __forceinline__ void st8(T* p, const Pac
 template <typename T, int V>
 __device__ __forceinline__ void mid_sources(const MidOps& m, int comp, int p, int j, int k0, int row, Pack<T, V>& v)
 {
-    for (int q = 0; q < m.n_src; ++q) {
-        const SrcOp& op = m.src[q];
+    const int n_all = m.n_src + m.n_gsrc;
+    for (int q = 0; q < n_all; ++q) {
+        const SrcOp& op = q < m.n_src ? m.src[q] : m.gsrc[q - m.n_src];
         if (op.comp != comp) continue;
         const unsigned dp = (unsigned)(p - op.lo[0]), dj = (unsigned)(j - op.lo[1]);
         if (dp >= (unsigned)op.n[0] || dj >= (unsigned)op.n[1]) continue;
@@ -110,11 +113,28 @@ __device__ __forceinline__ void mid_monitors(const MidOps& m, int comp, int p, i
     }
 }
 
-struct Masks { bool jy1, jy2; };
+// fp32 only: coefficient * 1/d products folded on the host, so an update is 2 FADD + 1 FMUL + 2 FFMA instead of 7 ops
+// (fp64 keeps the reference's exact operation sequence: separate rounding of every product, true divisions)
+struct Fold { float hx_, hy_, hz_, ex_, ey_, ez_; };     // db/dx, db/dy, db/dz, cb/dx, cb/dy, cb/dz
+
+template <typename T> __device__ __forceinline__ T upd_h2(const Coefs<T>& c, const Geom& g, const Fold& f, T h,
+                                                          T a1, T a0, double da_, float ra, float fa,
+                                                          T b1, T b0, double db_, float rb, float fb)
+{
+    if (sizeof(T) == 4) return fmaf(fb, (float)(b1 - b0), fmaf(-fa, (float)(a1 - a0), (float)c.uda * (float)h));
+    return upd_h<T>(c.uda, h, c.udb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
+}
+template <typename T> __device__ __forceinline__ T upd_e2(const Coefs<T>& c, const Geom& g, const Fold& f, T e,
+                                                          T a1, T a0, double da_, float ra, float fa,
+                                                          T b1, T b0, double db_, float rb, float fb)
+{
+    if (sizeof(T) == 4) return fmaf(-fb, (float)(b1 - b0), fmaf(fa, (float)(a1 - a0), (float)c.uca * (float)e));
+    return upd_e<T>(c.uca, e, c.ucb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
+}
 
 // H stage: (hx,hy,hz) <- f(h, e (own, j+1: ez_j/ex_j, k+1: ey_n/ex_n), e_next plane (ey, ez own)); plane gi
-template <typename T, int V>
-__device__ __forceinline__ void stage_h(const Coefs<T>& c, const Geom& g, int gi, bool jy1, bool jy2, int k,
+template <typename T, int V, bool MASKED>
+__device__ __forceinline__ void stage_h(const Coefs<T>& c, const Geom& g, const Fold& fo, int gi, bool jy1, bool jy2, int k,
                                         const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
                                         const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
                                         const Pack<T, V>& ez_j, const Pack<T, V>& ex_j, T ey_n, T ex_n,
@@ -128,21 +148,18 @@ __device__ __forceinline__ void stage_h(const Coefs<T>& c, const Geom& g, int gi
         const bool kz1 = (k + e) < g.nz - 1, kz2 = (k + e) < g.nz - 2;
         const T ey_k = (e + 1 < V) ? ey.v[(e + 1) % V] : ey_n;
         const T ex_k = (e + 1 < V) ? ex.v[(e + 1) % V] : ex_n;
-        T n = upd_h<T>(c.uda, hx.v[e], c.udb, Ar<T>::diff(ez_j.v[e], ez.v[e], g.dy, g.rdy),
-                       Ar<T>::diff(ey_k, ey.v[e], g.dz, g.rdz));
-        if (ix1 && jy2 && kz2) ox.v[e] = n;
-        n = upd_h<T>(c.uda, hy.v[e], c.udb, Ar<T>::diff(ex_k, ex.v[e], g.dz, g.rdz),
-                     Ar<T>::diff(ez_p.v[e], ez.v[e], g.dx, g.rdx));
-        if (ix2 && jy1 && kz2) oy.v[e] = n;
-        n = upd_h<T>(c.uda, hz.v[e], c.udb, Ar<T>::diff(ey_p.v[e], ey.v[e], g.dx, g.rdx),
-                     Ar<T>::diff(ex_j.v[e], ex.v[e], g.dy, g.rdy));
-        if (ix2 && jy2 && kz1) oz.v[e] = n;
+        T n = upd_h2<T>(c, g, fo, hx.v[e], ez_j.v[e], ez.v[e], g.dy, g.rdy, fo.hy_, ey_k, ey.v[e], g.dz, g.rdz, fo.hz_);
+        if (!MASKED || (ix1 && jy2 && kz2)) ox.v[e] = n;
+        n = upd_h2<T>(c, g, fo, hy.v[e], ex_k, ex.v[e], g.dz, g.rdz, fo.hz_, ez_p.v[e], ez.v[e], g.dx, g.rdx, fo.hx_);
+        if (!MASKED || (ix2 && jy1 && kz2)) oy.v[e] = n;
+        n = upd_h2<T>(c, g, fo, hz.v[e], ey_p.v[e], ey.v[e], g.dx, g.rdx, fo.hx_, ex_j.v[e], ex.v[e], g.dy, g.rdy, fo.hy_);
+        if (!MASKED || (ix2 && jy2 && kz1)) oz.v[e] = n;
     }
 }
 
 // E stage: (ex,ey,ez) <- g(e, h (own, j+1: hz_j/hx_j, k+1: hy_n/hx_n), h_next plane (hy, hz own)); plane gi
-template <typename T, int V>
-__device__ __forceinline__ void stage_e(const Coefs<T>& c, const Geom& g, int gi, bool jy1, int k,
+template <typename T, int V, bool MASKED>
+__device__ __forceinline__ void stage_e(const Coefs<T>& c, const Geom& g, const Fold& fo, int gi, bool jy1, int k,
                                         const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
                                         const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
                                         const Pack<T, V>& hz_j, const Pack<T, V>& hx_j, T hy_n, T hx_n,
@@ -156,15 +173,12 @@ __device__ __forceinline__ void stage_e(const Coefs<T>& c, const Geom& g, int gi
         const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;
         const T hy_k = (e + 1 < V) ? hy.v[(e + 1) % V] : hy_n;
         const T hx_k = (e + 1 < V) ? hx.v[(e + 1) % V] : hx_n;
-        T n = upd_e<T>(c.uca, ex.v[e], c.ucb, Ar<T>::diff(hz_j.v[e], hz.v[e], g.dy, g.rdy),
-                       Ar<T>::diff(hy_k, hy.v[e], g.dz, g.rdz));
-        if (ex0 && jy1 && kz1) ox.v[e] = n;
-        n = upd_e<T>(c.uca, ey.v[e], c.ucb, Ar<T>::diff(hx_k, hx.v[e], g.dz, g.rdz),
-                     Ar<T>::diff(hz_p.v[e], hz.v[e], g.dx, g.rdx));
-        if (ex1 && kz1) oy.v[e] = n;
-        n = upd_e<T>(c.uca, ez.v[e], c.ucb, Ar<T>::diff(hy_p.v[e], hy.v[e], g.dx, g.rdx),
-                     Ar<T>::diff(hx_j.v[e], hx.v[e], g.dy, g.rdy));
-        if (ex1 && jy1 && kz0) oz.v[e] = n;
+        T n = upd_e2<T>(c, g, fo, ex.v[e], hz_j.v[e], hz.v[e], g.dy, g.rdy, fo.ey_, hy_k, hy.v[e], g.dz, g.rdz, fo.ez_);
+        if (!MASKED || (ex0 && jy1 && kz1)) ox.v[e] = n;
+        n = upd_e2<T>(c, g, fo, ey.v[e], hx_k, hx.v[e], g.dz, g.rdz, fo.ez_, hz_p.v[e], hz.v[e], g.dx, g.rdx, fo.ex_);
+        if (!MASKED || (ex1 && kz1)) oy.v[e] = n;
+        n = upd_e2<T>(c, g, fo, ez.v[e], hy_p.v[e], hy.v[e], g.dx, g.rdx, fo.ex_, hx_j.v[e], hx.v[e], g.dy, g.rdy, fo.ey_);
+        if (!MASKED || (ex1 && jy1 && kz0)) oz.v[e] = n;
     }
 }
 
@@ -175,7 +189,7 @@ template <typename T, int R> constexpr size_t tb2_smem_bytes() { return 2 * (siz
 
 template <typename T, int R>
 __global__ void __launch_bounds__(32 * R, 1)
-k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, MidOps m, int planes_alloc)
+k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, MidOps m, int planes_alloc, Fold fo)
 {
     constexpr int V = Vec8<T>::V;
     typedef Pack<T, V> P;
@@ -199,18 +213,21 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
     const bool ld_ok = (j < g.ny) && (k < g.pz);
     const bool owner = ld_ok && row < R - 4 && lane < t.own_lanes;
     const int rown = min(row + 1, R - 1);
-    const long long o = (long long)j * g.sy + k;
+    // element offsets fit 32 bits (host checks planes_alloc * sx < 2^32): one IMAD.WIDE per access
+    const unsigned ofs = (unsigned)j * (unsigned)g.sy + (unsigned)k;
     const bool jy1 = j < g.ny - 1, jy2 = j < g.ny - 2;
     const int step_row = m.step_ptr ? (*m.step_ptr + m.step_off) : 0;
+    // interior tile: every thread of the CTA (rim rows / lanes included) is clear of the +j / +k boundary ranges
+    const bool interior = (tj * (R - 4) + R - 1 < g.ny - 2) && ((tk * t.own_lanes + 31) * V + V - 1 < g.nz - 2);
 
-    const T* pex = in.ex + o; const T* pey = in.ey + o; const T* pez = in.ez + o;
-    const T* phx = in.hx + o; const T* phy = in.hy + o; const T* phz = in.hz + o;
+    const T* pex = in.ex + ofs; const T* pey = in.ey + ofs; const T* pez = in.ez + ofs;
+    const T* phx = in.hx + ofs; const T* phy = in.hy + ofs; const T* phz = in.hz + ofs;
     P z_;
 #pragma unroll
     for (int e = 0; e < V; ++e) z_.v[e] = (T)0;
     // window at i = i0-3
     P e0ax = z_, e0ay = z_, e0az = z_;                                   // E0[i+2]
-    long long po = (long long)i0 * g.sx;
+    unsigned po = (unsigned)i0 * (unsigned)g.sx;
     P e0bx = ld8<T, V>(pex + po, ld_ok), e0by = ld8<T, V>(pey + po, ld_ok), e0bz = ld8<T, V>(pez + po, ld_ok);   // E0[i+3]
     P ne0x = ld8<T, V>(pex + po + g.sx, ld_ok), ne0y = ld8<T, V>(pey + po + g.sx, ld_ok),
       ne0z = ld8<T, V>(pez + po + g.sx, ld_ok);                          // E0[i+4]
@@ -224,13 +241,13 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
         // ---- prefetch for the next iteration: E0[i+5], H0[i+4] ----------------------------------------------
         const bool more = ld_ok && (i + 1 < i1);
         const bool pe_ok = more && (i + 5 < planes_alloc), ph_ok = more && (i + 4 < planes_alloc);
-        const long long pp = (long long)(i + 4) * g.sx;
+        const unsigned pp = (unsigned)(i + 4) * (unsigned)g.sx;
         const P pe0x = ld8<T, V>(pex + pp + g.sx, pe_ok), pe0y = ld8<T, V>(pey + pp + g.sx, pe_ok),
                 pe0z = ld8<T, V>(pez + pp + g.sx, pe_ok);
         const P ph0x = ld8<T, V>(phx + pp, ph_ok), ph0y = ld8<T, V>(phy + pp, ph_ok), ph0z = ld8<T, V>(phz + pp, ph_ok);
 
         // ---- intermediate-step H sources / monitors on H1[i+1] (all of its pre-source uses are done) --------------
-        if (m.plane_flags && i + 1 >= i0 && i + 1 < g.nx) {
+        if (m.plane_flags && i + 1 >= i0 && i + 1 < m.n_planes) {
             const unsigned char fl = m.plane_flags[i + 1];
             if (fl & 1) {
                 mid_sources<T, V>(m, 3, i + 1, j, k, step_row, h1ax);
@@ -265,45 +282,47 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
         const T e1y_n = shfl_next<T>(e1by.v[0]), e1x_n = shfl_next<T>(e1bx.v[0]);
         const T h2y_n = shfl_next<T>(h2ay.v[0]), h2x_n = shfl_next<T>(h2ax.v[0]);
 
-        // ---- A: H1[i+3] ------------------------------------------------------------------------------------------------------
-        P h1cx, h1cy, h1cz;
-        stage_h<T, V>(c, g, g.x0 + i + 3, jy1, jy2, k, nh0x, nh0y, nh0z, e0bx, e0by, e0bz, e0z_j, e0x_j, e0y_n, e0x_n,
-                      ne0y, ne0z, h1cx, h1cy, h1cz);
-        // ---- B: E1[i+2] (+ intermediate-step E sources / monitors) ----------------------------------------------------------------
-        P e1cx, e1cy, e1cz;
-        stage_e<T, V>(c, g, g.x0 + i + 2, jy1, k, e0ax, e0ay, e0az, h1bx, h1by, h1bz, h1z_j, h1x_j, h1y_n, h1x_n,
-                      h1cy, h1cz, e1cx, e1cy, e1cz);
-        if (m.plane_flags && i + 2 >= i0 && i + 2 < g.nx) {
-            const unsigned char fl = m.plane_flags[i + 2];
-            if (fl & 1) {
-                mid_sources<T, V>(m, 0, i + 2, j, k, step_row, e1cx);
-                mid_sources<T, V>(m, 1, i + 2, j, k, step_row, e1cy);
-                mid_sources<T, V>(m, 2, i + 2, j, k, step_row, e1cz);
-            }
-            if ((fl & 2) && owner && i + 2 < i1) {
-                mid_monitors<T, V>(m, 0, i + 2, j, k, step_row, e1cx);
-                mid_monitors<T, V>(m, 1, i + 2, j, k, step_row, e1cy);
-                mid_monitors<T, V>(m, 2, i + 2, j, k, step_row, e1cz);
-            }
+#define TB2_STAGES(MASKED, STEADY)                                                                                      \
+        stage_h<T, V, MASKED>(c, g, fo, g.x0 + i + 3, jy1, jy2, k, nh0x, nh0y, nh0z, e0bx, e0by, e0bz, e0z_j, e0x_j, e0y_n,  \
+                              e0x_n, ne0y, ne0z, h1cx, h1cy, h1cz);                                                  \
+        stage_e<T, V, MASKED>(c, g, fo, g.x0 + i + 2, jy1, k, e0ax, e0ay, e0az, h1bx, h1by, h1bz, h1z_j, h1x_j, h1y_n,        \
+                              h1x_n, h1cy, h1cz, e1cx, e1cy, e1cz);                                                  \
+        if (m.plane_flags && (STEADY || (i + 2 >= i0 && i + 2 < m.n_planes))) {                                    \
+            const unsigned char fl = m.plane_flags[i + 2];                                                         \
+            if (fl & 1) {                                                                                          \
+                mid_sources<T, V>(m, 0, i + 2, j, k, step_row, e1cx);                                              \
+                mid_sources<T, V>(m, 1, i + 2, j, k, step_row, e1cy);                                              \
+                mid_sources<T, V>(m, 2, i + 2, j, k, step_row, e1cz);                                              \
+            }                                                                                                      \
+            if ((fl & 2) && owner && (STEADY || i + 2 < i1)) {                                                     \
+                mid_monitors<T, V>(m, 0, i + 2, j, k, step_row, e1cx);                                             \
+                mid_monitors<T, V>(m, 1, i + 2, j, k, step_row, e1cy);                                             \
+                mid_monitors<T, V>(m, 2, i + 2, j, k, step_row, e1cz);                                             \
+            }                                                                                                      \
+        }                                                                                                          \
+        stage_h<T, V, MASKED>(c, g, fo, g.x0 + i + 1, jy1, jy2, k, h1ax, h1ay, h1az, e1bx, e1by, e1bz, e1z_j, e1x_j, e1y_n,  \
+                              e1x_n, e1cy, e1cz, h2bx, h2by, h2bz);                                                  \
+        if (owner && (STEADY || (i + 1 >= i0 && i + 1 < i1))) {                                                    \
+            st8<T, V>(out.hx + ost1, h2bx); st8<T, V>(out.hy + ost1, h2by);                                        \
+            st8<T, V>(out.hz + ost1, h2bz);                                                                        \
+        }                                                                                                          \
+        if (STEADY || i >= i0) {                                                                                   \
+            P e2x, e2y, e2z;                                                                                       \
+            stage_e<T, V, MASKED>(c, g, fo, g.x0 + i, jy1, k, e1ax, e1ay, e1az, h2ax, h2ay, h2az, h2z_j, h2x_j, h2y_n,     \
+                                  h2x_n, h2by, h2bz, e2x, e2y, e2z);                                               \
+            if (owner) { st8<T, V>(out.ex + ost, e2x); st8<T, V>(out.ey + ost, e2y); st8<T, V>(out.ez + ost, e2z); } \
         }
-        // ---- C: H2[i+1] ---------------------------------------------------------------------------------------------------------------
-        P h2bx, h2by, h2bz;
-        stage_h<T, V>(c, g, g.x0 + i + 1, jy1, jy2, k, h1ax, h1ay, h1az, e1bx, e1by, e1bz, e1z_j, e1x_j, e1y_n, e1x_n,
-                      e1cy, e1cz, h2bx, h2by, h2bz);
-        if (owner && i + 1 >= i0 && i + 1 < i1) {
-            const long long q = (long long)(i + 1) * g.sx;
-            st8<T, V>(out.hx + o + q, h2bx); st8<T, V>(out.hy + o + q, h2by); st8<T, V>(out.hz + o + q, h2bz);
-        }
-        // ---- D: E2[i] -----------------------------------------------------------------------------------------------------------------
-        if (i >= i0) {
-            P e2x, e2y, e2z;
-            stage_e<T, V>(c, g, g.x0 + i, jy1, k, e1ax, e1ay, e1az, h2ax, h2ay, h2az, h2z_j, h2x_j, h2y_n, h2x_n,
-                          h2by, h2bz, e2x, e2y, e2z);
-            if (owner) {
-                const long long q = (long long)i * g.sx;
-                st8<T, V>(out.ex + o + q, e2x); st8<T, V>(out.ey + o + q, e2y); st8<T, V>(out.ez + o + q, e2z);
-            }
-        }
+
+        // ---- A: H1[i+3], B: E1[i+2] (+ intermediate-step E sources / monitors), C: H2[i+1], D: E2[i] -------------------
+        // Interior CTAs on interior planes skip every boundary mask (the reference's "never updated" ranges and the
+        // staggered array ends only touch the last two rows / columns / planes).
+        P h1cx, h1cy, h1cz, e1cx, e1cy, e1cz, h2bx, h2by, h2bz;
+        const unsigned ost = ofs + (unsigned)i * (unsigned)g.sx;            // plane i   (used only when i   >= i0 >= 0)
+        const unsigned ost1 = ofs + (unsigned)(i + 1) * (unsigned)g.sx;     // plane i+1 (used only when i+1 >= i0 >= 0)
+        if (!(interior && g.x0 + i + 3 < g.nxg - 2)) { TB2_STAGES(true, false) }
+        else if (i >= i0 && i + 2 < i1) { TB2_STAGES(false, true) }
+        else { TB2_STAGES(false, false) }
+#undef TB2_STAGES
         // ---- rotate ---------------------------------------------------------------------------------------------------------------------
         e0ax = e0bx; e0ay = e0by; e0az = e0bz;
         e0bx = ne0x; e0by = ne0y; e0bz = ne0z;

@@ -24,6 +24,7 @@ class SourceOp:
     profile: Optional[np.ndarray] = None
     divisor: float = 1.0
     group: int = 0
+    ghost: bool = False     # x-slabs: the right neighbour's op on our ghost planes [nx, nx+3) (two-step sweep only)
 
 
 @dataclass
@@ -191,7 +192,7 @@ class Engine:
         c.component = COMP_ID[op.component]
         c.lo[:] = _pad3(op.lo, 0)
         c.hi[:] = _pad3(op.hi, 1)
-        c.table, c.divisor, c.group, c.reserved = int(op.table), float(op.divisor), int(op.group), 0
+        c.table, c.divisor, c.group, c.reserved = int(op.table), float(op.divisor), int(op.group), int(bool(op.ghost))
         prof = None
         if op.profile is not None:
             prof = np.ascontiguousarray(op.profile, dtype=np.float64)

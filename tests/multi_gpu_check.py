@@ -40,13 +40,18 @@ def main():
     init = {c: rng.standard_normal(whole_shape[c]) * (1.0 if c[0] == "E" else 1 / 377.0) for c in comps}
     amp = np.sin(np.arange(1, steps + 1)[:, None] * np.array([[0.3, 0.7]]))
     ph = np.exp(-1j * np.arange(1, steps + 1)[:, None] * np.array([[0.2, 0.5]]))
-    src_plane, mon_plane = dims[0] // 2, dims[0] - 3
+    # first plane of the second slab: a local op for that rank AND a ghost op for the rank on its left
+    src_plane, mon_plane = slab_range(dims[0], 1, world)[0] if world > 1 else dims[0] // 2, dims[0] - 3
 
     def ops(x0, nxl, shape_of):
         s, m = [], []
         if x0 <= src_plane < x0 + nxl:
             i = src_plane - x0
             s = [pb.SourceOp("Ey", (i, 0, 0), (i + 1,) + shape_of("Ey")[1:], 0), pb.SourceOp("Hz", (i, 0, 0), (i + 1,) + shape_of("Hz")[1:], 1)]
+        elif x0 + nxl <= src_plane < x0 + nxl + 3:          # ghost ops for the two-step sweep
+            i = src_plane - x0
+            s = [pb.SourceOp("Ey", (i, 0, 0), (i + 1,) + shape_of("Ey")[1:], 0, ghost=True),
+                 pb.SourceOp("Hz", (i, 0, 0), (i + 1,) + shape_of("Hz")[1:], 1, ghost=True)]
         if x0 <= mon_plane < x0 + nxl:
             i = mon_plane - x0
             m = [pb.MonitorOp("Ez", (i, 0, 0), (i + 1,) + shape_of("Ez")[1:], False, 2, 0)]
