@@ -88,7 +88,8 @@ def run_multi(args, rank, world, local):
                                           + ("NCCL send/recv" if halo == "nccl" else
                                              "DMA push into the neighbour's ghost planes over NVLink (CUDA IPC) + "
                                              "release/acquire flags, in-kernel wait"),
-                           "kernel_path": "fused single sweep, ping-pong"},
+                           "kernel_path": "temporally blocked fused sweep (2 steps per HBM pass), ping-pong"
+                                          if os.environ.get("FDTD_B200_TB2", "1") != "0" else "fused single sweep, ping-pong"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src,
                              "kernel": "k_fused3d, per GPU, whole step incl. halo wait (max over ranks)"},

@@ -86,7 +86,7 @@ struct fdtd_engine {
     // graph
     cudaGraphExec_t gexec[2] = {nullptr, nullptr}; int graph_steps = 0; int graph_kernels[2] = {0, 0};
     int fused_lx = 0;               // planes per fused segment (0 = auto)
-    int tb2 = 0;                    // 1: temporally blocked sweep (two steps per pass) where applicable
+    int tb2 = 1;                    // 1: temporally blocked sweep (two steps per pass) where applicable
     unsigned char* d_plane_flags = nullptr;
     int fused_tj = 15;              // owner rows per CTA (15: one 16-warp CTA/SM; 7: two 8-warp CTAs/SM)
     int fused_pol = 0;              // bit0: streaming (evict-first) stores (measured 1.4% slower: off)
@@ -138,6 +138,16 @@ template <typename T> static Coefs<T> coefs_of(const fdtd_engine* e)
     c.da = (const T*)e->coef[2]; c.db = (const T*)e->coef[3];
     c.uca = (T)e->uni[0]; c.ucb = (T)e->uni[1]; c.uda = (T)e->uni[2]; c.udb = (T)e->uni[3];
     return c;
+}
+// fp32 fused kernels: db/d and cb/d folded once (both the one-step and the two-step sweep use the SAME folded
+// arithmetic, so fp32 results do not depend on how steps are paired)
+static Fold fold_of(const fdtd_engine* e)
+{
+    Fold fo;
+    const Geom& g = e->g;
+    fo.hx_ = (float)(e->uni[3] / g.dx); fo.hy_ = (float)(e->uni[3] / g.dy); fo.hz_ = (float)(e->uni[3] / g.dz);
+    fo.ex_ = (float)(e->uni[1] / g.dx); fo.ey_ = (float)(e->uni[1] / g.dy); fo.ez_ = (float)(e->uni[1] / g.dz);
+    return fo;
 }
 static void** cur_fields(fdtd_engine* e) { return e->cur ? e->fldB : e->fld; }
 
@@ -907,7 +917,7 @@ template <typename T, int TJ> static int launch_fused_tj(fdtd_engine* e, int i_b
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, TJ + 1, 1);
     const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
-    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t);
+    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, fold_of(e));
     e->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -972,10 +982,7 @@ template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaSt
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, R, 1);
     const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
-    Fold fo;
-    fo.hx_ = (float)(e->uni[3] / g.dx); fo.hy_ = (float)(e->uni[3] / g.dy); fo.hz_ = (float)(e->uni[3] / g.dz);
-    fo.ex_ = (float)(e->uni[1] / g.dx); fo.ey_ = (float)(e->uni[1] / g.dy); fo.ez_ = (float)(e->uni[1] / g.dz);
-    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, m, (int)e->planes_alloc, fo);
+    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, m, (int)e->planes_alloc, fold_of(e));
     e->launches++;
     CU(cudaGetLastError());
     e->cur ^= 1;

@@ -74,6 +74,25 @@ template <typename T, int TJ> constexpr size_t fused_smem_bytes()
     return 2 * 2 * (size_t)(TJ + 1) * 2 * 32 * sizeof(typename VecOf<T>::type);
 }
 
+// fp32 only: coefficient * 1/d products folded on the host, so an update is 2 FADD + 1 FMUL + 2 FFMA instead of 7 ops
+// (fp64 keeps the reference's exact operation sequence: separate rounding of every product, true divisions)
+struct Fold { float hx_, hy_, hz_, ex_, ey_, ez_; };     // db/dx, db/dy, db/dz, cb/dx, cb/dy, cb/dz
+
+template <typename T> __device__ __forceinline__ T upd_h2(const Coefs<T>& c, const Geom& g, const Fold& f, T h,
+                                                          T a1, T a0, double da_, float ra, float fa,
+                                                          T b1, T b0, double db_, float rb, float fb)
+{
+    if (sizeof(T) == 4) return fmaf(fb, (float)(b1 - b0), fmaf(-fa, (float)(a1 - a0), (float)c.uda * (float)h));
+    return upd_h<T>(c.uda, h, c.udb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
+}
+template <typename T> __device__ __forceinline__ T upd_e2(const Coefs<T>& c, const Geom& g, const Fold& f, T e,
+                                                          T a1, T a0, double da_, float ra, float fa,
+                                                          T b1, T b0, double db_, float rb, float fb)
+{
+    if (sizeof(T) == 4) return fmaf(-fb, (float)(b1 - b0), fmaf(fa, (float)(a1 - a0), (float)c.uca * (float)e));
+    return upd_e<T>(c.uca, e, c.ucb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
+}
+
 template <typename T> __device__ __forceinline__ Pack<T, VecOf<T>::V> zero_pack()
 {
     Pack<T, VecOf<T>::V> r;
@@ -116,7 +135,7 @@ template <typename T, int POL> __device__ __forceinline__ void stv_pol(T* p, con
 // TJ owner rows per CTA; blockDim = (32, TJ + 1);  POL bit0: streaming stores
 template <typename T, int TJ, int POL>
 __global__ void __launch_bounds__(32 * (TJ + 1), (TJ <= 7 ? 2 : 1))
-k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
+k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold fo)
 {
     constexpr int V = VecOf<T>::V;
     typedef Pack<T, V> P;
@@ -202,14 +221,11 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
         for (int e = 0; e < V; ++e) {
             const T ey_k = (e + 1 < V) ? e1y.v[(e + 1) % V] : ey1_n;
             const T ex_k = (e + 1 < V) ? e1x.v[(e + 1) % V] : ex1_n;
-            T n = upd_h<T>(c.uda, h1x.v[e], c.udb, Ar<T>::diff(ez_j.v[e], e1z.v[e], g.dy, g.rdy),
-                           Ar<T>::diff(ey_k, e1y.v[e], g.dz, g.rdz));
+            T n = upd_h2<T>(c, g, fo, h1x.v[e], ez_j.v[e], e1z.v[e], g.dy, g.rdy, fo.hy_, ey_k, e1y.v[e], g.dz, g.rdz, fo.hz_);
             if (ix1 && jy2 && kz2[e]) hnx.v[e] = n;
-            n = upd_h<T>(c.uda, h1y.v[e], c.udb, Ar<T>::diff(ex_k, e1x.v[e], g.dz, g.rdz),
-                         Ar<T>::diff(e2z.v[e], e1z.v[e], g.dx, g.rdx));
+            n = upd_h2<T>(c, g, fo, h1y.v[e], ex_k, e1x.v[e], g.dz, g.rdz, fo.hz_, e2z.v[e], e1z.v[e], g.dx, g.rdx, fo.hx_);
             if (ix2 && jy1 && kz2[e]) hny.v[e] = n;
-            n = upd_h<T>(c.uda, h1z.v[e], c.udb, Ar<T>::diff(e2y.v[e], e1y.v[e], g.dx, g.rdx),
-                         Ar<T>::diff(ex_j.v[e], e1x.v[e], g.dy, g.rdy));
+            n = upd_h2<T>(c, g, fo, h1z.v[e], e2y.v[e], e1y.v[e], g.dx, g.rdx, fo.hx_, ex_j.v[e], e1x.v[e], g.dy, g.rdy, fo.hy_);
             if (ix2 && jy2 && kz1[e]) hnz.v[e] = n;
         }
         if (owner && i + 1 < i1) {
@@ -224,14 +240,11 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t)
             for (int e = 0; e < V; ++e) {
                 const T hy_k = (e + 1 < V) ? hpy.v[(e + 1) % V] : hpy_n;
                 const T hx_k = (e + 1 < V) ? hpx.v[(e + 1) % V] : hpx_n;
-                T n = upd_e<T>(c.uca, e0x.v[e], c.ucb, Ar<T>::diff(hz_j.v[e], hpz.v[e], g.dy, g.rdy),
-                               Ar<T>::diff(hy_k, hpy.v[e], g.dz, g.rdz));
+                T n = upd_e2<T>(c, g, fo, e0x.v[e], hz_j.v[e], hpz.v[e], g.dy, g.rdy, fo.ey_, hy_k, hpy.v[e], g.dz, g.rdz, fo.ez_);
                 if (ex0 && jy1 && kz1[e]) nx_.v[e] = n;
-                n = upd_e<T>(c.uca, e0y.v[e], c.ucb, Ar<T>::diff(hx_k, hpx.v[e], g.dz, g.rdz),
-                             Ar<T>::diff(hnz.v[e], hpz.v[e], g.dx, g.rdx));
+                n = upd_e2<T>(c, g, fo, e0y.v[e], hx_k, hpx.v[e], g.dz, g.rdz, fo.ez_, hnz.v[e], hpz.v[e], g.dx, g.rdx, fo.ex_);
                 if (ex1 && kz1[e]) ny_.v[e] = n;
-                n = upd_e<T>(c.uca, e0z.v[e], c.ucb, Ar<T>::diff(hny.v[e], hpy.v[e], g.dx, g.rdx),
-                             Ar<T>::diff(hx_j.v[e], hpx.v[e], g.dy, g.rdy));
+                n = upd_e2<T>(c, g, fo, e0z.v[e], hny.v[e], hpy.v[e], g.dx, g.rdx, fo.ex_, hx_j.v[e], hpx.v[e], g.dy, g.rdy, fo.ey_);
                 if (ex1 && jy1 && kz0[e]) nz_.v[e] = n;
             }
             if (owner) {

@@ -113,25 +113,6 @@ __device__ __forceinline__ void mid_monitors(const MidOps& m, int comp, int p, i
     }
 }
 
-// fp32 only: coefficient * 1/d products folded on the host, so an update is 2 FADD + 1 FMUL + 2 FFMA instead of 7 ops
-// (fp64 keeps the reference's exact operation sequence: separate rounding of every product, true divisions)
-struct Fold { float hx_, hy_, hz_, ex_, ey_, ez_; };     // db/dx, db/dy, db/dz, cb/dx, cb/dy, cb/dz
-
-template <typename T> __device__ __forceinline__ T upd_h2(const Coefs<T>& c, const Geom& g, const Fold& f, T h,
-                                                          T a1, T a0, double da_, float ra, float fa,
-                                                          T b1, T b0, double db_, float rb, float fb)
-{
-    if (sizeof(T) == 4) return fmaf(fb, (float)(b1 - b0), fmaf(-fa, (float)(a1 - a0), (float)c.uda * (float)h));
-    return upd_h<T>(c.uda, h, c.udb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
-}
-template <typename T> __device__ __forceinline__ T upd_e2(const Coefs<T>& c, const Geom& g, const Fold& f, T e,
-                                                          T a1, T a0, double da_, float ra, float fa,
-                                                          T b1, T b0, double db_, float rb, float fb)
-{
-    if (sizeof(T) == 4) return fmaf(-fb, (float)(b1 - b0), fmaf(fa, (float)(a1 - a0), (float)c.uca * (float)e));
-    return upd_e<T>(c.uca, e, c.ucb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
-}
-
 // H stage: (hx,hy,hz) <- f(h, e (own, j+1: ez_j/ex_j, k+1: ey_n/ex_n), e_next plane (ey, ez own)); plane gi
 template <typename T, int V, bool MASKED>
 __device__ __forceinline__ void stage_h(const Coefs<T>& c, const Geom& g, const Fold& fo, int gi, bool jy1, bool jy2, int k,
