@@ -992,7 +992,8 @@ template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaSt
 // two full steps: temporally blocked sweep (step A's sources/monitors inside), then step B's sources/monitors
 template <typename T> static int two_steps(fdtd_engine* e, int step_off, cudaStream_t s)
 {
-    return launch_tb2<T>(e, step_off, s);        // both steps' sources / monitors run inside the sweep
+    if (int rc = launch_tb2<T>(e, step_off, s)) return rc;
+    return launch_post<T>(e, step_off + 1, 0, s);
 }
 
 // 3-D field update of one step, in two halves: half 0 = H pass (or the whole fused sweep), half 1 = E pass
@@ -1121,7 +1122,10 @@ template <typename T> static int run_profiled(fdtd_engine* e, int n, double* out
         // one temporally blocked sweep = two steps: its time goes to slot 0, step B's sources/monitors to slot 2
         int rc = launch_tb2<T>(e, q, s);
         if (rc) return rc;
-        for (int k = 1; k <= 6; ++k) CU(cudaEventRecord(ev[3 * q + k], s));   // sources / monitors are inside the sweep
+        CU(cudaEventRecord(ev[3 * q + 1], s));
+        CU(cudaEventRecord(ev[3 * q + 2], s));
+        if ((rc = launch_post<T>(e, q + 1, 0, s))) return rc;
+        for (int k = 3; k <= 6; ++k) CU(cudaEventRecord(ev[3 * q + k], s));
     }
     for (int q = 0; !tb2 && q < n; ++q) {
         int rc;
@@ -1341,7 +1345,7 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
         // the push read the set that is now the output set of the NEXT sweep: it must finish before that sweep
         if (sl.has_left) CU(cudaStreamWaitEvent(cs, sl.push_done, 0));
         q += pair ? 2 : 1;
-        if (!pair && has_post(e)) if (int rc = launch_post<T>(e, q - 1, 0, cs)) return rc;
+        if (has_post(e)) if (int rc = launch_post<T>(e, q - 1, 0, cs)) return rc;
         CU(cudaEventRecord(sl.post_done, cs));
         sl.step++;
     }

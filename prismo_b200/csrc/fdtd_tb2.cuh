@@ -10,8 +10,6 @@
 // next lane) of the previous stage's result, so validity shrinks by one row and one lane per stage: of R warp
 // rows the first R-4 own cells, of 32 lanes the first 28; the rest are rim providers that store nothing.
 //
-// The second step's sources / monitors are applied to the values being stored (stage D keeps the pre-source H2),
-// so a pair of steps is ONE kernel launch: no separate source / monitor pass touches HBM.
 // What the reference does BETWEEN the two steps — sources added to E1/H1, monitors sampling them
 // (core/simulation.py:158-164) — happens on the register window: E sources right after stage B (stage C must
 // see them, stage B of the neighbouring plane must not see H sources: they are added one iteration later, just
@@ -286,44 +284,14 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
         stage_h<T, V, MASKED>(c, g, fo, g.x0 + i + 1, jy1, jy2, k, h1ax, h1ay, h1az, e1bx, e1by, e1bz, e1z_j, e1x_j, e1y_n,  \
                               e1x_n, e1cy, e1cz, h2bx, h2by, h2bz);                                                  \
         if (owner && (STEADY || (i + 1 >= i0 && i + 1 < i1))) {                                                    \
-            /* second step's sources / monitors on the value being stored; stage D keeps the pre-source H2 */      \
-            P sx_ = h2bx, sy_ = h2by, sz_ = h2bz;                                                                  \
-            if (m.plane_flags) {                                                                                   \
-                const unsigned char fl = m.plane_flags[i + 1];                                                     \
-                if (fl & 1) {                                                                                      \
-                    mid_sources<T, V>(m, 3, i + 1, j, k, step_row + 1, sx_);                                       \
-                    mid_sources<T, V>(m, 4, i + 1, j, k, step_row + 1, sy_);                                       \
-                    mid_sources<T, V>(m, 5, i + 1, j, k, step_row + 1, sz_);                                       \
-                }                                                                                                  \
-                if (fl & 2) {                                                                                      \
-                    mid_monitors<T, V>(m, 3, i + 1, j, k, step_row + 1, sx_);                                      \
-                    mid_monitors<T, V>(m, 4, i + 1, j, k, step_row + 1, sy_);                                      \
-                    mid_monitors<T, V>(m, 5, i + 1, j, k, step_row + 1, sz_);                                      \
-                }                                                                                                  \
-            }                                                                                                      \
-            st8<T, V>(out.hx + ost1, sx_); st8<T, V>(out.hy + ost1, sy_);                                          \
-            st8<T, V>(out.hz + ost1, sz_);                                                                         \
+            st8<T, V>(out.hx + ost1, h2bx); st8<T, V>(out.hy + ost1, h2by);                                        \
+            st8<T, V>(out.hz + ost1, h2bz);                                                                        \
         }                                                                                                          \
         if (STEADY || i >= i0) {                                                                                   \
             P e2x, e2y, e2z;                                                                                       \
             stage_e<T, V, MASKED>(c, g, fo, g.x0 + i, jy1, k, e1ax, e1ay, e1az, h2ax, h2ay, h2az, h2z_j, h2x_j, h2y_n,     \
                                   h2x_n, h2by, h2bz, e2x, e2y, e2z);                                               \
-            if (owner) {                                                                                           \
-                if (m.plane_flags) {                                                                               \
-                    const unsigned char fl = m.plane_flags[i];                                                     \
-                    if (fl & 1) {                                                                                  \
-                        mid_sources<T, V>(m, 0, i, j, k, step_row + 1, e2x);                                       \
-                        mid_sources<T, V>(m, 1, i, j, k, step_row + 1, e2y);                                       \
-                        mid_sources<T, V>(m, 2, i, j, k, step_row + 1, e2z);                                       \
-                    }                                                                                              \
-                    if (fl & 2) {                                                                                  \
-                        mid_monitors<T, V>(m, 0, i, j, k, step_row + 1, e2x);                                      \
-                        mid_monitors<T, V>(m, 1, i, j, k, step_row + 1, e2y);                                      \
-                        mid_monitors<T, V>(m, 2, i, j, k, step_row + 1, e2z);                                      \
-                    }                                                                                              \
-                }                                                                                                  \
-                st8<T, V>(out.ex + ost, e2x); st8<T, V>(out.ey + ost, e2y); st8<T, V>(out.ez + ost, e2z);          \
-            }                                                                                                      \
+            if (owner) { st8<T, V>(out.ex + ost, e2x); st8<T, V>(out.ey + ost, e2y); st8<T, V>(out.ez + ost, e2z); } \
         }
 
         // ---- A: H1[i+3], B: E1[i+2] (+ intermediate-step E sources / monitors), C: H2[i+1], D: E2[i] -------------------
