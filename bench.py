@@ -276,6 +276,7 @@ def main():
     ap.add_argument("--two-pass", action="store_true", help="force the un-fused H/E kernels")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ops", action="store_true", help="bare field update: no source, no monitor (tuning only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -300,6 +301,8 @@ def main():
     flags = _lib.FLAG_TWO_PASS if args.two_pass else 0
     eng, dt, spacing, x0, nxl = make_engine(dims, args.dtype, device=local, flags=flags)
     src, mon = workload_ops(dims, dt, spacing)
+    if args.no_ops:
+        src, mon = [], []
     for op in src:
         eng.add_source_op(op)
     mon_ids = [eng.add_monitor_op(op) for op in mon]

@@ -26,6 +26,8 @@ struct FusedTiling {
     int lx;                 // planes per segment
     int nseg, ntj, ntk;     // items = nseg * ntj * ntk
     int own_lanes;          // lanes per row that own (store) cells; lanes >= own_lanes are rim providers
+    int seg_map[32];        // two-step sweep: the x-segments this launch covers (op-free and op-carrying
+                            // segments run different instantiations); ignored by the one-step sweep
     // x-slabs: items that read the ghost planes (their segment ends at plane nx) first wait until the right
     // neighbour has pushed them:  *halo_flag >= halo_need  (system-scope acquire; null = no wait)
     const int* halo_flag;

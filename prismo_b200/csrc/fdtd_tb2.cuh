@@ -168,7 +168,7 @@ constexpr int kTb2OwnLanes = 28;       // owner lanes per row: 28 of 32
 
 template <typename T, int R> constexpr size_t tb2_smem_bytes() { return 2 * (size_t)R * 8 * 32 * 8; }
 
-template <typename T, int R>
+template <typename T, int R, bool OPS>
 __global__ void __launch_bounds__(32 * R, 1)
 k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, MidOps m, int planes_alloc, Fold fo)
 {
@@ -181,7 +181,8 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
 
     const int lane = threadIdx.x, row = threadIdx.y;
     const int ntiles = t.ntj * t.ntk;
-    const int seg = blockIdx.x / ntiles, tile = blockIdx.x - seg * ntiles;
+    const int slot = blockIdx.x / ntiles, tile = blockIdx.x - slot * ntiles;
+    const int seg = t.seg_map[slot];
     const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
     const int j = tj * (R - 4) + row;
     const int k = (tk * t.own_lanes + lane) * V;
@@ -228,7 +229,7 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
         const P ph0x = ld8<T, V>(phx + pp, ph_ok), ph0y = ld8<T, V>(phy + pp, ph_ok), ph0z = ld8<T, V>(phz + pp, ph_ok);
 
         // ---- intermediate-step H sources / monitors on H1[i+1] (all of its pre-source uses are done) --------------
-        if (m.plane_flags && i + 1 >= i0 && i + 1 < m.n_planes) {
+        if (OPS && m.plane_flags && i + 1 >= i0 && i + 1 < m.n_planes) {
             const unsigned char fl = m.plane_flags[i + 1];
             if (fl & 1) {
                 mid_sources<T, V>(m, 3, i + 1, j, k, step_row, h1ax);
@@ -268,7 +269,7 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
                               e0x_n, ne0y, ne0z, h1cx, h1cy, h1cz);                                                  \
         stage_e<T, V, MASKED>(c, g, fo, g.x0 + i + 2, jy1, k, e0ax, e0ay, e0az, h1bx, h1by, h1bz, h1z_j, h1x_j, h1y_n,        \
                               h1x_n, h1cy, h1cz, e1cx, e1cy, e1cz);                                                  \
-        if (m.plane_flags && (STEADY || (i + 2 >= i0 && i + 2 < m.n_planes))) {                                    \
+        if (OPS && m.plane_flags && (STEADY || (i + 2 >= i0 && i + 2 < m.n_planes))) {                             \
             const unsigned char fl = m.plane_flags[i + 2];                                                         \
             if (fl & 1) {                                                                                          \
                 mid_sources<T, V>(m, 0, i + 2, j, k, step_row, e1cx);                                              \
