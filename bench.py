@@ -276,6 +276,7 @@ def main():
     ap.add_argument("--two-pass", action="store_true", help="force the un-fused H/E kernels")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fast-f64", action="store_true", help="fp64 with folded FMA arithmetic (within 1e-10, not bit-exact)")
     ap.add_argument("--no-ops", action="store_true", help="bare field update: no source, no monitor (tuning only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -298,7 +299,7 @@ def main():
 
     name, dims = parse_workload(args.workload)
     cells = dims[0] * dims[1] * dims[2]
-    flags = _lib.FLAG_TWO_PASS if args.two_pass else 0
+    flags = (_lib.FLAG_TWO_PASS if args.two_pass else 0) | (_lib.FLAG_FAST_F64 if args.fast_f64 else 0)
     eng, dt, spacing, x0, nxl = make_engine(dims, args.dtype, device=local, flags=flags)
     src, mon = workload_ops(dims, dt, spacing)
     if args.no_ops:

@@ -15,7 +15,7 @@ ABI_VERSION = 1
 F32, F64 = 0, 1
 COMPONENTS = ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")
 COMP_ID = {c: i for i, c in enumerate(COMPONENTS)}
-FLAG_NO_GRAPH, FLAG_TWO_PASS, FLAG_YEE = 1, 2, 4
+FLAG_NO_GRAPH, FLAG_TWO_PASS, FLAG_YEE, FLAG_FAST_F64 = 1, 2, 4, 8
 
 _ERR_TYPES = {-1: ValueError, -2: RuntimeError, -3: MemoryError, -4: RuntimeError}
 

@@ -145,8 +145,13 @@ static Fold fold_of(const fdtd_engine* e)
 {
     Fold fo;
     const Geom& g = e->g;
-    fo.hx_ = (float)(e->uni[3] / g.dx); fo.hy_ = (float)(e->uni[3] / g.dy); fo.hz_ = (float)(e->uni[3] / g.dz);
-    fo.ex_ = (float)(e->uni[1] / g.dx); fo.ey_ = (float)(e->uni[1] / g.dy); fo.ez_ = (float)(e->uni[1] / g.dz);
+    const double d[3] = {g.dx, g.dy, g.dz};
+    for (int a = 0; a < 3; ++a) {
+        fo.d[a] = e->uni[3] / d[a];          // db / d
+        fo.d[3 + a] = e->uni[1] / d[a];      // cb / d
+    }
+    for (int a = 0; a < 6; ++a) fo.f[a] = (float)fo.d[a];
+    fo.fast64 = (e->cfg.flags & FDTD_FLAG_FAST_F64) ? 1 : 0;
     return fo;
 }
 static void** cur_fields(fdtd_engine* e) { return e->cur ? e->fldB : e->fld; }
@@ -979,6 +984,8 @@ template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaSt
         long long want = (148ll * 24 + tiles - 1) / tiles;
         lx = (int)std::max<long long>(64, (g.nx + want - 1) / std::max<long long>(want, 1));
         if (any_ops) lx = std::min(lx, 128);
+        // small grids: keep >= ~2 CTAs per SM's worth of items even at the price of more prologue planes
+        while (lx > 12 && tiles * ((g.nx + lx - 1) / lx) < 148 * 2) lx = (lx + 1) / 2;
     }
     lx = std::max(lx, (g.nx + 31) / 32);                 // at most 32 segments (seg_map)
     t.lx = std::min(lx, g.nx);

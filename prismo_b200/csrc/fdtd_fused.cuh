@@ -76,22 +76,36 @@ template <typename T, int TJ> constexpr size_t fused_smem_bytes()
     return 2 * 2 * (size_t)(TJ + 1) * 2 * 32 * sizeof(typename VecOf<T>::type);
 }
 
-// fp32 only: coefficient * 1/d products folded on the host, so an update is 2 FADD + 1 FMUL + 2 FFMA instead of 7 ops
-// (fp64 keeps the reference's exact operation sequence: separate rounding of every product, true divisions)
-struct Fold { float hx_, hy_, hz_, ex_, ey_, ez_; };     // db/dx, db/dy, db/dz, cb/dx, cb/dy, cb/dz
+// Folded arithmetic: coefficient * 1/d products computed once on the host, so an update is 2 ADD + 1 MUL + 2 FMA
+// instead of 7 separately rounded operations with two divisions.  fp32 always uses it.  fp64 uses it only in the
+// opt-in FAST mode (FDTD_FLAG_FAST_F64: results within ~1e-15 relative per step of the exact mode, far inside the
+// 1e-10 north-star tolerance); the default fp64 mode keeps the reference's exact operation sequence and is
+// bit-identical to NumPy.
+struct Fold {
+    float f[6];             // db/dx, db/dy, db/dz, cb/dx, cb/dy, cb/dz
+    double d[6];
+    int fast64;
+};
+enum { FHX = 0, FHY = 1, FHZ = 2, FEX = 3, FEY = 4, FEZ = 5 };
 
 template <typename T> __device__ __forceinline__ T upd_h2(const Coefs<T>& c, const Geom& g, const Fold& f, T h,
-                                                          T a1, T a0, double da_, float ra, float fa,
-                                                          T b1, T b0, double db_, float rb, float fb)
+                                                          T a1, T a0, double da_, float ra, int ia,
+                                                          T b1, T b0, double db_, float rb, int ib)
 {
-    if (sizeof(T) == 4) return fmaf(fb, (float)(b1 - b0), fmaf(-fa, (float)(a1 - a0), (float)c.uda * (float)h));
+    if (sizeof(T) == 4)
+        return fmaf(f.f[ib], (float)(b1 - b0), fmaf(-f.f[ia], (float)(a1 - a0), (float)c.uda * (float)h));
+    if (f.fast64)
+        return fma(f.d[ib], (double)(b1 - b0), fma(-f.d[ia], (double)(a1 - a0), (double)c.uda * (double)h));
     return upd_h<T>(c.uda, h, c.udb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
 }
 template <typename T> __device__ __forceinline__ T upd_e2(const Coefs<T>& c, const Geom& g, const Fold& f, T e,
-                                                          T a1, T a0, double da_, float ra, float fa,
-                                                          T b1, T b0, double db_, float rb, float fb)
+                                                          T a1, T a0, double da_, float ra, int ia,
+                                                          T b1, T b0, double db_, float rb, int ib)
 {
-    if (sizeof(T) == 4) return fmaf(-fb, (float)(b1 - b0), fmaf(fa, (float)(a1 - a0), (float)c.uca * (float)e));
+    if (sizeof(T) == 4)
+        return fmaf(-f.f[ib], (float)(b1 - b0), fmaf(f.f[ia], (float)(a1 - a0), (float)c.uca * (float)e));
+    if (f.fast64)
+        return fma(-f.d[ib], (double)(b1 - b0), fma(f.d[ia], (double)(a1 - a0), (double)c.uca * (double)e));
     return upd_e<T>(c.uca, e, c.ucb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
 }
 
@@ -223,11 +237,11 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
         for (int e = 0; e < V; ++e) {
             const T ey_k = (e + 1 < V) ? e1y.v[(e + 1) % V] : ey1_n;
             const T ex_k = (e + 1 < V) ? e1x.v[(e + 1) % V] : ex1_n;
-            T n = upd_h2<T>(c, g, fo, h1x.v[e], ez_j.v[e], e1z.v[e], g.dy, g.rdy, fo.hy_, ey_k, e1y.v[e], g.dz, g.rdz, fo.hz_);
+            T n = upd_h2<T>(c, g, fo, h1x.v[e], ez_j.v[e], e1z.v[e], g.dy, g.rdy, FHY, ey_k, e1y.v[e], g.dz, g.rdz, FHZ);
             if (ix1 && jy2 && kz2[e]) hnx.v[e] = n;
-            n = upd_h2<T>(c, g, fo, h1y.v[e], ex_k, e1x.v[e], g.dz, g.rdz, fo.hz_, e2z.v[e], e1z.v[e], g.dx, g.rdx, fo.hx_);
+            n = upd_h2<T>(c, g, fo, h1y.v[e], ex_k, e1x.v[e], g.dz, g.rdz, FHZ, e2z.v[e], e1z.v[e], g.dx, g.rdx, FHX);
             if (ix2 && jy1 && kz2[e]) hny.v[e] = n;
-            n = upd_h2<T>(c, g, fo, h1z.v[e], e2y.v[e], e1y.v[e], g.dx, g.rdx, fo.hx_, ex_j.v[e], e1x.v[e], g.dy, g.rdy, fo.hy_);
+            n = upd_h2<T>(c, g, fo, h1z.v[e], e2y.v[e], e1y.v[e], g.dx, g.rdx, FHX, ex_j.v[e], e1x.v[e], g.dy, g.rdy, FHY);
             if (ix2 && jy2 && kz1[e]) hnz.v[e] = n;
         }
         if (owner && i + 1 < i1) {
@@ -242,11 +256,11 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
             for (int e = 0; e < V; ++e) {
                 const T hy_k = (e + 1 < V) ? hpy.v[(e + 1) % V] : hpy_n;
                 const T hx_k = (e + 1 < V) ? hpx.v[(e + 1) % V] : hpx_n;
-                T n = upd_e2<T>(c, g, fo, e0x.v[e], hz_j.v[e], hpz.v[e], g.dy, g.rdy, fo.ey_, hy_k, hpy.v[e], g.dz, g.rdz, fo.ez_);
+                T n = upd_e2<T>(c, g, fo, e0x.v[e], hz_j.v[e], hpz.v[e], g.dy, g.rdy, FEY, hy_k, hpy.v[e], g.dz, g.rdz, FEZ);
                 if (ex0 && jy1 && kz1[e]) nx_.v[e] = n;
-                n = upd_e2<T>(c, g, fo, e0y.v[e], hx_k, hpx.v[e], g.dz, g.rdz, fo.ez_, hnz.v[e], hpz.v[e], g.dx, g.rdx, fo.ex_);
+                n = upd_e2<T>(c, g, fo, e0y.v[e], hx_k, hpx.v[e], g.dz, g.rdz, FEZ, hnz.v[e], hpz.v[e], g.dx, g.rdx, FEX);
                 if (ex1 && kz1[e]) ny_.v[e] = n;
-                n = upd_e2<T>(c, g, fo, e0z.v[e], hny.v[e], hpy.v[e], g.dx, g.rdx, fo.ex_, hx_j.v[e], hpx.v[e], g.dy, g.rdy, fo.ey_);
+                n = upd_e2<T>(c, g, fo, e0z.v[e], hny.v[e], hpy.v[e], g.dx, g.rdx, FEX, hx_j.v[e], hpx.v[e], g.dy, g.rdy, FEY);
                 if (ex1 && jy1 && kz0[e]) nz_.v[e] = n;
             }
             if (owner) {

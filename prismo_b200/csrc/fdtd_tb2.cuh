@@ -129,11 +129,11 @@ __device__ __forceinline__ void stage_h(const Coefs<T>& c, const Geom& g, const 
         const bool kz1 = (k + e) < g.nz - 1, kz2 = (k + e) < g.nz - 2;
         const T ey_k = (e + 1 < V) ? ey.v[(e + 1) % V] : ey_n;
         const T ex_k = (e + 1 < V) ? ex.v[(e + 1) % V] : ex_n;
-        T n = upd_h2<T>(c, g, fo, hx.v[e], ez_j.v[e], ez.v[e], g.dy, g.rdy, fo.hy_, ey_k, ey.v[e], g.dz, g.rdz, fo.hz_);
+        T n = upd_h2<T>(c, g, fo, hx.v[e], ez_j.v[e], ez.v[e], g.dy, g.rdy, FHY, ey_k, ey.v[e], g.dz, g.rdz, FHZ);
         if (!MASKED || (ix1 && jy2 && kz2)) ox.v[e] = n;
-        n = upd_h2<T>(c, g, fo, hy.v[e], ex_k, ex.v[e], g.dz, g.rdz, fo.hz_, ez_p.v[e], ez.v[e], g.dx, g.rdx, fo.hx_);
+        n = upd_h2<T>(c, g, fo, hy.v[e], ex_k, ex.v[e], g.dz, g.rdz, FHZ, ez_p.v[e], ez.v[e], g.dx, g.rdx, FHX);
         if (!MASKED || (ix2 && jy1 && kz2)) oy.v[e] = n;
-        n = upd_h2<T>(c, g, fo, hz.v[e], ey_p.v[e], ey.v[e], g.dx, g.rdx, fo.hx_, ex_j.v[e], ex.v[e], g.dy, g.rdy, fo.hy_);
+        n = upd_h2<T>(c, g, fo, hz.v[e], ey_p.v[e], ey.v[e], g.dx, g.rdx, FHX, ex_j.v[e], ex.v[e], g.dy, g.rdy, FHY);
         if (!MASKED || (ix2 && jy2 && kz1)) oz.v[e] = n;
     }
 }
@@ -154,11 +154,11 @@ __device__ __forceinline__ void stage_e(const Coefs<T>& c, const Geom& g, const 
         const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;
         const T hy_k = (e + 1 < V) ? hy.v[(e + 1) % V] : hy_n;
         const T hx_k = (e + 1 < V) ? hx.v[(e + 1) % V] : hx_n;
-        T n = upd_e2<T>(c, g, fo, ex.v[e], hz_j.v[e], hz.v[e], g.dy, g.rdy, fo.ey_, hy_k, hy.v[e], g.dz, g.rdz, fo.ez_);
+        T n = upd_e2<T>(c, g, fo, ex.v[e], hz_j.v[e], hz.v[e], g.dy, g.rdy, FEY, hy_k, hy.v[e], g.dz, g.rdz, FEZ);
         if (!MASKED || (ex0 && jy1 && kz1)) ox.v[e] = n;
-        n = upd_e2<T>(c, g, fo, ey.v[e], hx_k, hx.v[e], g.dz, g.rdz, fo.ez_, hz_p.v[e], hz.v[e], g.dx, g.rdx, fo.ex_);
+        n = upd_e2<T>(c, g, fo, ey.v[e], hx_k, hx.v[e], g.dz, g.rdz, FEZ, hz_p.v[e], hz.v[e], g.dx, g.rdx, FEX);
         if (!MASKED || (ex1 && kz1)) oy.v[e] = n;
-        n = upd_e2<T>(c, g, fo, ez.v[e], hy_p.v[e], hy.v[e], g.dx, g.rdx, fo.ex_, hx_j.v[e], hx.v[e], g.dy, g.rdy, fo.ey_);
+        n = upd_e2<T>(c, g, fo, ez.v[e], hy_p.v[e], hy.v[e], g.dx, g.rdx, FEX, hx_j.v[e], hx.v[e], g.dy, g.rdy, FEY);
         if (!MASKED || (ex1 && jy1 && kz0)) oz.v[e] = n;
     }
 }

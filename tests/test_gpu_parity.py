@@ -329,3 +329,14 @@ def test_tb2_graph_replay_with_sources_and_monitors(monkeypatch):
     ro, rm = S.results_oracle(o), S.results_mirror(sim)
     for k in ro:
         assert np.array_equal(ro[k], rm[k], equal_nan=True), k
+
+
+def test_fast_fp64_mode_within_north_star_tolerance():
+    """Opt-in FDTD_FLAG_FAST_F64: folded FMA arithmetic in fp64 (no true divisions).  Not bit-exact, but far inside
+    the 1e-10 relative-L2 north-star tolerance after 40 steps; the default fp64 mode stays bit-identical."""
+    from prismo_b200 import _lib
+
+    a, F, _ = _engine_vs_oracle((48, 40, 66), 3, 0.5, 40, "float64", False, flags=_lib.FLAG_FAST_F64)
+    worst = max(S.rel_l2(a[c], F[c]) for c in F)
+    assert 0 < worst <= FP64_TOL, worst
+    assert worst < 1e-12
