@@ -169,7 +169,7 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
     const int k = (tk * t.own_lanes + lane) * V;
     const int i0 = t.i_begin + seg * t.lx;
     const int i1 = min(i0 + t.lx, t.i_end);
-    if (t.halo_flag && i1 == g.nx) {
+    if (t.halo_flag && i1 + 1 >= g.nx) {          // this segment reads E up to plane i1+1: ghost planes start at nx
         if (threadIdx.x == 0 && threadIdx.y == 0) wait_flag_ge(t.halo_flag, t.halo_need, t.error_word, t.timeout_ns);
         __syncthreads();
     }

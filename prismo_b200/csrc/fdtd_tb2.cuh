@@ -188,7 +188,7 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
     const int k = (tk * t.own_lanes + lane) * V;
     const int i0 = t.i_begin + seg * t.lx;
     const int i1 = min(i0 + t.lx, t.i_end);
-    if (t.halo_flag && i1 == g.nx) {
+    if (t.halo_flag && i1 + 3 >= g.nx) {          // this segment reads E0 up to plane i1+3: ghost planes start at nx
         if (threadIdx.x == 0 && threadIdx.y == 0) wait_flag_ge(t.halo_flag, t.halo_need, t.error_word, t.timeout_ns);
         __syncthreads();
     }
