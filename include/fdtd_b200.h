@@ -145,6 +145,7 @@ int  fdtd_run(fdtd_engine* e, int32_t n_steps);   /* H pass, E pass, sources, mo
 int  fdtd_update_h(fdtd_engine* e);               /* MaxwellUpdater.update_magnetic_fields :135-149 */
 int  fdtd_update_e(fdtd_engine* e);               /* MaxwellUpdater.update_electric_fields :151-165 */
 int  fdtd_sync(fdtd_engine* e);
+int  fdtd_set_option(fdtd_engine* e, const char* key, int32_t value);   /* "tb2" 0/1, "fused_lx" planes (0 = auto) */
 /* measurement: CUDA events on the engine's own stream (torch.cuda.Event cannot see it).
  * fdtd_run_profiled runs n real steps without a graph and returns summed kernel times in ms:
  * out_ms[0] H pass (or the fused sweep), [1] E pass, [2] sources+monitors, [3] first-to-last event. */

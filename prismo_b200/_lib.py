@@ -79,6 +79,7 @@ _PROTOS = {
     "fdtd_update_h": (C.c_int, [_P]),
     "fdtd_update_e": (C.c_int, [_P]),
     "fdtd_sync": (C.c_int, [_P]),
+    "fdtd_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "fdtd_timer_start": (C.c_int, [_P]),
     "fdtd_timer_stop": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "fdtd_run_profiled": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double)]),

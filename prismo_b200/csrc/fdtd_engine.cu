@@ -1220,6 +1220,17 @@ extern "C" int fdtd_timer_stop(fdtd_engine* e, double* ms)
     return 0;
 }
 
+// tuning knobs, by name: "tb2" (0/1 two-step sweep), "fused_lx" (planes per x-segment, 0 = auto)
+extern "C" int fdtd_set_option(fdtd_engine* e, const char* key, int32_t value)
+{
+    if (!e || !key) return fail(FDTD_EINVAL, "fdtd_set_option: null argument");
+    if (!strcmp(key, "tb2")) e->tb2 = value ? 1 : 0;
+    else if (!strcmp(key, "fused_lx")) e->fused_lx = value;
+    else return fail(FDTD_EINVAL, "unknown option '%s'", key);
+    drop_graph(e);
+    return 0;
+}
+
 extern "C" int fdtd_sync(fdtd_engine* e)
 {
     if (!e) return fail(FDTD_EINVAL, "null engine");

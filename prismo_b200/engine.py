@@ -266,6 +266,9 @@ class Engine:
     def sync(self):
         _lib.check(self._lib.fdtd_sync(self._h))
 
+    def set_option(self, key: str, value: int) -> None:
+        _lib.check(self._lib.fdtd_set_option(self._h, key.encode(), int(value)))
+
     def timer_start(self):
         _lib.check(self._lib.fdtd_timer_start(self._h))
 

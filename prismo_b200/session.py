@@ -25,8 +25,13 @@ _state = {"dtype": os.environ.get("PRISMO_B200_DTYPE", "float64"), "device": int
           "flags": 0}
 
 
-def configure(dtype: Optional[str] = None, device: Optional[int] = None, flags: Optional[int] = None) -> dict:
-    """Engine-wide options: storage/arithmetic dtype ('float64' = parity default, 'float32' = fast), device."""
+def configure(dtype: Optional[str] = None, device: Optional[int] = None, flags: Optional[int] = None,
+              distributed: Optional[bool] = None) -> dict:
+    """Engine-wide options: storage/arithmetic dtype ('float64' = parity default, 'float32' = fast), device,
+    distributed (default True: under an initialised torch.distributed group with world_size > 1, 3-D simulations
+    are slab-decomposed along x, one process per GPU)."""
+    if distributed is not None:
+        _state["distributed"] = bool(distributed)
     if dtype is not None:
         dt = np.dtype({"fp32": "float32", "fp64": "float64", "f32": "float32", "f64": "float64"}.get(dtype, dtype))
         if dt not in (np.float32, np.float64):
@@ -37,6 +42,15 @@ def configure(dtype: Optional[str] = None, device: Optional[int] = None, flags: 
     if flags is not None:
         _state["flags"] = int(flags)
     return dict(_state)
+
+
+def _device_count() -> int:
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 1
 
 
 def _fingerprint(arrs):
@@ -60,9 +74,18 @@ class Session:
                 raise NotImplementedError("physics mode (stable Yee + CPML) is implemented for 3-D grids")
             fl |= _lib.FLAG_YEE
             params = physics if isinstance(physics, cpml.PMLParams) else cpml.PMLParams(thickness=g.pml_layers)
-        self.engine = Engine(3 if g.is_3d else 2, g.dimensions, g.spacing, self.dt,
-                             dtype=dtype or _state["dtype"], device=_state["device"] if device is None else device,
-                             flags=fl)
+        from .distributed import SlabExecutor, active_world
+
+        rank, world = active_world()
+        self.distributed = bool(_state.get("distributed", True)) and world > 1 and g.is_3d and not physics
+        if self.distributed:
+            # one process per GPU under torchrun: this rank owns an x-slab (see distributed.py)
+            dev = device if device is not None else rank % max(_device_count(), 1)
+            self.engine = SlabExecutor(g, self.dt, dtype or _state["dtype"], dev, flags=fl, engine_cls=Engine)
+        else:
+            self.engine = Engine(3 if g.is_3d else 2, g.dimensions, g.spacing, self.dt,
+                                 dtype=dtype or _state["dtype"], device=_state["device"] if device is None else device,
+                                 flags=fl)
         if physics and params.thickness > 0:
             self.engine.set_cpml(params.thickness, cpml.coefficient_table(g.dimensions, g.spacing, self.dt, params))
         self._coef_sig = None
@@ -83,7 +106,7 @@ class Session:
         sig = _fingerprint(arrs)
         if sig == self._coef_sig:
             return
-        if all(a.min() == a.max() for a in arrs):
+        if all(a.min() == a.max() for a in arrs):    # piecewise-constant everywhere -> the fused sweeps apply
             self.engine.set_uniform_coeffs(*[float(a.flat[0]) for a in arrs])
         else:
             self.engine.set_coeffs(*arrs)

@@ -176,6 +176,10 @@ class FakeSlabEngine(FakeEngine):
         self.F = {c: self.G[c][: self.field_shape(c)[0]] for c in COMPONENTS}     # local views
         self.pending = []
 
+    def set_uniform_coeffs(self, ca, cb, da, db):
+        ed = (self.ext, self.dims[1], self.dims[2])
+        self.coeffs = [np.full(ed, float(v)) for v in (ca, cb, da, db)]
+
     @staticmethod
     def _shape(d, comp):
         n = list(d)
@@ -210,10 +214,19 @@ class FakeSlabEngine(FakeEngine):
         s = self.cursor
         for g in sorted({o.group for o in self.src}):
             for o in (o for o in self.src if o.group == g):
-                self.F[o.component][self._sl(o)] += self.amp[s, o.table]
+                if getattr(o, "ghost", False):
+                    continue
+                a = self.amp[s, o.table]
+                if o.profile is not None:
+                    a = a * np.asarray(o.profile)
+                    if o.divisor != 1.0:
+                        a = a / o.divisor
+                self.F[o.component][self._sl(o)] += a
         for m in self.mon:
             o = m["op"]
             d = self.F[o.component][self._sl(o)].copy()
+            if o.record:
+                m["rec"].append(d)
             for k in range(o.n_freq):
                 ph = self.ph[s, o.phasor_col + k]
                 m["dft"][k] += (d * ph.real) * self.dt + 1j * ((d * ph.imag) * self.dt)

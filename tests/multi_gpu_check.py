@@ -20,6 +20,8 @@ def main():
     from prismo_b200.multigpu import PeerSlabRunner, SlabStepper, slab_range
 
     same = "--same-device" in sys.argv
+    if "--sim" in sys.argv:
+        return sim_check(same)
     mode = "nccl" if "--nccl" in sys.argv else "p2p"
     dtype = "float32" if "--f32" in sys.argv else "float64"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -101,6 +103,46 @@ def main():
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
+
+
+def sim_check(same):
+    """Whole Simulations (every 3-D vacuum scenario: sources, monitors) through prismo_b200.Simulation under an
+    initialised process group: Session slab-decomposes them; every rank must reproduce the reference goldens."""
+    import torch
+    import torch.distributed as dist
+
+    import prismo_b200 as pb
+    from tests import scenarios as S
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = 0 if same else int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo" if same else "nccl")
+    pb.configure(device=local)
+    ok = True
+    names = ["upd3d_vac", "src3d_point", "src3d_plane", "src3d_tfsf", "src3d_mode", "mon3d_field"]
+    for name in names:
+        spec = S.SCENARIOS[name]
+        gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        sim = S.build_mirror(spec, pb, dtype="float64")
+        sim._device = local
+        sim.run_steps(3)
+        sim.run_steps(spec["steps"] - 3)
+        assert sim.solver.updater.session().distributed
+        res = S.results_mirror(sim)
+        for k in gold.files:
+            tol = 1e-14 if name == "src3d_mode" else 0.0
+            err = S.rel_l2(res[k], gold[k])
+            if not (err <= tol):
+                ok = False
+                print(f"MISMATCH rank {rank} {name}:{k} rel-L2 {err:.3e}", flush=True)
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if rank == 0:
+        print(f"MULTI_GPU_SIM_CHECK {'OK' if all(flags) else 'FAILED'} world={world} scenarios={len(names)}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if all(flags) else 1)
 
 
 if __name__ == "__main__":

@@ -184,7 +184,7 @@ def test_two_slabs_on_one_gpu_match_single_engine(dtype):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["p2p"])
+@pytest.mark.parametrize("mode", ["p2p", "sim"])
 def test_peer_to_peer_slabs_two_processes_one_gpu(mode):
     """The production halo protocol (CUDA IPC mappings, DMA push, release/acquire flags, in-kernel wait) with two
     processes time-slicing one GPU: bitwise equal to a single engine.  Halo waits time out after 5 s."""
@@ -194,6 +194,52 @@ def test_peer_to_peer_slabs_two_processes_one_gpu(mode):
     env = dict(os.environ, FDTD_B200_HALO_TIMEOUT_MS="5000")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(os.path.dirname(__file__), "multi_gpu_check.py"),
-           "--same-device"]
-    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
-    assert "MULTI_GPU_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+           "--same-device"] + (["--sim"] if mode == "sim" else [])
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    want = "MULTI_GPU_SIM_CHECK OK" if mode == "sim" else "MULTI_GPU_CHECK OK"
+    assert want in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---- whole Simulations (sources + monitors) slab-decomposed through Session / SlabExecutor -----------------------
+DIST_SCENARIOS = ["upd3d_vac", "src3d_point", "src3d_plane", "src3d_tfsf", "src3d_mode", "mon3d_field"]
+
+
+def _sim_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    import prismo_b200 as pb
+    import prismo_b200.session as session
+    from tests._fake_engine import FakeSlabEngine
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    session.Engine = FakeSlabEngine
+    for name in DIST_SCENARIOS:
+        spec = S.SCENARIOS[name]
+        sim = S.build_mirror(spec, pb)
+        sim.run_steps(3)
+        sim.run_steps(spec["steps"] - 3)
+        assert sim.solver.updater.session().distributed
+        np.savez(os.path.join(out_dir, f"{name}_rank{rank}.npz"), **S.results_mirror(sim))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_simulation_run_is_slab_decomposed_under_torch_distributed(tmp_path):
+    """Every rank builds the same Simulation; Session sees an initialised process group and runs its x-slab only
+    (ops clipped, monitor pieces re-assembled).  Every rank must end with the single-process reference results."""
+    import torch.multiprocessing as mp
+
+    world = 2
+    mp.spawn(_sim_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    gold_dir = os.path.join(os.path.dirname(__file__), "golden")
+    for name in DIST_SCENARIOS:
+        gold = np.load(os.path.join(gold_dir, name + ".npz"))
+        for r in range(world):
+            got = np.load(tmp_path / f"{name}_rank{r}.npz")
+            assert sorted(got.files) == sorted(gold.files)
+            for k in gold.files:
+                if name == "src3d_mode":
+                    assert S.rel_l2(got[k], gold[k]) <= 1e-14, (name, r, k)
+                else:
+                    assert np.array_equal(got[k], gold[k], equal_nan=True), (name, r, k, S.rel_l2(got[k], gold[k]))
