@@ -48,6 +48,7 @@ class SlabExecutor:
         self._runner = None
         self._mon = []           # per global monitor op: (global op, local id or None, local x-range in the box)
         self._tb2_ok = True
+        self._agreed = False
 
     # ---- lifetime / passthrough ------------------------------------------------------------------------------
     def close(self):
@@ -98,6 +99,7 @@ class SlabExecutor:
         self.eng.clear_ops()
         self._mon = []
         self._tb2_ok = True
+        self._agreed = False
 
     def _clip(self, comp, lo, hi):
         a, b = max(lo[0], self.x0), min(hi[0], self.x0 + self._planes(comp))
@@ -119,8 +121,6 @@ class SlabExecutor:
                     self.eng.add_source_op(SourceOp(op.component, (ga - self.x0,) + tuple(op.lo[1:]),
                                                     (gb - self.x0,) + tuple(op.hi[1:]), op.table, None, 1.0, op.group,
                                                     ghost=True))
-        if hasattr(self.eng, "set_option"):
-            self.eng.set_option("tb2", 1 if self._tb2_ok else 0)
 
     def add_monitor_op(self, op: MonitorOp) -> int:
         a, b = self._clip(op.component, op.lo, op.hi)
@@ -140,6 +140,14 @@ class SlabExecutor:
 
     # ---- stepping -------------------------------------------------------------------------------------------------------
     def run(self, n):
+        if not self._agreed:
+            # every rank must pair steps identically (the halo protocol counts exchanges): the two-step sweep is
+            # used only if NO rank has a reason to fall back to the one-step sweep
+            votes = [None] * self.world
+            self.dist.all_gather_object(votes, self._tb2_ok, group=self.group)
+            if hasattr(self.eng, "set_option"):
+                self.eng.set_option("tb2", 1 if all(votes) else 0)
+            self._agreed = True
         r = self._runner_()
         r.run(n)
         r.synchronize()
