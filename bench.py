@@ -328,7 +328,7 @@ def main():
     bpc = BYTES_PER_CELL[args.dtype]
     achieved = bpc * cells * args.steps / (kern_ms * 1e-3) / 1e9
     fused = not args.two_pass
-    tb2 = fused and os.environ.get("FDTD_B200_TB2", "1") != "0" and args.steps % 2 == 0
+    tb2 = fused and os.environ.get("FDTD_B200_TB2", "1") != "0" and args.steps >= 2
     kname = ("k_fused3d_tb2 (1 launch per TWO steps)" if tb2 else "k_fused3d (1 launch/step)") if fused \
         else "k_h3d + k_e3d (2 launches/step)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -337,6 +337,7 @@ def main():
                          "sweep keeps the intermediate step on chip, so its real DRAM traffic is ~27 B per cell-update "
                          "(ncu: profiles/) and frac can exceed 1") if tb2 else None,
                 "algorithmic_bytes_per_launch": (2 if tb2 else 1) * bpc * cells if fused else bpc * cells / 2,
+                "odd_last_step": "one-step sweep" if (tb2 and args.steps % 2) else None,
                 "kernel_ms_per_step": kern_ms / args.steps, "post_ms_per_step": prof["post_ms"] / args.steps}
 
     # ---- e2e: host buffers in, host buffers out ---------------------------------------------------------------

@@ -1145,8 +1145,9 @@ template <typename T> static int run_profiled(fdtd_engine* e, int n, double* out
     for (auto& x : ev) CU(cudaEventCreate(&x));
     if (e->cfg.ndim == 2) if (int rc = launch_count2d<T>(e, 0, s)) return rc;
     CU(cudaEventRecord(ev[0], s));
-    const bool tb2 = use_tb2(e) && n % 2 == 0;
-    for (int q = 0; tb2 && q < n; q += 2) {
+    const bool tb2 = use_tb2(e);
+    const int n_pairs = tb2 ? n / 2 * 2 : 0;              // an odd last step runs the one-step sweep
+    for (int q = 0; q < n_pairs; q += 2) {
         // one temporally blocked sweep = two steps: its time goes to slot 0, step B's sources/monitors to slot 2
         int rc = launch_tb2<T>(e, q, s);
         if (rc) return rc;
@@ -1155,7 +1156,7 @@ template <typename T> static int run_profiled(fdtd_engine* e, int n, double* out
         if ((rc = launch_post<T>(e, q + 1, 0, s))) return rc;
         for (int k = 3; k <= 6; ++k) CU(cudaEventRecord(ev[3 * q + k], s));
     }
-    for (int q = 0; !tb2 && q < n; ++q) {
+    for (int q = n_pairs; q < n; ++q) {
         int rc;
         if (e->cfg.ndim == 3) rc = step_fields3d<T>(e, 0, s); else rc = launch_pass2d<T>(e, 0, q, s);
         if (rc) return rc;
