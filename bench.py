@@ -183,6 +183,19 @@ def make_engine(dims, dtype, rank=0, world=1, device=0, flags=0):
     return eng, dt, spacing, x0, nxl
 
 
+def set_ridge_coefficients(eng, dims, dt):
+    """config 3 shape: Si ridge (eps 12.11) along x on an SiO2 (2.07) half space, air above; Ca=Da=1 (lossless)."""
+    nx, ny, nz = dims
+    eps = np.ones((ny, nz), dtype=np.float64)
+    eps[:, : nz // 2] = 2.07
+    eps[ny // 2 - ny // 16: ny // 2 + ny // 16, nz // 2: nz // 2 + nz // 12] = 12.11
+    eps0, mu0 = 8.854187817e-12, 4 * np.pi * 1e-7
+    cb = np.broadcast_to(dt / (eps0 * eps), (nx, ny, nz))
+    one = np.broadcast_to(np.ones((1, 1)), (nx, ny, nz))
+    eng.set_coeffs(np.ascontiguousarray(one), np.ascontiguousarray(cb), np.ascontiguousarray(one),
+                   np.ascontiguousarray(one * (dt / mu0)))
+
+
 def seed_fields(eng, scale=1e-3, seed=0):
     """Small white-noise fields so the arithmetic is not all-zero (the source keeps injecting anyway)."""
     rng = np.random.default_rng(seed)
@@ -277,6 +290,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fast-f64", action="store_true", help="fp64 with folded FMA arithmetic (within 1e-10, not bit-exact)")
+    ap.add_argument("--het", action="store_true", help="heterogeneous medium: Si ridge (eps 12.11) on SiO2 (2.07), "
+                                                       "cell-centred coefficient arrays (64 B/cell)")
     ap.add_argument("--no-ops", action="store_true", help="bare field update: no source, no monitor (tuning only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -301,6 +316,8 @@ def main():
     cells = dims[0] * dims[1] * dims[2]
     flags = (_lib.FLAG_TWO_PASS if args.two_pass else 0) | (_lib.FLAG_FAST_F64 if args.fast_f64 else 0)
     eng, dt, spacing, x0, nxl = make_engine(dims, args.dtype, device=local, flags=flags)
+    if args.het:
+        set_ridge_coefficients(eng, dims, dt)
     src, mon = workload_ops(dims, dt, spacing)
     if args.no_ops:
         src, mon = [], []
@@ -325,10 +342,10 @@ def main():
     # dominant kernel(s): fused sweep (one launch per step) or H + E pass
     kern_ms = prof["h_or_fused_ms"] + prof["e_ms"]
     peak, peak_src = peaks()
-    bpc = BYTES_PER_CELL[args.dtype]
+    bpc = BYTES_PER_CELL[args.dtype] + (16 if args.dtype == "float32" else 32) * int(args.het)   # + Ca,Cb,Da,Db reads
     achieved = bpc * cells * args.steps / (kern_ms * 1e-3) / 1e9
     fused = not args.two_pass
-    tb2 = fused and os.environ.get("FDTD_B200_TB2", "1") != "0" and args.steps >= 2
+    tb2 = fused and os.environ.get("FDTD_B200_TB2", "1") != "0" and args.steps >= 2 and not args.het
     kname = ("k_fused3d_tb2 (1 launch per TWO steps)" if tb2 else "k_fused3d (1 launch/step)") if fused \
         else "k_h3d + k_e3d (2 launches/step)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -9,6 +9,7 @@
 #include "fdtd_fused.cuh"
 #include "fdtd_yee.cuh"
 #include "fdtd_tb2.cuh"
+#include "fdtd_het.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -86,6 +87,7 @@ struct fdtd_engine {
     // graph
     cudaGraphExec_t gexec[2] = {nullptr, nullptr}; int graph_steps = 0; int graph_kernels[2] = {0, 0};
     int fused_lx = 0;               // planes per fused segment (0 = auto)
+    int het_fused = 1;              // heterogeneous media: fused one-step sweep (0: two-pass kernels)
     int tb2 = 1;                    // 1: temporally blocked sweep (two steps per pass) where applicable
     unsigned char* d_plane_flags = nullptr; std::vector<unsigned char> plane_flags_host;
     int fused_tj = 15;              // owner rows per CTA (15: one 16-warp CTA/SM; 7: two 8-warp CTAs/SM)
@@ -254,6 +256,7 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     if (const char* pol = getenv("FDTD_B200_FUSED_POL")) e->fused_pol = atoi(pol) & 3;
     if (const char* tj = getenv("FDTD_B200_FUSED_TJ")) e->fused_tj = atoi(tj);
     if (const char* tb = getenv("FDTD_B200_TB2")) e->tb2 = atoi(tb);
+    if (const char* hf = getenv("FDTD_B200_HET_FUSED")) e->het_fused = atoi(hf);
     *out = e;
     return 0;
 }
@@ -936,6 +939,49 @@ template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i
     return launch_fused_tj<T, kFusedTJ>(e, i_begin, i_end, s);
 }
 
+// heterogeneous media, one GPU: fused one-step sweep that also streams the four coefficient arrays
+static bool use_het_fused(const fdtd_engine* e)
+{
+    return e->cfg.ndim == 3 && e->het && !(e->cfg.flags & (FDTD_FLAG_TWO_PASS | FDTD_FLAG_YEE)) && e->g.nxg == e->g.nx &&
+           e->array_elems < (1ll << 32) && e->het_fused;
+}
+
+template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
+{
+    constexpr int R = kHetRows, V = Vec8<T>::V;
+    const Geom& g = e->g;
+    void** src = cur_fields(e);
+    void** dst = e->cur ? e->fld : e->fldB;
+    CFields<T> in;
+    in.ex = (const T*)src[0]; in.ey = (const T*)src[1]; in.ez = (const T*)src[2];
+    in.hx = (const T*)src[3]; in.hy = (const T*)src[4]; in.hz = (const T*)src[5];
+    Fields<T> out = fields_of<T>(dst);
+    FusedTiling t{};
+    t.i_begin = 0; t.i_end = g.nx;
+    t.own_lanes = kHetOwnLanes;
+    const int vec_per_row = g.pz / V;
+    t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
+    t.ntj = (g.ny + (R - 2) - 1) / (R - 2);
+    int lx = e->fused_lx;
+    if (lx <= 0) {
+        const long long tiles = (long long)t.ntj * t.ntk;
+        long long want = (148ll * 40 + tiles - 1) / tiles;
+        lx = (int)std::max<long long>(32, (g.nx + want - 1) / std::max<long long>(want, 1));
+        while (lx > 8 && tiles * ((g.nx + lx - 1) / lx) < 148 * 2) lx = (lx + 1) / 2;
+    }
+    t.lx = std::min(lx, g.nx);
+    t.nseg = (g.nx + t.lx - 1) / t.lx;
+    const size_t smem = het_smem_bytes<T, R>();
+    auto kern = k_fused3d_het<T, R>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 block(32, R, 1);
+    kern<<<(unsigned)t.nseg * t.ntj * t.ntk, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, (int)e->planes_alloc);
+    e->launches++;
+    CU(cudaGetLastError());
+    e->cur ^= 1;
+    return 0;
+}
+
 static bool tb2_ok(const fdtd_engine* e)
 {
     return e->tb2 && use_fused(e) && e->ade.empty() && e->array_elems < (1ll << 32);
@@ -1035,6 +1081,11 @@ template <typename T> static int step_fields3d(fdtd_engine* e, int half, cudaStr
         return 0;
     }
     if (e->cfg.flags & FDTD_FLAG_YEE) return launch_yee<T>(e, half, s);
+    if (use_het_fused(e)) {
+        if (half == 1) return 0;
+        if (int rc = ensure_set_b(e)) return rc;
+        return launch_het<T>(e, s);
+    }
     return launch_pass3d<T>(e, half, 0, e->g.nx, s);
 }
 
@@ -1056,7 +1107,7 @@ static bool has_post(const fdtd_engine* e) { return has_tables(e) || !e->ade.emp
 template <typename T> static int run_steps(fdtd_engine* e, int n)
 {
     cudaStream_t s = e->stream;
-    if (use_fused(e)) if (int rc = ensure_set_b(e)) return rc;
+    if (use_fused(e) || use_het_fused(e)) if (int rc = ensure_set_b(e)) return rc;
     if (e->cfg.ndim == 2) if (int rc = launch_count2d<T>(e, 0, s)) return rc;
     const bool use_graph = !(e->cfg.flags & FDTD_FLAG_NO_GRAPH) && n >= 32;
     int done = 0;
@@ -1226,6 +1277,7 @@ extern "C" int fdtd_set_option(fdtd_engine* e, const char* key, int32_t value)
 {
     if (!e || !key) return fail(FDTD_EINVAL, "fdtd_set_option: null argument");
     if (!strcmp(key, "tb2")) e->tb2 = value ? 1 : 0;
+    else if (!strcmp(key, "het_fused")) e->het_fused = value ? 1 : 0;
     else if (!strcmp(key, "fused_lx")) e->fused_lx = value;
     else return fail(FDTD_EINVAL, "unknown option '%s'", key);
     drop_graph(e);

@@ -1,0 +1,169 @@
+// fdtd_het.cuh — one-step fused sweep for HETEROGENEOUS media (cell-centred Ca, Cb, Da, Db arrays).
+//
+// Same idea as fdtd_fused.cuh (march ascending in x with a register window, k+1 from the next lane, j+1 from the
+// next warp-row through shared memory, ping-pong output) but the window also carries the four coefficient arrays,
+// so one step reads 6 + 4 arrays and writes 6: 64 B per cell-update in fp32 instead of the two-pass
+// kernels' 104 B.  The 2- / 4-point averaging that the reference recomputes into 12 full-grid temporaries every
+// step (core/solver.py:458-501) happens in registers, in the reference's summation order (fp64 stays bit-exact):
+//   Hx: mean2(D[i+1], D[i+2])           Hy: mean2(D[j], D[j+1])               Hz: mean2(D[k], D[k+1])      at plane i+1
+//   Ex: mean4(C, C[j+1], C[k+1], C[j+1,k+1])   Ey: mean4(C[i], C[i+1], C[i,k+1], C[i+1,k+1])
+//   Ez: mean4(C[i], C[i+1], C[i,j+1], C[i+1,j+1])                                                         at plane i
+// 8-byte vectors per thread (2 fp32 / 1 fp64 cells) keep the window in registers.  Of R warp rows the first R-2
+// own cells (row R-2 recomputes H+ on the rim, row R-1 only provides raw neighbours); of 32 lanes the first 30.
+#pragma once
+#include "fdtd_tb2.cuh"
+
+namespace fdtd {
+
+constexpr int kHetRows = 16;
+constexpr int kHetOwnLanes = 30;
+template <typename T, int R> constexpr size_t het_smem_bytes() { return 2 * (size_t)R * 8 * 32 * 8; }
+
+template <typename T, int R>
+__global__ void __launch_bounds__(32 * R, 1)
+k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, int planes_alloc)
+{
+    constexpr int V = Vec8<T>::V;
+    typedef Pack<T, V> P;
+    typedef typename Vec8<T>::type VT;
+    extern __shared__ __align__(16) unsigned char smem_[];
+    // [parity][row][q][lane], q: 0 Ez,1 Ex of plane i+1; 2 Hz+,3 Hx+ of plane i; 4 Da,5 Db of plane i+1; 6 Ca,7 Cb of plane i+1
+    VT (*s_x)[R][8][32] = reinterpret_cast<VT (*)[R][8][32]>(smem_);
+
+    const int lane = threadIdx.x, row = threadIdx.y;
+    const int ntiles = t.ntj * t.ntk;
+    const int seg = blockIdx.x / ntiles, tile = blockIdx.x - seg * ntiles;
+    const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
+    const int j = tj * (R - 2) + row;
+    const int k = (tk * t.own_lanes + lane) * V;
+    const int i0 = t.i_begin + seg * t.lx;
+    const int i1 = min(i0 + t.lx, t.i_end);
+    const bool ld_ok = (j < g.ny) && (k < g.pz);
+    const bool owner = ld_ok && row < R - 2 && lane < t.own_lanes;
+    const int rown = min(row + 1, R - 1);
+    const unsigned ofs = (unsigned)j * (unsigned)g.sy + (unsigned)k;
+    const bool jy1 = j < g.ny - 1, jy2 = j < g.ny - 2;
+
+    const T* pex = in.ex + ofs; const T* pey = in.ey + ofs; const T* pez = in.ez + ofs;
+    const T* phx = in.hx + ofs; const T* phy = in.hy + ofs; const T* phz = in.hz + ofs;
+    const T* pca = c.ca + ofs; const T* pcb = c.cb + ofs; const T* pda = c.da + ofs; const T* pdb = c.db + ofs;
+    P z_;
+#pragma unroll
+    for (int e = 0; e < V; ++e) z_.v[e] = (T)0;
+
+    // window at i = i0 - 1
+    unsigned po = (unsigned)i0 * (unsigned)g.sx;
+    P e0x = z_, e0y = z_, e0z = z_, hpx = z_, hpy = z_, hpz = z_;                        // E[i], H+[i]
+    P e1x = ld8<T, V>(pex + po, ld_ok), e1y = ld8<T, V>(pey + po, ld_ok), e1z = ld8<T, V>(pez + po, ld_ok);            // E[i+1]
+    P e2x = ld8<T, V>(pex + po + g.sx, ld_ok), e2y = ld8<T, V>(pey + po + g.sx, ld_ok), e2z = ld8<T, V>(pez + po + g.sx, ld_ok);
+    P h1x = ld8<T, V>(phx + po, ld_ok), h1y = ld8<T, V>(phy + po, ld_ok), h1z = ld8<T, V>(phz + po, ld_ok);            // H[i+1]
+    const bool pm_ok = ld_ok && i0 > 0;
+    P ca0 = ld8<T, V>(pca + po - g.sx, pm_ok), cb0 = ld8<T, V>(pcb + po - g.sx, pm_ok);     // C[i]   (unused while i < i0)
+    P ca1 = ld8<T, V>(pca + po, ld_ok), cb1 = ld8<T, V>(pcb + po, ld_ok);                 // C[i+1]
+    P da1 = ld8<T, V>(pda + po, ld_ok), db1 = ld8<T, V>(pdb + po, ld_ok);                 // D[i+1]
+    P da2 = ld8<T, V>(pda + po + g.sx, ld_ok), db2 = ld8<T, V>(pdb + po + g.sx, ld_ok);   // D[i+2]
+    P ca0_j = z_, cb0_j = z_;                                                           // C[i] at j+1
+
+    for (int i = i0 - 1; i < i1; ++i) {
+        const int par = (i - i0 + 1) & 1;
+        // ---- prefetch for the next iteration: E[i+3], H[i+2], C[i+2], D[i+3] ---------------------------------------
+        const bool more = ld_ok && (i + 1 < i1);
+        const bool p3 = more && (i + 3 < planes_alloc), p2 = more && (i + 2 < planes_alloc);
+        const unsigned pp = (unsigned)(i + 2) * (unsigned)g.sx;
+        const P n_ex = ld8<T, V>(pex + pp + g.sx, p3), n_ey = ld8<T, V>(pey + pp + g.sx, p3), n_ez = ld8<T, V>(pez + pp + g.sx, p3);
+        const P n_hx = ld8<T, V>(phx + pp, p2), n_hy = ld8<T, V>(phy + pp, p2), n_hz = ld8<T, V>(phz + pp, p2);
+        const P n_ca = ld8<T, V>(pca + pp, p2), n_cb = ld8<T, V>(pcb + pp, p2);
+        const P n_da = ld8<T, V>(pda + pp + g.sx, p3), n_db = ld8<T, V>(pdb + pp + g.sx, p3);
+        // ---- publish the j+1 inputs ------------------------------------------------------------------------------------
+        {
+            union { VT q; P r; } u;
+            u.r = e1z; s_x[par][row][0][lane] = u.q;  u.r = e1x; s_x[par][row][1][lane] = u.q;
+            u.r = hpz; s_x[par][row][2][lane] = u.q;  u.r = hpx; s_x[par][row][3][lane] = u.q;
+            u.r = da1; s_x[par][row][4][lane] = u.q;  u.r = db1; s_x[par][row][5][lane] = u.q;
+            u.r = ca1; s_x[par][row][6][lane] = u.q;  u.r = cb1; s_x[par][row][7][lane] = u.q;
+        }
+        __syncthreads();
+        P ez_j, ex_j, hz_j, hx_j, da1_j, db1_j, ca1_j, cb1_j;
+        {
+            union { VT q; P r; } u;
+            u.q = s_x[par][rown][0][lane]; ez_j = u.r;   u.q = s_x[par][rown][1][lane]; ex_j = u.r;
+            u.q = s_x[par][rown][2][lane]; hz_j = u.r;   u.q = s_x[par][rown][3][lane]; hx_j = u.r;
+            u.q = s_x[par][rown][4][lane]; da1_j = u.r;  u.q = s_x[par][rown][5][lane]; db1_j = u.r;
+            u.q = s_x[par][rown][6][lane]; ca1_j = u.r;  u.q = s_x[par][rown][7][lane]; cb1_j = u.r;
+        }
+        // ---- k+1 neighbours from the next lane --------------------------------------------------------------------------------
+        const T ey1_n = shfl_next<T>(e1y.v[0]), ex1_n = shfl_next<T>(e1x.v[0]);
+        const T hpy_n = shfl_next<T>(hpy.v[0]), hpx_n = shfl_next<T>(hpx.v[0]);
+        const T da1_n = shfl_next<T>(da1.v[0]), db1_n = shfl_next<T>(db1.v[0]);
+        const T ca0_n = shfl_next<T>(ca0.v[0]), cb0_n = shfl_next<T>(cb0.v[0]);
+        const T ca1_n = shfl_next<T>(ca1.v[0]), cb1_n = shfl_next<T>(cb1.v[0]);
+        const T ca0j_n = shfl_next<T>(ca0_j.v[0]), cb0j_n = shfl_next<T>(cb0_j.v[0]);
+
+        // ---- H+[i+1] ----------------------------------------------------------------------------------------------------------
+        const int gi1 = g.x0 + i + 1;
+        const bool ix1 = gi1 < g.nxg - 1, ix2 = gi1 < g.nxg - 2;
+        P hnx = h1x, hny = h1y, hnz = h1z;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const bool kz1 = (k + e) < g.nz - 1, kz2 = (k + e) < g.nz - 2;
+            const T ey_k = (e + 1 < V) ? e1y.v[(e + 1) % V] : ey1_n;
+            const T ex_k = (e + 1 < V) ? e1x.v[(e + 1) % V] : ex1_n;
+            const T da_k = (e + 1 < V) ? da1.v[(e + 1) % V] : da1_n;
+            const T db_k = (e + 1 < V) ? db1.v[(e + 1) % V] : db1_n;
+            T n = upd_h<T>(mean2<T>(da1.v[e], da2.v[e]), h1x.v[e], mean2<T>(db1.v[e], db2.v[e]),
+                           Ar<T>::diff(ez_j.v[e], e1z.v[e], g.dy, g.rdy), Ar<T>::diff(ey_k, e1y.v[e], g.dz, g.rdz));
+            if (ix1 && jy2 && kz2) hnx.v[e] = n;
+            n = upd_h<T>(mean2<T>(da1.v[e], da1_j.v[e]), h1y.v[e], mean2<T>(db1.v[e], db1_j.v[e]),
+                         Ar<T>::diff(ex_k, e1x.v[e], g.dz, g.rdz), Ar<T>::diff(e2z.v[e], e1z.v[e], g.dx, g.rdx));
+            if (ix2 && jy1 && kz2) hny.v[e] = n;
+            n = upd_h<T>(mean2<T>(da1.v[e], da_k), h1z.v[e], mean2<T>(db1.v[e], db_k),
+                         Ar<T>::diff(e2y.v[e], e1y.v[e], g.dx, g.rdx), Ar<T>::diff(ex_j.v[e], e1x.v[e], g.dy, g.rdy));
+            if (ix2 && jy2 && kz1) hnz.v[e] = n;
+        }
+        if (owner && i + 1 < i1) {
+            const unsigned q = ofs + (unsigned)(i + 1) * (unsigned)g.sx;
+            st8<T, V>(out.hx + q, hnx); st8<T, V>(out.hy + q, hny); st8<T, V>(out.hz + q, hnz);
+        }
+        // ---- E+[i] --------------------------------------------------------------------------------------------------------------
+        if (i >= i0) {
+            const int gi = g.x0 + i;
+            const bool ex0 = gi < g.nxg, ex1 = gi < g.nxg - 1;
+            P ox = e0x, oy = e0y, oz = e0z;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;
+                const T hy_k = (e + 1 < V) ? hpy.v[(e + 1) % V] : hpy_n;
+                const T hx_k = (e + 1 < V) ? hpx.v[(e + 1) % V] : hpx_n;
+                const T ca0_k = (e + 1 < V) ? ca0.v[(e + 1) % V] : ca0_n, cb0_k = (e + 1 < V) ? cb0.v[(e + 1) % V] : cb0_n;
+                const T ca1_k = (e + 1 < V) ? ca1.v[(e + 1) % V] : ca1_n, cb1_k = (e + 1 < V) ? cb1.v[(e + 1) % V] : cb1_n;
+                const T ca0_jk = (e + 1 < V) ? ca0_j.v[(e + 1) % V] : ca0j_n, cb0_jk = (e + 1 < V) ? cb0_j.v[(e + 1) % V] : cb0j_n;
+                T n = upd_e<T>(mean4<T>(ca0.v[e], ca0_j.v[e], ca0_k, ca0_jk), e0x.v[e],
+                               mean4<T>(cb0.v[e], cb0_j.v[e], cb0_k, cb0_jk),
+                               Ar<T>::diff(hz_j.v[e], hpz.v[e], g.dy, g.rdy), Ar<T>::diff(hy_k, hpy.v[e], g.dz, g.rdz));
+                if (ex0 && jy1 && kz1) ox.v[e] = n;
+                n = upd_e<T>(mean4<T>(ca0.v[e], ca1.v[e], ca0_k, ca1_k), e0y.v[e], mean4<T>(cb0.v[e], cb1.v[e], cb0_k, cb1_k),
+                             Ar<T>::diff(hx_k, hpx.v[e], g.dz, g.rdz), Ar<T>::diff(hnz.v[e], hpz.v[e], g.dx, g.rdx));
+                if (ex1 && kz1) oy.v[e] = n;
+                n = upd_e<T>(mean4<T>(ca0.v[e], ca1.v[e], ca0_j.v[e], ca1_j.v[e]), e0z.v[e],
+                             mean4<T>(cb0.v[e], cb1.v[e], cb0_j.v[e], cb1_j.v[e]),
+                             Ar<T>::diff(hny.v[e], hpy.v[e], g.dx, g.rdx), Ar<T>::diff(hx_j.v[e], hpx.v[e], g.dy, g.rdy));
+                if (ex1 && jy1 && kz0) oz.v[e] = n;
+            }
+            if (owner) {
+                const unsigned q = ofs + (unsigned)i * (unsigned)g.sx;
+                st8<T, V>(out.ex + q, ox); st8<T, V>(out.ey + q, oy); st8<T, V>(out.ez + q, oz);
+            }
+        }
+        // ---- rotate -----------------------------------------------------------------------------------------------------------------
+        e0x = e1x; e0y = e1y; e0z = e1z;
+        e1x = e2x; e1y = e2y; e1z = e2z;
+        e2x = n_ex; e2y = n_ey; e2z = n_ez;
+        hpx = hnx; hpy = hny; hpz = hnz;
+        h1x = n_hx; h1y = n_hy; h1z = n_hz;
+        ca0 = ca1; cb0 = cb1; ca1 = n_ca; cb1 = n_cb;
+        ca0_j = ca1_j; cb0_j = cb1_j;
+        da1 = da2; db1 = db2; da2 = n_da; db2 = n_db;
+    }
+}
+
+}  // namespace fdtd

@@ -108,7 +108,7 @@ def _engine_vs_oracle(dims, ndim, courant, steps, dtype, het, flags=0, seed=3):
 def test_3d_fp64_exact_and_fp32_tolerance(courant, het):
     dims, steps = (70, 45, 37), 20
     out, F, n = _engine_vs_oracle(dims, 3, courant, steps, "float64", het)
-    assert n >= (2 * steps if het else steps // 2)  # two-step sweep: one kernel per two steps; two-pass: two per step
+    assert n >= (steps if het else steps // 2)      # het: one fused sweep per step; vacuum: one per two steps
     for c in F:
         assert np.array_equal(out[c], F[c]), f"{c}: {S.rel_l2(out[c], F[c]):.3e}"
     out, F, _ = _engine_vs_oracle(dims, 3, courant, steps, "float32", het)
@@ -340,3 +340,20 @@ def test_fast_fp64_mode_within_north_star_tolerance():
     worst = max(S.rel_l2(a[c], F[c]) for c in F)
     assert 0 < worst <= FP64_TOL, worst
     assert worst < 1e-12
+
+
+@pytest.mark.parametrize("dims", [(40, 47, 130), (33, 16, 121), (9, 31, 250), (5, 3, 3), (64, 100, 300)])
+def test_het_fused_sweep_equals_two_pass_and_oracle(dims, monkeypatch):
+    """Heterogeneous media: the fused sweep that streams Ca,Cb,Da,Db and averages them in registers must equal the
+    two-pass kernels and the oracle bit for bit in fp64."""
+    a, F, na = _engine_vs_oracle(dims, 3, 0.5, 6, "float64", True)
+    monkeypatch.setenv("FDTD_B200_HET_FUSED", "0")
+    b, _, nb = _engine_vs_oracle(dims, 3, 0.5, 6, "float64", True)
+    assert na < nb
+    for c in F:
+        assert np.array_equal(a[c], F[c]), f"het fused vs oracle {c}: {S.rel_l2(a[c], F[c]):.3e}"
+        assert np.array_equal(b[c], F[c]), f"two-pass vs oracle {c}"
+    monkeypatch.delenv("FDTD_B200_HET_FUSED")
+    a32, F, _ = _engine_vs_oracle(dims, 3, 0.5, 6, "float32", True)
+    for c in F:
+        assert S.rel_l2(a32[c], F[c]) <= FP32_TOL, c
