@@ -348,8 +348,16 @@ def main():
     tb2 = fused and os.environ.get("FDTD_B200_TB2", "1") != "0" and args.steps >= 2 and not args.het
     kname = ("k_fused3d_tb2 (1 launch per TWO steps)" if tb2 else "k_fused3d (1 launch/step)") if fused \
         else "k_h3d + k_e3d (2 launches/step)"
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        key = f"{name}:{args.dtype}:{'two-step' if tb2 else 'one-step'}"
+        if fused and not args.het and key in tr:
+            traffic = tr[key]["dram_bytes"]          # bytes per launch group, from the committed ncu capture
+    except (OSError, ValueError):
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": kname,
+                "traffic": traffic, "peak_source": peak_src, "kernel": kname,
                 "note": ("achieved = ALGORITHMIC bytes (48 B per cell-update, SURVEY 8d) / kernel time; the two-step "
                          "sweep keeps the intermediate step on chip, so its real DRAM traffic is ~27 B per cell-update "
                          "(ncu: profiles/) and frac can exceed 1") if tb2 else None,
