@@ -278,6 +278,57 @@ def run_reference_arm(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------------
+def run_c1(args, local):
+    """configs[0]: 2-D 1000x1000 Si strip waveguide (eps 12.11 in 2.07), Gaussian-beam line source, DFTMonitor corner
+    patch (reference placeholder semantics) + FieldMonitor DFT line, 11 frequencies.  Launch-bound (1e6 cells):
+    timed through the CUDA-graph step loop.  Parity for this shape: tests (src2d_gauss, mon2d_all, upd2d_het)."""
+    import prismo_b200 as pb
+
+    nx = ny = 1000
+    d = 2e-8
+    dt = 0.9 / (C0 * np.sqrt(2.0 / d ** 2))
+    eng = pb.Engine(2, (nx, ny, 1), (d, d, 0.0), dt, dtype=args.dtype, device=local)
+    eps = np.full((nx, ny), 2.07)
+    eps[:, ny // 2 - 11: ny // 2 + 11] = 12.11
+    eps0, mu0 = 8.854187817e-12, 4 * np.pi * 1e-7
+    one = np.ones((nx, ny))
+    eng.set_coeffs(one, dt / (eps0 * eps), one, one * (dt / mu0))
+    y = (np.arange(400, 600) - 500) * d
+    prof = np.exp(-(y / 1e-6) ** 2)[None, :]
+    eng.add_source_op(pb.SourceOp("Ey", (60, 400), (61, 600), 0, prof))
+    eng.add_source_op(pb.SourceOp("Hz", (60, 400), (61, 600), 0, prof, 377.0))
+    for c in ("Ex", "Ey", "Ez"):
+        eng.add_monitor_op(pb.MonitorOp(c, (0, 0), (10, 10), False, 11, 0))
+    eng.add_monitor_op(pb.MonitorOp("Ey", (800, 400), (801, 600), False, 11, 0))
+    total = args.warmup + args.steps
+    t = (np.arange(total) + 1) * dt
+    amp = (np.exp(-0.5 * ((t - 3e-14) / 1e-14) ** 2) * np.sin(2 * np.pi * F0 * t))[:, None]
+    ph = np.exp(-1j * 2 * np.pi * (C0 / np.linspace(1.5e-6, 1.6e-6, 11))[None, :] * t[:, None])
+    eng.set_tables(total, amp, ph)
+    eng.run(args.warmup)
+    eng.sync()
+    l0 = eng.kernel_launches
+    with ClockSampler(local) as clk:
+        eng.timer_start()
+        eng.run(args.steps)
+        ms = eng.timer_stop()
+    cells = nx * ny
+    value = cells * args.steps / (ms * 1e-3)
+    bpc = (48 if args.dtype == "float32" else 96) // 1
+    line = {"metric": "fdtd_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+            "config": {"workload": "c1: 2-D 1000x1000 Si strip waveguide, Gaussian-beam line source, DFT monitors (11 freq)",
+                       "l2": "working set 24-48 MB: L2-resident, launch-bound (HBM fraction not meaningful)",
+                       "kernel_path": "k_h2d + k_e2d + k_sources + k_monitors, 16 steps per CUDA graph replay"},
+            "roofline": {"bound": "hbm", "achieved": bpc * value / 1e9, "peak": peaks()[0], "unit": "GB/s",
+                         "frac": bpc * value / 1e9 / peaks()[0], "traffic": None,
+                         "note": "algorithmic GB/s of an L2-resident grid"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": eng.kernel_launches - l0, "clocks": clk.summary()}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -312,6 +363,8 @@ def main():
     import prismo_b200 as pb
     from prismo_b200 import _lib
 
+    if args.workload.lower() == "c1":
+        return run_c1(args, local)
     name, dims = parse_workload(args.workload)
     cells = dims[0] * dims[1] * dims[2]
     flags = (_lib.FLAG_TWO_PASS if args.two_pass else 0) | (_lib.FLAG_FAST_F64 if args.fast_f64 else 0)

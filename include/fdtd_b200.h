@@ -130,6 +130,10 @@ int  fdtd_clear_ops(fdtd_engine* e);
 int  fdtd_add_source_op(fdtd_engine* e, const fdtd_source_op* op);
 int  fdtd_add_monitor_op(fdtd_engine* e, const fdtd_monitor_op* op, int32_t* id);
 int  fdtd_add_ade_op(fdtd_engine* e, const fdtd_ade_op* op, int32_t* id);
+/* Extension (no reference counterpart: its FluxMonitor samples a corner patch and raises in 3-D): region-correct
+ * instantaneous power sum((E x H)_normal) over a box valid for all six components, one fp64 sample per step.     */
+int  fdtd_add_flux_op(fdtd_engine* e, int32_t direction, const int32_t* lo, const int32_t* hi, int32_t* id);
+int  fdtd_download_flux(fdtd_engine* e, int32_t id, double* host, int32_t max_steps);
 /* ADE state, host fp64 [cells of the box]: which = 0 current (P or J), 1 previous (Lorentz only) */
 int  fdtd_download_ade(fdtd_engine* e, int32_t id, int32_t which, double* host);
 int  fdtd_upload_ade(fdtd_engine* e, int32_t id, int32_t which, const double* host);

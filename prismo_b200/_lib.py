@@ -71,6 +71,8 @@ _PROTOS = {
     "fdtd_clear_ops": (C.c_int, [_P]),
     "fdtd_add_source_op": (C.c_int, [_P, C.POINTER(SourceOp)]),
     "fdtd_add_monitor_op": (C.c_int, [_P, C.POINTER(MonitorOp), C.POINTER(C.c_int32)]),
+    "fdtd_add_flux_op": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "fdtd_download_flux": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),
     "fdtd_add_ade_op": (C.c_int, [_P, C.POINTER(AdeOp), C.POINTER(C.c_int32)]),
     "fdtd_download_ade": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "fdtd_upload_ade": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),

@@ -65,6 +65,7 @@ struct fdtd_engine {
     std::vector<SrcOp> src_ghost; SrcOp* d_src_ghost = nullptr;   // slabs: neighbour's sources on our ghost planes
     std::vector<MonOp> mon;
     std::vector<double> prof_host;
+    std::vector<FluxOp> flux; FluxOp* d_flux = nullptr; double* d_flux_partial = nullptr; double* d_flux_out = nullptr;
     std::vector<AdeOp> ade; std::vector<unsigned char> ade_mask_host;
     AdeOp* d_ade = nullptr; void* d_aux = nullptr; unsigned char* d_ade_mask = nullptr;
     long long aux_elems = 0, ade_threads = 0;
@@ -271,6 +272,7 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     for (int c = 0; c < 4; ++c) cudaFree(e->coef[c]);
     cudaFree(e->d_src); cudaFree(e->d_mon); cudaFree(e->d_prof); cudaFree(e->d_src_ghost);
     cudaFree(e->d_ade); cudaFree(e->d_aux); cudaFree(e->d_ade_mask);
+    cudaFree(e->d_flux); cudaFree(e->d_flux_partial); cudaFree(e->d_flux_out);
     cudaFree(e->d_cpml_coef); cudaFree(e->d_plane_flags);
     for (int q = 0; q < 12; ++q) cudaFree(e->cpml.psi[q]);
     cudaFree(e->d_comp_ptr[0]); cudaFree(e->d_comp_ptr[1]);
@@ -451,7 +453,7 @@ extern "C" int fdtd_clear_ops(fdtd_engine* e)
 {
     if (!e) return fail(FDTD_EINVAL, "null engine");
     e->src.clear(); e->mon.clear(); e->prof_host.clear(); e->src_ghost.clear();
-    e->ade.clear(); e->ade_mask_host.clear();
+    e->ade.clear(); e->ade_mask_host.clear(); e->flux.clear();
     e->ops_dirty = true;
     drop_graph(e);
     return 0;
@@ -509,6 +511,36 @@ extern "C" int fdtd_add_monitor_op(fdtd_engine* e, const fdtd_monitor_op* op, in
     e->mon.push_back(m);
     e->ops_dirty = true;
     drop_graph(e);
+    return 0;
+}
+
+// region-correct flux (extension): power through [lo,hi) (a box valid for all six components), normal = direction
+extern "C" int fdtd_add_flux_op(fdtd_engine* e, int32_t direction, const int32_t* lo, const int32_t* hi, int32_t* id)
+{
+    if (!e || !lo || !hi || direction < 0 || direction > 2) return fail(FDTD_EINVAL, "fdtd_add_flux_op: bad argument");
+    FluxOp f{};
+    for (int c = 0; c < 6; ++c)
+        if (int rc = check_box(e, c, lo, hi, f.n)) return rc;
+    f.dir = direction;
+    for (int a = 0; a < 3; ++a) f.lo[a] = lo[a];
+    f.cells = (long long)f.n[0] * f.n[1] * f.n[2];
+    f.out_off = (long long)e->flux.size();
+    if (id) *id = (int32_t)e->flux.size();
+    e->flux.push_back(f);
+    e->ops_dirty = true;
+    drop_graph(e);
+    return 0;
+}
+
+// instantaneous power samples of flux op id: host fp64 [steps_run] (sum of (E x H)_n over the box; multiply by dA)
+extern "C" int fdtd_download_flux(fdtd_engine* e, int32_t id, double* host, int32_t max_steps)
+{
+    if (!e || !host || id < 0 || id >= (int)e->flux.size()) return fail(FDTD_EINVAL, "fdtd_download_flux: bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    const int steps = std::min<int>(max_steps, e->cursor);
+    if (steps <= 0 || !e->d_flux_out) return 0;
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(host, e->d_flux_out + (size_t)id * std::max(e->n_steps_tab, 1), steps * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -581,6 +613,13 @@ static int finalize_ops(fdtd_engine* e)
             CU(cudaMemset(e->d_dft, 0, dft * sizeof(double2)));
         }
         e->dft_elems = dft;
+    }
+    cudaFree(e->d_flux); e->d_flux = nullptr;
+    cudaFree(e->d_flux_partial); e->d_flux_partial = nullptr;
+    if (!e->flux.empty()) {
+        CU(cudaMalloc(&e->d_flux, e->flux.size() * sizeof(FluxOp)));
+        CU(cudaMemcpy(e->d_flux, e->flux.data(), e->flux.size() * sizeof(FluxOp), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&e->d_flux_partial, e->flux.size() * FLUX_BLOCKS * sizeof(double)));
     }
     // ADE ops: aux pool (cur [+ prev] per op), zero-initialised when the layout changes
     {
@@ -703,6 +742,11 @@ extern "C" int fdtd_set_tables(fdtd_engine* e, int32_t n_steps, int32_t n_amp, c
     }
     if (n_steps > 0 && e->rec_elems_per_step > 0)
         CU(cudaMalloc(&e->d_rec, (size_t)n_steps * e->rec_elems_per_step * e->esz));
+    cudaFree(e->d_flux_out); e->d_flux_out = nullptr;
+    if (n_steps > 0 && !e->flux.empty()) {
+        CU(cudaMalloc(&e->d_flux_out, (size_t)n_steps * e->flux.size() * sizeof(double)));
+        CU(cudaMemset(e->d_flux_out, 0, (size_t)n_steps * e->flux.size() * sizeof(double)));
+    }
     if (int rc = upload_mon_ops(e)) return rc;
     e->cursor = 0;
     CU(cudaMemset(e->d_step, 0, sizeof(int)));
@@ -787,6 +831,14 @@ template <typename T> static int launch_post(fdtd_engine* e, int step_off, int p
             (const T* const*)comp, e->d_mon, (int)e->mon.size(), e->mon_threads, e->st, e->d_phasor, e->n_phasor,
             e->d_step, step_off, e->cfg.dt, (T*)e->d_rec, e->d_dft);
         e->launches++;
+        CU(cudaGetLastError());
+    }
+    if (!e->flux.empty() && e->d_flux_out) {
+        dim3 grid(FLUX_BLOCKS, (unsigned)e->flux.size());
+        k_flux_partial<T><<<grid, 256, 0, s>>>((const T* const*)comp, e->d_flux, e->st, e->d_flux_partial);
+        k_flux_final<<<1, 64, 0, s>>>(e->d_flux, (int)e->flux.size(), e->d_flux_partial, e->d_flux_out, e->d_step, step_off,
+                                      std::max(e->n_steps_tab, 1));
+        e->launches += 2;
         CU(cudaGetLastError());
     }
     if (e->ade_threads > 0) {
@@ -984,7 +1036,7 @@ template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
 
 static bool tb2_ok(const fdtd_engine* e)
 {
-    return e->tb2 && use_fused(e) && e->ade.empty() && e->array_elems < (1ll << 32);
+    return e->tb2 && use_fused(e) && e->ade.empty() && e->flux.empty() && e->array_elems < (1ll << 32);
 }
 static bool use_tb2(const fdtd_engine* e) { return tb2_ok(e) && e->g.nxg == e->g.nx; }
 
@@ -1101,7 +1153,7 @@ template <typename T> static int one_step(fdtd_engine* e, int step_off, int pari
     return launch_post<T>(e, step_off, parity, s);
 }
 
-static bool has_tables(const fdtd_engine* e) { return !e->src.empty() || !e->mon.empty() || !e->src_ghost.empty(); }
+static bool has_tables(const fdtd_engine* e) { return !e->src.empty() || !e->mon.empty() || !e->src_ghost.empty() || !e->flux.empty(); }
 static bool has_post(const fdtd_engine* e) { return has_tables(e) || !e->ade.empty(); }
 
 template <typename T> static int run_steps(fdtd_engine* e, int n)

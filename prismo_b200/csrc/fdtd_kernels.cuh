@@ -43,7 +43,6 @@ template <> struct Ar<double> {
     static __device__ __forceinline__ double diff(double a1, double a0, double d, float) {
         return __ddiv_rn(__dsub_rn(a1, a0), d);
     }
-    static __device__ __forceinline__ double quarter() { return 0.25; }
 };
 template <> struct Ar<float> {
     static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
@@ -366,7 +365,7 @@ struct MonOp {
 struct Strides3 { long long s[3]; };   // 3-D: (sx, sy, 1); 2-D: (sx, 1, 0)
 
 // F[box] += amp[step][table] (* profile / divisor).  Arithmetic in fp64, rounded once to T on store
-// (what NumPy does for "f32_array += python_float").  Keeps the 2-D gate counters exact.
+// to T on store.  Keeps the 2-D gate counters exact.
 template <typename T>
 __global__ void k_sources(T* const* __restrict__ comp_ptr, const SrcOp* __restrict__ ops, int n_ops,
                           long long total, Strides3 st, const double* __restrict__ amp, int n_amp,
@@ -478,6 +477,53 @@ __global__ void k_ade(const T* const* __restrict__ comp_ptr, const AdeOp* __rest
         nv = __dadd_rn(__dmul_rn(op.c0, e), __dmul_rn(op.c1, a));
     }
     *cur = (T)nv;
+}
+
+// Region-correct flux (extension): instantaneous power through a box, P = sum (E x H)_n over the
+// box's cells, fields taken co-located like the reference's FluxMonitor does on its patch (monitors/flux.py:146-175).
+// Deterministic: FLUX_BLOCKS fixed partial sums per op (grid-stride, tree reduce), then one thread adds them in order.
+struct FluxOp { int dir; int lo[3], n[3]; long long cells; long long out_off; };
+constexpr int FLUX_BLOCKS = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_flux_partial(const T* const* __restrict__ comp_ptr, const FluxOp* __restrict__ ops, Strides3 st, double* __restrict__ partial)
+{
+    const FluxOp op = ops[blockIdx.y];
+    const T* ex = comp_ptr[0]; const T* ey = comp_ptr[1]; const T* ez = comp_ptr[2];
+    const T* hx = comp_ptr[3]; const T* hy = comp_ptr[4]; const T* hz = comp_ptr[5];
+    double acc = 0.0;
+    for (long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x; cell < op.cells;
+         cell += (long long)gridDim.x * blockDim.x) {
+        const int c2 = (int)(cell % op.n[2]);
+        const long long r = cell / op.n[2];
+        const int c1 = (int)(r % op.n[1]);
+        const int c0 = (int)(r / op.n[1]);
+        const long long o = (op.lo[0] + c0) * st.s[0] + (op.lo[1] + c1) * st.s[1] + (op.lo[2] + c2) * st.s[2];
+        double s;
+        if (op.dir == 0) s = (double)ey[o] * (double)hz[o] - (double)ez[o] * (double)hy[o];
+        else if (op.dir == 1) s = (double)ez[o] * (double)hx[o] - (double)ex[o] * (double)hz[o];
+        else s = (double)ex[o] * (double)hy[o] - (double)ey[o] * (double)hx[o];
+        acc += s;
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.y * FLUX_BLOCKS + blockIdx.x] = sh[0];
+}
+
+__global__ void k_flux_final(const FluxOp* __restrict__ ops, int n_ops, const double* __restrict__ partial,
+                             double* __restrict__ out, const int* __restrict__ step_ptr, int step_off, int n_steps)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_ops) return;
+    double s = 0.0;
+    for (int b = 0; b < FLUX_BLOCKS; ++b) s += partial[q * FLUX_BLOCKS + b];
+    out[ops[q].out_off * n_steps + (*step_ptr + step_off)] = s;
 }
 
 __global__ void k_bump(int* step_ptr, int n) { *step_ptr += n; }

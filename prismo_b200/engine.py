@@ -214,6 +214,19 @@ class Engine:
         self._mon_ops.append(op)
         return mid.value
 
+    def add_flux_op(self, direction: str, lo, hi) -> int:
+        """Region-correct power sum((E x H)_n) through box [lo, hi) (valid for all six components), every step."""
+        a, b = (C.c_int32 * 3)(*_pad3(lo, 0)), (C.c_int32 * 3)(*_pad3(hi, 1))
+        fid = C.c_int32()
+        _lib.check(self._lib.fdtd_add_flux_op(self._h, "xyz".index(direction), a, b, C.byref(fid)))
+        return fid.value
+
+    def flux(self, flux_id: int, steps: int) -> np.ndarray:
+        out = np.zeros(steps, dtype=np.float64)
+        if steps:
+            _lib.check(self._lib.fdtd_download_flux(self._h, flux_id, out.ctypes.data_as(C.c_void_p), int(steps)))
+        return out
+
     def add_ade_op(self, op: AdeOp) -> int:
         c = _lib.AdeOp()
         c.component, c.kind = COMP_ID[op.component], int(op.kind)

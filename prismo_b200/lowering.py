@@ -44,6 +44,7 @@ class Program:
     phasor_fns: list = field(default_factory=list)     # t -> complex
     binders: list = field(default_factory=list)
     ade_ops: list = field(default_factory=list)
+    flux_ops: list = field(default_factory=list)       # (direction, lo, hi): region-correct flux reductions
     _group: int = 0
 
     # -- building blocks ---------------------------------------------------------------------------
@@ -382,6 +383,45 @@ class _PatchBinder(_Binder):
         return {c: engine.records(i, n) for c, i in self.ids.items()}
 
 
+class _FluxRegionBinder(_Binder):
+    """Extension (FluxMonitor(region_correct=True)): the monitor's REAL surface, in 2-D and 3-D.  Power through the
+    box common to all six components is reduced on the device every step; the six DFTs run over the same box, so
+    the reference's own ``get_frequency_domain_power`` (monitors/flux.py:228-291) works unchanged on the result."""
+
+    def __init__(self, p: Program, m):
+        g = p.grid
+        self.m = m
+        bounds = g.region_bounds(m.center, m.size)
+        boxes = [_box(g, c, bounds) for c in COMPONENTS]
+        box = tuple((max(b[a][0] for b in boxes), min(b[a][1] for b in boxes)) for a in range(len(boxes[0])))
+        if any(hi <= lo for lo, hi in box):
+            raise ValueError("FluxMonitor region is empty on the staggered grid")
+        self.shape = tuple(hi - lo for lo, hi in box)
+        self.nf = 0 if m.frequencies is None else len(m.omega)
+        col = p.phasors([_phasor_omega(w) for w in m.omega]) if self.nf else 0
+        self.ids = {c: p.monitor_op(c, box, False, self.nf, col) for c in COMPONENTS} if self.nf else {}
+        p.flux_ops.append((m.direction, tuple(lo for lo, _ in box), tuple(hi for _, hi in box)))
+        self.flux_id = len(p.flux_ops) - 1
+        if self.nf:
+            for c in COMPONENTS:
+                name = "_dft_" + c.lower()
+                if getattr(m, name, None) is None or getattr(m, name).shape != (self.nf,) + self.shape:
+                    setattr(m, name, np.zeros((self.nf,) + self.shape, dtype=np.complex128))
+
+    def preload(self, engine):
+        for c, i in self.ids.items():
+            engine.set_dft(i, getattr(self.m, "_dft_" + c.lower()))
+
+    def collect(self, engine, times, dt, n):
+        m = self.m
+        dx, dy, dz = m._grid.spacing
+        dA = {"x": dy * (dz if dz else 1.0), "y": dx * (dz if dz else 1.0), "z": dx * dy}[m.direction]
+        m._power_flow_history.extend(float(v) * dA for v in engine.flux(self.flux_id, n))
+        m._time_history.extend(times)
+        for c, i in self.ids.items():
+            getattr(m, "_dft_" + c.lower())[...] = engine.dft(i)
+
+
 class _FluxBinder(_PatchBinder):
     def __init__(self, p: Program, m):
         self.nf = 0 if m.frequencies is None else len(m.omega)
@@ -492,7 +532,10 @@ def lower(grid, sources, monitors, ades=()) -> Program:
             raise NotImplementedError(
                 f"monitor type {type(m).__name__} cannot be lowered to the B200 engine (no CPU fallback); "
                 f"supported: {sorted(_MONITORS)}")
-        p.binders.append(_MONITORS[kind](p, m))
+        if kind == "FluxMonitor" and getattr(m, "region_correct", False):
+            p.binders.append(_FluxRegionBinder(p, m))
+        else:
+            p.binders.append(_MONITORS[kind](p, m))
     for solver, component, mask in ades:
         p.binders.append(_AdeBinder(p, solver, component, mask))
     return p

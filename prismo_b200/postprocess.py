@@ -67,3 +67,23 @@ def mode_overlap(six, mode, direction="z", dx=1.0, dy=1.0) -> complex:
     overlap = 0.5 * np.sum(s_sim + s_mode) * dx * dy
     power = mode_power(mode, direction, dx, dy)
     return complex(overlap / power) if abs(power) > 1e-20 else complex(0.0)
+
+
+# ---- region-correct S-parameter extraction from DFT planes (extension) ----------------------------
+def mode_coefficient_from_dft(flux_monitor, mode, frequency_index: int) -> complex:
+    """Overlap of the frequency-domain fields a region-correct FluxMonitor accumulated on its plane with a waveguide
+    mode (same formula as utils/mode_matching.py:41-131, evaluated on the monitor's real plane and with the grid's
+    cell area instead of the placeholder's dx = dy = 1)."""
+    six = []
+    for c in _C:
+        a = getattr(flux_monitor, "_dft_" + c.lower())[frequency_index]
+        six.append(np.squeeze(a))
+    d = flux_monitor.direction
+    sp = flux_monitor._grid.spacing
+    du, dv = [sp[a] for a in range(3) if "xyz"[a] != d][:2]
+    return mode_overlap(tuple(six), mode, d, du, dv if dv else 1.0)
+
+
+def s_parameter(coefficient_out: complex, coefficient_in: complex) -> complex:
+    """S_ij = a_out / a_in for mode coefficients taken at the output and input port planes."""
+    return coefficient_out / coefficient_in if coefficient_in != 0 else complex("nan")

@@ -148,8 +148,10 @@ class Session:
             eng.add_monitor_op(op)
         for op in prog.ade_ops:
             eng.add_ade_op(op)
+        for direction, lo, hi in prog.flux_ops:
+            eng.add_flux_op(direction, lo, hi)
         chunk = n
-        if prog.src_ops or prog.mon_ops:
+        if prog.src_ops or prog.mon_ops or prog.flux_ops:
             chunk = min(chunk, _MAX_TABLE_STEPS)
             rec = prog.record_cells * 8
             if rec:
@@ -160,7 +162,7 @@ class Session:
         while done < n:
             m = min(chunk, n - done)
             times = self.step_times(t, dt, m)
-            if prog.src_ops or prog.mon_ops:
+            if prog.src_ops or prog.mon_ops or prog.flux_ops:
                 amp, ph = prog.tables(times, dt)
                 eng.set_tables(m, amp, ph)
             if first:

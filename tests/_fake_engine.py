@@ -25,7 +25,7 @@ class FakeEngine:
         full = self.dims if ndim == 3 else (self.dims[0], self.dims[1], 1)
         eps0, mu0 = 8.854187817e-12, 4 * np.pi * 1e-7
         self.coeffs = [np.full(full, v) for v in (1.0, dt / eps0, 1.0, dt / mu0)]
-        self.src, self.mon, self.ade = [], [], []
+        self.src, self.mon, self.ade, self.fluxes = [], [], [], []
         self.cursor, self.n_tab = 0, 0
         self.kernel_launches = 0
         self.uploads = 0
@@ -63,7 +63,7 @@ class FakeEngine:
         return out
 
     def clear_ops(self):
-        self.src, self.mon, self.ade = [], [], []
+        self.src, self.mon, self.ade, self.fluxes = [], [], [], []
 
     def add_source_op(self, op):
         self.src.append(op)
@@ -72,6 +72,19 @@ class FakeEngine:
         op.shape = tuple(h - l for l, h in zip(op.lo, op.hi))
         self.mon.append(dict(op=op, rec=[], dft=np.zeros((op.n_freq,) + op.shape, dtype=np.complex128)))
         return len(self.mon) - 1
+
+    def add_flux_op(self, direction, lo, hi):
+        self.fluxes.append(dict(d=direction, sl=tuple(slice(a, b) for a, b in zip(lo, hi)), out=[]))
+        return len(self.fluxes) - 1
+
+    def flux(self, i, steps):
+        return np.array(self.fluxes[i]["out"][:steps])
+
+    def _run_flux(self):
+        for f in self.fluxes:
+            ex, ey, ez, hx, hy, hz = (self.F[c][f["sl"]] for c in COMPONENTS)
+            s = {"x": ey * hz - ez * hy, "y": ez * hx - ex * hz, "z": ex * hy - ey * hx}[f["d"]]
+            f["out"].append(float(np.sum(s)))
 
     def add_ade_op(self, op):
         op.shape = tuple(h - l for l, h in zip(op.lo, op.hi))
@@ -103,6 +116,8 @@ class FakeEngine:
         self.n_tab, self.cursor = n_steps, 0
         for m in self.mon:
             m["rec"] = []
+        for f in self.fluxes:
+            f["out"] = []
 
     def _sl(self, op):
         return tuple(slice(l, h) for l, h in zip(op.lo, op.hi))
@@ -130,6 +145,7 @@ class FakeEngine:
                 for k in range(o.n_freq):
                     ph = self.ph[s, o.phasor_col + k]
                     m["dft"][k] += (d * ph.real) * self.dt + 1j * ((d * ph.imag) * self.dt)
+            self._run_flux()
             self._run_ade()
             self.cursor += 1
             self.kernel_launches += 2

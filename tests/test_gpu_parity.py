@@ -357,3 +357,32 @@ def test_het_fused_sweep_equals_two_pass_and_oracle(dims, monkeypatch):
     a32, F, _ = _engine_vs_oracle(dims, 3, 0.5, 6, "float32", True)
     for c in F:
         assert S.rel_l2(a32[c], F[c]) <= FP32_TOL, c
+
+
+def test_region_correct_flux_monitor_3d_vs_oracle():
+    """Extension: FluxMonitor(region_correct=True) — device reduction of (E x H)_n over the monitor's real surface and
+    six DFT planes — against the same quantities formed step by step from the oracle's fields.  The reduction order
+    differs from np.sum, so the bound is 1e-12 of the absolute-value sum."""
+    spec = dict(S.SCENARIOS["mon3d_field"], monitors=[])
+    sim = S.build_mirror(spec, pb, dtype="float64")
+    fm = pb.FluxMonitor((0.3e-6, 0.25e-6, 0.2e-6), (0.0, 0.3e-6, 0.2e-6), "x", frequencies=[S.F0], region_correct=True)
+    sim.add_monitor(fm)
+    o = S.build_oracle(spec)
+    g = sim.grid
+    boxes = [g.component_box(c, *g.region_bounds(fm.center, fm.size)) for c in S.COMPONENTS]
+    common = tuple(slice(max(b[a][0] for b in boxes), min(b[a][1] for b in boxes)) for a in range(3))
+    want, scale, dft = [], [], np.zeros(o.F["Ey"][common].shape, dtype=np.complex128)
+    for _ in range(9):
+        o.step()
+        ey, hz, ez, hy = (o.F[c][common] for c in ("Ey", "Hz", "Ez", "Hy"))
+        want.append(float(np.sum(ey * hz - ez * hy)) * g.dy * g.dz)
+        scale.append(float(np.sum(np.abs(ey * hz) + np.abs(ez * hy))) * g.dy * g.dz)
+        dft += ey * np.exp(-1j * (2 * np.pi * S.F0) * o.current_time) * o.dt
+    sim.run_steps(4)
+    sim.run_steps(5)
+    t, p = fm.get_time_domain_power()
+    assert len(p) == 9 and np.array_equal(t, [s * 1.0 for s in t])
+    for a, b, sc in zip(p, want, scale):
+        assert abs(a - b) <= 1e-12 * sc
+    assert np.array_equal(fm._dft_ey[0], dft)
+    assert np.isfinite(fm.get_frequency_domain_power()).all()

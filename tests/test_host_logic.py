@@ -164,3 +164,37 @@ def test_grid_matches_reference_quirks():
     assert g3.get_field_shape("Ey") == (29, 30, 29)
     ix = g3.get_component_indices("Ez", 0, 100, 3, 4, 0, 100)
     assert ix[0].shape == (20, 1, 1) and ix[1].ravel().tolist() == [3] and ix[2].shape == (1, 1, 20)
+
+
+def test_region_correct_flux_monitor_and_s_parameter_helpers(fake):
+    """Extension (off by default): FluxMonitor(region_correct=True) integrates over its real surface in 3-D and its
+    six DFTs cover the same box, so P(w) from the reference's formula and mode coefficients come from real planes."""
+    import types
+
+    from prismo_b200 import postprocess as pp
+
+    spec = dict(S.SCENARIOS["mon3d_field"], monitors=[])
+    sim = S.build_mirror(spec, pb)
+    fm = pb.FluxMonitor((0.3e-6, 0.25e-6, 0.2e-6), (0.0, 0.3e-6, 0.2e-6), "x", frequencies=[S.F0, 1.1 * S.F0],
+                        region_correct=True)
+    sim.add_monitor(fm)
+    sim.run_steps(4)
+    sim.run_steps(3)
+    t, p = fm.get_time_domain_power()
+    assert len(t) == 7 and len(p) == 7 and np.all(np.isfinite(p)) and np.abs(p).max() > 0
+    assert fm._dft_ey.shape[0] == 2 and fm._dft_ey.ndim == 4 and fm._dft_ey.shape[1] == 1
+    pw = fm.get_frequency_domain_power()
+    assert pw.shape == (2,) and np.all(np.isfinite(pw))
+    # the device-side reduction equals the same sum formed from the fields after the last step
+    i = sim.grid.point_to_index((0.3e-6, 0.25e-6, 0.2e-6))[0]
+    box = (slice(i, i + 1),) + tuple(slice(0, s) for s in fm._dft_ey.shape[2:])
+    sl = tuple(slice(b.start, b.stop) for b in box)
+    g = sim.grid
+    lo = [g.component_box(c, *g.region_bounds(fm.center, fm.size)) for c in S.COMPONENTS]
+    common = tuple(slice(max(b[a][0] for b in lo), min(b[a][1] for b in lo)) for a in range(3))
+    ey, hz, ez, hy = (sim.fields[c][common] for c in ("Ey", "Hz", "Ez", "Hy"))
+    want = float(np.sum(ey * hz - ez * hy)) * g.dy * g.dz
+    assert abs(p[-1] - want) <= 1e-12 * max(abs(want), np.abs(ey * hz).sum() * g.dy * g.dz)
+    mode = types.SimpleNamespace(**S.make_mode(8, 8, 5))
+    a = pp.mode_coefficient_from_dft(fm, mode, 0)
+    assert np.isfinite(a) and pp.s_parameter(a, a) == 1
