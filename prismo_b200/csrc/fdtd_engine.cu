@@ -88,7 +88,6 @@ struct fdtd_engine {
     // graph
     cudaGraphExec_t gexec[2] = {nullptr, nullptr}; int graph_steps = 0; int graph_kernels[2] = {0, 0};
     int fused_lx = 0;               // planes per fused segment (0 = auto)
-    int tb2_split = 0;              // two 8-row pipelines per CTA with named barriers (experiment)
     int het_fused = 1;              // heterogeneous media: fused one-step sweep (0: two-pass kernels)
     int tb2 = 1;                    // 1: temporally blocked sweep (two steps per pass) where applicable
     unsigned char* d_plane_flags = nullptr; std::vector<unsigned char> plane_flags_host;
@@ -259,7 +258,6 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     if (const char* tj = getenv("FDTD_B200_FUSED_TJ")) e->fused_tj = atoi(tj);
     if (const char* tb = getenv("FDTD_B200_TB2")) e->tb2 = atoi(tb);
     if (const char* hf = getenv("FDTD_B200_HET_FUSED")) e->het_fused = atoi(hf);
-    if (const char* sp = getenv("FDTD_B200_TB2_SPLIT")) e->tb2_split = atoi(sp);
     *out = e;
     return 0;
 }
@@ -1106,8 +1104,7 @@ template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaSt
         }
         if (n == 0) continue;
         t.nseg = n;
-        auto kern = pass ? k_fused3d_tb2<T, R, true, false> : k_fused3d_tb2<T, R, false, false>;
-        if (e->tb2_split) kern = pass ? k_fused3d_tb2<T, R, true, true> : k_fused3d_tb2<T, R, false, true>;
+        auto kern = pass ? k_fused3d_tb2<T, R, true> : k_fused3d_tb2<T, R, false>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned items = (unsigned)n * t.ntj * t.ntk;
         kern<<<items, block, smem, s>>>(in, out, cf, g, t, m, (int)e->planes_alloc, fo);

@@ -168,13 +168,7 @@ constexpr int kTb2OwnLanes = 28;       // owner lanes per row: 28 of 32
 
 template <typename T, int R> constexpr size_t tb2_smem_bytes() { return 2 * (size_t)R * 8 * 32 * 8; }
 
-// SPLIT: the 16 warp rows run as two 8-row pipelines with their own named barriers.  Rows 8..15 never read rows
-// 0..7; row 7 reads row 8's slot, handed over through a full/empty named-barrier pair per buffer parity, so the two
-// halves may drift by one plane and overlap each other's barrier / latency stalls.
-__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-template <typename T, int R, bool OPS, bool SPLIT>
+template <typename T, int R, bool OPS>
 __global__ void __launch_bounds__(32 * R, 1)
 k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, MidOps m, int planes_alloc, Fold fo)
 {
@@ -249,7 +243,6 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
             }
         }
         // ---- publish the j+1 inputs of all four stages ------------------------------------------------------------------
-        if (SPLIT && row == R / 2 && i - (i0 - 3) >= 2) bar_sync(5 + par, 32 * (R / 2) + 32);   // upper half has read slot [par]
         {
             union { VT q; P r; } u;
             u.r = e0bz; s_x[par][row][0][lane] = u.q;  u.r = e0bx; s_x[par][row][1][lane] = u.q;
@@ -257,19 +250,7 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
             u.r = e1bz; s_x[par][row][4][lane] = u.q;  u.r = e1bx; s_x[par][row][5][lane] = u.q;
             u.r = h2az; s_x[par][row][6][lane] = u.q;  u.r = h2ax; s_x[par][row][7][lane] = u.q;
         }
-        if (!SPLIT) {
-            __syncthreads();
-        } else {
-            constexpr int H = R / 2;                     // rows per half
-            const int it = i - (i0 - 3);                 // iteration counter of this CTA
-            if (row >= H) {                              // lower half of the dependency chain: rows H..R-1
-                bar_sync(2, 32 * H);                     // everybody in this half has published
-                if (row == H) bar_arrive(3 + par, 32 * H + 32);          // slot [par][H] is full
-            } else {                                     // rows 0..H-1: row H-1 reads row H's slot
-                bar_sync(1, 32 * H);
-                bar_sync(3 + par, 32 * H + 32);          // wait until row H has published this plane
-            }
-        }
+        __syncthreads();
         P e0z_j, e0x_j, h1z_j, h1x_j, e1z_j, e1x_j, h2z_j, h2x_j;
         {
             union { VT q; P r; } u;
@@ -278,7 +259,6 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
             u.q = s_x[par][rown][4][lane]; e1z_j = u.r;  u.q = s_x[par][rown][5][lane]; e1x_j = u.r;
             u.q = s_x[par][rown][6][lane]; h2z_j = u.r;  u.q = s_x[par][rown][7][lane]; h2x_j = u.r;
         }
-        if (SPLIT && row < R / 2 && i + 2 < i1) bar_arrive(5 + par, 32 * (R / 2) + 32);          // slot [par][R/2] may be reused
         const T e0y_n = shfl_next<T>(e0by.v[0]), e0x_n = shfl_next<T>(e0bx.v[0]);
         const T h1y_n = shfl_next<T>(h1by.v[0]), h1x_n = shfl_next<T>(h1bx.v[0]);
         const T e1y_n = shfl_next<T>(e1by.v[0]), e1x_n = shfl_next<T>(e1bx.v[0]);
