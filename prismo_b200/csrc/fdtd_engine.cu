@@ -89,6 +89,7 @@ struct fdtd_engine {
     cudaGraphExec_t gexec[2] = {nullptr, nullptr}; int graph_steps = 0; int graph_kernels[2] = {0, 0};
     int fused_lx = 0;               // planes per fused segment (0 = auto)
     int het_fused = 1;              // heterogeneous media: fused one-step sweep (0: two-pass kernels)
+    int tb2_zones = -1;             // two-step sweep: narrow x-segments around op planes (-1 auto, 0 never, 1 always)
     int tb2 = 1;                    // 1: temporally blocked sweep (two steps per pass) where applicable
     unsigned char* d_plane_flags = nullptr; std::vector<unsigned char> plane_flags_host;
     int fused_tj = 15;              // owner rows per CTA (15: one 16-warp CTA/SM; 7: two 8-warp CTAs/SM)
@@ -257,6 +258,7 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     if (const char* pol = getenv("FDTD_B200_FUSED_POL")) e->fused_pol = atoi(pol) & 3;
     if (const char* tj = getenv("FDTD_B200_FUSED_TJ")) e->fused_tj = atoi(tj);
     if (const char* tb = getenv("FDTD_B200_TB2")) e->tb2 = atoi(tb);
+    if (const char* z = getenv("FDTD_B200_TB2_ZONES")) e->tb2_zones = atoi(z);
     if (const char* hf = getenv("FDTD_B200_HET_FUSED")) e->het_fused = atoi(hf);
     *out = e;
     return 0;
@@ -1040,6 +1042,95 @@ static bool tb2_ok(const fdtd_engine* e)
 }
 static bool use_tb2(const fdtd_engine* e) { return tb2_ok(e) && e->g.nxg == e->g.nx; }
 
+// x-segments of one two-step sweep (FusedTiling::seg_lo/seg_hi/seg_ops), in dispatch order.
+//  * A segment [a, b) applies the intermediate step's sources / monitors on planes [a, b+1]: planes that carry ops
+//    get NARROW zones of their own ([p-2, p+2) widened to >= 8 planes), so that the op-carrying code path (10 % slower)
+//    runs on a few planes only and everything else takes the op-free path.
+//  * Every segment pays 3 prologue planes; CTAs are dispatched in waves of 148: the number of bulk parts minimises
+//    ceil(tiles * n / 148) * (nx / n + 3).
+//  * Dispatch order: bulk parts first, zones (short items) last to fill the tail; within each kind the segment that
+//    reads the ghost planes (slabs: it spins until the right neighbour's push has landed) goes last.
+static void plan_tb2_segments(const fdtd_engine* e, long long tiles, bool any_ops, bool halo, FusedTiling& t)
+{
+    struct Iv { int lo, hi; bool ops; };
+    const int nx = e->g.nx;
+    const int nflag = any_ops ? (int)e->plane_flags_host.size() : 0;
+    // target length of a bulk part
+    int lxt = e->fused_lx;
+    if (lxt <= 0) {
+        double best = 1e300;
+        int best_n = 1;
+        // measured on 1024^3: parts of 64..256 planes within 0.5 % of each other, 512 planes 1.5 % slower (ragged tail)
+        for (int n = (nx + 255) / 256; n <= kMaxSegs / 2 && (n == 1 || nx / n >= 8); ++n) {
+            const double waves = std::ceil((double)tiles * n / 148.0);
+            const double cost = waves * ((double)(nx + n - 1) / n + 3.0);
+            if (cost < best * 0.999) { best = cost; best_n = n; }
+        }
+        lxt = (nx + best_n - 1) / best_n;
+    }
+    lxt = std::max(lxt, (nx + kMaxSegs / 2 - 1) / (kMaxSegs / 2));
+    std::vector<Iv> zones;
+    // narrow zones cost two more segments (6 prologue planes + CTA start-up): worth it only against long bulk parts
+    const bool want_zones = e->tb2_zones < 0 ? lxt >= 112 : e->tb2_zones != 0;
+    for (int W = 8; want_zones; W *= 2) {
+        zones.clear();
+        for (int p = 0; p < nflag; ++p) {
+            if (!e->plane_flags_host[p]) continue;
+            int lo = std::max(0, std::min(p - 2, nx - W));
+            int hi = std::min(nx, std::max(p + 2, lo + W));
+            if (lo >= nx) continue;
+            if (!zones.empty() && lo <= zones.back().hi) zones.back().hi = std::max(zones.back().hi, hi);
+            else zones.push_back({lo, hi, true});
+        }
+        if ((int)zones.size() <= kMaxSegs / 4 || W >= nx) break;
+    }
+    // intervals in x order: zones and the gaps between them, each cut into equal parts of about lxt planes
+    std::vector<Iv> ivs;
+    int at = 0;
+    for (size_t z = 0; z <= zones.size(); ++z) {
+        const int lo = z < zones.size() ? zones[z].lo : nx;
+        if (lo > at) ivs.push_back({at, lo, false});
+        if (z < zones.size()) { ivs.push_back(zones[z]); at = zones[z].hi; }
+    }
+    std::vector<Iv> parts;
+    for (const Iv& iv : ivs) {
+        const int len = iv.hi - iv.lo;
+        int n = std::max(1, (len + lxt / 2) / lxt);
+        for (int q = 0; q < n; ++q) parts.push_back({iv.lo + (int)((long long)len * q / n), iv.lo + (int)((long long)len * (q + 1) / n), iv.ops});
+    }
+    // a slab whose only segment reads the ghost planes would make every CTA spin for the neighbour's push: cut it
+    if (halo && parts.size() == 1 && nx >= 16) {
+        const Iv p = parts[0];
+        parts = {{p.lo, (p.lo + p.hi) / 2, p.ops}, {(p.lo + p.hi) / 2, p.hi, p.ops}};
+    }
+    while ((int)parts.size() > kMaxSegs) {                  // cannot happen with the caps above; stay safe: merge neighbours
+        size_t k = 0;
+        for (size_t q = 0; q + 1 < parts.size(); ++q)
+            if (parts[q + 1].hi - parts[q].lo < parts[k + 1].hi - parts[k].lo) k = q;
+        parts[k].hi = parts[k + 1].hi; parts[k].ops |= parts[k + 1].ops;
+        parts.erase(parts.begin() + k + 1);
+    }
+    for (Iv& pt : parts) {                                  // the rule the kernel needs: ops on planes [lo, hi + 1]
+        pt.ops = false;
+        for (int p = pt.lo; p <= pt.hi + 1 && p < nflag; ++p) pt.ops |= e->plane_flags_host[p] != 0;
+    }
+    // dispatch order
+    std::stable_sort(parts.begin(), parts.end(), [&](const Iv& a, const Iv& b) {
+        if (a.ops != b.ops) return !a.ops;
+        const bool ha = halo && a.hi + 3 >= nx, hb = halo && b.hi + 3 >= nx;
+        if (ha != hb) return !ha;
+        return a.lo < b.lo;
+    });
+    if (halo && parts.size() > 1 && parts[0].hi + 3 >= nx) std::rotate(parts.begin(), parts.begin() + 1, parts.end());
+    t.nseg = (int)parts.size();
+    t.seg_ops = 0;
+    for (int q = 0; q < t.nseg; ++q) {
+        t.seg_lo[q] = parts[q].lo; t.seg_hi[q] = parts[q].hi;
+        if (parts[q].ops) t.seg_ops |= 1ull << q;
+    }
+    t.lx = lxt;
+}
+
 // TWO steps in one pass over planes [0, nx): reads the current set, writes the other one; the intermediate
 // step's sources / monitors (table row *d_step + step_off) are applied inside the kernel
 template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaStream_t s)
@@ -1059,7 +1150,7 @@ template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaSt
         t.halo_flag = e->slab.flags; t.halo_need = (int)e->slab.step + 1; t.error_word = e->slab.flags + 2;
     }
     const int vec_per_row = g.pz / V;
-    t.own_lanes = kTb2OwnLanes;
+    t.own_lanes = tb2_own_lanes<T>();
     t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
     t.ntj = (g.ny + (R - 4) - 1) / (R - 4);
     MidOps m{};
@@ -1074,43 +1165,24 @@ template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaSt
     m.n_planes = g.nx + 4;
     const bool any_ops = m.n_src || m.n_mon || m.n_gsrc;
     m.plane_flags = any_ops ? e->d_plane_flags : nullptr;
-    int lx = e->fused_lx;
-    if (lx <= 0) {
-        // 3 prologue planes per segment; with ops present prefer more (<= 128-plane) segments so that most of
-        // them are op-free and run the instantiation without any op code in the loop (measured +10 %)
-        const long long tiles = (long long)t.ntj * t.ntk;
-        long long want = (148ll * 24 + tiles - 1) / tiles;
-        lx = (int)std::max<long long>(64, (g.nx + want - 1) / std::max<long long>(want, 1));
-        if (any_ops) lx = std::min(lx, 128);
-        // small grids: keep >= ~2 CTAs per SM's worth of items even at the price of more prologue planes
-        while (lx > 12 && tiles * ((g.nx + lx - 1) / lx) < 148 * 2) lx = (lx + 1) / 2;
+    m.op_lo = 1 << 30; m.op_span = 0;                    // no plane passes the range test
+    if (any_ops) {
+        int lo = -1, hi = -1;
+        for (int p = 0; p < (int)e->plane_flags_host.size() && p < m.n_planes; ++p)
+            if (e->plane_flags_host[p]) { if (lo < 0) lo = p; hi = p; }
+        if (lo >= 0) { m.op_lo = lo; m.op_span = hi - lo; }
     }
-    lx = std::max(lx, (g.nx + 31) / 32);                 // at most 32 segments (seg_map)
-    t.lx = std::min(lx, g.nx);
-    const int nseg_all = (g.nx + t.lx - 1) / t.lx;
     const size_t smem = tb2_smem_bytes<T, R>();
     dim3 block(32, R, 1);
     const Coefs<T> cf = coefs_of<T>(e);
     const Fold fo = fold_of(e);
-    // pass 0: op-free segments (bulk), pass 1: segments whose planes [i0, i1+1] carry a source or monitor
-    for (int pass = 0; pass < 2; ++pass) {
-        int n = 0;
-        for (int sg = 0; sg < nseg_all; ++sg) {
-            const int a = sg * t.lx, b = std::min(a + t.lx, g.nx);
-            bool ops = false;
-            if (any_ops)
-                for (int p = a; p <= b + 1 && p < (int)e->plane_flags_host.size(); ++p) ops |= e->plane_flags_host[p] != 0;
-            if ((int)ops == pass) t.seg_map[n++] = sg;
-        }
-        if (n == 0) continue;
-        t.nseg = n;
-        auto kern = pass ? k_fused3d_tb2<T, R, true> : k_fused3d_tb2<T, R, false>;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned items = (unsigned)n * t.ntj * t.ntk;
-        kern<<<items, block, smem, s>>>(in, out, cf, g, t, m, (int)e->planes_alloc, fo);
-        e->launches++;
-        CU(cudaGetLastError());
-    }
+    plan_tb2_segments(e, (long long)t.ntj * t.ntk, any_ops, t.halo_flag != nullptr, t);
+    auto kern = k_fused3d_tb2<T, R>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
+    kern<<<items, block, smem, s>>>(in, out, cf, g, t, m, (int)e->planes_alloc, fo);
+    e->launches++;
+    CU(cudaGetLastError());
     e->cur ^= 1;
     return 0;
 }

@@ -21,13 +21,18 @@
 
 namespace fdtd {
 
+constexpr int kMaxSegs = 48;
+
 struct FusedTiling {
     int i_begin, i_end;     // planes [i_begin, i_end) are produced by this launch
     int lx;                 // planes per segment
     int nseg, ntj, ntk;     // items = nseg * ntj * ntk
     int own_lanes;          // lanes per row that own (store) cells; lanes >= own_lanes are rim providers
-    int seg_map[32];        // two-step sweep: the x-segments this launch covers (op-free and op-carrying
-                            // segments run different instantiations); ignored by the one-step sweep
+    // two-step sweep only: explicit x-segments [seg_lo, seg_hi) in dispatch order (bulk first, narrow op-carrying
+    // ones next, the one that reads the ghost planes as late as possible); bit s of seg_ops = segment s has sources /
+    // monitors on its planes and runs the op-carrying code path
+    int seg_lo[kMaxSegs], seg_hi[kMaxSegs];
+    unsigned long long seg_ops;
     // x-slabs: items that read the ghost planes (their segment ends at plane nx) first wait until the right
     // neighbour has pushed them:  *halo_flag >= halo_need  (system-scope acquire; null = no wait)
     const int* halo_flag;

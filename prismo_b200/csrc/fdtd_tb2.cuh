@@ -31,6 +31,8 @@ struct MidOps {
     void* rec; double2* dft; double dt;
     const int* step_ptr; int step_off;          // table row of the intermediate step = *step_ptr + step_off
     const unsigned char* plane_flags;           // per local plane: bit0 a source op covers it, bit1 a monitor op
+    int op_lo, op_span;                         // flagged planes lie in [op_lo, op_lo + op_span]: a register compare
+                                                // keeps the flag load out of every other iteration
 };
 
 template <typename T> struct Vec8;
@@ -164,13 +166,17 @@ __device__ __forceinline__ void stage_e(const Coefs<T>& c, const Geom& g, const 
 }
 
 constexpr int kTb2Rows = 16;           // warp rows per CTA: 12 owners + 4 rim
-constexpr int kTb2OwnLanes = 28;       // owner lanes per row: 28 of 32
+// Owner lanes per row.  Each of the four stages consumes one more element in +k.  With one element per lane (fp64)
+// that costs a lane per stage: 28 owners.  With two elements per lane (fp32) validity shrinks by half a lane per
+// stage (lane 31 keeps a valid v[0] after stage A, lane 30 stays whole after stage B, ...): 30 owners.
+template <typename T> constexpr int tb2_own_lanes() { return Vec8<T>::V >= 2 ? 30 : 28; }
 
 template <typename T, int R> constexpr size_t tb2_smem_bytes() { return 2 * (size_t)R * 8 * 32 * 8; }
 
 template <typename T, int R, bool OPS>
-__global__ void __launch_bounds__(32 * R, 1)
-k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, MidOps m, int planes_alloc, Fold fo)
+__device__ __forceinline__ void
+tb2_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const Geom& g, const FusedTiling& t,
+          const MidOps& m, const int planes_alloc, const Fold& fo)
 {
     constexpr int V = Vec8<T>::V;
     typedef Pack<T, V> P;
@@ -182,12 +188,11 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
     const int lane = threadIdx.x, row = threadIdx.y;
     const int ntiles = t.ntj * t.ntk;
     const int slot = blockIdx.x / ntiles, tile = blockIdx.x - slot * ntiles;
-    const int seg = t.seg_map[slot];
     const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
     const int j = tj * (R - 4) + row;
     const int k = (tk * t.own_lanes + lane) * V;
-    const int i0 = t.i_begin + seg * t.lx;
-    const int i1 = min(i0 + t.lx, t.i_end);
+    const int i0 = t.seg_lo[slot];
+    const int i1 = t.seg_hi[slot];
     if (t.halo_flag && i1 + 3 >= g.nx) {          // this segment reads E0 up to plane i1+3: ghost planes start at nx
         if (threadIdx.x == 0 && threadIdx.y == 0) wait_flag_ge(t.halo_flag, t.halo_need, t.error_word, t.timeout_ns);
         __syncthreads();
@@ -229,7 +234,7 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
         const P ph0x = ld8<T, V>(phx + pp, ph_ok), ph0y = ld8<T, V>(phy + pp, ph_ok), ph0z = ld8<T, V>(phz + pp, ph_ok);
 
         // ---- intermediate-step H sources / monitors on H1[i+1] (all of its pre-source uses are done) --------------
-        if (OPS && m.plane_flags && i + 1 >= i0 && i + 1 < m.n_planes) {
+        if (OPS && (unsigned)(i + 1 - m.op_lo) <= (unsigned)m.op_span && i + 1 >= i0) {
             const unsigned char fl = m.plane_flags[i + 1];
             if (fl & 1) {
                 mid_sources<T, V>(m, 3, i + 1, j, k, step_row, h1ax);
@@ -269,7 +274,7 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
                               e0x_n, ne0y, ne0z, h1cx, h1cy, h1cz);                                                  \
         stage_e<T, V, MASKED>(c, g, fo, g.x0 + i + 2, jy1, k, e0ax, e0ay, e0az, h1bx, h1by, h1bz, h1z_j, h1x_j, h1y_n,        \
                               h1x_n, h1cy, h1cz, e1cx, e1cy, e1cz);                                                  \
-        if (OPS && m.plane_flags && (STEADY || (i + 2 >= i0 && i + 2 < m.n_planes))) {                             \
+        if (OPS && (unsigned)(i + 2 - m.op_lo) <= (unsigned)m.op_span && (STEADY || i + 2 >= i0)) {                 \
             const unsigned char fl = m.plane_flags[i + 2];                                                         \
             if (fl & 1) {                                                                                          \
                 mid_sources<T, V>(m, 0, i + 2, j, k, step_row, e1cx);                                              \
@@ -316,6 +321,19 @@ k_fused3d_tb2(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, M
         e1bx = e1cx; e1by = e1cy; e1bz = e1cz;
         h2ax = h2bx; h2ay = h2by; h2az = h2bz;
     }
+}
+
+// One launch covers every x-segment of the pair of steps.  Whether a segment carries sources / monitors is uniform per
+// CTA, so op-free segments run a loop without any op code (measured +10 %) and nothing serialises between the two kinds.
+template <typename T, int R>
+__global__ void __launch_bounds__(32 * R, 1)
+k_fused3d_tb2(const __grid_constant__ CFields<T> in, const __grid_constant__ Fields<T> out,
+              const __grid_constant__ Coefs<T> c, const __grid_constant__ Geom g, const __grid_constant__ FusedTiling t,
+              const __grid_constant__ MidOps m, const int planes_alloc, const __grid_constant__ Fold fo)
+{
+    const int slot = blockIdx.x / (t.ntj * t.ntk);
+    if ((t.seg_ops >> slot) & 1ull) tb2_sweep<T, R, true>(in, out, c, g, t, m, planes_alloc, fo);
+    else tb2_sweep<T, R, false>(in, out, c, g, t, m, planes_alloc, fo);
 }
 
 }  // namespace fdtd
