@@ -23,6 +23,8 @@ def run_multi(args, rank, world, local):
     cells = dims[0] * dims[1] * dims[2]
     eng, dt, spacing, x0, nxl = B.make_engine(dims, args.dtype, rank, world, device=local)
     src, mon = B.workload_ops(dims, dt, spacing, x0, nxl)
+    if args.no_ops:
+        src, mon = [], []
     for op in src:
         eng.add_source_op(op)
     mon_ids = [eng.add_monitor_op(op) for op in mon]

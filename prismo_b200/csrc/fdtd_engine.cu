@@ -104,6 +104,7 @@ struct fdtd_engine {
                                          // [1] ghost_consumed (written by us, read by the right neighbour), [2] error
         void* left_fld[2][6] = {};       // left neighbour's arrays (IPC-mapped): we push into its ghost planes
         int* left_flags = nullptr;       // left neighbour's flags (we write [0], read [1])
+        int* seq = nullptr;              // seq[i] = i: source of the 4-byte DMA that publishes halo_ready = i
         void* left_base[13] = {};        // mapped bases to close
         cudaStream_t comm = nullptr;
         cudaEvent_t post_done = nullptr, push_done = nullptr;
@@ -283,6 +284,7 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     fused_release(e->fused);
     if (e->t0) { cudaEventDestroy(e->t0); cudaEventDestroy(e->t1); }
     if (e->slab.comm) { cudaStreamSynchronize(e->slab.comm); cudaStreamDestroy(e->slab.comm); }
+    if (e->slab.seq) cudaFree(e->slab.seq);
     if (e->slab.post_done) { cudaEventDestroy(e->slab.post_done); cudaEventDestroy(e->slab.push_done); }
     for (void* b : e->slab.left_base) if (b) cudaIpcCloseMemHandle(b);
     cudaFree(e->slab.flags);
@@ -1450,6 +1452,8 @@ extern "C" int fdtd_sweep(fdtd_engine* e, int32_t i_begin, int32_t i_end, int32_
 }
 
 // ---- peer-to-peer slabs ------------------------------------------------------------------------------------------
+constexpr int kSeqLen = 1 << 20;          // exchanges per connect that publish their flag by DMA (then: a kernel)
+
 struct IpcBlob {
     cudaIpcMemHandle_t fld[2][6];
     cudaIpcMemHandle_t flags;
@@ -1489,7 +1493,13 @@ extern "C" int fdtd_ipc_connect(fdtd_engine* e, const void* left_blob, int32_t h
     auto& sl = e->slab;
     if (!sl.flags) return fail(FDTD_ESTATE, "call fdtd_ipc_export first");
     if (!sl.comm) {
+        // The comm stream carries DMA only (plane copies + a 4-byte copy of the exchange number into the neighbour's
+        // halo_ready word): nothing on it needs an SM slot while the sweep occupies every SM.
         CU(cudaStreamCreateWithFlags(&sl.comm, cudaStreamNonBlocking));
+        std::vector<int> seq(kSeqLen);
+        for (int i = 0; i < kSeqLen; ++i) seq[i] = i;
+        CU(cudaMalloc(&sl.seq, sizeof(int) * kSeqLen));
+        CU(cudaMemcpy(sl.seq, seq.data(), sizeof(int) * kSeqLen, cudaMemcpyHostToDevice));
         CU(cudaEventCreateWithFlags(&sl.post_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&sl.push_done, cudaEventDisableTiming));
     }
@@ -1521,13 +1531,17 @@ extern "C" int fdtd_ipc_connect(fdtd_engine* e, const void* left_blob, int32_t h
 }
 
 // n full steps of this slab, everything enqueued asynchronously (no host synchronisation inside):
-//   comm stream    : wait until the left neighbour has consumed the ghosts of two steps ago, DMA our planes 0/1
-//                    (7 planes) into its ghost planes over NVLink, release-store its halo_ready flag
-//   compute stream : ONE fused sweep over all planes — only the CTAs of the last x-segment wait (in-kernel) for
-//                    our own halo_ready flag —, publish ghost_consumed, then sources + monitors
+//   comm stream    : DMA only — our first planes (7 per step, 21 per pair of steps) into the left neighbour's ghost
+//                    planes over NVLink, then a 4-byte copy of the exchange number into its halo_ready word
+//   compute stream : ONE fused sweep over all planes — only the CTAs of the ghost-reading x-segment wait (in-kernel)
+//                    for our own halo_ready word —, publish ghost_consumed and wait until the left neighbour has
+//                    consumed the ghosts our next push overwrites (1 thread, SMs idle), then sources + monitors
 template <typename T> static int slab_run(fdtd_engine* e, int n)
 {
     auto& sl = e->slab;
+    // FDTD_B200_SLAB_DEBUG=1: print this rank's mean sweep duration and pair period to stderr (synchronises)
+    static const bool dbg = getenv("FDTD_B200_SLAB_DEBUG") && atoi(getenv("FDTD_B200_SLAB_DEBUG"));
+    std::vector<cudaEvent_t> dbg_ev;
     cudaStream_t cs = e->stream, ms = sl.comm;
     // single-step sweep: plane 0 of Ex Ey Ez Hy Hz + plane 1 of Ey Ez; two-step sweep: planes 0..3 of E, 0..2 of H
     static const int planes1[6] = {1, 2, 2, 0, 1, 1};
@@ -1541,23 +1555,32 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
         const long long st = sl.step;                    // exchange counter, identical on every rank
         if (sl.has_left) {
             CU(cudaStreamWaitEvent(ms, sl.post_done, 0));        // our first planes of the current set are final
-            if (st >= 2) { k_wait<<<1, 1, 0, ms>>>(sl.left_flags + 1, (int)(st - 1), sl.flags + 2, sl.timeout_ns); e->launches++; }
             void** mine = cur_fields(e);
             void** theirs = sl.left_fld[e->cur];
             for (int c = 0; c < 6; ++c)
                 if (planes[c])
                     CU(cudaMemcpyAsync((char*)theirs[c] + (size_t)sl.left_nx * pbytes, mine[c], planes[c] * pbytes,
                                        cudaMemcpyDefault, ms));
-            k_signal<<<1, 1, 0, ms>>>(sl.left_flags, (int)(st + 1)); e->launches++;
+            if (st + 1 < kSeqLen)
+                CU(cudaMemcpyAsync(sl.left_flags, sl.seq + (st + 1), sizeof(int), cudaMemcpyDefault, ms));
+            else { k_signal<<<1, 1, 0, ms>>>(sl.left_flags, (int)(st + 1)); e->launches++; }
             CU(cudaEventRecord(sl.push_done, ms));
         }
         if (pair) {
+            if (dbg) { dbg_ev.emplace_back(); cudaEventCreate(&dbg_ev.back()); cudaEventRecord(dbg_ev.back(), cs); }
             if (int rc = launch_tb2<T>(e, q, cs)) return rc;             // flips the sets itself
+            if (dbg) { dbg_ev.emplace_back(); cudaEventCreate(&dbg_ev.back()); cudaEventRecord(dbg_ev.back(), cs); }
         } else {
             if (int rc = launch_fused<T>(e, 0, e->g.nx, cs)) return rc;   // reads the current set (+ ghosts)
             e->cur ^= 1;
         }
-        k_signal<<<1, 1, 0, cs>>>(sl.flags + 1, (int)(st + 1)); e->launches++;
+        // ghosts consumed; and (for our NEXT push) wait until the left neighbour has finished the sweep that read the
+        // ghost planes that push will overwrite — in order on the compute stream, when the SMs are idle anyway
+        if (sl.has_left && st >= 1)
+            k_signal_wait<<<1, 1, 0, cs>>>(sl.flags + 1, (int)(st + 1), sl.left_flags + 1, (int)st, sl.flags + 2, sl.timeout_ns);
+        else
+            k_signal<<<1, 1, 0, cs>>>(sl.flags + 1, (int)(st + 1));
+        e->launches++;
         // the push read the set that is now the output set of the NEXT sweep: it must finish before that sweep
         if (sl.has_left) CU(cudaStreamWaitEvent(cs, sl.push_done, 0));
         q += pair ? 2 : 1;
@@ -1567,6 +1590,18 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
     }
     k_bump<<<1, 1, 0, cs>>>(e->d_step, n); e->launches++;
     CU(cudaGetLastError());
+    if (dbg_ev.size() >= 4) {
+        cudaStreamSynchronize(cs);
+        double kern = 0, period = 0;
+        const size_t np = dbg_ev.size() / 2;
+        for (size_t p = 0; p < np; ++p) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, dbg_ev[2 * p], dbg_ev[2 * p + 1]); kern += ms;
+            if (p + 1 < np) { cudaEventElapsedTime(&ms, dbg_ev[2 * p], dbg_ev[2 * p + 2]); period += ms; }
+        }
+        fprintf(stderr, "[fdtd dbg] dev %d pairs %zu sweep %.4f ms period %.4f ms\n", e->cfg.device, np, kern / np, period / (np - 1));
+        for (auto ev : dbg_ev) cudaEventDestroy(ev);
+    }
     return 0;
 }
 

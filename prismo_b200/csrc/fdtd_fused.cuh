@@ -67,6 +67,12 @@ __device__ __forceinline__ void wait_flag_ge(const int* flag, int need, int* err
     }
 }
 __global__ void k_signal(int* flag, int v) { __threadfence_system(); st_release_sys(flag, v); }
+__global__ void k_signal_wait(int* flag, int v, const int* other, int need, int* error_word, unsigned long long timeout_ns)
+{
+    __threadfence_system();
+    st_release_sys(flag, v);
+    wait_flag_ge(other, need, error_word, timeout_ns);
+}
 __global__ void k_wait(const int* flag, int need, int* error_word, unsigned long long timeout_ns)
 {
     wait_flag_ge(flag, need, error_word, timeout_ns);
