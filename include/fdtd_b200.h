@@ -192,6 +192,15 @@ int  fdtd_steps_done(fdtd_engine* e, int64_t* steps);
 int  fdtd_kernel_launches(fdtd_engine* e, int64_t* launches); /* kernels launched by this handle  */
 int  fdtd_mem_info(fdtd_engine* e, int64_t* free_bytes, int64_t* total_bytes);
 
+/* Host-only (no device needed): the x-segment plan of one two-step sweep over nx planes.  plane_flags[p] != 0 marks
+ * planes that carry source / monitor ops (n_flags may exceed nx by the ghost planes of a slab); tiles = (j,k) tiles
+ * per segment; halo != 0: the slab reads ghost planes; fused_lx > 0 forces the bulk part length; zones_mode -1 auto,
+ * 0 off, 1 on.  Writes segments in dispatch order ([lo, hi), ops flag) and returns their count (< 0: error).
+ * No reference counterpart (the reference has no tiling); exported for the planner's unit tests. */
+int  fdtd_plan_segments(int32_t nx, const uint8_t* plane_flags, int32_t n_flags, int64_t tiles, int32_t halo,
+                        int32_t fused_lx, int32_t zones_mode, int32_t* seg_lo, int32_t* seg_hi, int32_t* seg_ops,
+                        int32_t max_segs);
+
 #ifdef __cplusplus
 }
 #endif

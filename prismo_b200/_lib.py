@@ -99,6 +99,8 @@ _PROTOS = {
     "fdtd_steps_done": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "fdtd_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "fdtd_mem_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fdtd_plan_segments": (C.c_int, [C.c_int32, C.POINTER(C.c_uint8), C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]),
 }
 EXPORTS = tuple(_PROTOS)
 

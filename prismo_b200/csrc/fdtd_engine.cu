@@ -1052,13 +1052,13 @@ static bool use_tb2(const fdtd_engine* e) { return tb2_ok(e) && e->g.nxg == e->g
 //    ceil(tiles * n / 148) * (nx / n + 3).
 //  * Dispatch order: bulk parts first, zones (short items) last to fill the tail; within each kind the segment that
 //    reads the ghost planes (slabs: it spins until the right neighbour's push has landed) goes last.
-static void plan_tb2_segments(const fdtd_engine* e, long long tiles, bool any_ops, bool halo, FusedTiling& t)
+struct SegIv { int lo, hi; bool ops; };
+static std::vector<SegIv> plan_segments(int nx, const unsigned char* flags, int nflag, long long tiles, bool halo,
+                                        int fused_lx, int zones_mode, int* lx_out)
 {
-    struct Iv { int lo, hi; bool ops; };
-    const int nx = e->g.nx;
-    const int nflag = any_ops ? (int)e->plane_flags_host.size() : 0;
+    typedef SegIv Iv;
     // target length of a bulk part
-    int lxt = e->fused_lx;
+    int lxt = fused_lx;
     if (lxt <= 0) {
         double best = 1e300;
         int best_n = 1;
@@ -1073,11 +1073,11 @@ static void plan_tb2_segments(const fdtd_engine* e, long long tiles, bool any_op
     lxt = std::max(lxt, (nx + kMaxSegs / 2 - 1) / (kMaxSegs / 2));
     std::vector<Iv> zones;
     // narrow zones cost two more segments (6 prologue planes + CTA start-up): worth it only against long bulk parts
-    const bool want_zones = e->tb2_zones < 0 ? lxt >= 112 : e->tb2_zones != 0;
+    const bool want_zones = zones_mode < 0 ? lxt >= 112 : zones_mode != 0;
     for (int W = 8; want_zones; W *= 2) {
         zones.clear();
         for (int p = 0; p < nflag; ++p) {
-            if (!e->plane_flags_host[p]) continue;
+            if (!flags[p]) continue;
             int lo = std::max(0, std::min(p - 2, nx - W));
             int hi = std::min(nx, std::max(p + 2, lo + W));
             if (lo >= nx) continue;
@@ -1114,7 +1114,7 @@ static void plan_tb2_segments(const fdtd_engine* e, long long tiles, bool any_op
     }
     for (Iv& pt : parts) {                                  // the rule the kernel needs: ops on planes [lo, hi + 1]
         pt.ops = false;
-        for (int p = pt.lo; p <= pt.hi + 1 && p < nflag; ++p) pt.ops |= e->plane_flags_host[p] != 0;
+        for (int p = pt.lo; p <= pt.hi + 1 && p < nflag; ++p) pt.ops |= flags[p] != 0;
     }
     // dispatch order
     std::stable_sort(parts.begin(), parts.end(), [&](const Iv& a, const Iv& b) {
@@ -1124,13 +1124,34 @@ static void plan_tb2_segments(const fdtd_engine* e, long long tiles, bool any_op
         return a.lo < b.lo;
     });
     if (halo && parts.size() > 1 && parts[0].hi + 3 >= nx) std::rotate(parts.begin(), parts.begin() + 1, parts.end());
+    if (lx_out) *lx_out = lxt;
+    return parts;
+}
+
+static void plan_tb2_segments(const fdtd_engine* e, long long tiles, bool any_ops, bool halo, FusedTiling& t)
+{
+    const int nflag = any_ops ? (int)e->plane_flags_host.size() : 0;
+    const std::vector<SegIv> parts = plan_segments(e->g.nx, e->plane_flags_host.data(), nflag, tiles, halo, e->fused_lx,
+                                                   e->tb2_zones, &t.lx);
     t.nseg = (int)parts.size();
     t.seg_ops = 0;
     for (int q = 0; q < t.nseg; ++q) {
         t.seg_lo[q] = parts[q].lo; t.seg_hi[q] = parts[q].hi;
         if (parts[q].ops) t.seg_ops |= 1ull << q;
     }
-    t.lx = lxt;
+}
+
+// host-only: the segment plan for a hypothetical slab (unit tests of the planner run without a GPU)
+extern "C" int fdtd_plan_segments(int32_t nx, const uint8_t* plane_flags, int32_t n_flags, int64_t tiles, int32_t halo,
+                                  int32_t fused_lx, int32_t zones_mode, int32_t* seg_lo, int32_t* seg_hi, int32_t* seg_ops,
+                                  int32_t max_segs)
+{
+    if (nx <= 0 || tiles <= 0 || n_flags < 0 || (n_flags && !plane_flags) || !seg_lo || !seg_hi || !seg_ops)
+        return fail(FDTD_EINVAL, "fdtd_plan_segments: bad argument");
+    const std::vector<SegIv> parts = plan_segments(nx, plane_flags, n_flags, tiles, halo != 0, fused_lx, zones_mode, nullptr);
+    if ((int)parts.size() > max_segs) return fail(FDTD_EINVAL, "fdtd_plan_segments: %d segments > max_segs", (int)parts.size());
+    for (size_t q = 0; q < parts.size(); ++q) { seg_lo[q] = parts[q].lo; seg_hi[q] = parts[q].hi; seg_ops[q] = parts[q].ops; }
+    return (int)parts.size();
 }
 
 // TWO steps in one pass over planes [0, nx): reads the current set, writes the other one; the intermediate
