@@ -170,15 +170,22 @@ def tables(n_steps, dt, t0=0.0):
     return amp, ph, t
 
 
-def make_engine(dims, dtype, rank=0, world=1, device=0, flags=0):
+def workload_timestep():
+    spacing = (2e-8, 2e-8, 2e-8)
+    return 0.9 / (C0 * np.sqrt(3.0 / spacing[0] ** 2)), spacing
+
+
+def make_engine(dims, dtype, rank=0, world=1, device=0, flags=0, span=None):
+    """span = (x0, n) overrides the uniform x-slab of this rank (load-balanced slabs, bench_multi.py)."""
     import prismo_b200 as pb
 
     nx, ny, nz = dims
-    spacing = (2e-8, 2e-8, 2e-8)
-    dt = 0.9 / (C0 * np.sqrt(3.0 / spacing[0] ** 2))
+    dt, spacing = workload_timestep()
     base, rem = divmod(nx, world)
     nxl = base + (1 if rank < rem else 0)
     x0 = rank * base + min(rank, rem)
+    if span is not None:
+        x0, nxl = span
     eng = pb.Engine(3, (nxl, ny, nz), spacing, dt, dtype=dtype, device=device, nx_global=nx, x_offset=x0, flags=flags)
     return eng, dt, spacing, x0, nxl
 

@@ -21,7 +21,17 @@ def run_multi(args, rank, world, local):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name, dims = B.parse_workload(args.workload)
     cells = dims[0] * dims[1] * dims[2]
-    eng, dt, spacing, x0, nxl = B.make_engine(dims, args.dtype, rank, world, device=local)
+    span = None
+    balanced = os.environ.get("FDTD_B200_BALANCE", "0") == "1" and not args.no_ops
+    if balanced:
+        # load-balanced slabs: ranks run in lock step, so the rank that owns the DFT plane (complex128 read-modify-
+        # write of 10 planes per step on top of its sweep) gets fewer planes.  Same cut on every rank (pure function).
+        from prismo_b200.multigpu import balanced_slab_ranges, plane_costs
+
+        dt0, spacing0 = B.workload_timestep()
+        g_src, g_mon = B.workload_ops(dims, dt0, spacing0)
+        span = balanced_slab_ranges(plane_costs(dims[0], dims[1] * dims[2], g_src, g_mon), world)[rank]
+    eng, dt, spacing, x0, nxl = B.make_engine(dims, args.dtype, rank, world, device=local, span=span)
     src, mon = B.workload_ops(dims, dt, spacing, x0, nxl)
     if args.no_ops:
         src, mon = [], []
@@ -85,8 +95,9 @@ def run_multi(args, rank, world, local):
                 "config": {"workload": f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} vacuum (uniform coefficients), TFSF +x "
                                        f"plane source, FieldMonitor DFT plane (Ey,Hz x 5 freq)",
                            "l2": "per-rank working set >> 126 MB L2 (no flush needed)",
-                           "parallelism": f"x-slabs over {world} GPUs, {dims[0] // world} planes each, "
-                                          f"{halo_bytes / 1e6:.1f} MB halo per interface per step, "
+                           "parallelism": f"x-slabs over {world} GPUs, "
+                                          + (f"load-balanced (this rank: {nxl} planes), " if balanced else f"{dims[0] // world} planes each, ")
+                                          + f"{halo_bytes / 1e6:.1f} MB halo per interface per step, "
                                           + ("NCCL send/recv" if halo == "nccl" else
                                              "DMA push into the neighbour's ghost planes over NVLink (CUDA IPC) + "
                                              "release/acquire flags, in-kernel wait"),

@@ -30,6 +30,72 @@ def slab_range(nx: int, rank: int, world: int):
     return rank * base + min(rank, rem), n
 
 
+def plane_costs(nx: int, plane_cells: int, source_ops=(), monitor_ops=(), op_path_planes: float = 6.0):
+    """Cost of every x-plane in units of "one plane of the sweep", for load-balanced slabs.
+
+    A plane of the two-step sweep moves ~24 B per cell and step.  A DFT monitor read-modify-writes one complex128
+    per cell, component and frequency each step (32 B): a monitor op adds n_freq * 32 / 24 * (its cells in the
+    plane / plane_cells) plane-equivalents to every plane it covers; a recording op 8 B per cell.  Every plane that
+    carries any op also puts its x-segment on the op-carrying code path (~9 % slower over ~64 planes):
+    `op_path_planes`.  Ops are GLOBAL ops (x in global planes) with .lo / .hi boxes (SourceOp / MonitorOp)."""
+    import numpy as np
+
+    cost = np.ones(nx, dtype=np.float64)
+    touched = np.zeros(nx, dtype=bool)
+    for op in source_ops:
+        touched[max(op.lo[0], 0):min(op.hi[0], nx)] = True
+    for op in monitor_ops:
+        a, b = max(op.lo[0], 0), min(op.hi[0], nx)
+        if b <= a:
+            continue
+        touched[a:b] = True
+        frac = (op.hi[1] - op.lo[1]) * (op.hi[2] - op.lo[2]) / float(plane_cells)
+        per_cell = 32.0 * getattr(op, "n_freq", 0) + (8.0 if getattr(op, "record", False) else 0.0)
+        cost[a:b] += per_cell / 24.0 * frac
+    cost[touched] += op_path_planes
+    return cost
+
+
+def balanced_slab_ranges(costs, world: int, min_planes: int = 4):
+    """Contiguous x-slabs [(x0, n)] * world that minimise the LARGEST summed plane cost (the ranks run in lock
+    step, so the most expensive slab sets the pace): bisection on the capacity + greedy fill.  Every slab keeps
+    >= min_planes planes (the two-step sweep ships 4 of them).  Unit costs give slabs whose sizes differ by <= 1."""
+    import numpy as np
+
+    costs = np.asarray(costs, dtype=np.float64)
+    nx = len(costs)
+    if world < 1 or nx < world * min_planes:
+        raise ValueError(f"{nx} planes cannot give {world} slabs of >= {min_planes} planes")
+    cum = np.concatenate([[0.0], np.cumsum(costs)])
+
+    def fill(cap):
+        cuts = [0]
+        for r in range(world):
+            a = cuts[-1]
+            hi_allowed = nx - (world - r - 1) * min_planes
+            b = int(np.searchsorted(cum, cum[a] + cap * (1 + 1e-12), side="right")) - 1      # largest b: cost[a:b] <= cap
+            b = min(max(b, a + min_planes), hi_allowed)
+            cuts.append(b)
+        return cuts
+
+    lo, hi = cum[-1] / world, cum[-1]
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if fill(mid)[-1] >= nx:
+            hi = mid
+        else:
+            lo = mid
+    cuts = fill(hi)
+    cuts[-1] = nx
+    # the greedy fill leaves the slack in the last slab: hand planes back from the left while that lowers nothing
+    # below the others (keeps unit-cost slabs within one plane of each other)
+    for r in range(world - 1, 0, -1):
+        while cuts[r] - cuts[r - 1] > min_planes and \
+                (cum[cuts[r + 1]] - cum[cuts[r] - 1]) <= (cum[cuts[r]] - cum[cuts[r - 1]]):
+            cuts[r] -= 1
+    return [(cuts[r], cuts[r + 1] - cuts[r]) for r in range(world)]
+
+
 # (component, planes to ship): plane 0 of everything the ghost-plane H+ recompute reads, plane 1 of Ey/Ez
 HALO_SPEC = (("Ex", 1), ("Ey", 2), ("Ez", 2), ("Hy", 1), ("Hz", 1))
 

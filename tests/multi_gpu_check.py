@@ -17,7 +17,7 @@ def main():
     import torch.distributed as dist
 
     import prismo_b200 as pb
-    from prismo_b200.multigpu import PeerSlabRunner, SlabStepper, slab_range
+    from prismo_b200.multigpu import PeerSlabRunner, SlabStepper, balanced_slab_ranges, slab_range
 
     same = "--same-device" in sys.argv
     if "--sim" in sys.argv:
@@ -29,6 +29,12 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("gloo" if same else "nccl")
     dims, steps = (8 * world + 5, 45, 70), 9
+    if "--balanced" in sys.argv:                 # uneven slabs (load-balanced decomposition): same results required
+        w = np.ones(dims[0])
+        w[dims[0] - 3] = 9.0
+        w[3] = 5.0
+        spans = balanced_slab_ranges(w, world)
+        slab_range = lambda nx, r, wd: spans[r]  # noqa: E731
     spacing = (2e-8, 2.5e-8, 3e-8)
     dt = 0.5 / (299792458.0 * np.sqrt(sum((1 / s) ** 2 for s in spacing)))
     comps = ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")

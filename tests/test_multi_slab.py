@@ -69,7 +69,18 @@ def _reference_run():
     return F, dft
 
 
-def _worker(rank, world, port, out_dir):
+def _uneven_spans(world):
+    """Load-balanced slabs for a grid whose DFT plane (11) and source planes (7, 15) are expensive."""
+    from prismo_b200.multigpu import balanced_slab_ranges
+
+    w = np.ones(DIMS[0])
+    w[11] += 6.0
+    w[7] += 2.0
+    w[15] += 2.0
+    return balanced_slab_ranges(w, world, min_planes=4)
+
+
+def _worker(rank, world, port, out_dir, uneven=False):
     import torch.distributed as dist
 
     import prismo_b200 as pb
@@ -78,7 +89,7 @@ def _worker(rank, world, port, out_dir):
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    x0, nxl = slab_range(DIMS[0], rank, world)
+    x0, nxl = _uneven_spans(world)[rank] if uneven else slab_range(DIMS[0], rank, world)
     eng = FakeSlabEngine(3, (nxl, DIMS[1], DIMS[2]), SPACING, DT, nx_global=DIMS[0], x_offset=x0)
     init = _initial(DIMS)
     for c in S.COMPONENTS:
@@ -105,11 +116,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_slab_stepper_gloo_bitwise(world, tmp_path):
+@pytest.mark.parametrize("world,uneven", [(2, False), (3, False), (3, True)])
+def test_slab_stepper_gloo_bitwise(world, uneven, tmp_path):
     import torch.multiprocessing as mp
 
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    if uneven:
+        sizes = [n for _, n in _uneven_spans(world)]
+        assert max(sizes) - min(sizes) >= 2                     # really uneven
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), uneven), nprocs=world, join=True)
     F, dft = _reference_run()
     seen_dft = False
     for r in range(world):
@@ -133,6 +147,39 @@ def test_slab_ranges_cover_the_grid():
             assert spans[0][0] == 0 and sum(n for _, n in spans) == nx
             assert all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(n for _, n in spans) - min(n for _, n in spans) <= 1
+
+
+def test_balanced_slab_ranges():
+    from prismo_b200 import MonitorOp, SourceOp
+    from prismo_b200.multigpu import balanced_slab_ranges, plane_costs, slab_range
+
+    rng = np.random.default_rng(5)
+    for nx in (8, 23, 128, 1024):
+        for world in (1, 2, 3, 8):
+            if nx < 4 * world:
+                with pytest.raises(ValueError):
+                    balanced_slab_ranges(np.ones(nx), world)
+                continue
+            # unit costs: as even as slab_range
+            spans = balanced_slab_ranges(np.ones(nx), world)
+            assert sorted(n for _, n in spans) == sorted(slab_range(nx, r, world)[1] for r in range(world))
+            # random costs: a partition, >= 4 planes each, never worse than the uniform cut
+            cost = 1.0 + 30.0 * (rng.random(nx) < 0.02) * rng.random(nx)
+            spans = balanced_slab_ranges(cost, world)
+            assert spans[0][0] == 0 and sum(n for _, n in spans) == nx
+            assert all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert min(n for _, n in spans) >= 4
+            worst = max(cost[a:a + n].sum() for a, n in spans)
+            uniform = max(cost[a:a + n].sum() for a, n in (slab_range(nx, r, world) for r in range(world)))
+            assert worst <= uniform + 1e-9
+    # the bench workload: the rank that owns the DFT plane gets fewer planes
+    src = [SourceOp("Ey", (256, 0, 0), (257, 1024, 1023), 0), SourceOp("Hz", (256, 0, 0), (257, 1023, 1023), 1)]
+    mon = [MonitorOp("Ey", (768, 0, 0), (769, 1024, 1023), False, 5, 0), MonitorOp("Hz", (768, 0, 0), (769, 1023, 1023), False, 5, 0)]
+    cost = plane_costs(1024, 1024 * 1024, src, mon)
+    assert cost[0] == 1.0 and 6.9 < cost[256] < 7.1 and 20.0 < cost[768] < 20.7
+    spans = balanced_slab_ranges(cost, 8)
+    owner = [n for a, n in spans if a <= 768 < a + n][0]
+    assert owner < 120 and max(cost[a:a + n].sum() for a, n in spans) < 135
 
 
 @pytest.mark.gpu
