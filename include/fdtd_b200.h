@@ -192,6 +192,20 @@ int  fdtd_steps_done(fdtd_engine* e, int64_t* steps);
 int  fdtd_kernel_launches(fdtd_engine* e, int64_t* launches); /* kernels launched by this handle  */
 int  fdtd_mem_info(fdtd_engine* e, int64_t* free_bytes, int64_t* total_bytes);
 
+/* Anisotropic tensor update on caller-supplied HOST arrays of n elements each (function level, not a stage of the
+ * step — the reference never couples it either): replaces AnisotropicUpdater.update_e_from_curl_h and
+ * update_h_from_curl_e, /root/reference/src/prismo/materials/tensor.py:482-536 and :538-588.
+ *   mode & 1 == 0 : out[c] = f[c] (+|-) ((scale * curl[c]) / d_c),        negative != 0 selects "-" (H update)
+ *   mode & 1 == 1 : out[c] = f[c] + scale * ((r_c0*curl[0] + r_c1*curl[1]) + r_c2*curl[2])   (pass -dt/mu0 for H)
+ *   mode & 2 / mode & 4 (diagonal, dtype f64): round scale*curl / the division in float32 first — what NumPy's
+ *   promotion does when a float32 curl meets a float64 field or tensor array (values staged as exact f64 copies).
+ * coef = d_x,d_y,d_z (diagonal) or the row-major INVERSE tensor (9, inverted by the caller like the reference does);
+ * coef_arrays (may be NULL) holds optional per-cell arrays of the same dtype overriding single entries.  f[c] == NULL
+ * skips component c.  Every operation is rounded separately in the reference's order: bit-exact in fp64 and fp32. */
+int  fdtd_tensor_update(int32_t device, int32_t dtype, int64_t n, const void* const* f, const void* const* curl,
+                        void* const* out, double scale, int32_t negative, int32_t mode, const double* coef,
+                        const void* const* coef_arrays);
+
 /* Host-only (no device needed): the x-segment plan of one two-step sweep over nx planes.  plane_flags[p] != 0 marks
  * planes that carry source / monitor ops (n_flags may exceed nx by the ghost planes of a slab); tiles = (j,k) tiles
  * per segment; halo != 0: the slab reads ghost planes; fused_lx > 0 forces the bulk part length; zones_mode -1 auto,

@@ -12,7 +12,8 @@ from .waveform import ContinuousWave, CustomWaveform, GaussianPulse, RickerWavel
 from .sources import (ElectricDipole, GaussianBeamSource, MagneticDipole, ModeSource, PlaneWaveSource, PointSource,
                       Source, TFSFSource)
 from .monitors import DFTMonitor, FieldMonitor, FluxMonitor, ModeExpansionMonitor, Monitor
-from .materials import (ADESolver, DebyeMaterial, DrudeMaterial, LorentzMaterial, LorentzPole, attach_ade)
+from .materials import (ADESolver, AnisotropicUpdater, DebyeMaterial, DrudeMaterial, LorentzMaterial, LorentzPole,
+                        TensorComponents, TensorMaterial, attach_ade, tensor_update)
 from .cpml import PMLParams
 from .session import Session, configure
 from .simulation import ElectromagneticFields, FDTDSolver, MaxwellUpdater, Simulation

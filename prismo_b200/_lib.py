@@ -99,6 +99,9 @@ _PROTOS = {
     "fdtd_steps_done": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "fdtd_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "fdtd_mem_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fdtd_tensor_update": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_double),
+                                     C.POINTER(C.c_void_p)]),
     "fdtd_plan_segments": (C.c_int, [C.c_int32, C.POINTER(C.c_uint8), C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]),
 }

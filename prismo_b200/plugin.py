@@ -274,6 +274,43 @@ def register(prismo=None):
         fn._b200_original = orig
         setattr(cls, name, fn)
 
+    # ---- anisotropic tensor update (row a23, materials/tensor.py:482-588): function-level operator ------------------
+    try:
+        import importlib
+
+        tensor_mod = importlib.import_module(prismo.__name__ + ".materials.tensor")
+    except Exception:                                     # optional sub-package: nothing to patch
+        tensor_mod = None
+    if tensor_mod is not None:
+        from .materials import tensor_update
+
+        AU = tensor_mod.AnisotropicUpdater
+        o_e, o_h = AU.update_e_from_curl_h, AU.update_h_from_curl_e
+
+        def au_e(self, E, curl_H):
+            if not _is_b200(self):
+                return o_e(self, E, curl_H)
+            m = self.material
+            if m.is_diagonal:
+                return tensor_update(E, curl_H, self.dt / self.eps0, (m.epsilon.xx, m.epsilon.yy, m.epsilon.zz),
+                                     device=self.backend.device_id)
+            return tensor_update(E, curl_H, self.dt / self.eps0, None, inverse=self.inv_epsilon, device=self.backend.device_id)
+
+        def au_h(self, H, curl_E):
+            if not _is_b200(self):
+                return o_h(self, H, curl_E)
+            m = self.material
+            if m.is_diagonal:
+                return tensor_update(H, curl_E, self.dt / self.mu0, (m.mu.xx, m.mu.yy, m.mu.zz), negative=True,
+                                     device=self.backend.device_id)
+            return tensor_update(H, curl_E, self.dt / self.mu0, None, inverse=self.inv_mu, negative=True,
+                                 device=self.backend.device_id)
+
+        for name, fn, orig in (("update_e_from_curl_h", au_e, o_e), ("update_h_from_curl_e", au_h, o_h)):
+            fn.__doc__, fn.__name__, fn.__qualname__ = orig.__doc__, orig.__name__, orig.__qualname__
+            fn._b200_original = orig
+            setattr(AU, name, fn)
+
     bm._b200_registered = True
     _registered = True
     return B200Backend

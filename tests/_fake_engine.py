@@ -247,3 +247,46 @@ class FakeSlabEngine(FakeEngine):
                 ph = self.ph[s, o.phasor_col + k]
                 m["dft"][k] += (d * ph.real) * self.dt + 1j * ((d * ph.imag) * self.dt)
         self.cursor += 1
+
+
+class FakeTensorLib:
+    """Stands in for libfdtd_b200.so's fdtd_tensor_update on machines without a GPU: same argument protocol (ctypes
+    pointer tables, mode bits), NumPy arithmetic in the kernel's operation order (csrc/fdtd_tensor.cuh)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def fdtd_last_error(self):
+        return b""
+
+    def fdtd_tensor_update(self, device, dtype, n, fp, cp, op, s, negative, mode, coef, arrs):
+        import ctypes as C
+
+        T = np.float32 if dtype == 0 else np.float64
+        self.calls.append((dtype, n, negative, mode))
+
+        def arr(ptr):
+            return None if not ptr else np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float if T == np.float32 else C.c_double)), (n,))
+
+        f, c, o = [arr(p) for p in fp], [arr(p) for p in cp], [arr(p) for p in op]
+        ca = [arr(p) for p in arrs]
+        s = T(s)
+        full, mul32, div32 = mode & 1, (mode >> 1) & 1, (mode >> 2) & 1
+        for k in range(3):
+            if f[k] is None:
+                continue
+            if not full:
+                d = ca[k] if ca[k] is not None else T(coef[k])
+                if mul32 and T == np.float64:
+                    t = (np.float32(s) * c[k].astype(np.float32)).astype(np.float64)
+                else:
+                    t = s * c[k]
+                if div32 and T == np.float64:
+                    t = (t.astype(np.float32) / np.asarray(d).astype(np.float32)).astype(np.float64)
+                else:
+                    t = t / d
+                o[k][:] = f[k] - t if negative else f[k] + t
+            else:
+                r = [ca[3 * k + j] if ca[3 * k + j] is not None else T(coef[3 * k + j]) for j in range(3)]
+                o[k][:] = f[k] + s * ((r[0] * c[0] + r[1] * c[1]) + r[2] * c[2])
+        return 0

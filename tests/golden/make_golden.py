@@ -29,5 +29,29 @@ def main():
         print(f"{name}: grid {sim.grid.dimensions}, {len(res)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def main_tensor():
+    """Row a23: AnisotropicUpdater.update_e_from_curl_h / update_h_from_curl_e of the real reference on the cases of
+    tests/tensor_cases.py, float64 and float32 inputs -> tests/golden/aniso.npz (outputs only; inputs are seeded)."""
+    ref_loader.load()
+    from prismo.materials.tensor import AnisotropicUpdater, TensorComponents, TensorMaterial
+
+    from tests import tensor_cases as T
+
+    res = {}
+    for name, spec in T.cases().items():
+        mat = TensorMaterial(TensorComponents(**spec["eps"]), None if spec["mu"] is None else TensorComponents(**spec["mu"]))
+        upd = AnisotropicUpdater(mat, T.DT)
+        for dt in ("float64", "float32"):
+            f, c = T.inputs(dt)
+            for which, fn in (("e", upd.update_e_from_curl_h), ("h", upd.update_h_from_curl_e)):
+                for k, a in enumerate(fn(tuple(f), tuple(c))):
+                    res[f"{name}.{dt}.{which}{k}"] = np.asarray(a)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "aniso.npz")
+    np.savez_compressed(path, **res)
+    print(f"aniso: {len(res)} arrays, dtypes {sorted({str(a.dtype) for a in res.values()})}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--tensor-only" not in sys.argv:
+        main()
+    main_tensor()
