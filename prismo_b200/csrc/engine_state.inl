@@ -1,0 +1,162 @@
+// engine state, error reporting, small helpers
+// (textual part of fdtd_engine.cu — one translation unit; not compiled on its own)
+
+using namespace fdtd;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? FDTD_ENOMEM : FDTD_ECUDA, "%s: %s",     \
+                        #call, cudaGetErrorString(e_));                                           \
+    } while (0)
+
+static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+struct HostSrc { SrcOp op; int group; };
+
+struct fdtd_engine {
+    fdtd_config cfg{};
+    Geom g{};
+    Strides3 st{};
+    size_t esz = 4;                 // element size of T
+    long long plane_elems = 0;      // sx
+    long long planes_alloc = 0;     // nx + 2
+    long long array_elems = 0;
+    void* fld[6] = {};              // set A
+    void* fldB[6] = {};             // set B (fused ping-pong), allocated lazily
+    int cur = 0;                    // which set holds the current fields (fused path)
+    void* coef[4] = {};             // Ca Cb Da Db arrays (T) or null
+    bool het = false;
+    double uni[4] = {1, 0, 1, 0};
+    cudaStream_t stream = nullptr;
+    // ops
+    std::vector<HostSrc> src;
+    std::vector<SrcOp> src_ghost; SrcOp* d_src_ghost = nullptr;   // slabs: neighbour's sources on our ghost planes
+    std::vector<MonOp> mon;
+    std::vector<double> prof_host;
+    std::vector<FluxOp> flux; FluxOp* d_flux = nullptr; double* d_flux_partial = nullptr; double* d_flux_out = nullptr;
+    std::vector<AdeOp> ade; std::vector<unsigned char> ade_mask_host;
+    AdeOp* d_ade = nullptr; void* d_aux = nullptr; unsigned char* d_ade_mask = nullptr;
+    long long aux_elems = 0, ade_threads = 0;
+    bool ops_dirty = true;
+    Cpml cpml{}; SlabGeom slabg{}; double* d_cpml_coef = nullptr; size_t psi_bytes[12] = {};
+    SrcOp* d_src = nullptr;         // all source ops, ordered by group
+    std::vector<int> grp_first, grp_count; std::vector<long long> grp_threads;
+    MonOp* d_mon = nullptr; long long mon_threads = 0;
+    double* d_prof = nullptr;
+    void** d_comp_ptr[2] = {nullptr, nullptr};   // device arrays of 6 component pointers (set A / B)
+    // tables
+    int n_steps_tab = 0, n_amp = 0, n_phasor = 0;
+    double *d_amp = nullptr, *d_phasor = nullptr;
+    void* d_rec = nullptr; long long rec_elems_per_step = 0;
+    double2* d_dft = nullptr; long long dft_elems = 0;
+    int* d_step = nullptr;          // table cursor (device)
+    int cursor = 0;                 // host mirror of the cursor
+    int* d_cnt = nullptr;           // 2 x 6 gate counters (2-D)
+    long long steps_done = 0, launches = 0;
+    // graph
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr}; int graph_steps = 0; int graph_kernels[2] = {0, 0};
+    int fused_lx = 0;               // planes per fused segment (0 = auto)
+    int het_fused = 1;              // heterogeneous media: fused one-step sweep (0: two-pass kernels)
+    int tb2_zones = -1;             // two-step sweep: narrow x-segments around op planes (-1 auto, 0 never, 1 always)
+    int tb2 = 1;                    // 1: temporally blocked sweep (two steps per pass) where applicable
+    unsigned char* d_plane_flags = nullptr; std::vector<unsigned char> plane_flags_host;
+    int fused_tj = 15;              // owner rows per CTA (15: one 16-warp CTA/SM; 7: two 8-warp CTAs/SM)
+    int fused_pol = 0;              // bit0: streaming (evict-first) stores (measured 1.4% slower: off)
+    // staging
+    void* d_stage = nullptr; size_t stage_bytes = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // x-slab peer-to-peer halo (one process per GPU, CUDA IPC over NVLink)
+    struct Slab {
+        bool connected = false, has_left = false, has_right = false;
+        int* flags = nullptr;            // own device words: [0] halo_ready (written by the right neighbour),
+                                         // [1] ghost_consumed (written by us, read by the right neighbour), [2] error
+        void* left_fld[2][6] = {};       // left neighbour's arrays (IPC-mapped): we push into its ghost planes
+        int* left_flags = nullptr;       // left neighbour's flags (we write [0], read [1])
+        int* seq = nullptr;              // seq[i] = i: source of the 4-byte DMA that publishes halo_ready = i
+        void* left_base[13] = {};        // mapped bases to close
+        cudaStream_t comm = nullptr;
+        cudaEvent_t post_done = nullptr, push_done = nullptr;
+        long long step = 0;              // steps run through fdtd_slab_run (same on every rank)
+        int left_nx = 0;
+        unsigned long long timeout_ns = 20000000000ull;
+    } slab;
+    FusedPlan fused{};
+};
+
+// ---------------------------------------------------------------------------------------------------
+static void comp_shape(const fdtd_engine* e, int comp, int shp[3])
+{
+    // staggered shapes, core/grid.py:157-168 (LOCAL nx; the global trim of the last plane is applied
+    // by the caller through x_offset/nx_global)
+    const int nx = e->g.nx, ny = e->g.ny, nz = e->g.nz;
+    const bool last = (e->g.x0 + nx == e->g.nxg);
+    const int nxm = last ? nx - 1 : nx;
+    static const int shortx[6] = {0, 1, 1, 1, 0, 0}, shorty[6] = {1, 0, 1, 0, 1, 0}, shortz[6] = {1, 1, 0, 0, 0, 1};
+    shp[0] = shortx[comp] ? nxm : nx;
+    shp[1] = shorty[comp] ? ny - 1 : ny;
+    if (e->cfg.ndim == 3) shp[2] = shortz[comp] ? nz - 1 : nz;
+    else shp[2] = 1;
+}
+
+template <typename T> static Fields<T> fields_of(void* const* p)
+{
+    Fields<T> f;
+    f.ex = (T*)p[0]; f.ey = (T*)p[1]; f.ez = (T*)p[2]; f.hx = (T*)p[3]; f.hy = (T*)p[4]; f.hz = (T*)p[5];
+    return f;
+}
+template <typename T> static Coefs<T> coefs_of(const fdtd_engine* e)
+{
+    Coefs<T> c;
+    c.ca = (const T*)e->coef[0]; c.cb = (const T*)e->coef[1];
+    c.da = (const T*)e->coef[2]; c.db = (const T*)e->coef[3];
+    c.uca = (T)e->uni[0]; c.ucb = (T)e->uni[1]; c.uda = (T)e->uni[2]; c.udb = (T)e->uni[3];
+    return c;
+}
+// fp32 fused kernels: db/d and cb/d folded once (both the one-step and the two-step sweep use the SAME folded
+// arithmetic, so fp32 results do not depend on how steps are paired)
+static Fold fold_of(const fdtd_engine* e)
+{
+    Fold fo;
+    const Geom& g = e->g;
+    const double d[3] = {g.dx, g.dy, g.dz};
+    for (int a = 0; a < 3; ++a) {
+        fo.d[a] = e->uni[3] / d[a];          // db / d
+        fo.d[3 + a] = e->uni[1] / d[a];      // cb / d
+    }
+    for (int a = 0; a < 6; ++a) fo.f[a] = (float)fo.d[a];
+    fo.fast64 = (e->cfg.flags & FDTD_FLAG_FAST_F64) ? 1 : 0;
+    return fo;
+}
+static void** cur_fields(fdtd_engine* e) { return e->cur ? e->fldB : e->fld; }
+
+static int ensure_stage(fdtd_engine* e, size_t bytes)
+{
+    if (e->stage_bytes >= bytes) return 0;
+    if (e->d_stage) cudaFree(e->d_stage);
+    e->d_stage = nullptr; e->stage_bytes = 0;
+    CU(cudaMalloc(&e->d_stage, bytes));
+    e->stage_bytes = bytes;
+    return 0;
+}
+
+static void drop_graph(fdtd_engine* e)
+{
+    for (int q = 0; q < 2; ++q)
+        if (e->gexec[q]) { cudaGraphExecDestroy(e->gexec[q]); e->gexec[q] = nullptr; }
+    e->graph_steps = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-"""Host logic of the two-step sweep: the x-segment planner (csrc/fdtd_engine.cu: plan_segments), called through
+"""Host logic of the two-step sweep: the x-segment planner (csrc/engine_launch.inl: plan_segments), called through
 the C ABI's host-only entry fdtd_plan_segments — no GPU needed.  Invariants the kernel relies on:
   * segments partition [0, nx) exactly;
   * a segment [a, b) is flagged `ops` iff a source / monitor plane lies in [a, b + 1] (the planes on which the sweep
