@@ -21,4 +21,6 @@ from .engine import Engine, MonitorOp, SourceOp
 from .plugin import register
 
 __version__ = "0.1.0"
+from .sweep import ParameterSweep, SweepParameter
+
 __all__ = [n for n in dir() if not n.startswith("_")]
