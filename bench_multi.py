@@ -22,7 +22,7 @@ def run_multi(args, rank, world, local):
     name, dims = B.parse_workload(args.workload)
     cells = dims[0] * dims[1] * dims[2]
     span = None
-    balanced = os.environ.get("FDTD_B200_BALANCE", "0") == "1" and not args.no_ops
+    balanced = os.environ.get("FDTD_B200_BALANCE", "1") == "1" and not args.no_ops and world > 1
     if balanced:
         # load-balanced slabs: ranks run in lock step, so the rank that owns the DFT plane (complex128 read-modify-
         # write of 10 planes per step on top of its sweep) gets fewer planes.  Same cut on every rank (pure function).

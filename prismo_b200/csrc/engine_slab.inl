@@ -54,6 +54,11 @@ extern "C" int fdtd_ipc_connect(fdtd_engine* e, const void* left_blob, int32_t h
     }
     sl.has_left = left_blob != nullptr;
     sl.has_right = has_right != 0;
+    if (e->stream) CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(sl.comm));
+    for (void*& m : sl.left_base)                    // re-connect: drop the previous neighbour's mappings first
+        if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+    sl.left_flags = nullptr;
     if (left_blob) {
         IpcBlob b;
         memcpy(&b, left_blob, sizeof b);
