@@ -350,6 +350,8 @@ def main():
     ap.add_argument("--fast-f64", action="store_true", help="fp64 with folded FMA arithmetic (within 1e-10, not bit-exact)")
     ap.add_argument("--het", action="store_true", help="heterogeneous medium: Si ridge (eps 12.11) on SiO2 (2.07), "
                                                        "cell-centred coefficient arrays (64 B/cell)")
+    ap.add_argument("--physics", action="store_true", help="opt-in physics mode: stable Yee leap-frog + 10-cell CPML "
+                    "(two-pass kernels with slab psi updates; no reference numbers exist for it)")
     ap.add_argument("--no-ops", action="store_true", help="bare field update: no source, no monitor (tuning only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -375,7 +377,13 @@ def main():
     name, dims = parse_workload(args.workload)
     cells = dims[0] * dims[1] * dims[2]
     flags = (_lib.FLAG_TWO_PASS if args.two_pass else 0) | (_lib.FLAG_FAST_F64 if args.fast_f64 else 0)
+    if args.physics:
+        flags |= _lib.FLAG_YEE
     eng, dt, spacing, x0, nxl = make_engine(dims, args.dtype, device=local, flags=flags)
+    if args.physics:
+        from prismo_b200 import cpml
+
+        eng.set_cpml(10, cpml.coefficient_table(dims, spacing, dt, cpml.PMLParams(thickness=10)))
     if args.het:
         set_ridge_coefficients(eng, dims, dt)
     src, mon = workload_ops(dims, dt, spacing)
@@ -411,10 +419,11 @@ def main():
     peak, peak_src = peaks()
     bpc = BYTES_PER_CELL[args.dtype] + (16 if args.dtype == "float32" else 32) * int(args.het)   # + Ca,Cb,Da,Db reads
     achieved = bpc * cells * args.steps / (kern_ms * 1e-3) / 1e9
-    fused = not args.two_pass
+    fused = not (args.two_pass or args.physics)
     tb2 = fused and os.environ.get("FDTD_B200_TB2", "1") != "0" and args.steps >= 2 and not args.het
     kname = ("k_fused3d_tb2 (1 launch per TWO steps)" if tb2 else "k_fused3d (1 launch/step)") if fused \
-        else "k_h3d + k_e3d (2 launches/step)"
+        else ("k_h3d_yee + k_e3d_yee (physics mode: Yee leap-frog + CPML slabs, 2 launches/step)" if args.physics
+              else "k_h3d + k_e3d (2 launches/step)")
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
@@ -453,7 +462,8 @@ def main():
                        "l2": f"working set {2 * bpc // 2 * cells / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"
                              if cells * bpc / 2 > 1e9 else "working set fits L2: HBM fraction not meaningful",
                        "parallelism": "1 GPU", "kernel_path": ("temporally blocked fused sweep (2 steps per HBM pass), ping-pong" if tb2 else
-                                       "fused single sweep, ping-pong") if fused else "two-pass"},
+                                       "fused single sweep, ping-pong") if fused else
+                                       ("physics mode (opt-in): Yee leap-frog + 10-cell CPML, two-pass" if args.physics else "two-pass")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
     print(json.dumps(line), flush=True)
     eng.close()
