@@ -128,7 +128,7 @@ extern "C" int fdtd_set_cpml(fdtd_engine* e, int32_t thickness, const double* co
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaStreamSynchronize(e->stream));
     cudaFree(e->d_cpml_coef); e->d_cpml_coef = nullptr;
-    for (int q = 0; q < 12; ++q) { cudaFree(e->cpml.psi[q]); e->cpml.psi[q] = nullptr; }
+    for (int q = 0; q < 12; ++q) { cudaFree(e->cpml.psi[q]); e->cpml.psi[q] = nullptr; cudaFree(e->psiB[q]); e->psiB[q] = nullptr; }
     e->cpml = Cpml{};
     drop_graph(e);
     if (thickness == 0) return 0;
@@ -154,6 +154,8 @@ extern "C" int fdtd_set_cpml(fdtd_engine* e, int32_t thickness, const double* co
         const size_t b = family[q] == 0 ? bx : (family[q] == 1 ? by : bz);
         CU(cudaMalloc(&e->cpml.psi[q], b));
         CU(cudaMemset(e->cpml.psi[q], 0, b));
+        CU(cudaMalloc(&e->psiB[q], b));
+        CU(cudaMemset(e->psiB[q], 0, b));
         e->psi_bytes[q] = b;
     }
     return 0;
@@ -227,6 +229,56 @@ template <typename T, int TJ> static int launch_fused_tj(fdtd_engine* e, int i_b
     kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, fold_of(e));
     e->launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+
+// physics mode, opt-in: Yee leap-frog + CPML as one fused sweep; fields AND psi go from the current set to the other one
+static bool use_yee_fused(const fdtd_engine* e)
+{
+    return e->cfg.ndim == 3 && (e->cfg.flags & FDTD_FLAG_YEE) && e->yee_fused && !e->het && e->g.nxg == e->g.nx;
+}
+
+template <typename T> static int launch_yee_fused(fdtd_engine* e, cudaStream_t s)
+{
+    constexpr int V = VecOf<T>::V, TJ = kFusedTJ;
+    const Geom& g = e->g;
+    void** src = cur_fields(e);
+    void** dst = e->cur ? e->fld : e->fldB;
+    CFields<T> in;
+    in.ex = (const T*)src[0]; in.ey = (const T*)src[1]; in.ez = (const T*)src[2];
+    in.hx = (const T*)src[3]; in.hy = (const T*)src[4]; in.hz = (const T*)src[5];
+    Fields<T> out = fields_of<T>(dst);
+    Cpml pm = e->cpml;                                   // psi of the CURRENT set in, the other set out
+    PsiOut pout;
+    for (int q = 0; q < 12; ++q) {
+        pm.psi[q] = e->cur ? e->psiB[q] : e->cpml.psi[q];
+        pout.p[q] = e->cur ? e->cpml.psi[q] : e->psiB[q];
+    }
+    FusedTiling t{};
+    t.i_begin = 0; t.i_end = g.nx;
+    const int vec_per_row = g.pz / V;
+    const int ncols = (vec_per_row + 29) / 30;
+    int own = (vec_per_row + ncols - 1) / ncols;
+    own += own & 1;
+    t.own_lanes = std::min(own, 30);
+    t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
+    t.ntj = (g.ny + TJ - 1) / TJ;
+    int lx = e->fused_lx;
+    if (lx <= 0) {
+        const long long tiles = (long long)t.ntj * t.ntk;
+        long long want = (148ll * 40 + tiles - 1) / tiles;
+        lx = (int)std::max<long long>(32, (g.nx + want - 1) / std::max<long long>(want, 1));
+    }
+    t.lx = std::min(lx, g.nx);
+    t.nseg = (g.nx + t.lx - 1) / t.lx;
+    const size_t smem = fused_smem_bytes<T, TJ>();
+    auto kern = k_fused3d_yee<T, TJ>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 block(32, TJ + 1, 1);
+    kern<<<(unsigned)t.nseg * t.ntj * t.ntk, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, pm, pout, e->slabg);
+    e->launches++;
+    CU(cudaGetLastError());
+    e->cur ^= 1;
     return 0;
 }
 
@@ -469,6 +521,11 @@ template <typename T> static int step_fields3d(fdtd_engine* e, int half, cudaStr
         e->cur ^= 1;
         return 0;
     }
+    if (use_yee_fused(e)) {
+        if (half == 1) return 0;
+        if (int rc = ensure_set_b(e)) return rc;
+        return launch_yee_fused<T>(e, s);
+    }
     if (e->cfg.flags & FDTD_FLAG_YEE) return launch_yee<T>(e, half, s);
     if (use_het_fused(e)) {
         if (half == 1) return 0;
@@ -496,7 +553,7 @@ static bool has_post(const fdtd_engine* e) { return has_tables(e) || !e->ade.emp
 template <typename T> static int run_steps(fdtd_engine* e, int n)
 {
     cudaStream_t s = e->stream;
-    if (use_fused(e) || use_het_fused(e)) if (int rc = ensure_set_b(e)) return rc;
+    if (use_fused(e) || use_het_fused(e) || use_yee_fused(e)) if (int rc = ensure_set_b(e)) return rc;
     if (e->cfg.ndim == 2) if (int rc = launch_count2d<T>(e, 0, s)) return rc;
     const bool use_graph = !(e->cfg.flags & FDTD_FLAG_NO_GRAPH) && n >= 32;
     int done = 0;

@@ -129,6 +129,11 @@ extern "C" int fdtd_set_option(fdtd_engine* e, const char* key, int32_t value)
     if (!strcmp(key, "tb2")) e->tb2 = value ? 1 : 0;
     else if (!strcmp(key, "het_fused")) e->het_fused = value ? 1 : 0;
     else if (!strcmp(key, "fused_lx")) e->fused_lx = value;
+    else if (!strcmp(key, "yee_fused")) {
+        // the fused physics sweep ping-pongs fields and psi, the two-pass kernels update the current set in place:
+        // switch only between runs that start from freshly uploaded / zeroed state
+        e->yee_fused = value ? 1 : 0;
+    }
     else return fail(FDTD_EINVAL, "unknown option '%s'", key);
     drop_graph(e);
     return 0;

@@ -81,6 +81,7 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     if (const char* tj = getenv("FDTD_B200_FUSED_TJ")) e->fused_tj = atoi(tj);
     if (const char* tb = getenv("FDTD_B200_TB2")) e->tb2 = atoi(tb);
     if (const char* z = getenv("FDTD_B200_TB2_ZONES")) e->tb2_zones = atoi(z);
+    if (const char* yf = getenv("FDTD_B200_YEE_FUSED")) e->yee_fused = atoi(yf);
     if (const char* hf = getenv("FDTD_B200_HET_FUSED")) e->het_fused = atoi(hf);
     *out = e;
     return 0;
@@ -98,7 +99,7 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     cudaFree(e->d_ade); cudaFree(e->d_aux); cudaFree(e->d_ade_mask);
     cudaFree(e->d_flux); cudaFree(e->d_flux_partial); cudaFree(e->d_flux_out);
     cudaFree(e->d_cpml_coef); cudaFree(e->d_plane_flags);
-    for (int q = 0; q < 12; ++q) cudaFree(e->cpml.psi[q]);
+    for (int q = 0; q < 12; ++q) { cudaFree(e->cpml.psi[q]); cudaFree(e->psiB[q]); }
     cudaFree(e->d_comp_ptr[0]); cudaFree(e->d_comp_ptr[1]);
     cudaFree(e->d_amp); cudaFree(e->d_phasor); cudaFree(e->d_rec); cudaFree(e->d_dft);
     cudaFree(e->d_step); cudaFree(e->d_cnt); cudaFree(e->d_stage);
@@ -245,8 +246,10 @@ extern "C" int fdtd_zero_fields(fdtd_engine* e)
     if (!e) return fail(FDTD_EINVAL, "null engine");
     CU(cudaSetDevice(e->cfg.device));
     for (int c = 0; c < 6; ++c) CU(cudaMemsetAsync(cur_fields(e)[c], 0, e->array_elems * e->esz, e->stream));
-    for (int q = 0; q < 12; ++q)
+    for (int q = 0; q < 12; ++q) {
         if (e->cpml.psi[q]) CU(cudaMemsetAsync(e->cpml.psi[q], 0, e->psi_bytes[q], e->stream));
+        if (e->psiB[q]) CU(cudaMemsetAsync(e->psiB[q], 0, e->psi_bytes[q], e->stream));
+    }
     return 0;
 }
 

@@ -52,6 +52,8 @@ struct fdtd_engine {
     long long aux_elems = 0, ade_threads = 0;
     bool ops_dirty = true;
     Cpml cpml{}; SlabGeom slabg{}; double* d_cpml_coef = nullptr; size_t psi_bytes[12] = {};
+    void* psiB[12] = {};            // second psi set: the fused physics sweep ping-pongs psi like the fields
+    int yee_fused = 0;              // physics mode: 1 = fused one-sweep step (opt-in, fdtd_yee_fused.cuh), 0 = two-pass
     SrcOp* d_src = nullptr;         // all source ops, ordered by group
     std::vector<int> grp_first, grp_count; std::vector<long long> grp_threads;
     MonOp* d_mon = nullptr; long long mon_threads = 0;
