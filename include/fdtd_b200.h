@@ -149,7 +149,9 @@ int  fdtd_run(fdtd_engine* e, int32_t n_steps);   /* H pass, E pass, sources, mo
 int  fdtd_update_h(fdtd_engine* e);               /* MaxwellUpdater.update_magnetic_fields :135-149 */
 int  fdtd_update_e(fdtd_engine* e);               /* MaxwellUpdater.update_electric_fields :151-165 */
 int  fdtd_sync(fdtd_engine* e);
-int  fdtd_set_option(fdtd_engine* e, const char* key, int32_t value);   /* "tb2" 0/1, "fused_lx" planes (0 = auto) */
+/* tuning switches: "tb2" 0/1 (two-step sweep), "fused_lx" planes per x-segment (0 = auto), "het_fused" 0/1,
+ * "yee_fused" 0/1 (physics mode as one fused sweep; set it before the first step of a run) */
+int  fdtd_set_option(fdtd_engine* e, const char* key, int32_t value);
 /* measurement: CUDA events on the engine's own stream (torch.cuda.Event cannot see it).
  * fdtd_run_profiled runs n real steps without a graph and returns summed kernel times in ms:
  * out_ms[0] H pass (or the fused sweep), [1] E pass, [2] sources+monitors, [3] first-to-last event. */
