@@ -164,3 +164,27 @@ def test_plugin_routes_reference_anisotropic_updater(monkeypatch, ref):
     finally:
         monkeypatch.setattr(_lib, "load", real_load)
         ref.set_backend("numpy")
+
+
+def test_c_entry_argument_checks_without_a_gpu():
+    """fdtd_tensor_update validates its pointer tables before touching CUDA: exercised through the real library."""
+    import ctypes as C
+
+    from prismo_b200 import _lib
+
+    lib = _lib.load()
+    a = np.zeros(4)
+    tab = lambda *ptrs: (C.c_void_p * 3)(*ptrs)          # noqa: E731
+    coef = (C.c_double * 9)(*([1.0] * 9))
+    none9 = (C.c_void_p * 9)()
+    p = a.ctypes.data
+    # nothing to do: n == 0, or no field component selected
+    assert lib.fdtd_tensor_update(0, _lib.F64, 0, tab(p, p, p), tab(p, p, p), tab(p, p, p), 1.0, 0, 0, coef, none9) == 0
+    assert lib.fdtd_tensor_update(0, _lib.F64, 4, tab(None, None, None), tab(p, p, p), tab(p, p, p), 1.0, 0, 0, coef, none9) == 0
+    # a selected component without output / without its curl; the full tensor needs all three curls; bad dtype
+    for args in ((0, _lib.F64, 4, tab(p, None, None), tab(p, None, None), tab(None, None, None), 1.0, 0, 0, coef, none9),
+                 (0, _lib.F64, 4, tab(p, None, None), tab(None, p, p), tab(p, None, None), 1.0, 0, 0, coef, none9),
+                 (0, _lib.F64, 4, tab(p, None, None), tab(p, p, None), tab(p, None, None), 1.0, 0, 1, coef, none9),
+                 (0, 7, 4, tab(p, p, p), tab(p, p, p), tab(p, p, p), 1.0, 0, 0, coef, none9)):
+        with pytest.raises(ValueError):
+            _lib.check(lib.fdtd_tensor_update(*args))
