@@ -28,9 +28,12 @@ def run_multi(args, rank, world, local):
         # write of 10 planes per step on top of its sweep) gets fewer planes.  Same cut on every rank (pure function).
         from prismo_b200.multigpu import balanced_slab_ranges, plane_costs
 
-        dt0, spacing0 = B.workload_timestep()
-        g_src, g_mon = B.workload_ops(dims, dt0, spacing0)
-        span = balanced_slab_ranges(plane_costs(dims[0], dims[1] * dims[2], g_src, g_mon), world)[rank]
+        try:
+            dt0, spacing0 = B.workload_timestep()
+            g_src, g_mon = B.workload_ops(dims, dt0, spacing0)
+            span = balanced_slab_ranges(plane_costs(dims[0], dims[1] * dims[2], g_src, g_mon), world)[rank]
+        except ValueError:                       # grid too small for >= 4 planes per rank: equal slabs
+            span, balanced = None, False
     eng, dt, spacing, x0, nxl = B.make_engine(dims, args.dtype, rank, world, device=local, span=span)
     src, mon = B.workload_ops(dims, dt, spacing, x0, nxl)
     if args.no_ops:
