@@ -49,7 +49,8 @@ def main():
     amp = np.sin(np.arange(1, steps + 1)[:, None] * np.array([[0.3, 0.7]]))
     ph = np.exp(-1j * np.arange(1, steps + 1)[:, None] * np.array([[0.2, 0.5]]))
     # first plane of the second slab: a local op for that rank AND a ghost op for the rank on its left
-    src_plane, mon_plane = slab_range(dims[0], 1, world)[0] if world > 1 else dims[0] // 2, dims[0] - 3
+    src_off = int(sys.argv[sys.argv.index("--src-offset") + 1]) if "--src-offset" in sys.argv else 0
+    src_plane, mon_plane = (slab_range(dims[0], 1, world)[0] + src_off) if world > 1 else dims[0] // 2, dims[0] - 3
 
     def ops(x0, nxl, shape_of):
         s, m = [], []

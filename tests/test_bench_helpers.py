@@ -1,0 +1,61 @@
+"""bench.py's workload description on x-slabs (CPU): the ops every rank builds for its slab — equal or load-balanced —
+must tile the global source / monitor planes exactly once, with ghost copies of the source only on the rank whose
+three ghost planes contain it (the two-step sweep recomputes the intermediate step there)."""
+import numpy as np
+import pytest
+
+import bench as B
+from prismo_b200.multigpu import balanced_slab_ranges, plane_costs, slab_range
+
+
+def _spans(nx, world, balanced):
+    if not balanced:
+        return [slab_range(nx, r, world) for r in range(world)]
+    dt, sp = B.workload_timestep()
+    s, m = B.workload_ops((nx, 64, 64), dt, sp)
+    return balanced_slab_ranges(plane_costs(nx, 64 * 64, s, m), world)
+
+
+@pytest.mark.parametrize("nx,world", [(1024, 8), (1024, 4), (1024, 2), (96, 8), (100, 3)])
+@pytest.mark.parametrize("balanced", [False, True])
+def test_slab_ops_tile_the_global_ops(nx, world, balanced):
+    dims = (nx, 64, 64)
+    dt, sp = B.workload_timestep()
+    g_src, g_mon = B.workload_ops(dims, dt, sp)
+    src_plane, mon_plane = g_src[0].lo[0], g_mon[0].lo[0]
+    spans = _spans(nx, world, balanced)
+    assert spans[0][0] == 0 and sum(n for _, n in spans) == nx
+    owners_src, owners_mon, ghosts = [], [], []
+    for r, (x0, n) in enumerate(spans):
+        s, m = B.workload_ops(dims, dt, sp, x0, n)
+        real = [o for o in s if not o.ghost]
+        gh = [o for o in s if o.ghost]
+        if real:
+            owners_src.append(r)
+            assert all(o.lo[0] + x0 == src_plane and o.hi[0] == o.lo[0] + 1 and 0 <= o.lo[0] < n for o in real)
+            assert [o.component for o in real] == [o.component for o in g_src]
+        if gh:
+            ghosts.append(r)
+            assert all(n <= o.lo[0] < n + 3 and o.lo[0] + x0 == src_plane for o in gh)
+        if m:
+            owners_mon.append(r)
+            assert all(o.lo[0] + x0 == mon_plane and 0 <= o.lo[0] < n and o.n_freq == 5 for o in m)
+    assert len(owners_src) == 1 and len(owners_mon) == 1
+    x0s, ns = spans[owners_src[0]]
+    assert ghosts == ([owners_src[0] - 1] if (src_plane - x0s < 3 and owners_src[0] > 0) else [])
+
+
+def test_component_shapes_follow_the_staggering_on_every_slab():
+    dims = (40, 12, 10)
+    dt, sp = B.workload_timestep()
+    for x0, n in ((0, 13), (13, 14), (27, 13)):
+        s, m = B.workload_ops(dims, dt, sp, x0, n)
+        for o in s + m:
+            # Ey: (nx-1, ny, nz-1) ; Hz: (nx, ny, nz-1): full rows in y, one less in z
+            assert o.hi[1] == 12 and o.hi[2] == 9 and o.lo[1:] == (0, 0)
+
+
+def test_parse_workload_names():
+    assert B.parse_workload("c4")[1] == (1024, 1024, 1024)
+    assert B.parse_workload("128x1024x1024")[1] == (128, 1024, 1024)
+    assert B.parse_workload("c2")[1] == (121, 121, 121)
