@@ -130,6 +130,8 @@ def run_e2e_multi(eng, stepper, dims, args, mon_ids, dt, fence, dist, torch):
     for c in B.COMPONENTS:
         eng.upload(c, host[c])
     eng.set_tables(args.steps, amp, ph)
+    eng.sync()
+    dist.barrier()                 # every rank's upload is complete before any rank pushes a halo (fdtd_b200.h)
     stepper.run(args.steps)
     stepper.synchronize()
     d2h = 0

@@ -118,6 +118,9 @@ int  fdtd_set_coeffs(fdtd_engine* e, const double* ca, const double* cb, const d
 int  fdtd_set_cpml(fdtd_engine* e, int32_t thickness, const double* coef);
 
 /* ---- fields (core/fields.py:64-114) --------------------------------------------------------- */
+/* Upload replaces the OWNED planes [0, nx) of the current set.  On an x-slab (nx_global != nx) the ghost planes
+ * nx.. are written by the right neighbour's halo push and are left alone; every rank must finish its uploads
+ * before any rank calls fdtd_slab_run (one barrier between "upload" and "run").                             */
 int  fdtd_upload_field(fdtd_engine* e, int32_t component, const void* host, int32_t host_dtype);
 int  fdtd_download_field(fdtd_engine* e, int32_t component, void* host, int32_t host_dtype);
 int  fdtd_zero_fields(fdtd_engine* e);
@@ -193,6 +196,12 @@ int  fdtd_upload_dft(fdtd_engine* e, int32_t monitor_id, const double* host);
 int  fdtd_steps_done(fdtd_engine* e, int64_t* steps);
 int  fdtd_kernel_launches(fdtd_engine* e, int64_t* launches); /* kernels launched by this handle  */
 int  fdtd_mem_info(fdtd_engine* e, int64_t* free_bytes, int64_t* total_bytes);
+/* device-level services of the backend object (reference: Backend.synchronize / get_memory_info, backends/base.py:188-219)
+ * and page-locked host memory for the NumPy mirrors that Backend.zeros/ones/empty hand out (fields.py:70)            */
+int  fdtd_device_mem_info(int32_t device, int64_t* free_bytes, int64_t* total_bytes);
+int  fdtd_device_sync(int32_t device);
+int  fdtd_host_alloc(int64_t bytes, void** ptr);
+int  fdtd_host_free(void* ptr);
 
 /* Anisotropic tensor update on caller-supplied HOST arrays of n elements each (function level, not a stage of the
  * step — the reference never couples it either): replaces AnisotropicUpdater.update_e_from_curl_h and

@@ -1,7 +1,8 @@
 """Load the UNMODIFIED reference (rithulkamesh/prismo) for oracle pinning.  Test infrastructure.
 
-Works only where /root/reference exists (the build container).  Nothing that runs on the GPU
-box (``-m gpu`` tests, smoke(), bench.py) may call this; they use the committed goldens instead.
+Two places can hold it: /root/reference/src (the build container) and oracle/_ref (a staged copy of the package made
+by oracle/stage_reference.py: git-ignored, but it travels to the GPU box with gpurun like a built .so).  /root/reference
+itself never exists on the GPU box; the ``-m gpu`` plugin tests use the staged copy and skip when it is absent.
 """
 from __future__ import annotations
 
@@ -10,7 +11,9 @@ import os
 import sys
 import types
 
-REF_SRC = os.environ.get("PRISMO_REFERENCE_SRC", "/root/reference/src")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REF_SRC = os.environ.get("PRISMO_REFERENCE_SRC") or (
+    "/root/reference/src" if os.path.isdir("/root/reference/src/prismo") else _STAGED)
 
 
 def available() -> bool:

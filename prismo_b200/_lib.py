@@ -99,6 +99,10 @@ _PROTOS = {
     "fdtd_steps_done": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "fdtd_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "fdtd_mem_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fdtd_device_mem_info": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fdtd_device_sync": (C.c_int, [C.c_int32]),
+    "fdtd_host_alloc": (C.c_int, [C.c_int64, C.POINTER(_P)]),
+    "fdtd_host_free": (C.c_int, [_P]),
     "fdtd_tensor_update": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_double),
                                      C.POINTER(C.c_void_p)]),
@@ -133,6 +137,27 @@ def load() -> C.CDLL:
                           f"{C.sizeof(st)} in the binding")
     _lib = lib
     return lib
+
+
+def pinned_empty(shape, dtype):
+    """NumPy array over page-locked host memory (cudaHostAlloc), freed when the array's buffer is collected.
+    Falls back to pageable memory for tiny arrays (not worth a driver call)."""
+    import weakref
+
+    import numpy as np
+
+    dt = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(int(v) for v in shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    if nbytes < (1 << 16):
+        return np.empty(shape, dtype=dt)
+    lib = load()
+    p = _P()
+    if lib.fdtd_host_alloc(nbytes, C.byref(p)) != 0:      # no driver / pinning refused: a pageable mirror still works
+        return np.empty(shape, dtype=dt)
+    buf = (C.c_char * nbytes).from_address(p.value)
+    weakref.finalize(buf, lib.fdtd_host_free, p.value)
+    return np.frombuffer(buf, dtype=dt).reshape(shape)
 
 
 def check(rc: int) -> None:

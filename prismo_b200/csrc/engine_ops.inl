@@ -170,6 +170,12 @@ static int finalize_ops(fdtd_engine* e)
     e->mon_threads = t;
     e->rec_elems_per_step = rec;
     cudaFree(e->d_mon); e->d_mon = nullptr;
+    // The running sums survive a re-registration of the SAME ops (the Session re-lowers on every advance); any other
+    // op list starts from zero, even when the pool happens to have the same size.
+    std::vector<long long> dsig;
+    for (auto& m : e->mon)
+        if (m.n_freq > 0)
+            dsig.insert(dsig.end(), {(long long)m.comp, m.lo[0], m.lo[1], m.lo[2], m.n[0], m.n[1], m.n[2], m.n_freq, m.dft_off});
     if (dft != e->dft_elems || !e->d_dft) {
         cudaFree(e->d_dft); e->d_dft = nullptr;
         if (dft > 0) {
@@ -177,7 +183,10 @@ static int finalize_ops(fdtd_engine* e)
             CU(cudaMemset(e->d_dft, 0, dft * sizeof(double2)));
         }
         e->dft_elems = dft;
+    } else if (dft > 0 && dsig != e->dft_sig) {
+        CU(cudaMemset(e->d_dft, 0, dft * sizeof(double2)));
     }
+    e->dft_sig = dsig;
     cudaFree(e->d_flux); e->d_flux = nullptr;
     cudaFree(e->d_flux_partial); e->d_flux_partial = nullptr;
     if (!e->flux.empty()) {
@@ -205,6 +214,9 @@ static int finalize_ops(fdtd_engine* e)
                 CU(cudaMemcpy(e->d_ade_mask, e->ade_mask_host.data(), e->ade_mask_host.size(), cudaMemcpyHostToDevice));
             }
         }
+        std::vector<long long> asig;
+        for (auto& a : e->ade)
+            asig.insert(asig.end(), {(long long)a.comp, (long long)a.kind, a.lo[0], a.lo[1], a.lo[2], a.n[0], a.n[1], a.n[2], a.cur_off});
         if (aux != e->aux_elems || (!e->d_aux && aux > 0)) {
             cudaFree(e->d_aux); e->d_aux = nullptr;
             if (aux > 0) {
@@ -212,7 +224,10 @@ static int finalize_ops(fdtd_engine* e)
                 CU(cudaMemset(e->d_aux, 0, aux * e->esz));
             }
             e->aux_elems = aux;
+        } else if (aux > 0 && asig != e->aux_sig) {
+            CU(cudaMemset(e->d_aux, 0, aux * e->esz));
         }
+        e->aux_sig = asig;
     }
     // per-plane op flags for the temporally blocked sweep (bit0: a source op covers the plane, bit1: a monitor op)
     {

@@ -78,3 +78,32 @@ extern "C" int fdtd_mem_info(fdtd_engine* e, int64_t* free_bytes, int64_t* total
     if (total_bytes) *total_bytes = (int64_t)t;
     return 0;
 }
+
+// ---- device-level services for the backend object (backends/base.py:188-219: synchronize, get_memory_info) and pinned
+// host mirrors (array factories hand out page-locked NumPy memory so uploads are plain DMA) ------------------
+extern "C" int fdtd_device_mem_info(int32_t device, int64_t* free_bytes, int64_t* total_bytes)
+{
+    CU(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return 0;
+}
+extern "C" int fdtd_device_sync(int32_t device)
+{
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int fdtd_host_alloc(int64_t bytes, void** ptr)
+{
+    if (!ptr || bytes <= 0) return fail(FDTD_EINVAL, "fdtd_host_alloc: bad argument");
+    CU(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable));
+    return 0;
+}
+extern "C" int fdtd_host_free(void* ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return 0;
+}

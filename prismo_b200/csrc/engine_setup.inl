@@ -38,7 +38,8 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     g.nx = cfg->nx; g.ny = cfg->ny; g.nz = cfg->ndim == 3 ? cfg->nz : 1;
     g.nxg = nxg; g.x0 = cfg->x_offset;
     g.dx = cfg->dx; g.dy = cfg->dy; g.dz = cfg->ndim == 3 ? cfg->dz : 0.0;
-    g.rdx = (float)(1.0 / g.dx); g.rdy = (float)(1.0 / g.dy); g.rdz = cfg->ndim == 3 ? (float)(1.0 / g.dz) : 0.f;
+    g.rdx = make_rcp(g.dx); g.rdy = make_rcp(g.dy); g.rdz = cfg->ndim == 3 ? make_rcp(g.dz) : Rcp{0.f, 0.0};
+    if (const char* xd = getenv("FDTD_B200_EXACT_DIV")) if (atoi(xd)) g.rdx.y = g.rdy.y = g.rdz.y = 0.0;   // A/B: true divisions
     if (cfg->ndim == 3) {
         g.pz = (int)round_up(g.nz, 32);
         g.sy = g.pz; g.sx = (long long)g.ny * g.pz;
@@ -218,7 +219,11 @@ extern "C" int fdtd_upload_field(fdtd_engine* e, int32_t comp, const void* host,
     CU(cudaSetDevice(e->cfg.device));
     int s[3]; comp_shape(e, comp, s);
     void* dst = cur_fields(e)[comp];
-    CU(cudaMemsetAsync(dst, 0, e->array_elems * e->esz, e->stream));
+    // On an x-slab the planes from nx on are the right neighbour's: it pushes into them as soon as its own
+    // fdtd_slab_run starts, with no handshake against this upload.  Clear the owned planes only and leave the ghost
+    // planes to the halo protocol (callers still order "all uploads" before "any run" with a barrier, see the header).
+    const long long clear_planes = (e->g.nxg != e->g.nx || e->slab.connected) ? e->g.nx : e->planes_alloc;
+    CU(cudaMemsetAsync(dst, 0, (size_t)clear_planes * e->plane_elems * e->esz, e->stream));
     const bool d64 = e->cfg.dtype == FDTD_F64, h64 = host_dtype == FDTD_F64;
     if (host_dtype != FDTD_F32 && host_dtype != FDTD_F64) return fail(FDTD_EINVAL, "bad host dtype %d", host_dtype);
     if (d64 == h64) return copy_strided(e, dst, const_cast<void*>(host), s[0], s[1], s[2], true);

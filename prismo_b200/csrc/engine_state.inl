@@ -24,6 +24,17 @@ static int fail(int code, const char* fmt, ...)
 
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
+// Reciprocals of a spacing.  y = RN(1/d) (IEEE division on the host) drives the exact FMA division sequence of
+// Ar<double>::div_rn; it is offered only for divisors in [2^-60, 2^60] so that a = q*d stays far from the
+// exponent limits whenever the quotient passes the kernel's range test.
+static Rcp make_rcp(double d)
+{
+    Rcp r;
+    r.f = (float)(1.0 / d);
+    r.y = (d >= 0x1p-60 && d <= 0x1p60) ? 1.0 / d : 0.0;
+    return r;
+}
+
 struct HostSrc { SrcOp op; int group; };
 
 struct fdtd_engine {
@@ -64,6 +75,7 @@ struct fdtd_engine {
     double *d_amp = nullptr, *d_phasor = nullptr;
     void* d_rec = nullptr; long long rec_elems_per_step = 0;
     double2* d_dft = nullptr; long long dft_elems = 0;
+    std::vector<long long> dft_sig, aux_sig;   // layout of the DFT / ADE pools: sums are kept only across identical op lists
     int* d_step = nullptr;          // table cursor (device)
     int cursor = 0;                 // host mirror of the cursor
     int* d_cnt = nullptr;           // 2 x 6 gate counters (2-D)

@@ -100,8 +100,8 @@ struct Fold {
 enum { FHX = 0, FHY = 1, FHZ = 2, FEX = 3, FEY = 4, FEZ = 5 };
 
 template <typename T> __device__ __forceinline__ T upd_h2(const Coefs<T>& c, const Geom& g, const Fold& f, T h,
-                                                          T a1, T a0, double da_, float ra, int ia,
-                                                          T b1, T b0, double db_, float rb, int ib)
+                                                          T a1, T a0, double da_, Rcp ra, int ia,
+                                                          T b1, T b0, double db_, Rcp rb, int ib)
 {
     if (sizeof(T) == 4)
         return fmaf(f.f[ib], (float)(b1 - b0), fmaf(-f.f[ia], (float)(a1 - a0), (float)c.uda * (float)h));
@@ -110,8 +110,8 @@ template <typename T> __device__ __forceinline__ T upd_h2(const Coefs<T>& c, con
     return upd_h<T>(c.uda, h, c.udb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
 }
 template <typename T> __device__ __forceinline__ T upd_e2(const Coefs<T>& c, const Geom& g, const Fold& f, T e,
-                                                          T a1, T a0, double da_, float ra, int ia,
-                                                          T b1, T b0, double db_, float rb, int ib)
+                                                          T a1, T a0, double da_, Rcp ra, int ia,
+                                                          T b1, T b0, double db_, Rcp rb, int ib)
 {
     if (sizeof(T) == 4)
         return fmaf(-f.f[ib], (float)(b1 - b0), fmaf(f.f[ia], (float)(a1 - a0), (float)c.uca * (float)e));

@@ -23,13 +23,17 @@ template <typename T> struct Coefs {
     T uca, ucb, uda, udb;         // uniform values otherwise
 };
 
+// 1/d for the two arithmetic policies.  y = RN(1/d) in fp64, or 0 when the host could not validate the FMA
+// division sequence for this divisor (then fp64 falls back to a true division).
+struct Rcp { float f; double y; };
+
 struct Geom {
     int nx, ny, nz;        // local logical dims
     int nxg, x0;           // global nx, global index of local plane 0
     int pz;                // padded length of the contiguous axis
     long long sx, sy;      // strides (elements); 2-D: sy = 1
     double dx, dy, dz;     // spacings
-    float rdx, rdy, rdz;   // fp32 reciprocals
+    Rcp rdx, rdy, rdz;     // reciprocals: fp32, and the correctly rounded fp64 one for the exact division sequence
 };
 
 // ---- arithmetic policies ---------------------------------------------------------------------
@@ -40,16 +44,34 @@ template <> struct Ar<double> {
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    static __device__ __forceinline__ double diff(double a1, double a0, double d, float) {
-        return __ddiv_rn(__dsub_rn(a1, a0), d);
+    // a / d, correctly rounded, for a launch-constant divisor d with y = RN(1/d) formed once on the host.
+    //   q0 = RN(a*y)                                   within 1.5 ulp of a/d
+    //   r0 = a - q0*d (exact, FMA);  q1 = RN(q0 + r0*y)  faithful (error 0.5 ulp + 2^-52 ulp)
+    //   r1 = a - q1*d (exact, FMA);  q2 = RN(q1 + r1*y)  = RN(a/d)   (Markstein's theorem: y = RN(1/d), q1 faithful)
+    // Five FMA-pipe operations instead of __ddiv_rn's ~40-instruction sequence.  The theorem needs the absence of
+    // over/underflow: quotients outside [2^-900, 2^900] (zero, inf, nan, denormals included) take the exact slow
+    // path; a == 0 returns q0 = (+-0)*y, which carries the sign a true division gives (d > 0).
+    static __device__ __forceinline__ double div_rn(double a, double d, double y) {
+        if (y == 0.0) return __ddiv_rn(a, d);
+        const double q0 = __dmul_rn(a, y);
+        const double r0 = __fma_rn(-q0, d, a);
+        const double q1 = __fma_rn(r0, y, q0);
+        const double r1 = __fma_rn(-q1, d, a);
+        double q2 = __fma_rn(r1, y, q1);
+        const unsigned ex = ((unsigned)__double2hiint(q0) >> 20) & 0x7ffu;      // biased exponent of q0
+        if (ex - 123u > 1800u) q2 = (a == 0.0) ? q0 : __ddiv_rn(a, d);          // |q0| outside [2^-900, 2^901)
+        return q2;
+    }
+    static __device__ __forceinline__ double diff(double a1, double a0, double d, Rcp r) {
+        return div_rn(__dsub_rn(a1, a0), d, r.y);
     }
 };
 template <> struct Ar<float> {
     static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
     static __device__ __forceinline__ float add(float a, float b) { return a + b; }
     static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
-    static __device__ __forceinline__ float diff(float a1, float a0, double, float rd) {
-        return (a1 - a0) * rd;
+    static __device__ __forceinline__ float diff(float a1, float a0, double, Rcp rd) {
+        return (a1 - a0) * rd.f;
     }
 };
 

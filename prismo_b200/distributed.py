@@ -49,6 +49,7 @@ class SlabExecutor:
         self._mon = []           # per global monitor op: (global op, local id or None, local x-range in the box)
         self._tb2_ok = True
         self._agreed = False
+        self._uploaded = False
 
     # ---- lifetime / passthrough ------------------------------------------------------------------------------
     def close(self):
@@ -79,6 +80,7 @@ class SlabExecutor:
     def upload(self, comp, array):
         a = np.asarray(array)
         self.eng.upload(comp, np.ascontiguousarray(a[self.x0:self.x0 + self._planes(comp)]))
+        self._uploaded = True
 
     def download(self, comp, out=None):
         n = self._planes(comp)
@@ -149,6 +151,11 @@ class SlabExecutor:
                 self.eng.set_option("tb2", 1 if all(votes) else 0)
             self._agreed = True
         r = self._runner_()
+        if self._uploaded:
+            # the right neighbour pushes its halo into our ghost planes as soon as ITS run starts: every rank's
+            # uploads must be complete first (fdtd_upload_field in include/fdtd_b200.h)
+            self.dist.barrier(group=self.group)
+            self._uploaded = False
         r.run(n)
         r.synchronize()
 

@@ -21,6 +21,12 @@ from . import session as _session
 _registered = False
 
 
+def _lib_mod():
+    from . import _lib
+
+    return _lib
+
+
 def _make_backend_class(Backend):
     class B200Backend(Backend):
         """Backend ABC implementation (backends/base.py:14-219).  Array factories hand out HOST NumPy
@@ -44,14 +50,19 @@ def _make_backend_class(Backend):
         int64 = property(lambda self: np.int64)
         pi = property(lambda self: np.pi)
 
+        # array factories: page-locked host memory (uploads / downloads are then plain DMA at PCIe line rate)
         def zeros(self, shape, dtype=None):
-            return np.zeros(shape, dtype=dtype or np.float64)
+            a = _lib_mod().pinned_empty(shape, dtype or np.float64)
+            a[...] = 0
+            return a
 
         def ones(self, shape, dtype=None):
-            return np.ones(shape, dtype=dtype or np.float64)
+            a = _lib_mod().pinned_empty(shape, dtype or np.float64)
+            a[...] = 1
+            return a
 
         def empty(self, shape, dtype=None):
-            return np.empty(shape, dtype=dtype or np.float64)
+            return _lib_mod().pinned_empty(shape, dtype or np.float64)
 
         def array(self, data, dtype=None):
             return np.array(data, dtype=dtype)
@@ -99,14 +110,19 @@ def _make_backend_class(Backend):
             return np.fft.ifft2(array, axes=axes)
 
         def synchronize(self):
-            import ctypes as C
-
-            from . import _lib
-            # all engines run on their own streams and every host-visible call already synchronises
-            return None
+            """cudaDeviceSynchronize on this backend's device (every engine stream included)."""
+            m = _lib_mod()
+            m.check(m.load().fdtd_device_sync(self.device_id))
 
         def get_memory_info(self):
-            return {"backend": "b200", "device_id": self.device_id}
+            """cudaMemGetInfo of the device (the reference's CuPy backend reports the same two numbers)."""
+            import ctypes as C
+
+            m = _lib_mod()
+            f, t = C.c_int64(), C.c_int64()
+            m.check(m.load().fdtd_device_mem_info(self.device_id, C.byref(f), C.byref(t)))
+            return {"backend": "b200", "device_id": self.device_id, "free_bytes": f.value, "total_bytes": t.value,
+                    "used_bytes": t.value - f.value}
 
         def __repr__(self):
             return f"B200Backend(device_id={self.device_id})"

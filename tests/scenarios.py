@@ -112,6 +112,43 @@ SCENARIOS = {
 }
 
 
+# ---- BASELINE.json configs at the parity sizes of SURVEY 8(d) (too slow for the golden set: oracle-checked on the GPU box) ----
+def _exact_size(n, pml, res):
+    return ((n - 2 * pml) - 0.5) / res
+
+
+_C1 = _exact_size(1000, 10, 50e6)
+_C2 = _exact_size(121, 10, 20e6)
+_C3 = (_exact_size(128, 8, 40e6), _exact_size(128, 8, 40e6), _exact_size(64, 8, 40e6))
+CONFIG_SCENARIOS = {
+    # config 1: 2-D 1000 x 1000 Si strip waveguide, Gaussian-beam line source, DFTMonitor (corner-patch semantics) and a
+    # FieldMonitor DFT line, 11 wavelengths 1.5-1.6 um; 200 steps
+    "c1": dict(size=(_C1, _C1, 0.0), resolution=50e6, pml=10, courant=0.9, init="zero", steps=200, materials="c1_strip",
+               sources=[("GaussianBeamSource", dict(center=(1.2e-6, _C1 / 2, 0.0), size=(0.0, 2e-6, 0.0), direction="x",
+                                                    polarization="y", frequency=193e12, beam_waist=1e-6, pulse=True,
+                                                    pulse_width=10e-15))],
+               monitors=[("DFTMonitor", dict(center=(16e-6, _C1 / 2, 0.0), size=(0.0, 2e-6, 0.0),
+                                             frequencies=[299792458.0 / w for w in np.linspace(1.5e-6, 1.6e-6, 11)],
+                                             components=["Ex", "Ey", "Hz"])),
+                         ("FieldMonitor", dict(center=(16e-6, _C1 / 2, 0.0), size=(0.0, 2e-6, 0.0), components=["Ey"],
+                                               time_domain=False,
+                                               frequencies=[299792458.0 / w for w in np.linspace(1.5e-6, 1.6e-6, 11)]))]),
+    # config 2: 3-D 121^3 (100^3 + PML 10) vacuum, TFSF +x plane wave (CW), 20 steps, white-noise start
+    "c2": dict(size=(_C2, _C2, _C2), resolution=20e6, pml=10, courant=0.9, steps=20,
+               sources=[("TFSFSource", dict(center=(_C2 / 2,) * 3, size=(_C2 / 2,) * 3, direction="+x", polarization="y",
+                                            frequency=193e12, pulse=False))]),
+    # config 3, 128 x 128 x 64 crop: Si ridge on SiO2 (heterogeneous Ca..Db), library-Si Lorentz pole in the core
+    # (uncoupled recursion, like the reference), ModeSource (+x) with a .value-capable waveform; 20 steps
+    "c3_crop": dict(size=_C3, resolution=40e6, pml=8, courant=0.5, steps=20, materials="c3_ridge",
+                    sources=[("ModeSource", dict(center=(0.6e-6, _C3[1] / 2, _C3[2] / 2), size=(0.0, 2.0e-6, 1.0e-6),
+                                                 mode=("mode", 24, 16, 5), direction="+x",
+                                                 waveform=_wf("GaussianPulse", frequency=F0, pulse_width=5e-15)))],
+                    monitors=[("FieldMonitor", dict(center=(2.0e-6, _C3[1] / 2, _C3[2] / 2), size=(0.0, 2.0e-6, 1.0e-6),
+                                                    components=["Ey", "Hz"], time_domain=False, frequencies=[F0]))],
+                    ade=[("lorentz", [(2 * 3.141592653589793 * 299792458.0 / 1.2e-6, 1.0, 1e13)], "Ez", "c3_core")]),
+}
+
+
 # ---- helpers -------------------------------------------------------------------------------------------
 def grid_dims(spec):
     from oracle.grid import OGrid
@@ -120,7 +157,19 @@ def grid_dims(spec):
 
 
 def materials(spec):
-    if spec.get("materials") != "random":
+    kind = spec.get("materials")
+    if kind == "c1_strip":                     # BASELINE config 1: Si strip (eps 12.11) along x in SiO2 (2.07), 2-D
+        nx, ny, _ = grid_dims(spec)
+        eps = np.full((nx, ny, 1), 2.07)
+        eps[:, ny // 2 - 11: ny // 2 + 11] = 12.11
+        return dict(eps_rel=eps, mu_rel=np.ones_like(eps), sigma_e=np.zeros_like(eps), sigma_m=np.zeros_like(eps))
+    if kind == "c3_ridge":                     # BASELINE config 3: Si ridge on an SiO2 half space, air above
+        nx, ny, nz = grid_dims(spec)
+        eps = np.ones((nx, ny, nz))
+        eps[:, :, : nz // 2] = 2.07
+        eps[:, ny // 2 - ny // 16: ny // 2 + ny // 16, nz // 2: nz // 2 + nz // 12] = 12.11
+        return dict(eps_rel=eps, mu_rel=np.ones_like(eps), sigma_e=np.zeros_like(eps), sigma_m=np.zeros_like(eps))
+    if kind != "random":
         return None
     dims = grid_dims(spec)
     rng = np.random.default_rng(7)
@@ -143,6 +192,10 @@ def ade_mask(kind, shape):
     if kind is None:
         return None
     m = np.zeros(shape, dtype=bool)
+    if kind == "c3_core":                      # the ridge core of materials="c3_ridge" (Ez-shaped array)
+        ny, nz = shape[1] + 1, shape[2]
+        m[:, ny // 2 - ny // 16: ny // 2 + ny // 16, nz // 2: nz // 2 + nz // 12] = True
+        return m
     m[: shape[0] // 2] = True
     m[:, ::3] = False
     return m

@@ -247,6 +247,30 @@ def test_peer_to_peer_slabs_two_processes_one_gpu(mode):
     assert want in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [[], ["--f32"], ["--balanced"], ["--sim"], ["--src-offset", "2"], ["--het"]],
+                         ids=["p2p", "f32", "balanced", "sim", "ghost-src", "het"])
+def test_peer_to_peer_slabs_on_all_gpus(args):
+    """The same check on REAL separate GPUs (NCCL rendezvous, CUDA-IPC peer mappings over NVLink): one rank per
+    device, every device of the box.  Skips on a single-GPU box."""
+    import subprocess
+    import sys
+
+    from tests.conftest import _cuda_devices
+
+    n = _cuda_devices()
+    if n < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    if "--het" in args:
+        pytest.importorskip("prismo_b200")
+    env = dict(os.environ, FDTD_B200_HALO_TIMEOUT_MS="20000")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(os.path.dirname(__file__), "multi_gpu_check.py")] + args
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    want = "MULTI_GPU_SIM_CHECK OK" if "--sim" in args else "MULTI_GPU_CHECK OK"
+    assert want in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 # ---- whole Simulations (sources + monitors) slab-decomposed through Session / SlabExecutor -----------------------
 DIST_SCENARIOS = ["upd3d_vac", "src3d_point", "src3d_plane", "src3d_tfsf", "src3d_mode", "mon3d_field"]
 

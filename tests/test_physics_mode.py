@@ -91,3 +91,38 @@ def test_physics_mode_is_stable_and_cpml_absorbs():
     assert closed[0] > 0 and abs(closed[1] / closed[0] - 1) < 0.05, closed       # lossless box keeps the energy
     assert abs(opened[0] / closed[0] - 1) < 0.05                                 # same pulse was launched
     assert opened[1] / opened[0] < 1e-4, (opened, opened[1] / opened[0])         # > 40 dB absorbed
+
+
+def _run_physics(dims, dtype, thickness, fused, steps, lx=None, seed=1):
+    d = 2e-8
+    dt = 0.9 * d / (C0 * np.sqrt(3))
+    eng = pb.Engine(3, dims, (d,) * 3, dt, dtype=dtype, flags=_lib.FLAG_YEE)
+    if thickness:
+        eng.set_cpml(thickness, cpml.coefficient_table(dims, (d,) * 3, dt, cpml.PMLParams(thickness=thickness, alpha_max=0.05)))
+    eng.set_option("yee_fused", int(fused))
+    if lx:
+        eng.set_option("fused_lx", lx)
+    rng = np.random.default_rng(seed)
+    for c in COMPS:
+        eng.upload(c, rng.standard_normal(eng.field_shape(c)) * (1.0 if c[0] == "E" else 1 / 377.0))
+    eng.run(steps)
+    out = {c: eng.download(c) for c in COMPS}
+    eng.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,thickness,steps,lx", [((28, 24, 26), 0, 7, None), ((28, 24, 26), 3, 40, None),
+                                                     ((37, 33, 70), 3, 7, 5), ((9, 8, 7), 3, 1, None),
+                                                     ((64, 47, 130), 6, 12, None), ((64, 47, 130), 0, 5, 9)])
+def test_fused_physics_sweep_equals_two_pass(dims, thickness, steps, lx):
+    """The fused one-sweep physics step (Yee leap-frog + CPML, psi ping-pong, fdtd_yee_fused.cuh) against the
+    two-pass physics kernels, which test_physics_mode_matches_its_oracle pins to oracle/yee.py: fp64 bitwise, across
+    tile rims, x-segment seams, ragged edges and CPML slabs; fp32 within 1e-4.  PARITY UNPINNED (own oracle only)."""
+    a = _run_physics(dims, "float64", thickness, False, steps)
+    b = _run_physics(dims, "float64", thickness, True, steps, lx=lx)
+    for c in COMPS:
+        assert np.array_equal(a[c], b[c]), f"{c}: max rel {np.abs(a[c] - b[c]).max() / (np.abs(a[c]).max() + 1e-300):.2e}"
+    b32 = _run_physics(dims, "float32", thickness, True, steps, lx=lx)
+    for c in COMPS:
+        assert np.linalg.norm(a[c] - b32[c]) <= 1e-4 * np.linalg.norm(a[c]), c
