@@ -217,12 +217,7 @@ template <typename T, int TJ> static int launch_fused_tj(fdtd_engine* e, int i_b
     t.nseg = (planes + t.lx - 1) / t.lx;
     const size_t smem = fused_smem_bytes<T, TJ>();
     auto kern = k_fused3d<T, TJ, 0>;
-    switch (e->fused_pol & 3) {
-    case 1: kern = k_fused3d<T, TJ, 1>; break;
-    case 2: kern = k_fused3d<T, TJ, 2>; break;
-    case 3: kern = k_fused3d<T, TJ, 3>; break;
-    default: break;
-    }
+    if (sizeof(T) == 8 && fold64(e)) kern = k_fused3d<T, TJ, (sizeof(T) == 8 ? 1 : 0)>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, TJ + 1, 1);
     const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
@@ -285,7 +280,6 @@ template <typename T> static int launch_yee_fused(fdtd_engine* e, cudaStream_t s
 // one fused sweep over planes [i_begin, i_end): reads the current set, writes the other one
 template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i_end, cudaStream_t s)
 {
-    if (e->fused_tj == 7) return launch_fused_tj<T, 7>(e, i_begin, i_end, s);
     return launch_fused_tj<T, kFusedTJ>(e, i_begin, i_end, s);
 }
 
@@ -448,6 +442,76 @@ extern "C" int fdtd_plan_segments(int32_t nx, const uint8_t* plane_flags, int32_
     return (int)parts.size();
 }
 
+// ---- TMA-fed variant of the two-step sweep (fdtd_tb2x.cuh) ---------------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver; the library links only the runtime, so fetch the entry point at run time.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// descriptors of the six arrays of both buffer sets: tensor (pz, ny, planes_alloc), box (256 bytes, R rows, 1 plane);
+// rows / columns / planes outside the tensor read as zero (the padding and guard planes of the layout, for free)
+static int ensure_tmaps(fdtd_engine* e)
+{
+    if (e->tmaps_ok) return 0;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(FDTD_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const Geom& g = e->g;
+    const bool d64 = e->cfg.dtype == FDTD_F64;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.ny, (cuuint64_t)e->planes_alloc};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.sy * e->esz, (cuuint64_t)g.sx * e->esz};
+    const cuuint32_t box[3] = {(cuuint32_t)(kTb2xRowBytes / e->esz), (cuuint32_t)kTb2xRows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int s = 0; s < 2; ++s)
+        for (int c = 0; c < 6; ++c) {
+            void* base = s ? e->fldB[c] : e->fld[c];
+            CUresult r = enc(&e->tmaps[s].m[c], d64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
+                             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(FDTD_ECUDA, "cuTensorMapEncodeTiled failed (%d) for set %d array %d", (int)r, s, c);
+        }
+    e->tmaps_ok = true;
+    return 0;
+}
+
+static bool use_tb2x(const fdtd_engine* e)
+{
+    // the TMA box is 256 B wide and R rows high: rows of the arrays must be at least that long
+    return e->tb2x && (long long)e->g.pz * (long long)e->esz >= kTb2xRowBytes;
+}
+
+template <typename T> static int launch_tb2x(fdtd_engine* e, const Fields<T>& out, const FusedTiling& t, const MidOps& m,
+                                             cudaStream_t s)
+{
+    constexpr int R = kTb2xRows;
+    if (int rc = ensure_tmaps(e)) return rc;
+    const int S = e->tb2x_stages, D = e->tb2x_slots;
+    static const size_t pad = getenv("FDTD_B200_TB2X_PAD") ? (size_t)atoll(getenv("FDTD_B200_TB2X_PAD")) : 0;   // tuning experiment
+    const size_t smem = tb2x_smem_bytes<R>(S, D) + pad;
+    if (smem > 227 * 1024) return fail(FDTD_EINVAL, "two-step sweep rings (%d stages, %d slots) need %zu B of shared memory", S, D, smem);
+    auto kern = k_fused3d_tb2x<T, R, 0>;
+    if (sizeof(T) == 8 && fold64(e)) kern = k_fused3d_tb2x<T, R, (sizeof(T) == 8 ? 1 : 0)>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 block(32, R + 1, 1);
+    const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
+    static const int all_arrive = getenv("FDTD_B200_TB2X_ARRIVE_ALL") ? atoi(getenv("FDTD_B200_TB2X_ARRIVE_ALL")) : 0;
+    kern<<<items, block, smem, s>>>(e->tmaps[e->cur], out, coefs_of<T>(e), e->g, t, m, fold_of(e), S, D, all_arrive);
+    return 0;
+}
+
 // TWO steps in one pass over planes [0, nx): reads the current set, writes the other one; the intermediate
 // step's sources / monitors (table row *d_step + step_off) are applied inside the kernel
 template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaStream_t s)
@@ -468,8 +532,10 @@ template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaSt
     }
     const int vec_per_row = g.pz / V;
     t.own_lanes = tb2_own_lanes<T>();
+    if (const char* ow = getenv("FDTD_B200_TB2_OWN")) t.own_lanes = std::min(t.own_lanes, std::max(2, atoi(ow)));   // tuning experiment
     t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
-    t.ntj = (g.ny + (R - 4) - 1) / (R - 4);
+    const int own_rows = (use_tb2x(e) ? kTb2xRows : R) - 4;       // the four stages shrink validity by one row each
+    t.ntj = (g.ny + own_rows - 1) / own_rows;
     MidOps m{};
     m.src = e->d_src; m.n_src = 0;
     for (int c : e->grp_count) m.n_src += c;
@@ -494,10 +560,15 @@ template <typename T> static int launch_tb2(fdtd_engine* e, int step_off, cudaSt
     const Coefs<T> cf = coefs_of<T>(e);
     const Fold fo = fold_of(e);
     plan_tb2_segments(e, (long long)t.ntj * t.ntk, any_ops, t.halo_flag != nullptr, t);
-    auto kern = k_fused3d_tb2<T, R>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
-    kern<<<items, block, smem, s>>>(in, out, cf, g, t, m, (int)e->planes_alloc, fo);
+    if (use_tb2x(e)) {
+        if (int rc = launch_tb2x<T>(e, out, t, m, s)) return rc;
+    } else {
+        auto kern = k_fused3d_tb2<T, R, 0>;
+        if (sizeof(T) == 8 && fold64(e)) kern = k_fused3d_tb2<T, R, (sizeof(T) == 8 ? 1 : 0)>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
+        kern<<<items, block, smem, s>>>(in, out, cf, g, t, m, (int)e->planes_alloc, fo);
+    }
     e->launches++;
     CU(cudaGetLastError());
     e->cur ^= 1;

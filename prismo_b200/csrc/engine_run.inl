@@ -127,6 +127,9 @@ extern "C" int fdtd_set_option(fdtd_engine* e, const char* key, int32_t value)
 {
     if (!e || !key) return fail(FDTD_EINVAL, "fdtd_set_option: null argument");
     if (!strcmp(key, "tb2")) e->tb2 = value ? 1 : 0;
+    else if (!strcmp(key, "tb2x")) e->tb2x = value ? 1 : 0;
+    else if (!strcmp(key, "tb2x_stages")) e->tb2x_stages = std::max(3, (int)value);
+    else if (!strcmp(key, "tb2x_slots")) e->tb2x_slots = std::max(2, (int)value);
     else if (!strcmp(key, "het_fused")) e->het_fused = value ? 1 : 0;
     else if (!strcmp(key, "fused_lx")) e->fused_lx = value;
     else if (!strcmp(key, "yee_fused")) {

@@ -26,6 +26,12 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     if (cfg->x_offset < 0 || cfg->x_offset + cfg->nx > nxg)
         return fail(FDTD_EINVAL, "slab [%d,%d) outside global nx=%d", cfg->x_offset, cfg->x_offset + cfg->nx, nxg);
     if (cfg->ndim == 2 && nxg != cfg->nx) return fail(FDTD_EINVAL, "2-D grids are not slab-decomposed");
+    if (cfg->dtype == FDTD_F64) {
+        const double dd[3] = {cfg->dx, cfg->dy, cfg->ndim == 3 ? cfg->dz : cfg->dx};
+        for (double d : dd)
+            if (!(d >= 0x1p-60 && d <= 0x1p60))
+                return fail(FDTD_EINVAL, "fp64 engines take spacings in [2^-60, 2^60] (exact division by a constant), got %g", d);
+    }
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(FDTD_EINVAL, "device %d not in [0,%d)", cfg->device, ndev);
@@ -39,7 +45,6 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     g.nxg = nxg; g.x0 = cfg->x_offset;
     g.dx = cfg->dx; g.dy = cfg->dy; g.dz = cfg->ndim == 3 ? cfg->dz : 0.0;
     g.rdx = make_rcp(g.dx); g.rdy = make_rcp(g.dy); g.rdz = cfg->ndim == 3 ? make_rcp(g.dz) : Rcp{0.f, 0.0};
-    if (const char* xd = getenv("FDTD_B200_EXACT_DIV")) if (atoi(xd)) g.rdx.y = g.rdy.y = g.rdz.y = 0.0;   // A/B: true divisions
     if (cfg->ndim == 3) {
         g.pz = (int)round_up(g.nz, 32);
         g.sy = g.pz; g.sx = (long long)g.ny * g.pz;
@@ -78,10 +83,11 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     const double eps0 = 8.854187817e-12, mu0 = 4 * M_PI * 1e-7;
     e->uni[0] = 1.0; e->uni[1] = cfg->dt / eps0; e->uni[2] = 1.0; e->uni[3] = cfg->dt / mu0;
     if (const char* lx = getenv("FDTD_B200_FUSED_LX")) e->fused_lx = atoi(lx);    // tuning / tests
-    if (const char* pol = getenv("FDTD_B200_FUSED_POL")) e->fused_pol = atoi(pol) & 3;
-    if (const char* tj = getenv("FDTD_B200_FUSED_TJ")) e->fused_tj = atoi(tj);
     if (const char* tb = getenv("FDTD_B200_TB2")) e->tb2 = atoi(tb);
     if (const char* z = getenv("FDTD_B200_TB2_ZONES")) e->tb2_zones = atoi(z);
+    if (const char* x = getenv("FDTD_B200_TB2X")) e->tb2x = atoi(x);
+    if (const char* x = getenv("FDTD_B200_TB2X_STAGES")) e->tb2x_stages = std::max(3, atoi(x));
+    if (const char* x = getenv("FDTD_B200_TB2X_SLOTS")) e->tb2x_slots = std::max(2, atoi(x));
     if (const char* yf = getenv("FDTD_B200_YEE_FUSED")) e->yee_fused = atoi(yf);
     if (const char* hf = getenv("FDTD_B200_HET_FUSED")) e->het_fused = atoi(hf);
     *out = e;

@@ -25,15 +25,16 @@ static int fail(int code, const char* fmt, ...)
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
 // Reciprocals of a spacing.  y = RN(1/d) (IEEE division on the host) drives the exact FMA division sequence of
-// Ar<double>::div_rn; it is offered only for divisors in [2^-60, 2^60] so that a = q*d stays far from the
-// exponent limits whenever the quotient passes the kernel's range test.
+// Ar<double>::div_fast; fdtd_create accepts fp64 spacings in [2^-60, 2^60] only, so that a = q*d stays far from the
+// exponent limits whenever the quotient passes the kernels' range test.
 static Rcp make_rcp(double d)
 {
     Rcp r;
     r.f = (float)(1.0 / d);
-    r.y = (d >= 0x1p-60 && d <= 0x1p60) ? 1.0 / d : 0.0;
+    r.y = 1.0 / d;
     return r;
 }
+static bool fold64(const fdtd_engine* e);
 
 struct HostSrc { SrcOp op; int group; };
 
@@ -86,9 +87,11 @@ struct fdtd_engine {
     int het_fused = 1;              // heterogeneous media: fused one-step sweep (0: two-pass kernels)
     int tb2_zones = -1;             // two-step sweep: narrow x-segments around op planes (-1 auto, 0 never, 1 always)
     int tb2 = 1;                    // 1: temporally blocked sweep (two steps per pass) where applicable
+    int tb2x = 1;                   // two-step sweep variant: 1 = TMA-fed, mbarrier-synchronised (fdtd_tb2x.cuh), 0 = fdtd_tb2.cuh
+    int tb2x_stages = 4, tb2x_slots = 3;   // depth of its input ring (TMA stages) and of its row-exchange ring
+    Tb2xMaps tmaps[2];              // TMA descriptors of the six arrays of set A / set B
+    bool tmaps_ok = false;
     unsigned char* d_plane_flags = nullptr; std::vector<unsigned char> plane_flags_host;
-    int fused_tj = 15;              // owner rows per CTA (15: one 16-warp CTA/SM; 7: two 8-warp CTAs/SM)
-    int fused_pol = 0;              // bit0: streaming (evict-first) stores (measured 1.4% slower: off)
     // staging
     void* d_stage = nullptr; size_t stage_bytes = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -151,7 +154,6 @@ static Fold fold_of(const fdtd_engine* e)
         fo.d[3 + a] = e->uni[1] / d[a];      // cb / d
     }
     for (int a = 0; a < 6; ++a) fo.f[a] = (float)fo.d[a];
-    fo.fast64 = (e->cfg.flags & FDTD_FLAG_FAST_F64) ? 1 : 0;
     return fo;
 }
 static void** cur_fields(fdtd_engine* e) { return e->cur ? e->fldB : e->fld; }
@@ -174,3 +176,5 @@ static void drop_graph(fdtd_engine* e)
 }
 
 // ---------------------------------------------------------------------------------------------------
+
+static bool fold64(const fdtd_engine* e) { return (e->cfg.flags & FDTD_FLAG_FAST_F64) != 0; }

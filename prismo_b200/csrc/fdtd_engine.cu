@@ -10,6 +10,7 @@
 #include "fdtd_yee.cuh"
 #include "fdtd_yee_fused.cuh"
 #include "fdtd_tb2.cuh"
+#include "fdtd_tb2x.cuh"
 #include "fdtd_het.cuh"
 #include "fdtd_tensor.cuh"
 

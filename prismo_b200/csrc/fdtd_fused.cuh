@@ -95,29 +95,94 @@ template <typename T, int TJ> constexpr size_t fused_smem_bytes()
 struct Fold {
     float f[6];             // db/dx, db/dy, db/dz, cb/dx, cb/dy, cb/dz
     double d[6];
-    int fast64;
 };
 enum { FHX = 0, FHY = 1, FHZ = 2, FEX = 3, FEY = 4, FEZ = 5 };
 
-template <typename T> __device__ __forceinline__ T upd_h2(const Coefs<T>& c, const Geom& g, const Fold& f, T h,
-                                                          T a1, T a0, double da_, Rcp ra, int ia,
-                                                          T b1, T b0, double db_, Rcp rb, int ib)
+// AM = arithmetic mode of the fp64 instantiations: 0 exact (reference operation sequence, bit-identical to NumPy),
+// 1 folded (FDTD_FLAG_FAST_F64).  fp32 is always folded.  SLOW = the exact mode's fallback with true divisions.
+template <typename T, int AM, bool SLOW>
+__device__ __forceinline__ T upd_h2(const Coefs<T>& c, const Geom& g, const Fold& f, T h,
+                                    T a1, T a0, double da_, Rcp ra, int ia,
+                                    T b1, T b0, double db_, Rcp rb, int ib, unsigned& bad)
 {
     if (sizeof(T) == 4)
         return fmaf(f.f[ib], (float)(b1 - b0), fmaf(-f.f[ia], (float)(a1 - a0), (float)c.uda * (float)h));
-    if (f.fast64)
+    if (AM == 1)
         return fma(f.d[ib], (double)(b1 - b0), fma(-f.d[ia], (double)(a1 - a0), (double)c.uda * (double)h));
-    return upd_h<T>(c.uda, h, c.udb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
+    if (SLOW) return upd_h<T>(c.uda, h, c.udb, Ar<T>::diff_exact(a1, a0, da_, ra), Ar<T>::diff_exact(b1, b0, db_, rb));
+    return upd_h<T>(c.uda, h, c.udb, Ar<T>::diff_fast(a1, a0, da_, ra, bad), Ar<T>::diff_fast(b1, b0, db_, rb, bad));
 }
-template <typename T> __device__ __forceinline__ T upd_e2(const Coefs<T>& c, const Geom& g, const Fold& f, T e,
-                                                          T a1, T a0, double da_, Rcp ra, int ia,
-                                                          T b1, T b0, double db_, Rcp rb, int ib)
+template <typename T, int AM, bool SLOW>
+__device__ __forceinline__ T upd_e2(const Coefs<T>& c, const Geom& g, const Fold& f, T e,
+                                    T a1, T a0, double da_, Rcp ra, int ia,
+                                    T b1, T b0, double db_, Rcp rb, int ib, unsigned& bad)
 {
     if (sizeof(T) == 4)
         return fmaf(-f.f[ib], (float)(b1 - b0), fmaf(f.f[ia], (float)(a1 - a0), (float)c.uca * (float)e));
-    if (f.fast64)
+    if (AM == 1)
         return fma(-f.d[ib], (double)(b1 - b0), fma(f.d[ia], (double)(a1 - a0), (double)c.uca * (double)e));
-    return upd_e<T>(c.uca, e, c.ucb, Ar<T>::diff(a1, a0, da_, ra), Ar<T>::diff(b1, b0, db_, rb));
+    if (SLOW) return upd_e<T>(c.uca, e, c.ucb, Ar<T>::diff_exact(a1, a0, da_, ra), Ar<T>::diff_exact(b1, b0, db_, rb));
+    return upd_e<T>(c.uca, e, c.ucb, Ar<T>::diff_fast(a1, a0, da_, ra, bad), Ar<T>::diff_fast(b1, b0, db_, rb, bad));
+}
+
+// H stage: (ox,oy,oz) <- f(h, e (own, j+1: ez_j/ex_j, k+1: ey_n/ex_n), e of the next plane (ey_p, ez_p own)); plane gi.
+// Shared by the one-step sweep (H+[i+1]) and the two-step sweeps (stages A and C).  Outputs must not alias inputs: the
+// exact fp64 mode recomputes the stage with true divisions when a quotient left the fast sequence's range.
+template <typename T, int V, bool MASKED, int AM, bool SLOW = false>
+__device__ __forceinline__ void stage_h(const Coefs<T>& c, const Geom& g, const Fold& fo, int gi, bool jy1, bool jy2, int k,
+                                        const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
+                                        const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
+                                        const Pack<T, V>& ez_j, const Pack<T, V>& ex_j, T ey_n, T ex_n,
+                                        const Pack<T, V>& ey_p, const Pack<T, V>& ez_p,
+                                        Pack<T, V>& ox, Pack<T, V>& oy, Pack<T, V>& oz)
+{
+    const bool ix1 = gi < g.nxg - 1, ix2 = gi < g.nxg - 2;
+    unsigned bad = 0;
+    ox = hx; oy = hy; oz = hz;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const bool kz1 = (k + e) < g.nz - 1, kz2 = (k + e) < g.nz - 2;
+        const T ey_k = (e + 1 < V) ? ey.v[(e + 1) % V] : ey_n;
+        const T ex_k = (e + 1 < V) ? ex.v[(e + 1) % V] : ex_n;
+        T n = upd_h2<T, AM, SLOW>(c, g, fo, hx.v[e], ez_j.v[e], ez.v[e], g.dy, g.rdy, FHY, ey_k, ey.v[e], g.dz, g.rdz, FHZ, bad);
+        if (!MASKED || (ix1 && jy2 && kz2)) ox.v[e] = n;
+        n = upd_h2<T, AM, SLOW>(c, g, fo, hy.v[e], ex_k, ex.v[e], g.dz, g.rdz, FHZ, ez_p.v[e], ez.v[e], g.dx, g.rdx, FHX, bad);
+        if (!MASKED || (ix2 && jy1 && kz2)) oy.v[e] = n;
+        n = upd_h2<T, AM, SLOW>(c, g, fo, hz.v[e], ey_p.v[e], ey.v[e], g.dx, g.rdx, FHX, ex_j.v[e], ex.v[e], g.dy, g.rdy, FHY, bad);
+        if (!MASKED || (ix2 && jy2 && kz1)) oz.v[e] = n;
+    }
+    if (sizeof(T) == 8 && AM == 0 && !SLOW) {
+        if (bad) stage_h<T, V, MASKED, AM, true>(c, g, fo, gi, jy1, jy2, k, hx, hy, hz, ex, ey, ez, ez_j, ex_j, ey_n, ex_n, ey_p, ez_p, ox, oy, oz);
+    }
+}
+
+// E stage: (ox,oy,oz) <- g(e, h (own, j+1: hz_j/hx_j, k+1: hy_n/hx_n), h of the next plane (hy_p, hz_p own)); plane gi
+template <typename T, int V, bool MASKED, int AM, bool SLOW = false>
+__device__ __forceinline__ void stage_e(const Coefs<T>& c, const Geom& g, const Fold& fo, int gi, bool jy1, int k,
+                                        const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
+                                        const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
+                                        const Pack<T, V>& hz_j, const Pack<T, V>& hx_j, T hy_n, T hx_n,
+                                        const Pack<T, V>& hy_p, const Pack<T, V>& hz_p,
+                                        Pack<T, V>& ox, Pack<T, V>& oy, Pack<T, V>& oz)
+{
+    const bool ex0 = gi < g.nxg, ex1 = gi < g.nxg - 1;
+    unsigned bad = 0;
+    ox = ex; oy = ey; oz = ez;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;
+        const T hy_k = (e + 1 < V) ? hy.v[(e + 1) % V] : hy_n;
+        const T hx_k = (e + 1 < V) ? hx.v[(e + 1) % V] : hx_n;
+        T n = upd_e2<T, AM, SLOW>(c, g, fo, ex.v[e], hz_j.v[e], hz.v[e], g.dy, g.rdy, FEY, hy_k, hy.v[e], g.dz, g.rdz, FEZ, bad);
+        if (!MASKED || (ex0 && jy1 && kz1)) ox.v[e] = n;
+        n = upd_e2<T, AM, SLOW>(c, g, fo, ey.v[e], hx_k, hx.v[e], g.dz, g.rdz, FEZ, hz_p.v[e], hz.v[e], g.dx, g.rdx, FEX, bad);
+        if (!MASKED || (ex1 && kz1)) oy.v[e] = n;
+        n = upd_e2<T, AM, SLOW>(c, g, fo, ez.v[e], hy_p.v[e], hy.v[e], g.dx, g.rdx, FEX, hx_j.v[e], hx.v[e], g.dy, g.rdy, FEY, bad);
+        if (!MASKED || (ex1 && jy1 && kz0)) oz.v[e] = n;
+    }
+    if (sizeof(T) == 8 && AM == 0 && !SLOW) {
+        if (bad) stage_e<T, V, MASKED, AM, true>(c, g, fo, gi, jy1, k, ex, ey, ez, hx, hy, hz, hz_j, hx_j, hy_n, hx_n, hy_p, hz_p, ox, oy, oz);
+    }
 }
 
 template <typename T> __device__ __forceinline__ Pack<T, VecOf<T>::V> zero_pack()
@@ -159,11 +224,13 @@ template <typename T, int POL> __device__ __forceinline__ void stv_pol(T* p, con
     else *reinterpret_cast<VT*>(p) = u.q;
 }
 
-// TJ owner rows per CTA; blockDim = (32, TJ + 1);  POL bit0: streaming stores
-template <typename T, int TJ, int POL>
-__global__ void __launch_bounds__(32 * (TJ + 1), (TJ <= 7 ? 2 : 1))
+// TJ owner rows per CTA; blockDim = (32, TJ + 1);  AM = fp64 arithmetic mode (0 exact, 1 folded).
+// (Rejected by measurement, profiles/r01_tuning.md, and removed: evict-first stores, ld.global.cg loads, 2 CTAs x 8 warps.)
+template <typename T, int TJ, int AM>
+__global__ void __launch_bounds__(32 * (TJ + 1), 1)
 k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold fo)
 {
+    constexpr int POL = 0;
     constexpr int V = VecOf<T>::V;
     typedef Pack<T, V> P;
     typedef typename VecOf<T>::type VT;
@@ -241,39 +308,17 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
         const T hpy_n = shfl_next<T>(hpy.v[0]), hpx_n = shfl_next<T>(hpx.v[0]);
 
         // ---- H+[i+1] ---------------------------------------------------------------------------------------
-        const int gi1 = g.x0 + i + 1;
-        const bool ix1 = gi1 < g.nxg - 1, ix2 = gi1 < g.nxg - 2;
-        P hnx = h1x, hny = h1y, hnz = h1z;
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-            const T ey_k = (e + 1 < V) ? e1y.v[(e + 1) % V] : ey1_n;
-            const T ex_k = (e + 1 < V) ? e1x.v[(e + 1) % V] : ex1_n;
-            T n = upd_h2<T>(c, g, fo, h1x.v[e], ez_j.v[e], e1z.v[e], g.dy, g.rdy, FHY, ey_k, e1y.v[e], g.dz, g.rdz, FHZ);
-            if (ix1 && jy2 && kz2[e]) hnx.v[e] = n;
-            n = upd_h2<T>(c, g, fo, h1y.v[e], ex_k, e1x.v[e], g.dz, g.rdz, FHZ, e2z.v[e], e1z.v[e], g.dx, g.rdx, FHX);
-            if (ix2 && jy1 && kz2[e]) hny.v[e] = n;
-            n = upd_h2<T>(c, g, fo, h1z.v[e], e2y.v[e], e1y.v[e], g.dx, g.rdx, FHX, ex_j.v[e], e1x.v[e], g.dy, g.rdy, FHY);
-            if (ix2 && jy2 && kz1[e]) hnz.v[e] = n;
-        }
+        P hnx, hny, hnz;
+        stage_h<T, V, true, AM>(c, g, fo, g.x0 + i + 1, jy1, jy2, k, h1x, h1y, h1z, e1x, e1y, e1z, ez_j, ex_j, ey1_n, ex1_n,
+                                e2y, e2z, hnx, hny, hnz);
         if (owner && i + 1 < i1) {
             stv_pol<T, POL>(out.hx + o + po, hnx); stv_pol<T, POL>(out.hy + o + po, hny); stv_pol<T, POL>(out.hz + o + po, hnz);
         }
         // ---- E+[i] ---------------------------------------------------------------------------------------------
         if (i >= i0) {
-            const int gi = g.x0 + i;
-            const bool ex0 = gi < g.nxg, ex1 = gi < g.nxg - 1;
-            P nx_ = e0x, ny_ = e0y, nz_ = e0z;
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const T hy_k = (e + 1 < V) ? hpy.v[(e + 1) % V] : hpy_n;
-                const T hx_k = (e + 1 < V) ? hpx.v[(e + 1) % V] : hpx_n;
-                T n = upd_e2<T>(c, g, fo, e0x.v[e], hz_j.v[e], hpz.v[e], g.dy, g.rdy, FEY, hy_k, hpy.v[e], g.dz, g.rdz, FEZ);
-                if (ex0 && jy1 && kz1[e]) nx_.v[e] = n;
-                n = upd_e2<T>(c, g, fo, e0y.v[e], hx_k, hpx.v[e], g.dz, g.rdz, FEZ, hnz.v[e], hpz.v[e], g.dx, g.rdx, FEX);
-                if (ex1 && kz1[e]) ny_.v[e] = n;
-                n = upd_e2<T>(c, g, fo, e0z.v[e], hny.v[e], hpy.v[e], g.dx, g.rdx, FEX, hx_j.v[e], hpx.v[e], g.dy, g.rdy, FEY);
-                if (ex1 && jy1 && kz0[e]) nz_.v[e] = n;
-            }
+            P nx_, ny_, nz_;
+            stage_e<T, V, true, AM>(c, g, fo, g.x0 + i, jy1, k, e0x, e0y, e0z, hpx, hpy, hpz, hz_j, hx_j, hpy_n, hpx_n,
+                                    hny, hnz, nx_, ny_, nz_);
             if (owner) {
                 const long long pe = (long long)i * g.sx;
                 stv_pol<T, POL>(out.ex + o + pe, nx_); stv_pol<T, POL>(out.ey + o + pe, ny_); stv_pol<T, POL>(out.ez + o + pe, nz_);

@@ -23,8 +23,9 @@ template <typename T> struct Coefs {
     T uca, ucb, uda, udb;         // uniform values otherwise
 };
 
-// 1/d for the two arithmetic policies.  y = RN(1/d) in fp64, or 0 when the host could not validate the FMA
-// division sequence for this divisor (then fp64 falls back to a true division).
+// 1/d for the two arithmetic policies: fp32 multiplies by f; fp64 divides exactly through y = RN(1/d) (IEEE division on
+// the host; fdtd_create accepts fp64 spacings in [2^-60, 2^60] only, so that a = q*d stays far from the exponent limits
+// whenever the quotient passes the kernels' range test).
 struct Rcp { float f; double y; };
 
 struct Geom {
@@ -48,22 +49,35 @@ template <> struct Ar<double> {
     //   q0 = RN(a*y)                                   within 1.5 ulp of a/d
     //   r0 = a - q0*d (exact, FMA);  q1 = RN(q0 + r0*y)  faithful (error 0.5 ulp + 2^-52 ulp)
     //   r1 = a - q1*d (exact, FMA);  q2 = RN(q1 + r1*y)  = RN(a/d)   (Markstein's theorem: y = RN(1/d), q1 faithful)
-    // Five FMA-pipe operations instead of __ddiv_rn's ~40-instruction sequence.  The theorem needs the absence of
-    // over/underflow: quotients outside [2^-900, 2^900] (zero, inf, nan, denormals included) take the exact slow
-    // path; a == 0 returns q0 = (+-0)*y, which carries the sign a true division gives (d > 0).
-    static __device__ __forceinline__ double div_rn(double a, double d, double y) {
-        if (y == 0.0) return __ddiv_rn(a, d);
+    // Five FMA-pipe operations instead of __ddiv_rn's ~20-instruction sequence with two branches.  The theorem needs the
+    // absence of over/underflow: a quotient outside [2^-900, 2^901) (inf, nan, denormals) sets `bad` and the CALLER
+    // recomputes its whole stage with true divisions (one rarely taken branch per stage instead of two per division:
+    // the hot loop stays in large basic blocks).  a == 0 returns q0 = (+-0)*y, the signed zero a true division gives.
+    static __device__ __forceinline__ double div_fast(double a, double d, double y, unsigned& bad) {
         const double q0 = __dmul_rn(a, y);
         const double r0 = __fma_rn(-q0, d, a);
         const double q1 = __fma_rn(r0, y, q0);
         const double r1 = __fma_rn(-q1, d, a);
-        double q2 = __fma_rn(r1, y, q1);
+        const double q2 = __fma_rn(r1, y, q1);
         const unsigned ex = ((unsigned)__double2hiint(q0) >> 20) & 0x7ffu;      // biased exponent of q0
-        if (ex - 123u > 1800u) q2 = (a == 0.0) ? q0 : __ddiv_rn(a, d);          // |q0| outside [2^-900, 2^901)
-        return q2;
+        const bool zero = a == 0.0;
+        bad |= (unsigned)((ex - 123u > 1800u) && !zero);
+        return zero ? q0 : q2;
+    }
+    // the same with the fallback inline (kernels off the hot path: two-pass, 2-D, heterogeneous, physics mode)
+    static __device__ __forceinline__ double div_rn(double a, double d, double y) {
+        unsigned bad = 0;
+        const double q = div_fast(a, d, y, bad);
+        return bad ? __ddiv_rn(a, d) : q;
     }
     static __device__ __forceinline__ double diff(double a1, double a0, double d, Rcp r) {
         return div_rn(__dsub_rn(a1, a0), d, r.y);
+    }
+    static __device__ __forceinline__ double diff_fast(double a1, double a0, double d, Rcp r, unsigned& bad) {
+        return div_fast(__dsub_rn(a1, a0), d, r.y, bad);
+    }
+    static __device__ __forceinline__ double diff_exact(double a1, double a0, double d, Rcp) {
+        return __ddiv_rn(__dsub_rn(a1, a0), d);
     }
 };
 template <> struct Ar<float> {
@@ -73,6 +87,8 @@ template <> struct Ar<float> {
     static __device__ __forceinline__ float diff(float a1, float a0, double, Rcp rd) {
         return (a1 - a0) * rd.f;
     }
+    static __device__ __forceinline__ float diff_fast(float a1, float a0, double, Rcp rd, unsigned&) { return (a1 - a0) * rd.f; }
+    static __device__ __forceinline__ float diff_exact(float a1, float a0, double, Rcp rd) { return (a1 - a0) * rd.f; }
 };
 
 // H: da*h - db*(c1 - c2)     E: ca*e + cb*(c1 - c2)      (solver.py:201-205, :275)

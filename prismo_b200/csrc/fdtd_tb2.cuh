@@ -115,56 +115,6 @@ __device__ __forceinline__ void mid_monitors(const MidOps& m, int comp, int p, i
     }
 }
 
-// H stage: (hx,hy,hz) <- f(h, e (own, j+1: ez_j/ex_j, k+1: ey_n/ex_n), e_next plane (ey, ez own)); plane gi
-template <typename T, int V, bool MASKED>
-__device__ __forceinline__ void stage_h(const Coefs<T>& c, const Geom& g, const Fold& fo, int gi, bool jy1, bool jy2, int k,
-                                        const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
-                                        const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
-                                        const Pack<T, V>& ez_j, const Pack<T, V>& ex_j, T ey_n, T ex_n,
-                                        const Pack<T, V>& ey_p, const Pack<T, V>& ez_p,
-                                        Pack<T, V>& ox, Pack<T, V>& oy, Pack<T, V>& oz)
-{
-    const bool ix1 = gi < g.nxg - 1, ix2 = gi < g.nxg - 2;
-    ox = hx; oy = hy; oz = hz;
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-        const bool kz1 = (k + e) < g.nz - 1, kz2 = (k + e) < g.nz - 2;
-        const T ey_k = (e + 1 < V) ? ey.v[(e + 1) % V] : ey_n;
-        const T ex_k = (e + 1 < V) ? ex.v[(e + 1) % V] : ex_n;
-        T n = upd_h2<T>(c, g, fo, hx.v[e], ez_j.v[e], ez.v[e], g.dy, g.rdy, FHY, ey_k, ey.v[e], g.dz, g.rdz, FHZ);
-        if (!MASKED || (ix1 && jy2 && kz2)) ox.v[e] = n;
-        n = upd_h2<T>(c, g, fo, hy.v[e], ex_k, ex.v[e], g.dz, g.rdz, FHZ, ez_p.v[e], ez.v[e], g.dx, g.rdx, FHX);
-        if (!MASKED || (ix2 && jy1 && kz2)) oy.v[e] = n;
-        n = upd_h2<T>(c, g, fo, hz.v[e], ey_p.v[e], ey.v[e], g.dx, g.rdx, FHX, ex_j.v[e], ex.v[e], g.dy, g.rdy, FHY);
-        if (!MASKED || (ix2 && jy2 && kz1)) oz.v[e] = n;
-    }
-}
-
-// E stage: (ex,ey,ez) <- g(e, h (own, j+1: hz_j/hx_j, k+1: hy_n/hx_n), h_next plane (hy, hz own)); plane gi
-template <typename T, int V, bool MASKED>
-__device__ __forceinline__ void stage_e(const Coefs<T>& c, const Geom& g, const Fold& fo, int gi, bool jy1, int k,
-                                        const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
-                                        const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
-                                        const Pack<T, V>& hz_j, const Pack<T, V>& hx_j, T hy_n, T hx_n,
-                                        const Pack<T, V>& hy_p, const Pack<T, V>& hz_p,
-                                        Pack<T, V>& ox, Pack<T, V>& oy, Pack<T, V>& oz)
-{
-    const bool ex0 = gi < g.nxg, ex1 = gi < g.nxg - 1;
-    ox = ex; oy = ey; oz = ez;
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-        const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;
-        const T hy_k = (e + 1 < V) ? hy.v[(e + 1) % V] : hy_n;
-        const T hx_k = (e + 1 < V) ? hx.v[(e + 1) % V] : hx_n;
-        T n = upd_e2<T>(c, g, fo, ex.v[e], hz_j.v[e], hz.v[e], g.dy, g.rdy, FEY, hy_k, hy.v[e], g.dz, g.rdz, FEZ);
-        if (!MASKED || (ex0 && jy1 && kz1)) ox.v[e] = n;
-        n = upd_e2<T>(c, g, fo, ey.v[e], hx_k, hx.v[e], g.dz, g.rdz, FEZ, hz_p.v[e], hz.v[e], g.dx, g.rdx, FEX);
-        if (!MASKED || (ex1 && kz1)) oy.v[e] = n;
-        n = upd_e2<T>(c, g, fo, ez.v[e], hy_p.v[e], hy.v[e], g.dx, g.rdx, FEX, hx_j.v[e], hx.v[e], g.dy, g.rdy, FEY);
-        if (!MASKED || (ex1 && jy1 && kz0)) oz.v[e] = n;
-    }
-}
-
 constexpr int kTb2Rows = 16;           // warp rows per CTA: 12 owners + 4 rim
 // Owner lanes per row.  Each of the four stages consumes one more element in +k.  With one element per lane (fp64)
 // that costs a lane per stage: 28 owners.  With two elements per lane (fp32) validity shrinks by half a lane per
@@ -173,7 +123,7 @@ template <typename T> constexpr int tb2_own_lanes() { return Vec8<T>::V >= 2 ? 3
 
 template <typename T, int R> constexpr size_t tb2_smem_bytes() { return 2 * (size_t)R * 8 * 32 * 8; }
 
-template <typename T, int R, bool OPS>
+template <typename T, int R, bool OPS, int AM>
 __device__ __forceinline__ void
 tb2_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const Geom& g, const FusedTiling& t,
           const MidOps& m, const int planes_alloc, const Fold& fo)
@@ -270,9 +220,9 @@ tb2_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
         const T h2y_n = shfl_next<T>(h2ay.v[0]), h2x_n = shfl_next<T>(h2ax.v[0]);
 
 #define TB2_STAGES(MASKED, STEADY)                                                                                      \
-        stage_h<T, V, MASKED>(c, g, fo, g.x0 + i + 3, jy1, jy2, k, nh0x, nh0y, nh0z, e0bx, e0by, e0bz, e0z_j, e0x_j, e0y_n,  \
+        stage_h<T, V, MASKED, AM>(c, g, fo, g.x0 + i + 3, jy1, jy2, k, nh0x, nh0y, nh0z, e0bx, e0by, e0bz, e0z_j, e0x_j, e0y_n,  \
                               e0x_n, ne0y, ne0z, h1cx, h1cy, h1cz);                                                  \
-        stage_e<T, V, MASKED>(c, g, fo, g.x0 + i + 2, jy1, k, e0ax, e0ay, e0az, h1bx, h1by, h1bz, h1z_j, h1x_j, h1y_n,        \
+        stage_e<T, V, MASKED, AM>(c, g, fo, g.x0 + i + 2, jy1, k, e0ax, e0ay, e0az, h1bx, h1by, h1bz, h1z_j, h1x_j, h1y_n,        \
                               h1x_n, h1cy, h1cz, e1cx, e1cy, e1cz);                                                  \
         if (OPS && (unsigned)(i + 2 - m.op_lo) <= (unsigned)m.op_span && (STEADY || i + 2 >= i0)) {                 \
             const unsigned char fl = m.plane_flags[i + 2];                                                         \
@@ -287,7 +237,7 @@ tb2_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
                 mid_monitors<T, V>(m, 2, i + 2, j, k, step_row, e1cz);                                             \
             }                                                                                                      \
         }                                                                                                          \
-        stage_h<T, V, MASKED>(c, g, fo, g.x0 + i + 1, jy1, jy2, k, h1ax, h1ay, h1az, e1bx, e1by, e1bz, e1z_j, e1x_j, e1y_n,  \
+        stage_h<T, V, MASKED, AM>(c, g, fo, g.x0 + i + 1, jy1, jy2, k, h1ax, h1ay, h1az, e1bx, e1by, e1bz, e1z_j, e1x_j, e1y_n,  \
                               e1x_n, e1cy, e1cz, h2bx, h2by, h2bz);                                                  \
         if (owner && (STEADY || (i + 1 >= i0 && i + 1 < i1))) {                                                    \
             st8<T, V>(out.hx + ost1, h2bx); st8<T, V>(out.hy + ost1, h2by);                                        \
@@ -295,7 +245,7 @@ tb2_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
         }                                                                                                          \
         if (STEADY || i >= i0) {                                                                                   \
             P e2x, e2y, e2z;                                                                                       \
-            stage_e<T, V, MASKED>(c, g, fo, g.x0 + i, jy1, k, e1ax, e1ay, e1az, h2ax, h2ay, h2az, h2z_j, h2x_j, h2y_n,     \
+            stage_e<T, V, MASKED, AM>(c, g, fo, g.x0 + i, jy1, k, e1ax, e1ay, e1az, h2ax, h2ay, h2az, h2z_j, h2x_j, h2y_n,     \
                                   h2x_n, h2by, h2bz, e2x, e2y, e2z);                                               \
             if (owner) { st8<T, V>(out.ex + ost, e2x); st8<T, V>(out.ey + ost, e2y); st8<T, V>(out.ez + ost, e2z); } \
         }
@@ -325,15 +275,15 @@ tb2_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
 
 // One launch covers every x-segment of the pair of steps.  Whether a segment carries sources / monitors is uniform per
 // CTA, so op-free segments run a loop without any op code (measured +10 %) and nothing serialises between the two kinds.
-template <typename T, int R>
+template <typename T, int R, int AM>
 __global__ void __launch_bounds__(32 * R, 1)
 k_fused3d_tb2(const __grid_constant__ CFields<T> in, const __grid_constant__ Fields<T> out,
               const __grid_constant__ Coefs<T> c, const __grid_constant__ Geom g, const __grid_constant__ FusedTiling t,
               const __grid_constant__ MidOps m, const int planes_alloc, const __grid_constant__ Fold fo)
 {
     const int slot = blockIdx.x / (t.ntj * t.ntk);
-    if ((t.seg_ops >> slot) & 1ull) tb2_sweep<T, R, true>(in, out, c, g, t, m, planes_alloc, fo);
-    else tb2_sweep<T, R, false>(in, out, c, g, t, m, planes_alloc, fo);
+    if ((t.seg_ops >> slot) & 1ull) tb2_sweep<T, R, true, AM>(in, out, c, g, t, m, planes_alloc, fo);
+    else tb2_sweep<T, R, false, AM>(in, out, c, g, t, m, planes_alloc, fo);
 }
 
 }  // namespace fdtd
