@@ -422,9 +422,10 @@ def main():
     fused = not (args.two_pass or args.physics)
     tb2 = fused and os.environ.get("FDTD_B200_TB2", "1") != "0" and args.steps >= 2 and not args.het
     kname = ("k_fused3d_tb2 (1 launch per TWO steps)" if tb2 else "k_fused3d (1 launch/step)") if fused \
-        else (("k_fused3d_yee (physics mode: Yee leap-frog + CPML slabs fused into ONE sweep per step, psi ping-pong)"
-               if os.environ.get("FDTD_B200_YEE_FUSED", "0") != "0" else
-               "k_h3d_yee + k_e3d_yee (physics mode: Yee leap-frog + CPML slabs, 2 launches/step)") if args.physics
+        else ({"2": "k_fused3d_yeex (physics mode: Yee leap-frog + CPML slabs in ONE TMA-fed sweep per step, psi ping-pong)",
+               "1": "k_fused3d_yee (physics mode: Yee leap-frog + CPML slabs fused into ONE sweep per step, psi ping-pong)",
+               "0": "k_h3d_yee + k_e3d_yee (physics mode: Yee leap-frog + CPML slabs, 2 launches/step)"}[
+                   os.environ.get("FDTD_B200_YEE_FUSED", "2")] if args.physics
               else "k_h3d + k_e3d (2 launches/step)")
     traffic = None
     try:
@@ -466,7 +467,7 @@ def main():
                        "parallelism": "1 GPU", "kernel_path": ("temporally blocked fused sweep (2 steps per HBM pass), ping-pong" if tb2 else
                                        "fused single sweep, ping-pong") if fused else
                                        (("physics mode (opt-in, parity unpinned): Yee leap-frog + 10-cell CPML, "
-                                         + ("fused one-sweep step" if os.environ.get("FDTD_B200_YEE_FUSED", "0") != "0" else "two-pass"))
+                                         + ("fused one-sweep step" if os.environ.get("FDTD_B200_YEE_FUSED", "2") != "0" else "two-pass"))
                                         if args.physics else "two-pass")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
     print(json.dumps(line), flush=True)

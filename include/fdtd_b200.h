@@ -153,7 +153,8 @@ int  fdtd_update_h(fdtd_engine* e);               /* MaxwellUpdater.update_magne
 int  fdtd_update_e(fdtd_engine* e);               /* MaxwellUpdater.update_electric_fields :151-165 */
 int  fdtd_sync(fdtd_engine* e);
 /* tuning switches: "tb2" 0/1 (two-step sweep), "fused_lx" planes per x-segment (0 = auto), "het_fused" 0/1,
- * "yee_fused" 0/1 (physics mode as one fused sweep; set it before the first step of a run) */
+ * "yee_fused" 0/1/2 (physics mode: two-pass kernels / fused sweep / TMA-fed fused sweep, the default; set it before the
+ * first step of a run) */
 int  fdtd_set_option(fdtd_engine* e, const char* key, int32_t value);
 /* measurement: CUDA events on the engine's own stream (torch.cuda.Event cannot see it).
  * fdtd_run_profiled runs n real steps without a graph and returns summed kernel times in ms:
@@ -191,6 +192,15 @@ int  fdtd_halo_ptrs(fdtd_engine* e, int32_t component, void** first_plane, void*
 int  fdtd_download_records(fdtd_engine* e, int32_t monitor_id, double* host, int32_t max_steps);
 int  fdtd_download_dft(fdtd_engine* e, int32_t monitor_id, double* host);
 int  fdtd_upload_dft(fdtd_engine* e, int32_t monitor_id, const double* host);
+
+/* Cropped read-out: box [lo, hi) of a component's CURRENT array as dense C-order host fp64 (at most 2^27 cells).  The
+ * reference has no counterpart (its arrays are host NumPy: fields[c][box]); used by bench.py's self-check and by parity
+ * tests at sizes whose full arrays the host would not want to mirror.                                           */
+int  fdtd_download_box(fdtd_engine* e, int32_t component, const int32_t* lo, const int32_t* hi, double* host);
+/* Per-plane checksums of the logical cells of a component (planes = its local x extent): out[2p] = sum of the value
+ * bit patterns, out[2p+1] = sum of bits * (1 + j*n2 + k), modulo 2^64.  Independent of the summation order and of the
+ * x-slab decomposition, so the concatenation over ranks is identical at 1/2/4/8 GPUs iff the fields are.          */
+int  fdtd_field_checksum(fdtd_engine* e, int32_t component, uint64_t* out, int32_t planes);
 
 /* ---- introspection ----------------------------------------------------------------------------------- */
 int  fdtd_steps_done(fdtd_engine* e, int64_t* steps);

@@ -277,6 +277,54 @@ template <typename T> static int launch_yee_fused(fdtd_engine* e, cudaStream_t s
     return 0;
 }
 
+// physics mode, default where it applies: the TMA-fed fused sweep (fdtd_yeex.cuh)
+static bool use_yeex(const fdtd_engine* e)
+{
+    return use_yee_fused(e) && e->yee_fused >= 2 && (long long)e->g.pz * (long long)e->esz >= kYeexBoxBytes &&
+           e->array_elems < (1ll << 32);
+}
+static int ensure_ymaps(fdtd_engine* e);
+
+template <typename T> static int launch_yeex(fdtd_engine* e, cudaStream_t s)
+{
+    constexpr int R = kYeexRows, V = Vec8<T>::V;
+    if (int rc = ensure_ymaps(e)) return rc;
+    const Geom& g = e->g;
+    void** dst = e->cur ? e->fld : e->fldB;
+    Fields<T> out = fields_of<T>(dst);
+    Cpml pm = e->cpml;                                   // psi of the CURRENT set in, the other set out
+    PsiOut pout;
+    for (int q = 0; q < 12; ++q) {
+        pm.psi[q] = e->cur ? e->psiB[q] : e->cpml.psi[q];
+        pout.p[q] = e->cur ? e->cpml.psi[q] : e->psiB[q];
+    }
+    FusedTiling t{};
+    t.i_begin = 0; t.i_end = g.nx;
+    t.own_lanes = 30;
+    const int vec_per_row = g.pz / V;
+    t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
+    t.ntj = (g.ny + (R - 2) - 1) / (R - 2);
+    int lx = e->fused_lx;
+    if (lx <= 0) {
+        const long long tiles = (long long)t.ntj * t.ntk;
+        long long want = (148ll * 40 + tiles - 1) / tiles;
+        lx = (int)std::max<long long>(32, (g.nx + want - 1) / std::max<long long>(want, 1));
+    }
+    t.lx = std::min(lx, g.nx);
+    t.nseg = (g.nx + t.lx - 1) / t.lx;
+    const int S = e->yeex_stages, D = e->yeex_slots;
+    const size_t smem = yeex_smem_bytes<R>(S, D);
+    if (smem > 227 * 1024) return fail(FDTD_EINVAL, "physics sweep rings (%d stages, %d slots) need %zu B of shared memory", S, D, smem);
+    auto kern = k_fused3d_yeex<T, R, 0>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 block(32, R + 1, 1);
+    kern<<<(unsigned)t.nseg * t.ntj * t.ntk, block, smem, s>>>(e->ymaps[e->cur], out, coefs_of<T>(e), g, t, pm, pout, e->slabg, S, D);
+    e->launches++;
+    CU(cudaGetLastError());
+    e->cur ^= 1;
+    return 0;
+}
+
 // one fused sweep over planes [i_begin, i_end): reads the current set, writes the other one
 template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i_end, cudaStream_t s)
 {
@@ -464,26 +512,39 @@ static EncodeTiledFn encode_tiled_fn()
 
 // descriptors of the six arrays of both buffer sets: tensor (pz, ny, planes_alloc), box (256 bytes, R rows, 1 plane);
 // rows / columns / planes outside the tensor read as zero (the padding and guard planes of the layout, for free)
-static int ensure_tmaps(fdtd_engine* e)
+static int encode_maps(fdtd_engine* e, Tb2xMaps* maps, int box_bytes)
 {
-    if (e->tmaps_ok) return 0;
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail(FDTD_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const Geom& g = e->g;
     const bool d64 = e->cfg.dtype == FDTD_F64;
     const cuuint64_t dims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.ny, (cuuint64_t)e->planes_alloc};
     const cuuint64_t strides[2] = {(cuuint64_t)g.sy * e->esz, (cuuint64_t)g.sx * e->esz};
-    const cuuint32_t box[3] = {(cuuint32_t)(kTb2xRowBytes / e->esz), (cuuint32_t)kTb2xRows, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(box_bytes / e->esz), (cuuint32_t)kTb2xRows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     for (int s = 0; s < 2; ++s)
         for (int c = 0; c < 6; ++c) {
             void* base = s ? e->fldB[c] : e->fld[c];
-            CUresult r = enc(&e->tmaps[s].m[c], d64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
+            CUresult r = enc(&maps[s].m[c], d64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(FDTD_ECUDA, "cuTensorMapEncodeTiled failed (%d) for set %d array %d", (int)r, s, c);
         }
+    return 0;
+}
+static int ensure_tmaps(fdtd_engine* e)
+{
+    if (e->tmaps_ok) return 0;
+    if (int rc = encode_maps(e, e->tmaps, kTb2xRowBytes)) return rc;
     e->tmaps_ok = true;
+    return 0;
+}
+// the physics sweep's boxes are 16 B wider (fdtd_yeex.cuh: the box origin must stay 16-byte aligned)
+static int ensure_ymaps(fdtd_engine* e)
+{
+    if (e->ymaps_ok) return 0;
+    if (int rc = encode_maps(e, e->ymaps, kYeexBoxBytes)) return rc;
+    e->ymaps_ok = true;
     return 0;
 }
 
@@ -595,6 +656,7 @@ template <typename T> static int step_fields3d(fdtd_engine* e, int half, cudaStr
     if (use_yee_fused(e)) {
         if (half == 1) return 0;
         if (int rc = ensure_set_b(e)) return rc;
+        if (use_yeex(e)) return launch_yeex<T>(e, s);
         return launch_yee_fused<T>(e, s);
     }
     if (e->cfg.flags & FDTD_FLAG_YEE) return launch_yee<T>(e, half, s);

@@ -55,6 +55,55 @@ extern "C" int fdtd_upload_dft(fdtd_engine* e, int32_t id, const double* host)
     return 0;
 }
 
+// ---- cropped read-out and plane checksums (self-checking bench, parity tests at sizes the host cannot mirror) ---------
+extern "C" int fdtd_download_box(fdtd_engine* e, int32_t comp, const int32_t* lo, const int32_t* hi, double* host)
+{
+    if (!e || !host || !lo || !hi || comp < 0 || comp > 5) return fail(FDTD_EINVAL, "fdtd_download_box: bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    int s[3]; comp_shape(e, comp, s);
+    const int nd = e->cfg.ndim;
+    int l[3] = {lo[0], lo[1], nd == 3 ? lo[2] : 0}, h[3] = {hi[0], hi[1], nd == 3 ? hi[2] : 1};
+    for (int a = 0; a < 3; ++a)
+        if (l[a] < 0 || h[a] > s[a] || h[a] < l[a])
+            return fail(FDTD_EINVAL, "fdtd_download_box: box [%d,%d) outside axis %d of component %d (extent %d)", l[a], h[a], a, comp, s[a]);
+    const long long n = (long long)(h[0] - l[0]) * (h[1] - l[1]) * (h[2] - l[2]);
+    if (n == 0) return 0;
+    if (n > (1ll << 27)) return fail(FDTD_EINVAL, "fdtd_download_box: box of %lld cells is too large (max 2^27)", n);
+    if (int rc = ensure_stage(e, (size_t)n * sizeof(double))) return rc;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    const void* src = cur_fields(e)[comp];
+    if (e->cfg.dtype == FDTD_F64)
+        k_gather_box<double><<<blocks, 256, 0, e->stream>>>((double*)e->d_stage, (const double*)src, n, l[0], l[1], l[2], h[1] - l[1], h[2] - l[2], e->st);
+    else
+        k_gather_box<float><<<blocks, 256, 0, e->stream>>>((double*)e->d_stage, (const float*)src, n, l[0], l[1], l[2], h[1] - l[1], h[2] - l[2], e->st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, e->d_stage, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int fdtd_field_checksum(fdtd_engine* e, int32_t comp, uint64_t* out, int32_t planes)
+{
+    if (!e || !out || comp < 0 || comp > 5) return fail(FDTD_EINVAL, "fdtd_field_checksum: bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    int s[3]; comp_shape(e, comp, s);
+    if (planes != s[0]) return fail(FDTD_EINVAL, "fdtd_field_checksum: component %d has %d planes here, got room for %d", comp, s[0], planes);
+    if (planes == 0) return 0;
+    if (int rc = ensure_stage(e, (size_t)planes * 2 * sizeof(uint64_t))) return rc;
+    CU(cudaMemsetAsync(e->d_stage, 0, (size_t)planes * 2 * sizeof(uint64_t), e->stream));
+    const long long cells = (long long)s[1] * s[2];
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((cells + 255) / 256, 64)), (unsigned)planes);
+    const void* src = cur_fields(e)[comp];
+    if (e->cfg.dtype == FDTD_F64)
+        k_plane_checksum<double><<<grid, 256, 0, e->stream>>>((unsigned long long*)e->d_stage, (const double*)src, s[1], s[2], e->st);
+    else
+        k_plane_checksum<float><<<grid, 256, 0, e->stream>>>((unsigned long long*)e->d_stage, (const float*)src, s[1], s[2], e->st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, e->d_stage, (size_t)planes * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
 // ---- introspection ---------------------------------------------------------------------------------------------------
 extern "C" int fdtd_steps_done(fdtd_engine* e, int64_t* steps)
 {

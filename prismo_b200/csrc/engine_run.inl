@@ -135,7 +135,7 @@ extern "C" int fdtd_set_option(fdtd_engine* e, const char* key, int32_t value)
     else if (!strcmp(key, "yee_fused")) {
         // the fused physics sweep ping-pongs fields and psi, the two-pass kernels update the current set in place:
         // switch only between runs that start from freshly uploaded / zeroed state
-        e->yee_fused = value ? 1 : 0;
+        e->yee_fused = value < 0 ? 0 : (value > 2 ? 2 : value);
     }
     else return fail(FDTD_EINVAL, "unknown option '%s'", key);
     drop_graph(e);

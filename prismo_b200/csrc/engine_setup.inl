@@ -89,6 +89,8 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     if (const char* x = getenv("FDTD_B200_TB2X_STAGES")) e->tb2x_stages = std::max(3, atoi(x));
     if (const char* x = getenv("FDTD_B200_TB2X_SLOTS")) e->tb2x_slots = std::max(2, atoi(x));
     if (const char* yf = getenv("FDTD_B200_YEE_FUSED")) e->yee_fused = atoi(yf);
+    if (const char* x = getenv("FDTD_B200_YEEX_STAGES")) e->yeex_stages = std::max(2, atoi(x));
+    if (const char* x = getenv("FDTD_B200_YEEX_SLOTS")) e->yeex_slots = std::max(2, atoi(x));
     if (const char* hf = getenv("FDTD_B200_HET_FUSED")) e->het_fused = atoi(hf);
     *out = e;
     return 0;

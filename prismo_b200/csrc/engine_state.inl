@@ -65,7 +65,9 @@ struct fdtd_engine {
     bool ops_dirty = true;
     Cpml cpml{}; SlabGeom slabg{}; double* d_cpml_coef = nullptr; size_t psi_bytes[12] = {};
     void* psiB[12] = {};            // second psi set: the fused physics sweep ping-pongs psi like the fields
-    int yee_fused = 0;              // physics mode: 1 = fused one-sweep step (opt-in, fdtd_yee_fused.cuh), 0 = two-pass
+    int yee_fused = 2;              // physics mode: 2 = TMA-fed fused one-sweep step (fdtd_yeex.cuh, default where it applies),
+                                    // 1 = register-prefetch fused sweep (fdtd_yee_fused.cuh), 0 = two-pass kernels (fdtd_yee.cuh)
+    int yeex_stages = 4, yeex_slots = 3;
     SrcOp* d_src = nullptr;         // all source ops, ordered by group
     std::vector<int> grp_first, grp_count; std::vector<long long> grp_threads;
     MonOp* d_mon = nullptr; long long mon_threads = 0;
@@ -91,6 +93,8 @@ struct fdtd_engine {
     int tb2x_stages = 4, tb2x_slots = 3;   // depth of its input ring (TMA stages) and of its row-exchange ring
     Tb2xMaps tmaps[2];              // TMA descriptors of the six arrays of set A / set B
     bool tmaps_ok = false;
+    Tb2xMaps ymaps[2];              // the same arrays with the physics sweep's 272-byte boxes
+    bool ymaps_ok = false;
     unsigned char* d_plane_flags = nullptr; std::vector<unsigned char> plane_flags_host;
     // staging
     void* d_stage = nullptr; size_t stage_bytes = 0;

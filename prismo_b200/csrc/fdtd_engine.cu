@@ -11,6 +11,7 @@
 #include "fdtd_yee_fused.cuh"
 #include "fdtd_tb2.cuh"
 #include "fdtd_tb2x.cuh"
+#include "fdtd_yeex.cuh"
 #include "fdtd_het.cuh"
 #include "fdtd_tensor.cuh"
 

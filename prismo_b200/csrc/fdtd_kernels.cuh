@@ -597,6 +597,48 @@ __global__ void k_gather(TH* __restrict__ dst, const TD* __restrict__ src, long 
         dst[t] = (TH)src[i * st.s[0] + j * st.s[1] + k * st.s[2]];
     }
 }
+// box [lo, lo + n) of one array -> dense fp64 (bench self-check, cropped parity tests)
+template <typename TD>
+__global__ void k_gather_box(double* __restrict__ dst, const TD* __restrict__ src, long long count, int l0, int l1, int l2,
+                             int n1, int n2, Strides3 st)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t % n2);
+        const long long r = t / n2;
+        const int j = (int)(r % n1);
+        const long long i = r / n1;
+        dst[t] = (double)src[(l0 + i) * st.s[0] + (l1 + j) * st.s[1] + (l2 + k) * st.s[2]];
+    }
+}
+// Order-independent checksum of the logical cells of each x-plane: out[2p] = sum of the value bit patterns,
+// out[2p+1] = sum of bits * (1 + cell index in the plane), both modulo 2^64 (integer atomics: deterministic, and
+// independent of how planes are distributed over GPUs).  grid = (blocks per plane, planes).
+template <typename TD>
+__global__ void k_plane_checksum(unsigned long long* __restrict__ out, const TD* __restrict__ src, int c1, int c2, Strides3 st)
+{
+    const long long plane = blockIdx.y;
+    const long long cells = (long long)c1 * c2;
+    unsigned long long s1 = 0, s2 = 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < cells; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t % c2);
+        const int j = (int)(t / c2);
+        const TD v = src[plane * st.s[0] + j * st.s[1] + k * st.s[2]];
+        unsigned long long b;
+        if (sizeof(TD) == 8) b = (unsigned long long)__double_as_longlong((double)v);
+        else b = (unsigned long long)__float_as_uint((float)v);
+        s1 += b;
+        s2 += b * (unsigned long long)(t + 1);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out + 2 * plane, s1);
+        atomicAdd(out + 2 * plane + 1, s2);
+    }
+}
 template <typename TD, typename TH>
 __global__ void k_convert(TH* __restrict__ dst, const TD* __restrict__ src, long long n)
 {

@@ -173,6 +173,21 @@ class Engine:
         _lib.check(self._lib.fdtd_download_field(self._h, COMP_ID[comp], out.ctypes.data_as(C.c_void_p), _dtype_code(out.dtype)))
         return out
 
+    def download_box(self, comp: str, lo, hi) -> np.ndarray:
+        """fields[comp][lo:hi] as host fp64 without moving the whole array (fdtd_download_box)."""
+        lo3, hi3 = _pad3(lo, 0), _pad3(hi, 1)
+        out = np.empty(tuple(h - l for l, h in zip(lo, hi)), dtype=np.float64)
+        _lib.check(self._lib.fdtd_download_box(self._h, COMP_ID[comp], (C.c_int32 * 3)(*lo3), (C.c_int32 * 3)(*hi3),
+                                               out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def plane_checksums(self, comp: str) -> np.ndarray:
+        """(planes, 2) uint64: order- and decomposition-independent checksums of each x-plane (fdtd_field_checksum)."""
+        n = self.field_shape(comp)[0]
+        out = np.zeros((n, 2), dtype=np.uint64)
+        _lib.check(self._lib.fdtd_field_checksum(self._h, COMP_ID[comp], out.ctypes.data_as(C.c_void_p), n))
+        return out
+
     def zero_fields(self):
         _lib.check(self._lib.fdtd_zero_fields(self._h))
 

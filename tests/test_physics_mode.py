@@ -114,15 +114,18 @@ def _run_physics(dims, dtype, thickness, fused, steps, lx=None, seed=1):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dims,thickness,steps,lx", [((28, 24, 26), 0, 7, None), ((28, 24, 26), 3, 40, None),
                                                      ((37, 33, 70), 3, 7, 5), ((9, 8, 7), 3, 1, None),
-                                                     ((64, 47, 130), 6, 12, None), ((64, 47, 130), 0, 5, 9)])
-def test_fused_physics_sweep_equals_two_pass(dims, thickness, steps, lx):
-    """The fused one-sweep physics step (Yee leap-frog + CPML, psi ping-pong, fdtd_yee_fused.cuh) against the
-    two-pass physics kernels, which test_physics_mode_matches_its_oracle pins to oracle/yee.py: fp64 bitwise, across
-    tile rims, x-segment seams, ragged edges and CPML slabs; fp32 within 1e-4.  PARITY UNPINNED (own oracle only)."""
-    a = _run_physics(dims, "float64", thickness, False, steps)
-    b = _run_physics(dims, "float64", thickness, True, steps, lx=lx)
+                                                     ((64, 47, 130), 6, 12, None), ((64, 47, 130), 0, 5, 9),
+                                                     ((40, 64, 200), 5, 9, 16), ((33, 30, 64), 4, 6, None)])
+@pytest.mark.parametrize("fused", [1, 2], ids=["register-prefetch", "tma"])
+def test_fused_physics_sweep_equals_two_pass(dims, thickness, steps, lx, fused):
+    """The fused one-sweep physics steps (Yee leap-frog + CPML, psi ping-pong: fdtd_yee_fused.cuh and the TMA-fed
+    fdtd_yeex.cuh, the default) against the two-pass physics kernels, which test_physics_mode_matches_its_oracle pins to
+    oracle/yee.py: fp64 bitwise, across tile rims, x-segment seams, ragged edges and CPML slabs; fp32 within 1e-4.
+    PARITY UNPINNED (own oracle only)."""
+    a = _run_physics(dims, "float64", thickness, 0, steps)
+    b = _run_physics(dims, "float64", thickness, fused, steps, lx=lx)
     for c in COMPS:
         assert np.array_equal(a[c], b[c]), f"{c}: max rel {np.abs(a[c] - b[c]).max() / (np.abs(a[c]).max() + 1e-300):.2e}"
-    b32 = _run_physics(dims, "float32", thickness, True, steps, lx=lx)
+    b32 = _run_physics(dims, "float32", thickness, fused, steps, lx=lx)
     for c in COMPS:
         assert np.linalg.norm(a[c] - b32[c]) <= 1e-4 * np.linalg.norm(a[c]), c

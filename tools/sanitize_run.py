@@ -68,7 +68,7 @@ def main():
             eng.sync()
             eng.close()
         if "yee" in which:
-            for fused in (0, 1):
+            for fused in (0, 1, 2):
                 eng = pb.Engine(3, dims, (d,) * 3, dt, dtype=dtype, flags=_lib.FLAG_YEE)
                 eng.set_cpml(3, cpml.coefficient_table(dims, (d,) * 3, dt, cpml.PMLParams(thickness=3)))
                 eng.set_option("yee_fused", fused)
