@@ -203,19 +203,40 @@ def set_ridge_coefficients(eng, dims, dt):
                    np.ascontiguousarray(one * (dt / mu0)))
 
 
-def seed_fields(eng, scale=1e-3, seed=0):
-    """Small white-noise fields so the arithmetic is not all-zero (the source keeps injecting anyway)."""
-    rng = np.random.default_rng(seed)
-    for c in COMPONENTS:
-        shp = eng.field_shape(c)
-        plane = (rng.standard_normal(shp[1:]) * scale * (1.0 if c[0] == "E" else 1 / 377.0)).astype(np.float32)
-        eng.upload(c, np.broadcast_to(plane, shp).copy() if np.prod(shp) < 2 ** 27 else _tiled(plane, shp))
+def seed_fields(eng, dims, x0=0):
+    """Small white-noise fields as a pure function of the GLOBAL cell index (bench_check.py), so every decomposition
+    of the grid starts from the same global state and the end-of-run checksums are comparable across N."""
+    import bench_check as BC
+
+    return BC.seed_fields(eng, dims, x0)
 
 
-def _tiled(plane, shp):
-    out = np.empty(shp, dtype=np.float32)
-    out[...] = plane
-    return out
+def fields_sha(eng):
+    import bench_check as BC
+
+    return BC.sha_of_checksums({c: eng.plane_checksums(c) for c in COMPONENTS})
+
+
+def self_check(eng, dims, dt, spacing, args, mon_ids, do_oracle):
+    """Re-seed, run a few steps, compare two crops and the DFT plane with the oracle, checksum the fields (bench_check.py)."""
+    import bench_check as BC
+
+    def reseed(n, amp, ph):
+        eng.zero_fields()
+        planes = BC.seed_fields(eng, dims)
+        for i in mon_ids:
+            op = eng._mon_ops[i]
+            eng.set_dft(i, np.zeros((op.n_freq,) + op.shape, dtype=np.complex128))
+        eng.set_tables(n, amp, ph)
+        return planes
+
+    def fetch_dft(c, lo2, hi2):
+        i = mon_ids[("Ey", "Hz").index(c)]
+        return eng.dft(i)[:, 0, lo2[0]:hi2[0], lo2[1]:hi2[1]]
+
+    return BC.run_check(dims, dt, spacing, args.dtype, tables, dims[0] // 4, (3 * dims[0]) // 4, reseed, eng.run,
+                        lambda c, lo, hi: eng.download_box(c, lo, hi), fetch_dft,
+                        lambda: {c: eng.plane_checksums(c) for c in COMPONENTS}, do_oracle=do_oracle and bool(mon_ids))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -353,6 +374,7 @@ def main():
     ap.add_argument("--physics", action="store_true", help="opt-in physics mode: stable Yee leap-frog + 10-cell CPML "
                     "(two-pass kernels with slab psi updates; no reference numbers exist for it)")
     ap.add_argument("--no-ops", action="store_true", help="bare field update: no source, no monitor (tuning only)")
+    ap.add_argument("--no-check", action="store_true", help="skip the post-run self-check against the oracle")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -395,7 +417,7 @@ def main():
     total_steps = args.warmup + args.steps
     amp, ph, _ = tables(total_steps, dt)
     eng.set_tables(total_steps, amp, ph)
-    seed_fields(eng)
+    seed_fields(eng, dims)
 
     # ---- timed region: W warm-up steps, then exactly K steps between events on the engine stream -----------
     eng.run(args.warmup)
@@ -411,6 +433,7 @@ def main():
         else:
             prof = eng.run_profiled(args.steps)
     launches = eng.kernel_launches - l0
+    timed_sha = fields_sha(eng)                  # state after W + K steps: comparable across N for equal W, K
     ms = prof["total_ms"]
     value = cells * args.steps / (ms * 1e-3)
 
@@ -449,6 +472,11 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(eng, dims, args, mon_ids, dt)
 
+    check = None
+    if not args.no_check:
+        check = self_check(eng, dims, dt, spacing, args, mon_ids, do_oracle=not (args.physics or args.het or args.no_ops))
+        check["timed_fields_sha"] = timed_sha
+
     cpu = None
     if not args.no_cpu:
         v, side, st, el = cpu_baseline_sample(dims)
@@ -469,7 +497,7 @@ def main():
                                        (("physics mode (opt-in, parity unpinned): Yee leap-frog + 10-cell CPML, "
                                          + ("fused one-sweep step" if os.environ.get("FDTD_B200_YEE_FUSED", "2") != "0" else "two-pass"))
                                         if args.physics else "two-pass")},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary()}
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(), "check": check}
     print(json.dumps(line), flush=True)
     eng.close()
 

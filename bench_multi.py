@@ -44,7 +44,7 @@ def run_multi(args, rank, world, local):
     total = args.warmup + args.steps
     amp, ph, _ = B.tables(total, dt)
     eng.set_tables(total, amp, ph)
-    B.seed_fields(eng, seed=rank)
+    B.seed_fields(eng, dims, x0)
     eng.sync()
     halo = os.environ.get("FDTD_B200_HALO", "p2p")
     if halo == "nccl":
@@ -80,10 +80,20 @@ def run_multi(args, rank, world, local):
     launches = torch.tensor([eng.kernel_launches - l0], device="cuda", dtype=torch.int64)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
 
+    timed_cs = gather_checksums(eng, rank, world, dist)
+
     # e2e: host buffers in / out on every rank, wall clock, max over ranks
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e_multi(eng, stepper, dims, args, mon_ids, dt, fence, dist, torch)
+
+    check = None
+    if not args.no_check:
+        check = self_check_multi(eng, stepper, dims, dt, spacing, args, mon, mon_ids, x0, nxl, rank, world, fence, dist)
+        if rank == 0:
+            import bench_check as BC
+
+            check["timed_fields_sha"] = BC.sha_of_checksums(timed_cs)
 
     if rank == 0:
         bpc = B.BYTES_PER_CELL[args.dtype]
@@ -108,11 +118,73 @@ def run_multi(args, rank, world, local):
                                           if os.environ.get("FDTD_B200_TB2", "1") != "0" else "fused single sweep, ping-pong"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src,
-                             "kernel": "k_fused3d, per GPU, whole step incl. halo wait (max over ranks)"},
-                "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()), "clocks": clk.summary()}
+                             "kernel": ("k_fused3d_tb2 (two steps per launch)" if os.environ.get("FDTD_B200_TB2", "1") != "0"
+                                        else "k_fused3d (one step per launch)")
+                                       + ", per GPU, whole step incl. in-kernel halo wait (max over ranks)",
+                             "note": "achieved = 48 B (fp32) per cell-update x global cells / N / step time: the per-GPU "
+                                     "share of the single-GPU line's figure; traffic is not re-measured per rank (ncu is "
+                                     "single-process: see the 1-GPU line / profiles/)"},
+                "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()), "clocks": clk.summary(), "check": check}
         print(json.dumps(line), flush=True)
     eng.close()
     dist.destroy_process_group()
+
+
+def gather_checksums(eng, rank, world, dist):
+    """Per-plane checksums of every component, concatenated over the slabs in rank order (rank 0; None elsewhere)."""
+    import bench as B
+
+    mine = {c: eng.plane_checksums(c) for c in B.COMPONENTS}
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    if rank != 0:
+        return None
+    return {c: np.concatenate([p[c] for p in parts], axis=0) for c in B.COMPONENTS}
+
+
+def self_check_multi(eng, stepper, dims, dt, spacing, args, mon, mon_ids, x0, nxl, rank, world, fence, dist):
+    """bench_check.run_check over the slab decomposition: boxes are assembled from the ranks that own their planes."""
+    import bench as B
+    import bench_check as BC
+
+    def reseed(n, amp, ph):
+        planes = BC.seed_fields(eng, dims, x0)
+        for i in mon_ids:
+            op = eng._mon_ops[i]
+            eng.set_dft(i, np.zeros((op.n_freq,) + op.shape, dtype=np.complex128))
+        eng.set_tables(n, amp, ph)
+        eng.sync()
+        dist.barrier()             # every rank's upload is complete before any rank pushes a halo (fdtd_b200.h)
+        return planes
+
+    def run_steps(n):
+        stepper.run(n)
+        fence()
+
+    def fetch_box(c, lo, hi):
+        a, b = max(lo[0], x0), min(hi[0], x0 + eng.field_shape(c)[0])
+        piece = eng.download_box(c, (a - x0, lo[1], lo[2]), (b - x0, hi[1], hi[2])) if b > a else None
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(piece, parts, dst=0)
+        if rank != 0:
+            return None
+        return np.concatenate([p for p in parts if p is not None], axis=0)
+
+    def fetch_dft(c, lo2, hi2):
+        piece = None
+        names = [op.component for op in mon]
+        if c in names:
+            piece = eng.dft(mon_ids[names.index(c)])[:, 0, lo2[0]:hi2[0], lo2[1]:hi2[1]]
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(piece, parts, dst=0)
+        if rank != 0:
+            return None
+        got = [p for p in parts if p is not None]
+        return got[0] if got else None
+
+    return BC.run_check(dims, dt, spacing, args.dtype, B.tables, dims[0] // 4, (3 * dims[0]) // 4, reseed, run_steps,
+                        fetch_box, fetch_dft, lambda: gather_checksums(eng, rank, world, dist),
+                        do_oracle=not args.no_ops)
 
 
 def run_e2e_multi(eng, stepper, dims, args, mon_ids, dt, fence, dist, torch):

@@ -128,6 +128,7 @@ extern "C" int fdtd_set_cpml(fdtd_engine* e, int32_t thickness, const double* co
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaStreamSynchronize(e->stream));
     cudaFree(e->d_cpml_coef); e->d_cpml_coef = nullptr;
+    cudaFree(e->d_cpml_coef_f); e->d_cpml_coef_f = nullptr;
     for (int q = 0; q < 12; ++q) { cudaFree(e->cpml.psi[q]); e->cpml.psi[q] = nullptr; cudaFree(e->psiB[q]); e->psiB[q] = nullptr; }
     e->cpml = Cpml{};
     drop_graph(e);
@@ -137,9 +138,18 @@ extern "C" int fdtd_set_cpml(fdtd_engine* e, int32_t thickness, const double* co
     const size_t total = 6 * ((size_t)g.nx + g.ny + g.nz);
     CU(cudaMalloc(&e->d_cpml_coef, total * sizeof(double)));
     CU(cudaMemcpy(e->d_cpml_coef, coef, total * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        std::vector<float> cf(total);
+        for (size_t q = 0; q < total; ++q) cf[q] = (float)coef[q];
+        CU(cudaMalloc(&e->d_cpml_coef_f, total * sizeof(float)));
+        CU(cudaMemcpy(e->d_cpml_coef_f, cf.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    }
     size_t off = 0;
     for (int a = 0; a < 3; ++a) {
-        for (int v = 0; v < 6; ++v) e->cpml.ax[a].c[v] = e->d_cpml_coef + off + (size_t)v * N[a];
+        for (int v = 0; v < 6; ++v) {
+            e->cpml.ax[a].c[v] = e->d_cpml_coef + off + (size_t)v * N[a];
+            e->cpml.ax[a].f[v] = e->d_cpml_coef_f + off + (size_t)v * N[a];
+        }
         off += (size_t)6 * N[a];
     }
     e->cpml.t = thickness; e->cpml.ns = 2 * thickness + 1;
@@ -303,7 +313,7 @@ template <typename T> static int launch_yeex(fdtd_engine* e, cudaStream_t s)
     t.own_lanes = 30;
     const int vec_per_row = g.pz / V;
     t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
-    t.ntj = (g.ny + (R - 2) - 1) / (R - 2);
+    t.ntj = (g.ny + (R - 1) - 1) / (R - 1);
     int lx = e->fused_lx;
     if (lx <= 0) {
         const long long tiles = (long long)t.ntj * t.ntk;
@@ -353,7 +363,7 @@ template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
     t.own_lanes = kHetOwnLanes;
     const int vec_per_row = g.pz / V;
     t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
-    t.ntj = (g.ny + (R - 2) - 1) / (R - 2);
+    t.ntj = (g.ny + (R - 1) - 1) / (R - 1);
     int lx = e->fused_lx;
     if (lx <= 0) {
         const long long tiles = (long long)t.ntj * t.ntk;
@@ -512,7 +522,7 @@ static EncodeTiledFn encode_tiled_fn()
 
 // descriptors of the six arrays of both buffer sets: tensor (pz, ny, planes_alloc), box (256 bytes, R rows, 1 plane);
 // rows / columns / planes outside the tensor read as zero (the padding and guard planes of the layout, for free)
-static int encode_maps(fdtd_engine* e, Tb2xMaps* maps, int box_bytes)
+static int encode_maps(fdtd_engine* e, Tb2xMaps* maps, int box_bytes, int box_rows, int promo = 3)
 {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail(FDTD_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -520,14 +530,14 @@ static int encode_maps(fdtd_engine* e, Tb2xMaps* maps, int box_bytes)
     const bool d64 = e->cfg.dtype == FDTD_F64;
     const cuuint64_t dims[3] = {(cuuint64_t)g.pz, (cuuint64_t)g.ny, (cuuint64_t)e->planes_alloc};
     const cuuint64_t strides[2] = {(cuuint64_t)g.sy * e->esz, (cuuint64_t)g.sx * e->esz};
-    const cuuint32_t box[3] = {(cuuint32_t)(box_bytes / e->esz), (cuuint32_t)kTb2xRows, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(box_bytes / e->esz), (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     for (int s = 0; s < 2; ++s)
         for (int c = 0; c < 6; ++c) {
             void* base = s ? e->fldB[c] : e->fld[c];
             CUresult r = enc(&maps[s].m[c], d64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(FDTD_ECUDA, "cuTensorMapEncodeTiled failed (%d) for set %d array %d", (int)r, s, c);
         }
     return 0;
@@ -535,7 +545,7 @@ static int encode_maps(fdtd_engine* e, Tb2xMaps* maps, int box_bytes)
 static int ensure_tmaps(fdtd_engine* e)
 {
     if (e->tmaps_ok) return 0;
-    if (int rc = encode_maps(e, e->tmaps, kTb2xRowBytes)) return rc;
+    if (int rc = encode_maps(e, e->tmaps, kTb2xRowBytes, kTb2xRows)) return rc;
     e->tmaps_ok = true;
     return 0;
 }
@@ -543,7 +553,7 @@ static int ensure_tmaps(fdtd_engine* e)
 static int ensure_ymaps(fdtd_engine* e)
 {
     if (e->ymaps_ok) return 0;
-    if (int rc = encode_maps(e, e->ymaps, kYeexBoxBytes)) return rc;
+    if (int rc = encode_maps(e, e->ymaps, kYeexBoxBytes, kYeexBoxRows, getenv("FDTD_B200_YEEX_L2PROMO") ? atoi(getenv("FDTD_B200_YEEX_L2PROMO")) : 3)) return rc;
     e->ymaps_ok = true;
     return 0;
 }

@@ -63,7 +63,7 @@ struct fdtd_engine {
     AdeOp* d_ade = nullptr; void* d_aux = nullptr; unsigned char* d_ade_mask = nullptr;
     long long aux_elems = 0, ade_threads = 0;
     bool ops_dirty = true;
-    Cpml cpml{}; SlabGeom slabg{}; double* d_cpml_coef = nullptr; size_t psi_bytes[12] = {};
+    Cpml cpml{}; SlabGeom slabg{}; double* d_cpml_coef = nullptr; float* d_cpml_coef_f = nullptr; size_t psi_bytes[12] = {};
     void* psiB[12] = {};            // second psi set: the fused physics sweep ping-pongs psi like the fields
     int yee_fused = 2;              // physics mode: 2 = TMA-fed fused one-sweep step (fdtd_yeex.cuh, default where it applies),
                                     // 1 = register-prefetch fused sweep (fdtd_yee_fused.cuh), 0 = two-pass kernels (fdtd_yee.cuh)

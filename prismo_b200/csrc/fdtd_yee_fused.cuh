@@ -26,12 +26,11 @@ struct PsiOut { void* p[12]; };
 
 // psi <- b psi + a d ;  d_eff = d / kappa + psi        (same rounding sequence as cpml_apply in fdtd_yee.cuh)
 template <typename T>
-__device__ __forceinline__ T cpml_step(T d, const T* psi_in, T* psi_out, bool store, long long o, const double* b,
-                                       const double* a, const double* ki, int n)
+__device__ __forceinline__ T cpml_step(T d, const T* psi_in, T* psi_out, bool store, long long o, const CpmlAxis& ax, int v, int n)
 {
-    const T p = (T)__dadd_rn(__dmul_rn(b[n], (double)psi_in[o]), __dmul_rn(a[n], (double)d));
+    const T p = CpmlMath<T>::psi(cpml_tab<T>(ax, v)[n], psi_in[o], cpml_tab<T>(ax, v + 1)[n], d);
     if (store) psi_out[o] = p;
-    return (T)__dadd_rn(__dmul_rn(ki[n], (double)d), (double)p);
+    return CpmlMath<T>::eff(cpml_tab<T>(ax, v + 2)[n], d, p);
 }
 
 template <typename T> __device__ __forceinline__ T shfl_prev(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
@@ -140,20 +139,20 @@ k_fused3d_yee(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, C
             const T ex_k = e > 0 ? e1x.v[(e + V - 1) % V] : ex_km;
             if (px1 && jm && km) {                             // Hx(p+1/2, j, k)
                 T dy = Ar<T>::diff(e1z.v[e], ez_jm.v[e], g.dy, g.rdy), dz = Ar<T>::diff(e1y.v[e], ey_k, g.dz, g.rdz);
-                if (syj >= 0) dy = cpml_step<T>(dy, psi_in[6], psi_out[6], st_h, oy, pm.ax[1].c[3], pm.ax[1].c[4], pm.ax[1].c[5], j);
-                if (szk >= 0) dz = cpml_step<T>(dz, psi_in[7], psi_out[7], st_h, oz, pm.ax[2].c[3], pm.ax[2].c[4], pm.ax[2].c[5], ke);
+                if (syj >= 0) dy = cpml_step<T>(dy, psi_in[6], psi_out[6], st_h, oy, pm.ax[1], 3, j);
+                if (szk >= 0) dz = cpml_step<T>(dz, psi_in[7], psi_out[7], st_h, oz, pm.ax[2], 3, ke);
                 hnx.v[e] = upd_h<T>(c.uda, h1x.v[e], c.udb, dy, dz);
             }
             if (pxm && jy1 && km) {                            // Hy(p, j+1/2, k)
                 T dz = Ar<T>::diff(e1x.v[e], ex_k, g.dz, g.rdz), dx = Ar<T>::diff(e1z.v[e], e0z.v[e], g.dx, g.rdx);
-                if (szk >= 0) dz = cpml_step<T>(dz, psi_in[8], psi_out[8], st_h, oz, pm.ax[2].c[3], pm.ax[2].c[4], pm.ax[2].c[5], ke);
-                if (sxp >= 0) dx = cpml_step<T>(dx, psi_in[9], psi_out[9], st_h, ox, pm.ax[0].c[3], pm.ax[0].c[4], pm.ax[0].c[5], p);
+                if (szk >= 0) dz = cpml_step<T>(dz, psi_in[8], psi_out[8], st_h, oz, pm.ax[2], 3, ke);
+                if (sxp >= 0) dx = cpml_step<T>(dx, psi_in[9], psi_out[9], st_h, ox, pm.ax[0], 3, p);
                 hny.v[e] = upd_h<T>(c.uda, h1y.v[e], c.udb, dz, dx);
             }
             if (pxm && jm && kz1) {                            // Hz(p, j, k+1/2)
                 T dx = Ar<T>::diff(e1y.v[e], e0y.v[e], g.dx, g.rdx), dy = Ar<T>::diff(e1x.v[e], ex_jm.v[e], g.dy, g.rdy);
-                if (sxp >= 0) dx = cpml_step<T>(dx, psi_in[10], psi_out[10], st_h, ox, pm.ax[0].c[3], pm.ax[0].c[4], pm.ax[0].c[5], p);
-                if (syj >= 0) dy = cpml_step<T>(dy, psi_in[11], psi_out[11], st_h, oy, pm.ax[1].c[3], pm.ax[1].c[4], pm.ax[1].c[5], j);
+                if (sxp >= 0) dx = cpml_step<T>(dx, psi_in[10], psi_out[10], st_h, ox, pm.ax[0], 3, p);
+                if (syj >= 0) dy = cpml_step<T>(dy, psi_in[11], psi_out[11], st_h, oy, pm.ax[1], 3, j);
                 hnz.v[e] = upd_h<T>(c.uda, h1z.v[e], c.udb, dx, dy);
             }
         }
@@ -178,20 +177,20 @@ k_fused3d_yee(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, C
                 const T hx_k = (e + 1 < V) ? hpx.v[(e + 1) % V] : hx_kp;
                 if (jy1 && kz1 && !rim_row) {                  // Ex(i, j+1/2, k+1/2)
                     T dy = Ar<T>::diff(hz_jp.v[e], hpz.v[e], g.dy, g.rdy), dz = Ar<T>::diff(hy_k, hpy.v[e], g.dz, g.rdz);
-                    if (syj >= 0) dy = cpml_step<T>(dy, psi_in[0], psi_out[0], st_e, oy, pm.ax[1].c[0], pm.ax[1].c[1], pm.ax[1].c[2], j);
-                    if (szk >= 0) dz = cpml_step<T>(dz, psi_in[1], psi_out[1], st_e, oz, pm.ax[2].c[0], pm.ax[2].c[1], pm.ax[2].c[2], ke);
+                    if (syj >= 0) dy = cpml_step<T>(dy, psi_in[0], psi_out[0], st_e, oy, pm.ax[1], 0, j);
+                    if (szk >= 0) dz = cpml_step<T>(dz, psi_in[1], psi_out[1], st_e, oz, pm.ax[2], 0, ke);
                     nx_.v[e] = upd_e<T>(c.uca, e0x.v[e], c.ucb, dy, dz);
                 }
                 if (qx1 && kz1 && ld_ok && !rim_row) {         // Ey(i+1/2, j, k+1/2)
                     T dz = Ar<T>::diff(hx_k, hpx.v[e], g.dz, g.rdz), dx = Ar<T>::diff(hnz.v[e], hpz.v[e], g.dx, g.rdx);
-                    if (szk >= 0) dz = cpml_step<T>(dz, psi_in[2], psi_out[2], st_e, oz, pm.ax[2].c[0], pm.ax[2].c[1], pm.ax[2].c[2], ke);
-                    if (sxq >= 0) dx = cpml_step<T>(dx, psi_in[3], psi_out[3], st_e, ox, pm.ax[0].c[0], pm.ax[0].c[1], pm.ax[0].c[2], i);
+                    if (szk >= 0) dz = cpml_step<T>(dz, psi_in[2], psi_out[2], st_e, oz, pm.ax[2], 0, ke);
+                    if (sxq >= 0) dx = cpml_step<T>(dx, psi_in[3], psi_out[3], st_e, ox, pm.ax[0], 0, i);
                     ny_.v[e] = upd_e<T>(c.uca, e0y.v[e], c.ucb, dz, dx);
                 }
                 if (qx1 && jy1 && kz0 && !rim_row) {           // Ez(i+1/2, j+1/2, k)
                     T dx = Ar<T>::diff(hny.v[e], hpy.v[e], g.dx, g.rdx), dy = Ar<T>::diff(hx_jp.v[e], hpx.v[e], g.dy, g.rdy);
-                    if (sxq >= 0) dx = cpml_step<T>(dx, psi_in[4], psi_out[4], st_e, ox, pm.ax[0].c[0], pm.ax[0].c[1], pm.ax[0].c[2], i);
-                    if (syj >= 0) dy = cpml_step<T>(dy, psi_in[5], psi_out[5], st_e, oy, pm.ax[1].c[0], pm.ax[1].c[1], pm.ax[1].c[2], j);
+                    if (sxq >= 0) dx = cpml_step<T>(dx, psi_in[4], psi_out[4], st_e, ox, pm.ax[0], 0, i);
+                    if (syj >= 0) dy = cpml_step<T>(dy, psi_in[5], psi_out[5], st_e, oy, pm.ax[1], 0, j);
                     nz_.v[e] = upd_e<T>(c.uca, e0z.v[e], c.ucb, dx, dy);
                 }
             }

@@ -4,18 +4,24 @@
 // is that of fdtd_tb2x.cuh:
 //
 //   * the six input arrays of plane p arrive by cp.async.bulk.tensor (one producer thread, S-stage ring, full / empty
-//     mbarriers).  The tile carries its own halo — row 0 is j0 - 1, lane 0 is k0 - 1, zero-filled outside the grid —
-//     so the -j / -k neighbours of E that the backward-differenced H update needs are plain shared-memory reads;
+//     mbarriers).  The box carries the tile's low-side halo — box row 0 is j0 - 1, box lane 0 is k0 - 2 lanes, zero-
+//     filled outside the grid — so the -j neighbours of E that the backward-differenced H update needs are plain
+//     shared-memory reads of the staged tile and cost no warp: of R = 15 consumer rows 14 own cells, the 15th only
+//     provides H+ of the next tile's first row;
 //   * the +j neighbours of H+ (z, x components) that the E update needs travel through a D-slot ring with one mbarrier
 //     per row: neighbour-only synchronisation, no CTA-wide barrier in the plane loop;
 //   * CPML is applied by slab threads only, and decided per WARP and PLANE: a warp whose row lies outside the y slabs,
 //     in a tile outside the z slabs and clear of the grid faces, on planes outside the x slabs, runs a lean body with
 //     no masks and no psi code at all (about 85 % of the warp-iterations of a 1024^3 grid with 10-cell layers); the
-//     others run the full body (masks + psi recursion), whose psi arrays are ping-ponged like the fields.
+//     others run the full body (masks + psi recursion), whose psi arrays are ping-ponged like the fields;
+//   * the psi values a slab thread needs are LOADED ONE ITERATION AHEAD, all at once (x / y families as 8-byte vectors,
+//     z family per cell), into registers that the stage which consumed the previous set has just freed: the first
+//     version loaded each psi value right where the recursion used it, one exposed DRAM latency per derivative, and
+//     spent 30 % of its stall samples there (profiles/r02_ncu_yeex.md).
 //
 //   H+[p] = f(H[p], E[p] (own, j-1, k-1), E[p-1])          E+[q] = g(E[q], H+[q] (own, j+1, k+1), H+[q+1])
-// Iteration `it` (i = i0 - 1 + it) reads TMA stage it + 1 (E[i+1], H[i+1]), produces H+[i+1] and E+[i].  Of R = 15 rows
-// 13 own cells (row 0 and row 14 are halo providers), of 32 lanes 30 (lane 0 and lane 31).
+// Iteration `it` (i = i0 - 1 + it) reads TMA stage it + 1 (E[i+1], H[i+1]), produces H+[i+1] and E+[i].  Of 32 lanes 30
+// own cells (lane 0 and lane 31 are halo providers: -k comes by shuffle from the lane below, +k from the lane above).
 //
 // PARITY UNPINNED (there are no reference numbers for a working CPML): validated bitwise in fp64 against the two-pass
 // kernels and through them against oracle/yee.py.
@@ -26,12 +32,13 @@
 namespace fdtd {
 
 constexpr int kYeexRows = kTb2xRows;       // 15 consumer rows + 1 producer warp, as in the two-step sweep
-// TMA box: 272 B x R rows.  The first cell a tile CONSUMES is one lane (8 B) left of its first owner lane, i.e. at byte
-// 240 * tk - 8 of the row, but the box origin of cp.async.bulk.tensor must be 16-byte aligned in the innermost
+constexpr int kYeexBoxRows = kYeexRows + 1;
+// TMA box: 272 B x (R + 1) rows.  The first cell a tile CONSUMES is one lane (8 B) left of its first owner lane, i.e. at
+// byte 240 * tk - 8 of the row, but the box origin of cp.async.bulk.tensor must be 16-byte aligned in the innermost
 // dimension (a misaligned origin raises "illegal instruction": measured, gpurun_out/e2_sanitize_memcheck_yee.log), so the
 // box starts one more lane to the left and lane l reads its cells at byte (l + 1) * 8 of the staged row.
 constexpr int kYeexBoxBytes = 272;
-template <int R> __host__ __device__ constexpr size_t yeex_tile_bytes() { return ((size_t)R * kYeexBoxBytes + 127) / 128 * 128; }
+template <int R> __host__ __device__ constexpr size_t yeex_tile_bytes() { return ((size_t)(R + 1) * kYeexBoxBytes + 127) / 128 * 128; }
 template <int R> __host__ __device__ constexpr size_t yeex_stage_bytes() { return 6 * yeex_tile_bytes<R>(); }
 
 template <int R> static inline size_t yeex_smem_bytes(int S, int D)
@@ -39,12 +46,19 @@ template <int R> static inline size_t yeex_smem_bytes(int S, int D)
     return 128 + (size_t)S * yeex_stage_bytes<R>() + (size_t)D * R * 2 * kTb2xRowBytes + (size_t)(2 * S + R * D) * 8 + 64;
 }
 
-template <typename T> struct YeexCtx {
-    int j, k, row, lane;
-    bool owner, interior_tile, tile_z, row_y;
-    int syj;                         // y-slab index of this row (-1 outside)
-    unsigned ofs;                    // j * sy + k (owner threads only use it)
-};
+// the producer thread has nothing else to do: let the hardware park it for up to `ns` per try instead of spinning
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t ns)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAITP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONEP;\n"
+        "bra LAB_WAITP;\n"
+        "DONEP:\n"
+        "}" ::"r"(bar), "r"(parity), "r"(ns) : "memory");
+}
 
 // ---- lean bodies: interior cells, no masks, no CPML -------------------------------------------------------------------------
 template <typename T, int V, int AM, bool SLOW = false>
@@ -103,94 +117,180 @@ __device__ __forceinline__ void yee_e_lean(const Coefs<T>& c, const Geom& g,
     }
 }
 
+// ---- psi registers of one stage (E or H) of one thread and plane ------------------------------------------------------------------
+// The six psi arrays of a stage, in the order of Cpml::psi from `base` (0: E stage, 6: H stage):
+//   base+0 y0 (x-component, d/dy)   base+1 z0 (x-component, d/dz)   base+2 z1 (y-component, d/dz)
+//   base+3 x0 (y-component, d/dx)   base+4 x1 (z-component, d/dx)   base+5 y1 (z-component, d/dy)
+template <typename T, int V> struct YeexPsi { Pack<T, V> x0, x1, y0, y1, z0, z1; };
+
+template <typename T, int V> __device__ __forceinline__ Pack<T, V> ldnc8(const T* p)
+{
+    typedef typename Vec8<T>::type VT;
+    union { VT q; Pack<T, V> r; } u;
+    u.q = __ldg(reinterpret_cast<const VT*>(p));
+    return u.r;
+}
+
+// Issue the loads of the psi values that the thread at (plane pl, row j, cells k .. k+V-1) will use.  `ok`: the thread lies
+// inside the arrays (0 <= j < ny, 0 <= k < pz) and 0 <= pl < nx.  The x and y families are row-contiguous like the fields
+// (8-byte vector loads; entries outside the update range exist and stay zero), the z family holds 2t+1 entries per row.
+template <typename T, int V>
+__device__ __forceinline__ void yeex_psi_load(YeexPsi<T, V>& r, const T* const* __restrict__ psi_in, const int base, const Geom& g,
+                                              const SlabGeom& sg, const int tpm, const int pl, const int j, const int k,
+                                              const int syj, const bool ok)
+{
+    if (!ok || !tpm) return;
+    const int sxp = slab_index(pl, g.nx, tpm);
+    if (sxp >= 0) {
+        const long long oxs = (long long)sxp * sg.x_sx + (long long)j * g.sy + k;
+        r.x0 = ldnc8<T, V>(psi_in[base + 3] + oxs); r.x1 = ldnc8<T, V>(psi_in[base + 4] + oxs);
+    }
+    if (syj >= 0) {
+        const long long oys = (long long)pl * sg.y_sx + (long long)syj * g.sy + k;
+        r.y0 = ldnc8<T, V>(psi_in[base + 0] + oys); r.y1 = ldnc8<T, V>(psi_in[base + 5] + oys);
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const int ke = k + e;
+        const int szk = ke < g.nz ? slab_index(ke, g.nz, tpm) : -1;
+        if (szk >= 0) {
+            const long long ozs = ((long long)pl * g.ny + j) * sg.z_pitch + szk;
+            r.z0.v[e] = __ldg(psi_in[base + 1] + ozs); r.z1.v[e] = __ldg(psi_in[base + 2] + ozs);
+        }
+    }
+}
+
+// the same addresses, written to the OTHER psi set (psi is ping-ponged like the fields: rim threads and segment prologues
+// recompute the recursion without storing)
+template <typename T, int V>
+__device__ __forceinline__ void yeex_psi_store(const YeexPsi<T, V>& r, T* const* __restrict__ psi_out, const int base, const Geom& g,
+                                               const SlabGeom& sg, const int tpm, const int pl, const int j, const int k,
+                                               const int syj)
+{
+    const int sxp = slab_index(pl, g.nx, tpm);
+    if (sxp >= 0) {
+        const long long oxs = (long long)sxp * sg.x_sx + (long long)j * g.sy + k;
+        st8<T, V>(psi_out[base + 3] + oxs, r.x0); st8<T, V>(psi_out[base + 4] + oxs, r.x1);
+    }
+    if (syj >= 0) {
+        const long long oys = (long long)pl * sg.y_sx + (long long)syj * g.sy + k;
+        st8<T, V>(psi_out[base + 0] + oys, r.y0); st8<T, V>(psi_out[base + 5] + oys, r.y1);
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const int ke = k + e;
+        const int szk = ke < g.nz ? slab_index(ke, g.nz, tpm) : -1;
+        if (szk >= 0) {
+            const long long ozs = ((long long)pl * g.ny + j) * sg.z_pitch + szk;
+            psi_out[base + 1][ozs] = r.z0.v[e]; psi_out[base + 2][ozs] = r.z1.v[e];
+        }
+    }
+}
+
+// CPML coefficients of one stage at this thread's position: b, a, 1/kappa along x (plane), y (row), z (per cell)
+template <typename T, int V> struct YeexCoef { T bx, ax, kx, by, ay, ky; T bz[V], az[V], kz[V]; int szk[V]; int sxp; };
+
+template <typename T, int V>
+__device__ __forceinline__ void yeex_coef_load(YeexCoef<T, V>& q, const Cpml& pm, const int v0, const Geom& g, const int pl,
+                                               const int j, const int k, const int syj)
+{
+    const int tpm = pm.t;
+    q.sxp = (tpm && pl >= 0 && pl < g.nx) ? slab_index(pl, g.nx, tpm) : -1;
+    q.bx = q.ax = q.by = q.ay = (T)0; q.kx = q.ky = (T)1;
+    if (q.sxp >= 0) {
+        q.bx = __ldg(cpml_tab<T>(pm.ax[0], v0) + pl); q.ax = __ldg(cpml_tab<T>(pm.ax[0], v0 + 1) + pl); q.kx = __ldg(cpml_tab<T>(pm.ax[0], v0 + 2) + pl);
+    }
+    if (syj >= 0) {
+        q.by = __ldg(cpml_tab<T>(pm.ax[1], v0) + j); q.ay = __ldg(cpml_tab<T>(pm.ax[1], v0 + 1) + j); q.ky = __ldg(cpml_tab<T>(pm.ax[1], v0 + 2) + j);
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const int ke = k + e;
+        q.szk[e] = (tpm && ke >= 0 && ke < g.nz) ? slab_index(ke, g.nz, tpm) : -1;
+        q.bz[e] = q.az[e] = (T)0; q.kz[e] = (T)1;
+        if (q.szk[e] >= 0) {
+            q.bz[e] = __ldg(cpml_tab<T>(pm.ax[2], v0) + ke); q.az[e] = __ldg(cpml_tab<T>(pm.ax[2], v0 + 1) + ke); q.kz[e] = __ldg(cpml_tab<T>(pm.ax[2], v0 + 2) + ke);
+        }
+    }
+}
+
 // ---- full bodies: update-range masks + CPML recursion on slab cells (fdtd_yee.cuh:63-89, :106-138) --------------------------------
 template <typename T, int V>
-__device__ __forceinline__ void yee_h_full(const Coefs<T>& c, const Geom& g, const Cpml& pm, const SlabGeom& sg,
-                                           const T* const* psi_in, T* const* psi_out, bool store, int p, int j, int k, int syj,
+__device__ __forceinline__ void yee_h_full(const Coefs<T>& c, const Geom& g, const Cpml& pm, YeexPsi<T, V>& r,
+                                           const int p, const int j, const int k, const int syj,
                                            const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
                                            const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
                                            const Pack<T, V>& ez_jm, const Pack<T, V>& ex_jm, T ey_km, T ex_km,
                                            const Pack<T, V>& ey_im, const Pack<T, V>& ez_im,
                                            Pack<T, V>& ox, Pack<T, V>& oy, Pack<T, V>& oz)
 {
-    const int tpm = pm.t;
-    const int sxp = tpm ? slab_index(p, g.nx, tpm) : -1;
+    YeexCoef<T, V> q;
+    yeex_coef_load<T, V>(q, pm, 3, g, p, j, k, syj);
     const bool px1 = p < g.nx - 1, pxm = p >= 1 && p <= g.nx - 2;
     const bool jm = j >= 1 && j <= g.ny - 2, jy1 = j >= 0 && j < g.ny - 1;
-    const long long o = (long long)j * g.sy + k;
     ox = hx; oy = hy; oz = hz;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
         const int ke = k + e;
         const bool km = ke >= 1 && ke <= g.nz - 2, kz1 = ke >= 0 && ke < g.nz - 1;
-        const int szk = (tpm && ke >= 0) ? slab_index(ke, g.nz, tpm) : -1;
-        const long long oxs = (long long)sxp * sg.x_sx + o + e;
-        const long long oys = (long long)p * sg.y_sx + (long long)syj * g.sy + ke;
-        const long long ozs = ((long long)p * g.ny + j) * sg.z_pitch + szk;
         const T ey_k = e > 0 ? ey.v[(e + V - 1) % V] : ey_km;
         const T ex_k = e > 0 ? ex.v[(e + V - 1) % V] : ex_km;
         if (px1 && jm && km) {                             // Hx(p+1/2, j, k)
             T dy = Ar<T>::diff(ez.v[e], ez_jm.v[e], g.dy, g.rdy), dz = Ar<T>::diff(ey.v[e], ey_k, g.dz, g.rdz);
-            if (syj >= 0) dy = cpml_step<T>(dy, psi_in[6], psi_out[6], store, oys, pm.ax[1].c[3], pm.ax[1].c[4], pm.ax[1].c[5], j);
-            if (szk >= 0) dz = cpml_step<T>(dz, psi_in[7], psi_out[7], store, ozs, pm.ax[2].c[3], pm.ax[2].c[4], pm.ax[2].c[5], ke);
+            if (syj >= 0) { r.y0.v[e] = CpmlMath<T>::psi(q.by, r.y0.v[e], q.ay, dy); dy = CpmlMath<T>::eff(q.ky, dy, r.y0.v[e]); }
+            if (q.szk[e] >= 0) { r.z0.v[e] = CpmlMath<T>::psi(q.bz[e], r.z0.v[e], q.az[e], dz); dz = CpmlMath<T>::eff(q.kz[e], dz, r.z0.v[e]); }
             ox.v[e] = upd_h<T>(c.uda, hx.v[e], c.udb, dy, dz);
         }
         if (pxm && jy1 && km) {                            // Hy(p, j+1/2, k)
             T dz = Ar<T>::diff(ex.v[e], ex_k, g.dz, g.rdz), dx = Ar<T>::diff(ez.v[e], ez_im.v[e], g.dx, g.rdx);
-            if (szk >= 0) dz = cpml_step<T>(dz, psi_in[8], psi_out[8], store, ozs, pm.ax[2].c[3], pm.ax[2].c[4], pm.ax[2].c[5], ke);
-            if (sxp >= 0) dx = cpml_step<T>(dx, psi_in[9], psi_out[9], store, oxs, pm.ax[0].c[3], pm.ax[0].c[4], pm.ax[0].c[5], p);
+            if (q.szk[e] >= 0) { r.z1.v[e] = CpmlMath<T>::psi(q.bz[e], r.z1.v[e], q.az[e], dz); dz = CpmlMath<T>::eff(q.kz[e], dz, r.z1.v[e]); }
+            if (q.sxp >= 0) { r.x0.v[e] = CpmlMath<T>::psi(q.bx, r.x0.v[e], q.ax, dx); dx = CpmlMath<T>::eff(q.kx, dx, r.x0.v[e]); }
             oy.v[e] = upd_h<T>(c.uda, hy.v[e], c.udb, dz, dx);
         }
         if (pxm && jm && kz1) {                            // Hz(p, j, k+1/2)
             T dx = Ar<T>::diff(ey.v[e], ey_im.v[e], g.dx, g.rdx), dy = Ar<T>::diff(ex.v[e], ex_jm.v[e], g.dy, g.rdy);
-            if (sxp >= 0) dx = cpml_step<T>(dx, psi_in[10], psi_out[10], store, oxs, pm.ax[0].c[3], pm.ax[0].c[4], pm.ax[0].c[5], p);
-            if (syj >= 0) dy = cpml_step<T>(dy, psi_in[11], psi_out[11], store, oys, pm.ax[1].c[3], pm.ax[1].c[4], pm.ax[1].c[5], j);
+            if (q.sxp >= 0) { r.x1.v[e] = CpmlMath<T>::psi(q.bx, r.x1.v[e], q.ax, dx); dx = CpmlMath<T>::eff(q.kx, dx, r.x1.v[e]); }
+            if (syj >= 0) { r.y1.v[e] = CpmlMath<T>::psi(q.by, r.y1.v[e], q.ay, dy); dy = CpmlMath<T>::eff(q.ky, dy, r.y1.v[e]); }
             oz.v[e] = upd_h<T>(c.uda, hz.v[e], c.udb, dx, dy);
         }
     }
 }
 
 template <typename T, int V>
-__device__ __forceinline__ void yee_e_full(const Coefs<T>& c, const Geom& g, const Cpml& pm, const SlabGeom& sg,
-                                           const T* const* psi_in, T* const* psi_out, bool store, bool can, int i, int j, int k, int syj,
+__device__ __forceinline__ void yee_e_full(const Coefs<T>& c, const Geom& g, const Cpml& pm, YeexPsi<T, V>& r,
+                                           const int i, const int j, const int k, const int syj,
                                            const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
                                            const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
                                            const Pack<T, V>& hz_jp, const Pack<T, V>& hx_jp, T hy_kp, T hx_kp,
                                            const Pack<T, V>& hy_ip, const Pack<T, V>& hz_ip,
                                            Pack<T, V>& ox, Pack<T, V>& oy, Pack<T, V>& oz)
 {
-    const int tpm = pm.t;
-    const int sxq = tpm ? slab_index(i, g.nx, tpm) : -1;
+    YeexCoef<T, V> q;
+    yeex_coef_load<T, V>(q, pm, 0, g, i, j, k, syj);
     const bool qx1 = i < g.nx - 1, jy1 = j >= 0 && j < g.ny - 1, jy0 = j >= 0 && j < g.ny;
-    const long long o = (long long)j * g.sy + k;
     ox = ex; oy = ey; oz = ez;
-    if (!can) return;                                      // last row / lane of the tile: no +j / +k neighbour at hand
 #pragma unroll
     for (int e = 0; e < V; ++e) {
         const int ke = k + e;
         const bool kz0 = ke >= 0 && ke < g.nz, kz1 = ke >= 0 && ke < g.nz - 1;
-        const int szk = (tpm && ke >= 0) ? slab_index(ke, g.nz, tpm) : -1;
-        const long long oxs = (long long)sxq * sg.x_sx + o + e;
-        const long long oys = (long long)i * sg.y_sx + (long long)syj * g.sy + ke;
-        const long long ozs = ((long long)i * g.ny + j) * sg.z_pitch + szk;
         const T hy_k = (e + 1 < V) ? hy.v[(e + 1) % V] : hy_kp;
         const T hx_k = (e + 1 < V) ? hx.v[(e + 1) % V] : hx_kp;
         if (jy1 && kz1) {                                  // Ex(i, j+1/2, k+1/2)
             T dy = Ar<T>::diff(hz_jp.v[e], hz.v[e], g.dy, g.rdy), dz = Ar<T>::diff(hy_k, hy.v[e], g.dz, g.rdz);
-            if (syj >= 0) dy = cpml_step<T>(dy, psi_in[0], psi_out[0], store, oys, pm.ax[1].c[0], pm.ax[1].c[1], pm.ax[1].c[2], j);
-            if (szk >= 0) dz = cpml_step<T>(dz, psi_in[1], psi_out[1], store, ozs, pm.ax[2].c[0], pm.ax[2].c[1], pm.ax[2].c[2], ke);
+            if (syj >= 0) { r.y0.v[e] = CpmlMath<T>::psi(q.by, r.y0.v[e], q.ay, dy); dy = CpmlMath<T>::eff(q.ky, dy, r.y0.v[e]); }
+            if (q.szk[e] >= 0) { r.z0.v[e] = CpmlMath<T>::psi(q.bz[e], r.z0.v[e], q.az[e], dz); dz = CpmlMath<T>::eff(q.kz[e], dz, r.z0.v[e]); }
             ox.v[e] = upd_e<T>(c.uca, ex.v[e], c.ucb, dy, dz);
         }
         if (qx1 && kz1 && jy0) {                           // Ey(i+1/2, j, k+1/2)
             T dz = Ar<T>::diff(hx_k, hx.v[e], g.dz, g.rdz), dx = Ar<T>::diff(hz_ip.v[e], hz.v[e], g.dx, g.rdx);
-            if (szk >= 0) dz = cpml_step<T>(dz, psi_in[2], psi_out[2], store, ozs, pm.ax[2].c[0], pm.ax[2].c[1], pm.ax[2].c[2], ke);
-            if (sxq >= 0) dx = cpml_step<T>(dx, psi_in[3], psi_out[3], store, oxs, pm.ax[0].c[0], pm.ax[0].c[1], pm.ax[0].c[2], i);
+            if (q.szk[e] >= 0) { r.z1.v[e] = CpmlMath<T>::psi(q.bz[e], r.z1.v[e], q.az[e], dz); dz = CpmlMath<T>::eff(q.kz[e], dz, r.z1.v[e]); }
+            if (q.sxp >= 0) { r.x0.v[e] = CpmlMath<T>::psi(q.bx, r.x0.v[e], q.ax, dx); dx = CpmlMath<T>::eff(q.kx, dx, r.x0.v[e]); }
             oy.v[e] = upd_e<T>(c.uca, ey.v[e], c.ucb, dz, dx);
         }
         if (qx1 && jy1 && kz0) {                           // Ez(i+1/2, j+1/2, k)
             T dx = Ar<T>::diff(hy_ip.v[e], hy.v[e], g.dx, g.rdx), dy = Ar<T>::diff(hx_jp.v[e], hx.v[e], g.dy, g.rdy);
-            if (sxq >= 0) dx = cpml_step<T>(dx, psi_in[4], psi_out[4], store, oxs, pm.ax[0].c[0], pm.ax[0].c[1], pm.ax[0].c[2], i);
-            if (syj >= 0) dy = cpml_step<T>(dy, psi_in[5], psi_out[5], store, oys, pm.ax[1].c[0], pm.ax[1].c[1], pm.ax[1].c[2], j);
+            if (q.sxp >= 0) { r.x1.v[e] = CpmlMath<T>::psi(q.bx, r.x1.v[e], q.ax, dx); dx = CpmlMath<T>::eff(q.kx, dx, r.x1.v[e]); }
+            if (syj >= 0) { r.y1.v[e] = CpmlMath<T>::psi(q.by, r.y1.v[e], q.ay, dy); dy = CpmlMath<T>::eff(q.ky, dy, r.y1.v[e]); }
             oz.v[e] = upd_e<T>(c.uca, ez.v[e], c.ucb, dx, dy);
         }
     }
@@ -218,8 +318,8 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
     const int ntiles = t.ntj * t.ntk;
     const int seg = blockIdx.x / ntiles, tile = blockIdx.x - seg * ntiles;
     const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
-    const int j0 = tj * (R - 2) - 1, k0 = (tk * t.own_lanes - 1) * V;      // tile origin: one halo row / lane on the low side
-    const int kbox = k0 - V;                               // box origin: 16-byte aligned (own_lanes is even)
+    const int j0 = tj * (R - 1), k0 = (tk * t.own_lanes - 1) * V;      // row 0 / lane 0 of the CTA (lane 0 is the -k halo lane)
+    const int jbox = j0 - 1, kbox = k0 - V;                // box origin: one halo row; 16-byte aligned (own_lanes is even)
     const int i0 = t.i_begin + seg * t.lx;
     const int i1 = min(i0 + t.lx, t.i_end);
     const int n_it = i1 - i0 + 1;                          // i = i0 - 1 .. i1 - 1
@@ -237,15 +337,15 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
         if (lane == 0) {
             int s = 0, ph = 0;
             for (int q = 0; q <= n_it; ++q) {
-                mbar_wait(empty + 8u * s, (uint32_t)(ph ^ 1));
+                mbar_wait_parked(empty + 8u * s, (uint32_t)(ph ^ 1), 2000u);
                 const uint32_t dst = tiles + (uint32_t)s * (uint32_t)yeex_stage_bytes<R>();
                 const uint32_t bar = full + 8u * s;
-                mbar_arrive_expect_tx(bar, (uint32_t)((q > 0 ? 6 : 3) * R * kYeexBoxBytes));
+                mbar_arrive_expect_tx(bar, (uint32_t)((q > 0 ? 6 : 3) * (R + 1) * kYeexBoxBytes));
 #pragma unroll
-                for (int a = 0; a < 3; ++a) tma_load_3d(dst + a * ROWS, &maps.m[a], kbox, j0, i0 - 1 + q, bar);
+                for (int a = 0; a < 3; ++a) tma_load_3d(dst + a * ROWS, &maps.m[a], kbox, jbox, i0 - 1 + q, bar);
                 if (q > 0) {
 #pragma unroll
-                    for (int a = 3; a < 6; ++a) tma_load_3d(dst + a * ROWS, &maps.m[a], kbox, j0, i0 - 1 + q, bar);
+                    for (int a = 3; a < 6; ++a) tma_load_3d(dst + a * ROWS, &maps.m[a], kbox, jbox, i0 - 1 + q, bar);
                 }
                 if (++s == S) { s = 0; ph ^= 1; }
             }
@@ -255,21 +355,22 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
 
     // ---- consumers ---------------------------------------------------------------------------------------------------------------------
     const int j = j0 + row, k = k0 + lane * V;
-    const int rowm = max(row - 1, 0), rowp = min(row + 1, R - 1);
-    const uint32_t own_off = (uint32_t)(row * kYeexBoxBytes + (lane + 1) * 8);
-    const uint32_t dn_off = (uint32_t)(rowm * kYeexBoxBytes + (lane + 1) * 8);
-    const bool in_grid = j >= 0 && j < g.ny && k >= 0 && k < g.pz;
-    const bool owner = in_grid && row >= 1 && row <= R - 2 && lane >= 1 && lane <= t.own_lanes;
-    const bool can_e = row <= R - 2 && lane <= 30;         // has its +j row and +k lane inside the tile
-    const unsigned ofs = (unsigned)max(j, 0) * (unsigned)g.sy + (unsigned)max(k, 0);
+    const int rowp = min(row + 1, R - 1);
+    const uint32_t own_off = (uint32_t)((row + 1) * kYeexBoxBytes + (lane + 1) * 8);
+    const uint32_t dn_off = (uint32_t)(row * kYeexBoxBytes + (lane + 1) * 8);
+    const bool in_grid = j < g.ny && k >= 0 && k < g.pz;
+    const bool owner = in_grid && row <= R - 2 && lane >= 1 && lane <= t.own_lanes;
+    const unsigned ofs = (unsigned)j * (unsigned)g.sy + (unsigned)max(k, 0);
     const int tpm = pm.t;
-    const int syj = (tpm && j >= 0 && j < g.ny) ? slab_index(j, g.ny, tpm) : -1;
-    // lean test: every CONSUMED cell of the tile (rows 1..R-1, lanes 1..31 for H+; one less for E+) is strictly inside the
-    // grid faces (1 <= j <= ny-2, 1 <= k <= nz-2) and outside the y / z slabs
-    const int jlo = j0 + 1, jhi = j0 + R - 1, klo = k0 + V, khi = k0 + 32 * V - 1;
+    const int syj = (tpm && j < g.ny) ? slab_index(j, g.ny, tpm) : -1;
+    // lean test: every CONSUMED cell of the tile (rows 0..R-1, lanes 1..31 for H+; one less on the high side for E+) is
+    // strictly inside the grid faces (1 <= j <= ny-2, 1 <= k <= nz-2) and outside the y / z slabs
+    const int jlo = j0, jhi = j0 + R - 1, klo = k0 + V, khi = k0 + 32 * V - 1;
     const bool tile_in = jlo >= 1 && jhi <= g.ny - 2 && klo >= 1 && khi <= g.nz - 2;
     const bool tile_z = tpm && (klo < tpm || khi >= g.nz - tpm - 1);
     const bool lean_thread = tile_in && !tile_z && syj < 0;
+    // planes on which the H stage (plane p) / the E stage (plane i) of a lean thread need neither masks nor x psi
+    const int hl_lo = max(1, tpm), el_lo = tpm, xl_hi = g.nx - 2 - tpm;
     const T* const* psi_in = reinterpret_cast<const T* const*>(pm.psi);
     T* const* psi_out = reinterpret_cast<T* const*>(pout.p);
 
@@ -282,20 +383,29 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
         __syncwarp();
         if (lane == 0) mbar_arrive(xfull + (uint32_t)((row * D) * 8));
     }
+    // psi of the first H stage (plane i0); the E stage's first set (plane i0) is requested at the end of iteration 0
+    YeexPsi<T, V> hps, eps;
+    hps.x0 = hps.x1 = hps.y0 = hps.y1 = hps.z0 = hps.z1 = z_;
+    eps = hps;
+    if (!(lean_thread && i0 >= hl_lo && i0 <= xl_hi))
+        yeex_psi_load<T, V>(hps, psi_in, 6, g, sg, tpm, i0, j, k, syj, in_grid && i0 < g.nx);
     // window at it = 0 (i = i0 - 1): E[i] = stage 0 (Ey, Ez feed the x-differences of H+[i0]); H+[i] unused
     mbar_wait(full, 0);
-    P e0x = lds8<T, V>(tiles + 0 * ROWS + own_off), e0y = lds8<T, V>(tiles + 1 * ROWS + own_off), e0z = lds8<T, V>(tiles + 2 * ROWS + own_off);
+    P eAx = lds8<T, V>(tiles + 0 * ROWS + own_off), eAy = lds8<T, V>(tiles + 1 * ROWS + own_off), eAz = lds8<T, V>(tiles + 2 * ROWS + own_off);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty);
-    P hpx = z_, hpy = z_, hpz = z_;
+    P hAx = z_, hAy = z_, hAz = z_;
+    P eBx = z_, eBy = z_, eBz = z_, hBx = z_, hBy = z_, hBz = z_;
     int sq = 1 % S, sph = (1 / S) & 1, xd = 0, xph = 0;
 
-    for (int it = 0; it < n_it; ++it) {
+    // one plane: (E[i], H+[i]) in, (E[p], H+[p]) out; the caller alternates the two register windows instead of moving them
+    auto iter = [&](const int it, const P& e0x, const P& e0y, const P& e0z, const P& hpx, const P& hpy, const P& hpz,
+                    P& e1x, P& e1y, P& e1z, P& hnx, P& hny, P& hnz) {
         const int i = i0 - 1 + it, p = i + 1;
         // ---- stage it + 1: E[p] (own, -j rows), H[p] own; hand the stage back as soon as it is in registers ------------------------
         const uint32_t st = tiles + (uint32_t)sq * (uint32_t)yeex_stage_bytes<R>();
         mbar_wait(full + (uint32_t)sq * 8u, (uint32_t)sph);
-        const P e1x = lds8<T, V>(st + 0 * ROWS + own_off), e1y = lds8<T, V>(st + 1 * ROWS + own_off), e1z = lds8<T, V>(st + 2 * ROWS + own_off);
+        e1x = lds8<T, V>(st + 0 * ROWS + own_off); e1y = lds8<T, V>(st + 1 * ROWS + own_off); e1z = lds8<T, V>(st + 2 * ROWS + own_off);
         const P h1x = lds8<T, V>(st + 3 * ROWS + own_off), h1y = lds8<T, V>(st + 4 * ROWS + own_off), h1z = lds8<T, V>(st + 5 * ROWS + own_off);
         const P ez_jm = lds8<T, V>(st + 2 * ROWS + dn_off), ex_jm = lds8<T, V>(st + 0 * ROWS + dn_off);
         __syncwarp();
@@ -310,18 +420,22 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
         const T hy_kp = shfl_next<T>(hpy.v[0]), hx_kp = shfl_next<T>(hpx.v[0]);
 
         // ---- H+[p] ------------------------------------------------------------------------------------------------------------------------
-        const bool px_lean = p >= 1 && p <= g.nx - 2 && !(tpm && (p < tpm || p >= g.nx - tpm - 1));
+        const bool more = it + 1 < n_it;
         const bool st_h = owner && p < i1;
-        P hnx, hny, hnz;
-        if (lean_thread && px_lean)
+        if (lean_thread && p >= hl_lo && p <= xl_hi)
             yee_h_lean<T, V, AM>(c, g, h1x, h1y, h1z, e1x, e1y, e1z, ez_jm, ex_jm, ey_km, ex_km, e0y, e0z, hnx, hny, hnz);
-        else
-            yee_h_full<T, V>(c, g, pm, sg, psi_in, psi_out, st_h, p, j, k, syj, h1x, h1y, h1z, e1x, e1y, e1z, ez_jm, ex_jm,
-                             ey_km, ex_km, e0y, e0z, hnx, hny, hnz);
+        else {
+            yee_h_full<T, V>(c, g, pm, hps, p, j, k, syj, h1x, h1y, h1z, e1x, e1y, e1z, ez_jm, ex_jm, ey_km, ex_km, e0y, e0z,
+                             hnx, hny, hnz);
+            if (st_h && tpm) yeex_psi_store<T, V>(hps, psi_out, 6, g, sg, tpm, p, j, k, syj);
+        }
+        // psi of the next H stage (plane p + 1): the registers are free now, the loads have a whole iteration to land
+        if (more && !(lean_thread && p + 1 >= hl_lo && p + 1 <= xl_hi))
+            yeex_psi_load<T, V>(hps, psi_in, 6, g, sg, tpm, p + 1, j, k, syj, in_grid && p + 1 < g.nx);
         // ---- publish Hz+, Hx+ of plane p for the row below (its E+ of the next iteration) ----------------------------------------------
         int xd1 = xd + 1, xph1 = xph;
         if (xd1 == D) { xd1 = 0; xph1 ^= 1; }
-        if (it + 1 < n_it) {
+        if (more) {
             if (row > 0 && it + 1 >= D) {
                 int bd = xd1 + 1, bph = xph1 ^ 1;
                 if (bd == D) { bd = 0; bph ^= 1; }
@@ -337,23 +451,32 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
             const unsigned oh = ofs + (unsigned)p * (unsigned)g.sx;
             st8<T, V>(out.hx + oh, hnx); st8<T, V>(out.hy + oh, hny); st8<T, V>(out.hz + oh, hnz);
         }
-        // ---- E+[i] ------------------------------------------------------------------------------------------------------------------------
+        // ---- E+[i]: owners only (nobody consumes the E+ of a rim thread) -------------------------------------------------------------------
         if (it > 0) {
-            const bool qx_lean = i <= g.nx - 2 && !(tpm && (i < tpm || i >= g.nx - tpm - 1));
-            P nx_, ny_, nz_;
-            if (lean_thread && qx_lean)
+            P nx_ = e0x, ny_ = e0y, nz_ = e0z;
+            if (lean_thread && i >= el_lo && i <= xl_hi)
                 yee_e_lean<T, V, AM>(c, g, e0x, e0y, e0z, hpx, hpy, hpz, hz_jp, hx_jp, hy_kp, hx_kp, hny, hnz, nx_, ny_, nz_);
-            else
-                yee_e_full<T, V>(c, g, pm, sg, psi_in, psi_out, owner, can_e, i, j, k, syj, e0x, e0y, e0z, hpx, hpy, hpz, hz_jp, hx_jp,
-                                 hy_kp, hx_kp, hny, hnz, nx_, ny_, nz_);
+            else if (owner) {
+                yee_e_full<T, V>(c, g, pm, eps, i, j, k, syj, e0x, e0y, e0z, hpx, hpy, hpz, hz_jp, hx_jp, hy_kp, hx_kp, hny, hnz,
+                                 nx_, ny_, nz_);
+                if (tpm) yeex_psi_store<T, V>(eps, psi_out, 0, g, sg, tpm, i, j, k, syj);
+            }
             if (owner) {
                 const unsigned oe = ofs + (unsigned)i * (unsigned)g.sx;
                 st8<T, V>(out.ex + oe, nx_); st8<T, V>(out.ey + oe, ny_); st8<T, V>(out.ez + oe, nz_);
             }
         }
-        e0x = e1x; e0y = e1y; e0z = e1z;
-        hpx = hnx; hpy = hny; hpz = hnz;
+        // psi of the next E stage (plane i + 1 = p)
+        if (more && owner && !(lean_thread && p >= el_lo && p <= xl_hi))
+            yeex_psi_load<T, V>(eps, psi_in, 0, g, sg, tpm, p, j, k, syj, p < g.nx);
+    };
+
+    int it = 0;
+    for (; it + 2 <= n_it; it += 2) {
+        iter(it, eAx, eAy, eAz, hAx, hAy, hAz, eBx, eBy, eBz, hBx, hBy, hBz);
+        iter(it + 1, eBx, eBy, eBz, hBx, hBy, hBz, eAx, eAy, eAz, hAx, hAy, hAz);
     }
+    if (it < n_it) iter(it, eAx, eAy, eAz, hAx, hAy, hAz, eBx, eBy, eBz, hBx, hBy, hBz);
 }
 
 }  // namespace fdtd
