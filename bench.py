@@ -405,7 +405,8 @@ def main():
     if args.physics:
         from prismo_b200 import cpml
 
-        eng.set_cpml(10, cpml.coefficient_table(dims, spacing, dt, cpml.PMLParams(thickness=10)))
+        thick = int(os.environ.get("FDTD_B200_BENCH_CPML", "10"))       # 0: tuning experiment (no absorbing layer)
+        eng.set_cpml(thick, cpml.coefficient_table(dims, spacing, dt, cpml.PMLParams(thickness=max(thick, 1))))
     if args.het:
         set_ridge_coefficients(eng, dims, dt)
     src, mon = workload_ops(dims, dt, spacing)

@@ -57,3 +57,41 @@ class OAde:
             self.J = self.c[0] * E + self.c[1] * self.J                # ade.py:149
         else:
             self.P = self.c[0] * E + self.c[1] * self.P                # ade.py:160
+
+
+# ---- coupled mode (OPT-IN extension of the engine, no reference counterpart: PARITY UNPINNED) -------------------------
+# The reference never feeds the polarisation back into E.  The engine's opt-in "ade_coupled" mode does, with
+# the reference's own recursions, applied at the BEGINNING of a step on the current E:
+#     P+  = recursion(E^n, P, P_prev)                          (same left-to-right arithmetic as OAde.update)
+#     J   = sum over the recursions driving a component of  (P+ - P) * (eps0/dt)   (Lorentz, Debye)   or   J+ * eps0
+#           (Drude): the reference's recursion coefficients carry no eps0, so its P and J are in units of eps0
+#     E^{n+1} = [reference E update](E^n, H^{n+1})  -  Cb_c * J        Cb_c: the 4-point mean the update itself uses
+def coupled_step(F, coeffs, spacing, ades, dt, kernels):
+    """One coupled step of the fields (no sources / monitors): mirrors ade_in_sweep + the E stage of fdtd_het.cuh /
+    fdtd_fused.cuh operation for operation (fp64 results are compared bitwise)."""
+    from .kernels import _crop, _mean4
+
+    Ca, Cb, Da, Db = coeffs
+    kj = 8.854187817e-12
+    kp = kj / dt
+    J = {}
+    for a in ades:
+        acc = J.setdefault(a.component, np.zeros(F[a.component].shape))
+        if a.kind == "lorentz":
+            old = [p.copy() for p in a.P]
+            a.update(F)
+            for o, n in zip(old, a.P):
+                acc += (n - o) * kp
+        elif a.kind == "drude":
+            a.update(F)
+            acc += a.J * kj
+        else:
+            old = a.P.copy()
+            a.update(F)
+            acc += (a.P - old) * kp
+    kernels.update_h(F, Da, Db, spacing, False)
+    kernels.update_e(F, Ca, Cb, spacing, False)
+    axes = {"Ex": (1, 2), "Ey": (0, 2), "Ez": (0, 1)}
+    for c, j in J.items():
+        cb = _crop(_mean4(Cb, *axes[c]), F[c].shape)
+        F[c] -= cb * j

@@ -59,7 +59,17 @@ template <typename T> static int launch_count2d(fdtd_engine* e, int parity, cuda
 }
 
 // sources (group by group, list order) then monitors, for table row (*d_step + step_off)
-template <typename T> static int launch_post(fdtd_engine* e, int step_off, int parity, cudaStream_t s)
+static AdeIn ade_in_of(fdtd_engine* e)
+{
+    AdeIn ad{};
+    ad.ops = e->d_ade; ad.n = (int)e->ade.size(); ad.aux = e->d_aux; ad.mask = e->d_ade_mask;
+    ad.coupled = e->ade_coupled; ad.kj = 8.854187817e-12; ad.kp = 8.854187817e-12 / e->cfg.dt;
+    return ad;
+}
+// does the sweep being launched now carry the dispersive-medium recursions (of the previous step)?
+static bool ade_in_this_sweep(const fdtd_engine* e) { return !e->ade.empty() && (e->ade_coupled || e->ade_deferred); }
+
+template <typename T> static int launch_post(fdtd_engine* e, int step_off, int parity, cudaStream_t s, bool defer_ade = false)
 {
     void** comp = e->d_comp_ptr[e->cur];
     int* cnt_next = e->cfg.ndim == 2 ? e->d_cnt + 6 * ((parity + 1) & 1) : nullptr;
@@ -87,7 +97,11 @@ template <typename T> static int launch_post(fdtd_engine* e, int step_off, int p
         e->launches += 2;
         CU(cudaGetLastError());
     }
-    if (e->ade_threads > 0) {
+    if (e->ade_threads > 0 && e->ade_coupled) {
+        // coupled mode: the recursion runs at the beginning of every step, inside the sweep, never here
+    } else if (e->ade_threads > 0 && defer_ade) {
+        e->ade_deferred = true;                              // the next fused sweep applies it on its input planes
+    } else if (e->ade_threads > 0) {
         k_ade<T><<<(unsigned)((e->ade_threads + 255) / 256), 256, 0, s>>>(
             (const T* const*)comp, e->d_ade, (int)e->ade.size(), e->ade_threads, e->st, (T*)e->d_aux, e->d_ade_mask);
         e->launches++;
@@ -226,12 +240,18 @@ template <typename T, int TJ> static int launch_fused_tj(fdtd_engine* e, int i_b
     t.lx = std::min(lx, planes);
     t.nseg = (planes + t.lx - 1) / t.lx;
     const size_t smem = fused_smem_bytes<T, TJ>();
-    auto kern = k_fused3d<T, TJ, 0>;
-    if (sizeof(T) == 8 && fold64(e)) kern = k_fused3d<T, TJ, (sizeof(T) == 8 ? 1 : 0)>;
+    const bool ade = ade_in_this_sweep(e) && e->g.nxg == e->g.nx;
+    auto kern = k_fused3d<T, TJ, 0, false>;
+    if (sizeof(T) == 8 && fold64(e)) kern = k_fused3d<T, TJ, (sizeof(T) == 8 ? 1 : 0), false>;
+    if (ade) {
+        kern = k_fused3d<T, TJ, 0, true>;
+        if (sizeof(T) == 8 && fold64(e)) kern = k_fused3d<T, TJ, (sizeof(T) == 8 ? 1 : 0), true>;
+    }
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, TJ + 1, 1);
     const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
-    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, fold_of(e));
+    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, fold_of(e), ade ? ade_in_of(e) : AdeIn{});
+    if (ade && i_end == g.nx) e->ade_deferred = false;
     e->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -342,11 +362,12 @@ template <typename T> static int launch_fused(fdtd_engine* e, int i_begin, int i
 }
 
 // heterogeneous media, one GPU: fused one-step sweep that also streams the four coefficient arrays
-static bool use_het_fused(const fdtd_engine* e)
+static bool het_sweep_ok(const fdtd_engine* e)          // the kernel itself also runs on an x-slab (fdtd_slab_run)
 {
-    return e->cfg.ndim == 3 && e->het && !(e->cfg.flags & (FDTD_FLAG_TWO_PASS | FDTD_FLAG_YEE)) && e->g.nxg == e->g.nx &&
+    return e->cfg.ndim == 3 && e->het && !(e->cfg.flags & (FDTD_FLAG_TWO_PASS | FDTD_FLAG_YEE)) &&
            e->array_elems < (1ll << 32) && e->het_fused;
 }
+static bool use_het_fused(const fdtd_engine* e) { return het_sweep_ok(e) && e->g.nxg == e->g.nx; }
 
 template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
 {
@@ -360,10 +381,18 @@ template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
     Fields<T> out = fields_of<T>(dst);
     FusedTiling t{};
     t.i_begin = 0; t.i_end = g.nx;
+    t.timeout_ns = e->slab.timeout_ns;
+    if (e->slab.connected && e->slab.has_right) {
+        // the last x-segment reads the right neighbour's planes 0 and 1 (same 7 halo planes as the uniform one-step sweep)
+        // and one ghost plane of the coefficient arrays, which is static (fdtd_set_coeffs with nx + 1 planes)
+        if (e->coef_planes < g.nx + 1)
+            return fail(FDTD_ESTATE, "x-slab with a right neighbour: fdtd_set_coeffs needs nx + 1 = %d planes", g.nx + 1);
+        t.halo_flag = e->slab.flags; t.halo_need = (int)e->slab.step + 1; t.error_word = e->slab.flags + 2;
+    }
     t.own_lanes = kHetOwnLanes;
     const int vec_per_row = g.pz / V;
     t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
-    t.ntj = (g.ny + (R - 1) - 1) / (R - 1);
+    t.ntj = (g.ny + (R - 2) - 1) / (R - 2);
     int lx = e->fused_lx;
     if (lx <= 0) {
         const long long tiles = (long long)t.ntj * t.ntk;
@@ -374,10 +403,13 @@ template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
     t.lx = std::min(lx, g.nx);
     t.nseg = (g.nx + t.lx - 1) / t.lx;
     const size_t smem = het_smem_bytes<T, R>();
-    auto kern = k_fused3d_het<T, R>;
+    const bool ade = ade_in_this_sweep(e);
+    auto kern = ade ? k_fused3d_het<T, R, true> : k_fused3d_het<T, R, false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, R, 1);
-    kern<<<(unsigned)t.nseg * t.ntj * t.ntk, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, (int)e->planes_alloc);
+    kern<<<(unsigned)t.nseg * t.ntj * t.ntk, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, (int)e->planes_alloc,
+                                                              ade ? ade_in_of(e) : AdeIn{});
+    e->ade_deferred = false;
     e->launches++;
     CU(cudaGetLastError());
     e->cur ^= 1;
@@ -678,7 +710,13 @@ template <typename T> static int step_fields3d(fdtd_engine* e, int half, cudaStr
     return launch_pass3d<T>(e, half, 0, e->g.nx, s);
 }
 
-template <typename T> static int one_step(fdtd_engine* e, int step_off, int parity, cudaStream_t s)
+// can the step after this one apply this step's dispersive-medium recursions inside its sweep?
+static bool ade_sweep_capable(const fdtd_engine* e)
+{
+    return e->ade_fused && !e->ade.empty() && e->cfg.ndim == 3 && e->g.nxg == e->g.nx && (use_fused(e) || use_het_fused(e));
+}
+
+template <typename T> static int one_step(fdtd_engine* e, int step_off, int parity, cudaStream_t s, bool defer_ade = false)
 {
     if (e->cfg.ndim == 3) {
         if (int rc = step_fields3d<T>(e, 0, s)) return rc;
@@ -687,7 +725,7 @@ template <typename T> static int one_step(fdtd_engine* e, int step_off, int pari
         if (int rc = launch_pass2d<T>(e, 0, parity, s)) return rc;
         if (int rc = launch_pass2d<T>(e, 1, parity, s)) return rc;
     }
-    return launch_post<T>(e, step_off, parity, s);
+    return launch_post<T>(e, step_off, parity, s, defer_ade);
 }
 
 static bool has_tables(const fdtd_engine* e) { return !e->src.empty() || !e->mon.empty() || !e->src_ghost.empty() || !e->flux.empty(); }
@@ -696,6 +734,8 @@ static bool has_post(const fdtd_engine* e) { return has_tables(e) || !e->ade.emp
 template <typename T> static int run_steps(fdtd_engine* e, int n)
 {
     cudaStream_t s = e->stream;
+    if (e->ade_coupled && !e->ade.empty() && !(e->cfg.ndim == 3 && e->g.nxg == e->g.nx && (use_fused(e) || use_het_fused(e))))
+        return fail(FDTD_ESTATE, "coupled dispersive media need the fused one-step sweeps (3-D, one GPU, no two-pass / physics flag)");
     if (use_fused(e) || use_het_fused(e) || use_yee_fused(e)) if (int rc = ensure_set_b(e)) return rc;
     if (e->cfg.ndim == 2) if (int rc = launch_count2d<T>(e, 0, s)) return rc;
     const bool use_graph = !(e->cfg.flags & FDTD_FLAG_NO_GRAPH) && n >= 32;
@@ -709,7 +749,7 @@ template <typename T> static int run_steps(fdtd_engine* e, int n)
             CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             int rc = 0;
             if (use_tb2(e)) for (int q = 0; q < G && !rc; q += 2) rc = two_steps<T>(e, q, s);
-            else for (int q = 0; q < G && !rc; ++q) rc = one_step<T>(e, q, q, s);
+            else for (int q = 0; q < G && !rc; ++q) rc = one_step<T>(e, q, q, s, ade_sweep_capable(e) && q + 1 < G);
             if (!rc) { k_bump<<<1, 1, 0, s>>>(e->d_step, G); e->launches++; }
             cudaError_t ce = cudaStreamEndCapture(s, &graph);
             e->cur = c0;
@@ -734,7 +774,7 @@ template <typename T> static int run_steps(fdtd_engine* e, int n)
         for (; q + 2 <= rest; q += 2)
             if (int rc = two_steps<T>(e, q, s)) return rc;
     for (; q < rest; ++q)
-        if (int rc = one_step<T>(e, q, done + q, s)) return rc;
+        if (int rc = one_step<T>(e, q, done + q, s, ade_sweep_capable(e) && q + 1 < rest)) return rc;
     if (rest > 0) { k_bump<<<1, 1, 0, s>>>(e->d_step, rest); e->launches++; CU(cudaGetLastError()); }
     return 0;
 }

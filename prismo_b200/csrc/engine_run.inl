@@ -65,7 +65,7 @@ template <typename T> static int run_profiled(fdtd_engine* e, int n, double* out
         if (e->cfg.ndim == 3) rc = step_fields3d<T>(e, 1, s); else rc = launch_pass2d<T>(e, 1, q, s);
         if (rc) return rc;
         CU(cudaEventRecord(ev[3 * q + 2], s));
-        if ((rc = launch_post<T>(e, q, q, s))) return rc;
+        if ((rc = launch_post<T>(e, q, q, s, ade_sweep_capable(e) && q + 1 < n))) return rc;
         CU(cudaEventRecord(ev[3 * q + 3], s));
     }
     k_bump<<<1, 1, 0, s>>>(e->d_step, n); e->launches++;
@@ -132,6 +132,8 @@ extern "C" int fdtd_set_option(fdtd_engine* e, const char* key, int32_t value)
     else if (!strcmp(key, "tb2x_slots")) e->tb2x_slots = std::max(2, (int)value);
     else if (!strcmp(key, "het_fused")) e->het_fused = value ? 1 : 0;
     else if (!strcmp(key, "fused_lx")) e->fused_lx = value;
+    else if (!strcmp(key, "ade_fused")) e->ade_fused = value ? 1 : 0;
+    else if (!strcmp(key, "ade_coupled")) e->ade_coupled = value ? 1 : 0;
     else if (!strcmp(key, "yee_fused")) {
         // the fused physics sweep ping-pongs fields and psi, the two-pass kernels update the current set in place:
         // switch only between runs that start from freshly uploaded / zeroed state

@@ -216,6 +216,7 @@ extern "C" int fdtd_set_coeffs(fdtd_engine* e, const double* ca, const double* c
         if (rc) return rc;
     }
     e->het = true;
+    e->coef_planes = planes;
     drop_graph(e);
     return 0;
 }

@@ -15,7 +15,8 @@ extern "C" int fdtd_ipc_export(fdtd_engine* e, void* blob, int32_t* nbytes)
     if (!e || !nbytes) return fail(FDTD_EINVAL, "fdtd_ipc_export: bad argument");
     if (!blob) { *nbytes = (int32_t)sizeof(IpcBlob); return 0; }
     if (*nbytes < (int32_t)sizeof(IpcBlob)) return fail(FDTD_EINVAL, "blob too small (%d < %d)", *nbytes, (int)sizeof(IpcBlob));
-    if (!use_fused(e)) return fail(FDTD_ESTATE, "peer-to-peer slabs need the fused path (3-D, uniform coefficients)");
+    if (!use_fused(e) && !het_sweep_ok(e))
+        return fail(FDTD_ESTATE, "peer-to-peer slabs need a fused one-sweep path (3-D, no two-pass / physics flag)");
     CU(cudaSetDevice(e->cfg.device));
     if (int rc = ensure_set_b(e)) return rc;
     if (!e->slab.flags) {
@@ -104,7 +105,7 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
     CU(cudaEventRecord(sl.post_done, cs));
     int q = 0;
     while (q < n) {
-        const bool pair = tb2_ok(e) && q + 2 <= n;
+        const bool pair = tb2_ok(e) && q + 2 <= n;        // never for heterogeneous media (tb2_ok needs use_fused)
         const int* planes = pair ? planes2 : planes1;
         const long long st = sl.step;                    // exchange counter, identical on every rank
         if (sl.has_left) {
@@ -124,6 +125,8 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
             if (dbg) { dbg_ev.emplace_back(); cudaEventCreate(&dbg_ev.back()); cudaEventRecord(dbg_ev.back(), cs); }
             if (int rc = launch_tb2<T>(e, q, cs)) return rc;             // flips the sets itself
             if (dbg) { dbg_ev.emplace_back(); cudaEventCreate(&dbg_ev.back()); cudaEventRecord(dbg_ev.back(), cs); }
+        } else if (e->het) {
+            if (int rc = launch_het<T>(e, cs)) return rc;                 // heterogeneous media: flips the sets itself
         } else {
             if (int rc = launch_fused<T>(e, 0, e->g.nx, cs)) return rc;   // reads the current set (+ ghosts)
             e->cur ^= 1;

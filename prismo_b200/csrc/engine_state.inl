@@ -51,6 +51,7 @@ struct fdtd_engine {
     int cur = 0;                    // which set holds the current fields (fused path)
     void* coef[4] = {};             // Ca Cb Da Db arrays (T) or null
     bool het = false;
+    int coef_planes = 0;            // planes of Ca..Db supplied by the caller (nx, or nx + 1 with the right neighbour's first)
     double uni[4] = {1, 0, 1, 0};
     cudaStream_t stream = nullptr;
     // ops
@@ -62,6 +63,9 @@ struct fdtd_engine {
     std::vector<AdeOp> ade; std::vector<unsigned char> ade_mask_host;
     AdeOp* d_ade = nullptr; void* d_aux = nullptr; unsigned char* d_ade_mask = nullptr;
     long long aux_elems = 0, ade_threads = 0;
+    int ade_fused = 1;              // apply the recursions inside the next fused sweep where one follows (0: always k_ade)
+    int ade_coupled = 0;            // OPT-IN, not the reference's behaviour: feed the polarisation current back into E
+    bool ade_deferred = false;      // the recursion of the last enqueued step is still to be applied by the next sweep
     bool ops_dirty = true;
     Cpml cpml{}; SlabGeom slabg{}; double* d_cpml_coef = nullptr; float* d_cpml_coef_f = nullptr; size_t psi_bytes[12] = {};
     void* psiB[12] = {};            // second psi set: the fused physics sweep ping-pongs psi like the fields

@@ -226,9 +226,10 @@ template <typename T, int POL> __device__ __forceinline__ void stv_pol(T* p, con
 
 // TJ owner rows per CTA; blockDim = (32, TJ + 1);  AM = fp64 arithmetic mode (0 exact, 1 folded).
 // (Rejected by measurement, profiles/r01_tuning.md, and removed: evict-first stores, ld.global.cg loads, 2 CTAs x 8 warps.)
-template <typename T, int TJ, int AM>
+// ADE: apply the dispersive-medium recursions of the PREVIOUS step on the E stage's input values (ade_in_sweep).
+template <typename T, int TJ, int AM, bool ADE = false>
 __global__ void __launch_bounds__(32 * (TJ + 1), 1)
-k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold fo)
+k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold fo, AdeIn ad)
 {
     constexpr int POL = 0;
     constexpr int V = VecOf<T>::V;
@@ -319,6 +320,22 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
             P nx_, ny_, nz_;
             stage_e<T, V, true, AM>(c, g, fo, g.x0 + i, jy1, k, e0x, e0y, e0z, hpx, hpy, hpz, hz_j, hx_j, hpy_n, hpx_n,
                                     hny, hnz, nx_, ny_, nz_);
+            if (ADE) {
+                if (owner) {
+                    double jx[V], jy[V], jz[V];
+#pragma unroll
+                    for (int e = 0; e < V; ++e) jx[e] = jy[e] = jz[e] = 0.0;
+                    ade_in_sweep<T, V>(ad, i, j, k, e0x, e0y, e0z, jx, jy, jz);
+                    if (ad.coupled) {
+#pragma unroll
+                        for (int e = 0; e < V; ++e) {                  // op boxes lie inside the updated range of their component
+                            if (jx[e] != 0.0) nx_.v[e] = Ar<T>::sub(nx_.v[e], Ar<T>::mul(c.ucb, (T)jx[e]));
+                            if (jy[e] != 0.0) ny_.v[e] = Ar<T>::sub(ny_.v[e], Ar<T>::mul(c.ucb, (T)jy[e]));
+                            if (jz[e] != 0.0) nz_.v[e] = Ar<T>::sub(nz_.v[e], Ar<T>::mul(c.ucb, (T)jz[e]));
+                        }
+                    }
+                }
+            }
             if (owner) {
                 const long long pe = (long long)i * g.sx;
                 stv_pol<T, POL>(out.ex + o + pe, nx_); stv_pol<T, POL>(out.ey + o + pe, ny_); stv_pol<T, POL>(out.ez + o + pe, nz_);

@@ -19,9 +19,10 @@ constexpr int kHetRows = 16;
 constexpr int kHetOwnLanes = 30;
 template <typename T, int R> constexpr size_t het_smem_bytes() { return 2 * (size_t)R * 8 * 32 * 8; }
 
-template <typename T, int R>
+// ADE: apply the dispersive-medium recursions of the PREVIOUS step on the E stage's input values (ade_in_sweep).
+template <typename T, int R, bool ADE>
 __global__ void __launch_bounds__(32 * R, 1)
-k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, int planes_alloc)
+k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, int planes_alloc, AdeIn ad)
 {
     constexpr int V = Vec8<T>::V;
     typedef Pack<T, V> P;
@@ -38,6 +39,10 @@ k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, i
     const int k = (tk * t.own_lanes + lane) * V;
     const int i0 = t.i_begin + seg * t.lx;
     const int i1 = min(i0 + t.lx, t.i_end);
+    if (t.halo_flag && i1 + 1 >= g.nx) {          // x-slabs: this segment reads E / H up to plane i1+1, ghost planes start at nx
+        if (threadIdx.x == 0 && threadIdx.y == 0) wait_flag_ge(t.halo_flag, t.halo_need, t.error_word, t.timeout_ns);
+        __syncthreads();
+    }
     const bool ld_ok = (j < g.ny) && (k < g.pz);
     const bool owner = ld_ok && row < R - 2 && lane < t.own_lanes;
     const int rown = min(row + 1, R - 1);
@@ -129,6 +134,10 @@ k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, i
             const int gi = g.x0 + i;
             const bool ex0 = gi < g.nxg, ex1 = gi < g.nxg - 1;
             P ox = e0x, oy = e0y, oz = e0z;
+            double jx[V], jy[V], jz[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) jx[e] = jy[e] = jz[e] = 0.0;
+            if (ADE) { if (owner) ade_in_sweep<T, V>(ad, i, j, k, e0x, e0y, e0z, jx, jy, jz); }
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;
@@ -140,13 +149,16 @@ k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, i
                 T n = upd_e<T>(mean4<T>(ca0.v[e], ca0_j.v[e], ca0_k, ca0_jk), e0x.v[e],
                                mean4<T>(cb0.v[e], cb0_j.v[e], cb0_k, cb0_jk),
                                Ar<T>::diff(hz_j.v[e], hpz.v[e], g.dy, g.rdy), Ar<T>::diff(hy_k, hpy.v[e], g.dz, g.rdz));
+                if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(mean4<T>(cb0.v[e], cb0_j.v[e], cb0_k, cb0_jk), (T)jx[e])); }
                 if (ex0 && jy1 && kz1) ox.v[e] = n;
                 n = upd_e<T>(mean4<T>(ca0.v[e], ca1.v[e], ca0_k, ca1_k), e0y.v[e], mean4<T>(cb0.v[e], cb1.v[e], cb0_k, cb1_k),
                              Ar<T>::diff(hx_k, hpx.v[e], g.dz, g.rdz), Ar<T>::diff(hnz.v[e], hpz.v[e], g.dx, g.rdx));
+                if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(mean4<T>(cb0.v[e], cb1.v[e], cb0_k, cb1_k), (T)jy[e])); }
                 if (ex1 && kz1) oy.v[e] = n;
                 n = upd_e<T>(mean4<T>(ca0.v[e], ca1.v[e], ca0_j.v[e], ca1_j.v[e]), e0z.v[e],
                              mean4<T>(cb0.v[e], cb1.v[e], cb0_j.v[e], cb1_j.v[e]),
                              Ar<T>::diff(hny.v[e], hpy.v[e], g.dx, g.rdx), Ar<T>::diff(hx_j.v[e], hpx.v[e], g.dy, g.rdy));
+                if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(mean4<T>(cb0.v[e], cb1.v[e], cb0_j.v[e], cb1_j.v[e]), (T)jz[e])); }
                 if (ex1 && jy1 && kz0) oz.v[e] = n;
             }
             if (owner) {

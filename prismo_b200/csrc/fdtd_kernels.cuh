@@ -486,6 +486,28 @@ struct AdeOp {
     long long cells, first_thread;
 };
 
+// one recursion step of one cell; returns the new state and leaves the old one in `old`
+template <typename T>
+__device__ __forceinline__ double ade_update(const AdeOp& op, long long cell, double e, T* __restrict__ aux,
+                                             const unsigned char* __restrict__ mask, double& old)
+{
+    if (op.mask_off >= 0) e = __dmul_rn(e, mask[op.mask_off + cell] ? 1.0 : 0.0);
+    T* cur = aux + op.cur_off + cell;
+    const double a = (double)*cur;
+    double nv;
+    if (op.kind == 0) {
+        T* prev = aux + op.prev_off + cell;
+        nv = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(op.c0, e), __dmul_rn(op.c1, e)), __dmul_rn(op.c2, a)),
+                       __dmul_rn(op.c3, (double)*prev));
+        *prev = (T)a;
+    } else {
+        nv = __dadd_rn(__dmul_rn(op.c0, e), __dmul_rn(op.c1, a));
+    }
+    *cur = (T)nv;
+    old = a;
+    return nv;
+}
+
 template <typename T>
 __global__ void k_ade(const T* const* __restrict__ comp_ptr, const AdeOp* __restrict__ ops, int n_ops,
                       long long total, Strides3 st, T* __restrict__ aux, const unsigned char* __restrict__ mask)
@@ -501,20 +523,45 @@ __global__ void k_ade(const T* const* __restrict__ comp_ptr, const AdeOp* __rest
     const int c1 = (int)(r % op.n[1]);
     const int c0 = (int)(r / op.n[1]);
     const long long o = (op.lo[0] + c0) * st.s[0] + (op.lo[1] + c1) * st.s[1] + (op.lo[2] + c2) * st.s[2];
-    double e = (double)comp_ptr[op.comp][o];
-    if (op.mask_off >= 0) e = __dmul_rn(e, mask[op.mask_off + cell] ? 1.0 : 0.0);
-    T* cur = aux + op.cur_off + cell;
-    const double a = (double)*cur;
-    double nv;
-    if (op.kind == 0) {
-        T* prev = aux + op.prev_off + cell;
-        nv = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(op.c0, e), __dmul_rn(op.c1, e)), __dmul_rn(op.c2, a)),
-                       __dmul_rn(op.c3, (double)*prev));
-        *prev = (T)a;
-    } else {
-        nv = __dadd_rn(__dmul_rn(op.c0, e), __dmul_rn(op.c1, a));
+    double old;
+    ade_update<T>(op, cell, (double)comp_ptr[op.comp][o], aux, mask, old);
+}
+
+// The same recursions INSIDE a fused sweep (north-star subsystem 4).  The sweep that computes step n+1 holds the final
+// E of step n (sources included) of every owner cell in registers exactly once — as the input of its E stage — so the
+// recursion "after step n" (ADEManager.update_all, materials/ade.py:291-308) is applied right there, one step late in
+// wall-clock order but on the same values: bit-identical to k_ade, and the E array is not read a second time.  The
+// step whose successor sweep is not known yet (last step of an fdtd_run call / of a graph) still uses k_ade.
+//   coupled != 0 (opt-in, NOT the reference's behaviour, which never feeds P back): the polarisation current of the
+//   recursion is subtracted in the same E update,  E+ -= Cb * eps0 * (P+ - P) / dt  (Lorentz, Debye)  or
+//   Cb * eps0 * J+  (Drude) — the reference's recursion coefficients (dispersion.py:189-336) carry no eps0, so P and J
+//   are in units of eps0 —, with the recursion applied at the BEGINNING of every step (oracle/ade.py: coupled_step).
+struct AdeIn { const AdeOp* ops; int n; void* aux; const unsigned char* mask; int coupled; double kp, kj; };   // kp = eps0/dt, kj = eps0
+
+template <typename T, int V>
+__device__ __forceinline__ void ade_in_sweep(const AdeIn& ad, int i, int j, int k, const Pack<T, V>& ex, const Pack<T, V>& ey,
+                                             const Pack<T, V>& ez, double (&jx)[V], double (&jy)[V], double (&jz)[V])
+{
+    for (int q = 0; q < ad.n; ++q) {
+        const AdeOp& op = ad.ops[q];
+        const int a0 = i - op.lo[0], a1 = j - op.lo[1];
+        if ((unsigned)a0 >= (unsigned)op.n[0] || (unsigned)a1 >= (unsigned)op.n[1]) continue;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const int a2 = k + e - op.lo[2];
+            if ((unsigned)a2 >= (unsigned)op.n[2]) continue;
+            const long long cell = ((long long)a0 * op.n[1] + a1) * op.n[2] + a2;
+            const double ev = (double)(op.comp == 0 ? ex.v[e] : (op.comp == 1 ? ey.v[e] : ez.v[e]));
+            double old;
+            const double nv = ade_update<T>(op, cell, ev, (T*)ad.aux, ad.mask, old);
+            if (ad.coupled) {
+                const double term = op.kind == 1 ? __dmul_rn(nv, ad.kj) : __dmul_rn(__dsub_rn(nv, old), ad.kp);
+                if (op.comp == 0) jx[e] = __dadd_rn(jx[e], term);
+                else if (op.comp == 1) jy[e] = __dadd_rn(jy[e], term);
+                else jz[e] = __dadd_rn(jz[e], term);
+            }
+        }
     }
-    *cur = (T)nv;
 }
 
 // Region-correct flux (extension): instantaneous power through a box, P = sum (E x H)_n over the

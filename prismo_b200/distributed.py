@@ -5,7 +5,9 @@ this rank's x-slab: global source / monitor ops are clipped to the slab (plus "g
 the three planes right of the slab, which the two-step sweep recomputes), the step loop is ``PeerSlabRunner`` (CUDA-IPC
 halo push over NVLink) — or ``SlabStepper`` where the engine has no IPC (CPU test double under gloo) — and monitor
 results are re-assembled from the ranks' pieces, so the reference's monitor objects end up with the same data on
-every rank as in a single-GPU run.  Uniform-coefficient 3-D grids only (the fused sweeps).
+every rank as in a single-GPU run.  3-D grids; uniform coefficients (one- and two-step fused sweeps) or heterogeneous
+media (one-step sweep with one static ghost plane of Ca..Db from the right neighbour); dispersive-medium recursions
+and region-correct flux sums are clipped to the slab like the monitors.
 """
 from __future__ import annotations
 
@@ -47,6 +49,7 @@ class SlabExecutor:
         self.dtype, self.dt = self.eng.dtype, dt
         self._runner = None
         self._mon = []           # per global monitor op: (global op, local id or None, local x-range in the box)
+        self._ade, self._flux = [], []
         self._tb2_ok = True
         self._agreed = False
         self._uploaded = False
@@ -61,9 +64,15 @@ class SlabExecutor:
 
     def set_uniform_coeffs(self, *a):
         self.eng.set_uniform_coeffs(*a)
+        self._het = False
 
-    def set_coeffs(self, *a):
-        raise NotImplementedError("heterogeneous media are not slab-decomposed yet (fused sweeps need uniform coefficients)")
+    def set_coeffs(self, Ca, Cb, Da, Db):
+        """Global cell-centred arrays (nx, ny, nz): this rank keeps its planes plus the right neighbour's first one (the
+        E / H updates of the last local plane average coefficients across the cut, core/solver.py:458-533)."""
+        hi = min(self.x0 + self.nxl + 1, self.nxg)
+        self.eng.set_coeffs(*[np.ascontiguousarray(np.asarray(a)[self.x0:hi]) for a in (Ca, Cb, Da, Db)])
+        self._het = True
+        self._tb2_ok = False                      # heterogeneous media step one sweep at a time on every rank
 
     def _runner_(self):
         if self._runner is None:
@@ -100,7 +109,8 @@ class SlabExecutor:
     def clear_ops(self):
         self.eng.clear_ops()
         self._mon = []
-        self._tb2_ok = True
+        self._ade, self._flux = [], []
+        self._tb2_ok = not getattr(self, "_het", False)
         self._agreed = False
 
     def _clip(self, comp, lo, hi):
@@ -134,8 +144,54 @@ class SlabExecutor:
         self._mon.append((op, local, (a - op.lo[0], b - op.lo[0])))
         return len(self._mon) - 1
 
-    def add_ade_op(self, op):
-        raise NotImplementedError("ADE ops are not slab-decomposed yet")
+    def add_ade_op(self, op) -> int:
+        """Cell-local recursion: each rank keeps the part of the box that lies on its planes."""
+        from .engine import AdeOp
+
+        a, b = self._clip(op.component, op.lo, op.hi)
+        op.shape = tuple(h - l for l, h in zip(op.lo, op.hi))
+        local = None
+        if b > a:
+            mask = None if op.mask is None else np.ascontiguousarray(np.asarray(op.mask)[a - op.lo[0]:b - op.lo[0]])
+            local = self.eng.add_ade_op(AdeOp(op.component, op.kind, (a - self.x0,) + tuple(op.lo[1:]),
+                                              (b - self.x0,) + tuple(op.hi[1:]), op.c0, op.c1, op.c2, op.c3, mask))
+        self._ade.append((op, local, (a - op.lo[0], b - op.lo[0])))
+        self._tb2_ok = False
+        return len(self._ade) - 1
+
+    def ade_state(self, idx, which=0):
+        op, local, (a, b) = self._ade[idx]
+        mine = self.eng.ade_state(local, which) if local is not None else None
+        pieces = [None] * self.world
+        self.dist.all_gather_object(pieces, (a, b, mine), group=self.group)
+        out = np.zeros(op.shape)
+        for pa, pb, arr in pieces:
+            if arr is not None:
+                out[pa:pb] = arr
+        return out
+
+    def set_ade_state(self, idx, which, values):
+        op, local, (a, b) = self._ade[idx]
+        if local is not None:
+            self.eng.set_ade_state(local, which, np.ascontiguousarray(np.asarray(values)[a:b]))
+
+    def add_flux_op(self, direction, lo, hi) -> int:
+        """Power through a box: per-rank partial sums over the planes it owns (all six components must exist there)."""
+        a, b = max(lo[0], self.x0), min(hi[0], self.x0 + min(self._planes(c) for c in ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")))
+        local = self.eng.add_flux_op(direction, (a - self.x0,) + tuple(lo[1:]), (b - self.x0,) + tuple(hi[1:])) if b > a else None
+        self._flux.append(local)
+        self._tb2_ok = False
+        return len(self._flux) - 1
+
+    def flux(self, idx, steps):
+        local = self._flux[idx]
+        mine = self.eng.flux(local, steps) if local is not None else np.zeros(steps)
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, mine, group=self.group)
+        out = np.zeros(steps)
+        for p in parts:                            # fixed rank order: every rank gets the same bits
+            out = out + p
+        return out
 
     def set_tables(self, n_steps, amp=None, phasors=None):
         self.eng.set_tables(n_steps, amp, phasors)

@@ -2,10 +2,19 @@
 
 Protocol per ``advance(n)`` call (SURVEY §8b "Step entry"):
   1. (re)compile sources/monitors into device ops           -> lowering.lower
-  2. push coefficients if they changed, push the six host field arrays (honours user-set fields)
-  3. tabulate amplitudes / phasors for the n steps on the host, run them on the device in chunks
-  4. pull fields back into the SAME NumPy objects, fill the monitors' own result attributes
-The host arrays stay the user-visible truth between calls, like the reference's in-place arrays.
+  2. push coefficients if they changed; push the host field arrays THE USER MAY HAVE TOUCHED since the last call
+  3. tabulate amplitudes / phasors for the n steps on the host (the next chunk's while the device runs the current
+     one), run them on the device in chunks
+  4. fill the monitors' own result attributes; the fields STAY ON THE DEVICE
+
+Field residency.  The reference's ``ElectromagneticFields`` (core/fields.py:61-144) keeps its arrays in the dict
+``_fields`` and every access — ``fields["Ez"]``, ``fields.Ez``, ``copy_fields_from``, ``zero_fields`` — goes through
+that dict.  The session swaps the dict for a ``ResidentFields`` (a dict subclass) holding the same NumPy arrays:
+  * after a run the host arrays are STALE; the first access to a component downloads it into the SAME array object,
+  * an array that was handed out may have been written through, so it is uploaded again by the next advance(),
+  * components nobody looked at never cross PCIe: a ``sim.step()`` loop or ``run(progress_callback=...)`` that does
+    not read fields moves nothing, one that reads ``Ez`` moves Ez (down once per access point, up once per advance).
+Containers without a ``_fields`` dict fall back to push-all / pull-all.
 """
 from __future__ import annotations
 
@@ -53,8 +62,62 @@ def _device_count() -> int:
         return 1
 
 
+class ResidentFields(dict):
+    """``fields._fields`` while a Session owns the device copy: component -> host mirror (the user's own array)."""
+
+    def __init__(self, base, session):
+        super().__init__(base)
+        self.session = session
+        self.stale = set()                      # host mirror older than the device copy
+        self.touched = set(base)                # host mirror possibly newer than the device copy (handed out / replaced)
+
+    def _raw(self, c):
+        return dict.__getitem__(self, c)
+
+    def __getitem__(self, c):
+        a = dict.__getitem__(self, c)
+        if c in self.stale:
+            self.session._download_into(c, a)
+            self.stale.discard(c)
+        self.touched.add(c)
+        return a
+
+    def __setitem__(self, c, a):
+        dict.__setitem__(self, c, a)
+        self.stale.discard(c)
+        self.touched.add(c)
+
+    def get(self, c, default=None):
+        return self[c] if c in self else default
+
+    def values(self):
+        return [self[c] for c in self.keys()]
+
+    def items(self):
+        return [(c, self[c]) for c in self.keys()]
+
+    def sync_all(self):
+        """Bring every host mirror up to date (the device copy is about to go away or be replaced)."""
+        for c in list(self.stale):
+            self.session._download_into(c, dict.__getitem__(self, c))
+        self.stale.clear()
+
+    def detach(self):
+        self.sync_all()
+        self.touched = set(self.keys())
+
+
 def _fingerprint(arrs):
-    return tuple((id(a), a.shape, float(a.flat[0]), float(a.flat[-1]), float(a.sum())) for a in arrs)
+    """Identity + a strided sample (<= 64 Ki elements) of every coefficient array: O(1) per advance() instead of three
+    full-grid reductions.  The reference builds Ca..Db once per MaxwellUpdater (core/solver.py:113-133) and never edits
+    them; an in-place edit that misses the sample needs ``session.invalidate_coefficients()``."""
+    out = []
+    for a in arrs:
+        flat = a.reshape(-1) if a.flags.c_contiguous else a.ravel()
+        step = max(1, flat.size // 65536)
+        sample = flat[::step]
+        out.append((id(a), a.shape, float(flat[0]), float(flat[-1]), float(sample.sum()), float(sample.min()), float(sample.max())))
+    return tuple(out)
 
 
 class Session:
@@ -89,9 +152,18 @@ class Session:
         if physics and params.thickness > 0:
             self.engine.set_cpml(params.thickness, cpml.coefficient_table(g.dimensions, g.spacing, self.dt, params))
         self._coef_sig = None
+        self._resident = None                   # the ResidentFields this session currently backs (if any)
+        self.h2d_arrays = self.d2h_arrays = 0   # field arrays moved so far (tests / diagnostics)
 
     def close(self):
+        if self._resident is not None:
+            self._resident.detach()
+            self._resident = None
         self.engine.close()
+
+    def invalidate_coefficients(self) -> None:
+        """Force the next advance() to re-send Ca, Cb, Da, Db (after editing them in place)."""
+        self._coef_sig = None
 
     # ---- coefficients ---------------------------------------------------------------------------------
     def set_coefficients(self, Ca, Cb, Da, Db) -> None:
@@ -106,24 +178,58 @@ class Session:
         sig = _fingerprint(arrs)
         if sig == self._coef_sig:
             return
-        if all(a.min() == a.max() for a in arrs):    # piecewise-constant everywhere -> the fused sweeps apply
+        if all(a.min() == a.max() for a in arrs):    # constant everywhere -> the uniform fused sweeps apply
             self.engine.set_uniform_coeffs(*[float(a.flat[0]) for a in arrs])
         else:
             self.engine.set_coeffs(*arrs)
         self._coef_sig = sig
 
     # ---- fields ------------------------------------------------------------------------------------------
+    def _download_into(self, c, a) -> None:
+        if isinstance(a, np.ndarray):
+            self.engine.download(c, a)
+        else:                                   # array-likes of foreign backends
+            a[...] = self.engine.download(c)
+        self.d2h_arrays += 1
+
+    def _bind(self, fields):
+        """The ResidentFields behind `fields` (installing it on first use), or None for unknown containers."""
+        d = getattr(fields, "_fields", None)
+        if not isinstance(d, dict) or os.environ.get("PRISMO_B200_RESIDENT", "1") == "0":
+            return None
+        if isinstance(d, ResidentFields) and d.session is not self:
+            d.detach()                          # another session's device copy: bring the host up to date first
+            d.session = self
+        elif not isinstance(d, ResidentFields):
+            d = ResidentFields(d, self)
+            fields._fields = d
+        if self._resident is not d:
+            if self._resident is not None:
+                self._resident.detach()
+            d.touched = set(d.keys())           # this engine has never seen these arrays
+            self._resident = d
+        return d
+
     def push_fields(self, fields) -> None:
+        d = self._bind(fields)
+        if d is None:
+            for c in COMPONENTS:
+                self.engine.upload(c, fields[c])
+                self.h2d_arrays += 1
+            return
         for c in COMPONENTS:
-            self.engine.upload(c, fields[c])
+            if c in d.touched:
+                self.engine.upload(c, d._raw(c))
+                self.h2d_arrays += 1
+        d.touched.clear()
 
     def pull_fields(self, fields) -> None:
-        for c in COMPONENTS:
-            a = fields[c]
-            if isinstance(a, np.ndarray):
-                self.engine.download(c, a)
-            else:                               # array-likes of foreign backends
-                a[...] = self.engine.download(c)
+        d = self._bind(fields)
+        if d is None:
+            for c in COMPONENTS:
+                self._download_into(c, fields[c])
+            return
+        d.stale = set(COMPONENTS)               # downloaded lazily, on access
 
     # ---- stepping ------------------------------------------------------------------------------------------
     @staticmethod
@@ -157,19 +263,27 @@ class Session:
             if rec:
                 chunk = max(1, min(chunk, _RECORD_POOL_BYTES // rec))
         self.push_fields(fields)
-        done, t = 0, t0
-        first = True
-        while done < n:
+        tabled = bool(prog.src_ops or prog.mon_ops or prog.flux_ops)
+
+        def plan(done, t):
             m = min(chunk, n - done)
             times = self.step_times(t, dt, m)
-            if prog.src_ops or prog.mon_ops or prog.flux_ops:
-                amp, ph = prog.tables(times, dt)
-                eng.set_tables(m, amp, ph)
+            return m, times, (prog.tables(times, dt) if tabled else None)
+
+        done, t = 0, t0
+        first = True
+        nxt = plan(0, t0)
+        while done < n:
+            m, times, tabs = nxt
+            if tabled:
+                eng.set_tables(m, *tabs)
             if first:
                 for b in prog.binders:
                     b.preload(eng)
                 first = False
-            eng.run(m)
+            eng.run(m)                          # asynchronous: the device works while the host tabulates the next chunk
+            if done + m < n:
+                nxt = plan(done + m, times[-1])
             for b in prog.binders:
                 b.collect(eng, times, dt, m)
             t = times[-1]

@@ -198,3 +198,53 @@ def test_region_correct_flux_monitor_and_s_parameter_helpers(fake):
     mode = types.SimpleNamespace(**S.make_mode(8, 8, 5))
     a = pp.mode_coefficient_from_dft(fm, mode, 0)
     assert np.isfinite(a) and pp.s_parameter(a, a) == 1
+
+
+# ---- field residency (session.ResidentFields) --------------------------------------------------------------------
+def test_fields_stay_resident_between_advances(fake):
+    """A step loop that does not look at the fields moves them once up and never down; reading one component brings
+    that component down (into the SAME array object) and sends it up again with the next advance; results are the
+    ones of the push-all / pull-all protocol."""
+    spec = S.SCENARIOS["src3d_plane"]
+    gold = dict(np.load(os.path.join(GOLD, "src3d_plane.npz")))
+    sim = S.build_mirror(spec, pb)
+    ez_obj = sim.fields._fields["Ez"] if not isinstance(sim.fields._fields, session.ResidentFields) else sim.fields._fields._raw("Ez")
+    sess = sim.solver.updater.session()
+    for _ in range(3):
+        sim.step()
+    assert (sess.h2d_arrays, sess.d2h_arrays) == (6, 0)
+    assert isinstance(sim.fields._fields, session.ResidentFields) and sim.fields._fields.stale == set(S.COMPONENTS)
+    ez = sim.fields["Ez"]                                   # lazy download of ONE component
+    assert ez is ez_obj and (sess.h2d_arrays, sess.d2h_arrays) == (6, 1)
+    assert sim.fields.Ez is ez and sess.d2h_arrays == 1     # second look: already fresh
+    sim.run_steps(spec["steps"] - 3)
+    assert (sess.h2d_arrays, sess.d2h_arrays) == (7, 1)     # only the array that was handed out went up again
+    _compare("src3d_plane", S.results_mirror(sim), gold)
+    assert sess.d2h_arrays == 7
+
+
+def test_user_writes_between_advances_are_honoured(fake):
+    spec = S.SCENARIOS["upd3d_vac"]
+    a, b = S.build_mirror(spec, pb), S.build_mirror(spec, pb)
+    for sim in (a, b):
+        sim.run_steps(2)
+    a.fields["Ey"][3, 2, 1] += 0.25                       # write through the handed-out array
+    b.fields["Ey"] = np.array(b.fields["Ey"]) ; b.fields["Ey"][3, 2, 1] += 0.25     # __setitem__ path
+    for sim in (a, b):
+        sim.run_steps(2)
+    for c in S.COMPONENTS:
+        assert np.array_equal(a.fields[c], b.fields[c])
+    ref = S.build_mirror(spec, pb)
+    ref.run_steps(4)
+    assert not np.array_equal(ref.fields["Hz"], a.fields["Hz"])
+
+
+def test_closing_a_session_brings_the_host_up_to_date(fake):
+    spec = S.SCENARIOS["upd3d_vac"]
+    a, b = S.build_mirror(spec, pb), S.build_mirror(spec, pb)
+    a.run_steps(3)
+    b.run_steps(3)
+    a.solver.updater.session().close()
+    assert not a.fields._fields.stale
+    for c in S.COMPONENTS:
+        assert np.array_equal(a.fields._fields._raw(c), b.fields[c])
