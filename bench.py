@@ -190,17 +190,69 @@ def make_engine(dims, dtype, rank=0, world=1, device=0, flags=0, span=None):
     return eng, dt, spacing, x0, nxl
 
 
-def set_ridge_coefficients(eng, dims, dt):
-    """config 3 shape: Si ridge (eps 12.11) along x on an SiO2 (2.07) half space, air above; Ca=Da=1 (lossless)."""
+def ridge_box(dims):
+    """(j0, j1, k0, k1) of the Si core of the config-3 ridge waveguide."""
     nx, ny, nz = dims
+    return ny // 2 - ny // 16, ny // 2 + ny // 16, nz // 2, nz // 2 + nz // 12
+
+
+def ridge_eps(dims):
+    """config 3 cross-section: Si ridge (eps 12.11) along x on an SiO2 (2.07) half space, air above."""
+    nx, ny, nz = dims
+    j0, j1, k0, k1 = ridge_box(dims)
     eps = np.ones((ny, nz), dtype=np.float64)
     eps[:, : nz // 2] = 2.07
-    eps[ny // 2 - ny // 16: ny // 2 + ny // 16, nz // 2: nz // 2 + nz // 12] = 12.11
+    eps[j0:j1, k0:k1] = 12.11
+    return eps
+
+
+def ridge_coefficients(dims, dt, x_planes, jk=None):
+    """Ca, Cb, Da, Db (lossless: Ca = Da = 1) of x_planes planes, optionally restricted to a (j, k) window."""
     eps0, mu0 = 8.854187817e-12, 4 * np.pi * 1e-7
-    cb = np.broadcast_to(dt / (eps0 * eps), (nx, ny, nz))
-    one = np.broadcast_to(np.ones((1, 1)), (nx, ny, nz))
-    eng.set_coeffs(np.ascontiguousarray(one), np.ascontiguousarray(cb), np.ascontiguousarray(one),
-                   np.ascontiguousarray(one * (dt / mu0)))
+    eps = ridge_eps(dims)
+    if jk is not None:
+        eps = eps[jk[0]:jk[1], jk[2]:jk[3]]
+    shp = (x_planes,) + eps.shape
+    one = np.ones(shp)
+    return one, np.ascontiguousarray(np.broadcast_to(dt / (eps0 * eps), shp)), one, one * (dt / mu0)
+
+
+def set_ridge_coefficients(eng, dims, dt, planes=None):
+    eng.set_coeffs(*ridge_coefficients(dims, dt, dims[0] if planes is None else planes))
+
+
+def ridge_mode_profiles(dims):
+    """Transverse profile of the config-3 mode source: a Gaussian centred on the Si core (stands in for the solved
+    mode profile a ModeSource injects, sources/mode.py:255-361), per injected component, on its own (ny', nz') grid."""
+    nx, ny, nz = dims
+    j0, j1, k0, k1 = ridge_box(dims)
+    out = {}
+    for c in ("Ey", "Hz"):
+        sy, sz = (ny, nz - 1)
+        y = (np.arange(sy) - 0.5 * (j0 + j1)) / max(0.5 * (j1 - j0), 1.0)
+        z = (np.arange(sz) - 0.5 * (k0 + k1)) / max(0.5 * (k1 - k0), 1.0)
+        out[c] = np.exp(-(y[:, None] ** 2) - (z[None, :] ** 2))
+    return out
+
+
+def ridge_ade_ops(dims, dt, x0=0, nxl=None):
+    """One Lorentz pole (Sellmeier-like resonance at 1.2 um) on the Si core, per E component, clipped to planes
+    [x0, x0 + nxl): materials/dispersion.py:189-231 coefficients, materials/ade.py:116-134 recursion."""
+    from prismo_b200.engine import AdeOp
+
+    nx, ny, nz = dims
+    nxl = nx if nxl is None else nxl
+    j0, j1, k0, k1 = ridge_box(dims)
+    w0, de, gam = 2 * np.pi * C0 / 1.2e-6, 1.0, 1e13
+    den = 4.0 + 2 * gam * dt + w0 ** 2 * dt ** 2
+    c0 = 2 * de * w0 ** 2 * dt ** 2 / den
+    c2, c3 = (8.0 - 2 * w0 ** 2 * dt ** 2) / den, -(4.0 - 2 * gam * dt + w0 ** 2 * dt ** 2) / den
+    last = x0 + nxl == nx
+    ops = []
+    for c, short in (("Ex", (0, 1, 1)), ("Ey", (1, 0, 1)), ("Ez", (1, 1, 0))):
+        hi_x = nxl - (1 if (short[0] and last) else 0)
+        ops.append(AdeOp(c, 0, (0, j0, k0), (hi_x, j1 - short[1], k1 - short[2]), c0, c0, c2, c3))
+    return ops
 
 
 def seed_fields(eng, dims, x0=0):
@@ -217,7 +269,7 @@ def fields_sha(eng):
     return BC.sha_of_checksums({c: eng.plane_checksums(c) for c in COMPONENTS})
 
 
-def self_check(eng, dims, dt, spacing, args, mon_ids, do_oracle):
+def self_check(eng, dims, dt, spacing, args, mon_ids, do_oracle, coef_fn=None, src_profile=None):
     """Re-seed, run a few steps, compare two crops and the DFT plane with the oracle, checksum the fields (bench_check.py)."""
     import bench_check as BC
 
@@ -236,7 +288,8 @@ def self_check(eng, dims, dt, spacing, args, mon_ids, do_oracle):
 
     return BC.run_check(dims, dt, spacing, args.dtype, tables, dims[0] // 4, (3 * dims[0]) // 4, reseed, eng.run,
                         lambda c, lo, hi: eng.download_box(c, lo, hi), fetch_dft,
-                        lambda: {c: eng.plane_checksums(c) for c in COMPONENTS}, do_oracle=do_oracle and bool(mon_ids))
+                        lambda: {c: eng.plane_checksums(c) for c in COMPONENTS}, do_oracle=do_oracle and bool(mon_ids),
+                        coef_fn=coef_fn, src_profile=src_profile)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -407,9 +460,18 @@ def main():
 
         thick = int(os.environ.get("FDTD_B200_BENCH_CPML", "10"))       # 0: tuning experiment (no absorbing layer)
         eng.set_cpml(thick, cpml.coefficient_table(dims, spacing, dt, cpml.PMLParams(thickness=max(thick, 1))))
+    real_c3 = name == "c3" and not args.no_ops and not args.physics      # BASELINE config 3 as named: het + ADE + mode source
+    if real_c3:
+        args.het = True
     if args.het:
         set_ridge_coefficients(eng, dims, dt)
     src, mon = workload_ops(dims, dt, spacing)
+    src_profile = None
+    if real_c3:
+        src_profile = ridge_mode_profiles(dims)
+        src = [pb.SourceOp(o.component, o.lo, o.hi, o.table, src_profile[o.component][None, :, :]) for o in src]
+        for op in ridge_ade_ops(dims, dt):
+            eng.add_ade_op(op)
     if args.no_ops:
         src, mon = [], []
     for op in src:
@@ -445,7 +507,9 @@ def main():
     achieved = bpc * cells * args.steps / (kern_ms * 1e-3) / 1e9
     fused = not (args.two_pass or args.physics)
     tb2 = fused and os.environ.get("FDTD_B200_TB2", "1") != "0" and args.steps >= 2 and not args.het
-    kname = ("k_fused3d_tb2 (1 launch per TWO steps)" if tb2 else "k_fused3d (1 launch/step)") if fused \
+    kname = ("k_fused3d_tb2x (TMA-fed, 1 launch per TWO steps)" if tb2 else
+             ("k_fused3d_het" + ("<ADE> (dispersive recursions applied in-sweep)" if real_c3 else "") + " (1 launch/step, "
+              "6 field + 4 coefficient arrays read, 6 written)") if args.het else "k_fused3d (1 launch/step)") if fused \
         else ({"2": "k_fused3d_yeex (physics mode: Yee leap-frog + CPML slabs in ONE TMA-fed sweep per step, psi ping-pong)",
                "1": "k_fused3d_yee (physics mode: Yee leap-frog + CPML slabs fused into ONE sweep per step, psi ping-pong)",
                "0": "k_h3d_yee + k_e3d_yee (physics mode: Yee leap-frog + CPML slabs, 2 launches/step)"}[
@@ -475,7 +539,11 @@ def main():
 
     check = None
     if not args.no_check:
-        check = self_check(eng, dims, dt, spacing, args, mon_ids, do_oracle=not (args.physics or args.het or args.no_ops))
+        coef_fn = None
+        if args.het:
+            coef_fn = lambda lo, sd: ridge_coefficients(dims, dt, sd[0], (lo[1], lo[1] + sd[1], lo[2], lo[2] + sd[2]))  # noqa: E731
+        check = self_check(eng, dims, dt, spacing, args, mon_ids, do_oracle=not (args.physics or args.no_ops),
+                           coef_fn=coef_fn, src_profile=src_profile)
         check["timed_fields_sha"] = timed_sha
 
     cpu = None
@@ -489,8 +557,12 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64",
             "data": "synthetic",
-            "config": {"workload": f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} vacuum (uniform coefficients), TFSF +x "
-                                   f"plane source, FieldMonitor DFT plane (Ey,Hz x 5 freq)",
+            "config": {"workload": (f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} Si ridge on SiO2 (cell-centred Ca,Cb,Da,Db arrays), "
+                                    f"Lorentz pole on the core (3 recursions, in-sweep), profiled mode-source plane, FieldMonitor "
+                                    f"DFT plane (Ey,Hz x 5 freq)") if real_c3 else
+                                   (f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} " + ("Si ridge on SiO2 (cell-centred coefficient arrays)"
+                                    if args.het else "vacuum (uniform coefficients)") + ", TFSF +x "
+                                    f"plane source, FieldMonitor DFT plane (Ey,Hz x 5 freq)"),
                        "l2": f"working set {2 * bpc // 2 * cells / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"
                              if cells * bpc / 2 > 1e9 else "working set fits L2: HBM fraction not meaningful",
                        "parallelism": "1 GPU", "kernel_path": ("temporally blocked fused sweep (2 steps per HBM pass), ping-pong" if tb2 else

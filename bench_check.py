@@ -81,9 +81,12 @@ def crop_plan(dims, src_plane, mon_plane, n=N_CHECK):
     return crops
 
 
-def oracle_crop(planes, dims, dt, spacing, lo, size, amp, phasors, src_plane, mon_plane, n=N_CHECK):
+def oracle_crop(planes, dims, dt, spacing, lo, size, amp, phasors, src_plane, mon_plane, n=N_CHECK, coef_fn=None,
+                src_profile=None):
     """Advance the crop with the oracle; returns the final crop fields and, if the crop starts at the monitor plane, the
-    DFT sums of (Ey, Hz) over its first plane."""
+    DFT sums of (Ey, Hz) over its first plane.  coef_fn(lo, sdims) -> (Ca, Cb, Da, Db) of the crop for heterogeneous
+    media (None: vacuum); src_profile: {component: global (ny', nz') profile} of a profiled plane source (None: the
+    uniform TFSF plane)."""
     from oracle import kernels
 
     sdims = tuple(s + 2 * n + 2 for s in size)
@@ -91,7 +94,7 @@ def oracle_crop(planes, dims, dt, spacing, lo, size, amp, phasors, src_plane, mo
     for c in COMPONENTS:
         shp = comp_shape(c, sdims)
         sub[c] = seed_box(planes, c, lo, tuple(l + s for l, s in zip(lo, shp))).astype(np.float64)
-    coeffs = kernels.vacuum_coefficients(sdims, dt)
+    coeffs = kernels.vacuum_coefficients(sdims, dt) if coef_fn is None else coef_fn(lo, sdims)
     isrc = src_plane - lo[0]
     dft = None
     if lo[0] == mon_plane:
@@ -99,8 +102,12 @@ def oracle_crop(planes, dims, dt, spacing, lo, size, amp, phasors, src_plane, mo
     for s in range(n):
         kernels.step(sub, coeffs, spacing, False)
         if 0 <= isrc < sdims[0] - 1:                       # TFSF plane (tfsf.py:333-338): whole-plane injection
-            sub["Ey"][isrc] += amp[s, 0]
-            sub["Hz"][isrc] += amp[s, 1]
+            for col, c in enumerate(("Ey", "Hz")):
+                if src_profile is None:
+                    sub[c][isrc] += amp[s, col]
+                else:                                      # mode-source style: amplitude x transverse profile (mode.py:255-361)
+                    shp = sub[c].shape
+                    sub[c][isrc] += amp[s, col] * src_profile[c][lo[1]:lo[1] + shp[1], lo[2]:lo[2] + shp[2]]
         if dft is not None:
             for c in dft:
                 d = sub[c][0, :size[1], :size[2]]
@@ -126,7 +133,7 @@ def sha_of_checksums(per_comp):
 
 
 def run_check(dims, dt, spacing, dtype, tables_fn, src_plane, mon_plane, reseed, run_steps, fetch_box, fetch_dft,
-              fetch_checksums, do_oracle=True, n=N_CHECK):
+              fetch_checksums, do_oracle=True, n=N_CHECK, coef_fn=None, src_profile=None):
     """Drive the check through callables so the single-GPU and the slab-decomposed bench share it.
 
       reseed()                 upload the seeded state, zero the DFT sums, install tables for n steps from t = 0
@@ -149,7 +156,7 @@ def run_check(dims, dt, spacing, dtype, tables_fn, src_plane, mon_plane, reseed,
                 gd = {c: fetch_dft(c, lo[1:], hi[1:]) for c in ("Ey", "Hz")}
             if got["Ex"] is None:
                 continue                                   # not rank 0
-            want, wd = oracle_crop(planes, dims, dt, spacing, lo, size, amp, ph, src_plane, mon_plane, n)
+            want, wd = oracle_crop(planes, dims, dt, spacing, lo, size, amp, ph, src_plane, mon_plane, n, coef_fn, src_profile)
             for c in COMPONENTS:
                 worst = max(worst, rel_l2(got[c], want[c]))
                 exact = exact and bool(np.array_equal(got[c], want[c]))

@@ -202,6 +202,14 @@ int  fdtd_download_box(fdtd_engine* e, int32_t component, const int32_t* lo, con
  * x-slab decomposition, so the concatenation over ranks is identical at 1/2/4/8 GPUs iff the fields are.          */
 int  fdtd_field_checksum(fdtd_engine* e, int32_t component, uint64_t* out, int32_t planes);
 
+/* Mode-overlap numerator on the RESIDENT DFT planes of six monitor ops that share one plane box and one frequency list
+ * (monitor_ids in component order Ex..Hz; the two normal components are not read):
+ *   out[f] = 0.5 * sum_cells [ (E_sim x conj(H_mode))_n + (E_mode x conj(H_sim))_n ]     (re, im), f = 0..n_freq-1
+ * i.e. the sum of utils/mode_matching.py:104-118 before "* dx * dy / mode_power", which the caller applies (the mode's own
+ * power is a host-side constant).  direction 0/1/2 = plane normal x/y/z; mode = host complex128 [6][cells] (Ex..Hz on the
+ * cells of the box, C order).  Replaces downloading 6 x n_freq planes to evaluate the sum in NumPy.              */
+int  fdtd_mode_overlap(fdtd_engine* e, const int32_t* monitor_ids, int32_t direction, const double* mode, double* out);
+
 /* ---- introspection ----------------------------------------------------------------------------------- */
 int  fdtd_steps_done(fdtd_engine* e, int64_t* steps);
 int  fdtd_kernel_launches(fdtd_engine* e, int64_t* launches); /* kernels launched by this handle  */

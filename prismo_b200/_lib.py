@@ -98,6 +98,7 @@ _PROTOS = {
     "fdtd_upload_dft": (C.c_int, [_P, C.c_int32, _P]),
     "fdtd_download_box": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
     "fdtd_field_checksum": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),
+    "fdtd_mode_overlap": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32, _P, _P]),
     "fdtd_steps_done": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "fdtd_kernel_launches": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "fdtd_mem_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -104,6 +104,48 @@ extern "C" int fdtd_field_checksum(fdtd_engine* e, int32_t comp, uint64_t* out, 
     return 0;
 }
 
+// ---- mode overlap on the resident DFT planes --------------------------------------------------------------
+extern "C" int fdtd_mode_overlap(fdtd_engine* e, const int32_t* monitor_ids, int32_t direction, const double* mode, double* out)
+{
+    if (!e || !monitor_ids || !mode || !out || direction < 0 || direction > 2)
+        return fail(FDTD_EINVAL, "fdtd_mode_overlap: bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    if (int rc = finalize_ops(e)) return rc;
+    // tangential components (e1, h2, e2, h1) of  S_n = e1 x conj(h2) - e2 x conj(h1)   (mode_matching.py:104-115)
+    static const int pick[3][4] = {{FDTD_EY, FDTD_HZ, FDTD_EZ, FDTD_HY}, {FDTD_EZ, FDTD_HX, FDTD_EX, FDTD_HZ},
+                                   {FDTD_EX, FDTD_HY, FDTD_EY, FDTD_HX}};
+    OverlapIn in{};
+    int nf = -1;
+    for (int q = 0; q < 4; ++q) {
+        const int id = monitor_ids[pick[direction][q]];
+        if (id < 0 || id >= (int)e->mon.size()) return fail(FDTD_EINVAL, "fdtd_mode_overlap: monitor id %d out of range", id);
+        const MonOp& m = e->mon[id];
+        if (m.comp != pick[direction][q]) return fail(FDTD_EINVAL, "fdtd_mode_overlap: monitor %d samples component %d, expected %d", id, m.comp, pick[direction][q]);
+        if (m.n_freq <= 0) return fail(FDTD_EINVAL, "fdtd_mode_overlap: monitor %d has no running DFT", id);
+        if (q == 0) { in.cells = m.cells; nf = m.n_freq; }
+        if (m.cells != in.cells || m.n_freq != nf) return fail(FDTD_EINVAL, "fdtd_mode_overlap: the monitors do not share one box / frequency list");
+        in.off[q] = m.dft_off;
+    }
+    const size_t mode_bytes = (size_t)4 * in.cells * sizeof(double2);
+    const size_t part_bytes = (size_t)nf * FLUX_BLOCKS * sizeof(double2), out_bytes = (size_t)nf * sizeof(double2);
+    if (int rc = ensure_stage(e, mode_bytes + part_bytes + out_bytes)) return rc;
+    char* base = (char*)e->d_stage;
+    // mode: host (6, cells) complex128 in component order Ex..Hz; only the four tangential planes travel
+    for (int q = 0; q < 4; ++q)
+        CU(cudaMemcpyAsync(base + (size_t)q * in.cells * sizeof(double2), mode + (size_t)pick[direction][q] * in.cells * 2,
+                           (size_t)in.cells * sizeof(double2), cudaMemcpyHostToDevice, e->stream));
+    double2* partial = (double2*)(base + mode_bytes);
+    double2* d_out = (double2*)(base + mode_bytes + part_bytes);
+    dim3 grid(FLUX_BLOCKS, (unsigned)nf);
+    k_overlap_partial<<<grid, 256, 0, e->stream>>>(e->d_dft, in, (const double2*)base, partial);
+    k_overlap_final<<<(nf + 63) / 64, 64, 0, e->stream>>>(partial, nf, d_out);
+    e->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
 // ---- introspection ---------------------------------------------------------------------------------------------------
 extern "C" int fdtd_steps_done(fdtd_engine* e, int64_t* steps)
 {

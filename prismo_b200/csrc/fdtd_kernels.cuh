@@ -611,6 +611,51 @@ __global__ void k_flux_final(const FluxOp* __restrict__ ops, int n_ops, const do
     out[ops[q].out_off * n_steps + (*step_ptr + step_off)] = s;
 }
 
+// Mode-overlap numerator over a monitor plane, per frequency (utils/mode_matching.py:41-131):
+//   0.5 * sum_cells [ (e1*conj(m_h2) - e2*conj(m_h1)) + (m_e1*conj(h2) - m_e2*conj(h1)) ]
+// (e1, h2, e2, h1) = the four tangential DFT planes the direction selects, m_* the mode's fields on the same cells.
+// Deterministic: FLUX_BLOCKS partial sums per frequency (grid-stride, tree reduce), then added in block order.
+struct OverlapIn { long long off[4]; long long cells; };      // offsets of the e1, h2, e2, h1 DFT planes of frequency 0
+
+__device__ __forceinline__ double2 cmul_conj(double2 a, double2 b)     // a * conj(b)
+{
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+__global__ void __launch_bounds__(256)
+k_overlap_partial(const double2* __restrict__ dft, OverlapIn in, const double2* __restrict__ mode, double2* __restrict__ partial)
+{
+    const int f = blockIdx.y;
+    const double2* e1 = dft + in.off[0] + f * in.cells; const double2* h2 = dft + in.off[1] + f * in.cells;
+    const double2* e2 = dft + in.off[2] + f * in.cells; const double2* h1 = dft + in.off[3] + f * in.cells;
+    const double2* me1 = mode; const double2* mh2 = mode + in.cells;
+    const double2* me2 = mode + 2 * in.cells; const double2* mh1 = mode + 3 * in.cells;
+    double2 acc = make_double2(0.0, 0.0);
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < in.cells; c += (long long)gridDim.x * blockDim.x) {
+        const double2 a = cmul_conj(e1[c], mh2[c]), b = cmul_conj(e2[c], mh1[c]);
+        const double2 p = cmul_conj(me1[c], h2[c]), q = cmul_conj(me2[c], h1[c]);
+        acc.x += (a.x - b.x) + (p.x - q.x);
+        acc.y += (a.y - b.y) + (p.y - q.y);
+    }
+    __shared__ double2 sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) { sh[threadIdx.x].x += sh[threadIdx.x + w].x; sh[threadIdx.x].y += sh[threadIdx.x + w].y; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[f * FLUX_BLOCKS + blockIdx.x] = sh[0];
+}
+
+__global__ void k_overlap_final(const double2* __restrict__ partial, int n_freq, double2* __restrict__ out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_freq) return;
+    double2 s = make_double2(0.0, 0.0);
+    for (int b = 0; b < FLUX_BLOCKS; ++b) { s.x += partial[f * FLUX_BLOCKS + b].x; s.y += partial[f * FLUX_BLOCKS + b].y; }
+    out[f] = make_double2(0.5 * s.x, 0.5 * s.y);
+}
+
 __global__ void k_bump(int* step_ptr, int n) { *step_ptr += n; }
 
 // =================================================================================================

@@ -198,6 +198,7 @@ class Engine:
 
     # ---- ops --------------------------------------------------------------------------------------------------
     def clear_ops(self):
+        self.ops_epoch = getattr(self, "ops_epoch", 0) + 1      # device handles to monitor ops die here
         _lib.check(self._lib.fdtd_clear_ops(self._h))
         self._mon_ops = []
         self._ade_ops = []
@@ -357,6 +358,18 @@ class Engine:
         out = np.zeros((op.n_freq,) + op.shape, dtype=np.complex128)
         if out.size:
             _lib.check(self._lib.fdtd_download_dft(self._h, monitor_id, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def mode_overlap(self, monitor_ids, direction: str, mode_fields) -> np.ndarray:
+        """0.5 * sum((E_sim x H_mode*)_n + (E_mode x H_sim*)_n) per frequency over the plane the six DFT monitor ops
+        `monitor_ids` (Ex..Hz order) share, reduced on the device (fdtd_mode_overlap).  mode_fields: six arrays (Ex..Hz)
+        of the box shape."""
+        op = self._mon_ops[monitor_ids[0]]
+        m = np.ascontiguousarray(np.stack([np.asarray(a, dtype=np.complex128).reshape(op.shape) for a in mode_fields]))
+        out = np.zeros(op.n_freq, dtype=np.complex128)
+        ids = (C.c_int32 * 6)(*[int(i) for i in monitor_ids])
+        _lib.check(self._lib.fdtd_mode_overlap(self._h, ids, "xyz".index(direction), m.ctypes.data_as(C.c_void_p),
+                                               out.ctypes.data_as(C.c_void_p)))
         return out
 
     def set_dft(self, monitor_id: int, values) -> None:

@@ -418,8 +418,14 @@ class _FluxRegionBinder(_Binder):
         dA = {"x": dy * (dz if dz else 1.0), "y": dx * (dz if dz else 1.0), "z": dx * dy}[m.direction]
         m._power_flow_history.extend(float(v) * dA for v in engine.flux(self.flux_id, n))
         m._time_history.extend(times)
+
+    def finish(self, engine):
+        # the six DFT planes come down once per advance(), not once per chunk; until the next advance() they are also
+        # still on the device, where postprocess.mode_coefficients reduces them without moving them
         for c, i in self.ids.items():
-            getattr(m, "_dft_" + c.lower())[...] = engine.dft(i)
+            getattr(self.m, "_dft_" + c.lower())[...] = engine.dft(i)
+        if self.ids and hasattr(engine, "mode_overlap"):
+            self.m._b200_device = (engine, [self.ids[c] for c in COMPONENTS], getattr(engine, "ops_epoch", 0))
 
 
 class _FluxBinder(_PatchBinder):

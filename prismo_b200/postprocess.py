@@ -84,6 +84,51 @@ def mode_coefficient_from_dft(flux_monitor, mode, frequency_index: int) -> compl
     return mode_overlap(tuple(six), mode, d, du, dv if dv else 1.0)
 
 
+def mode_coefficients(flux_monitor, mode) -> np.ndarray:
+    """Mode coefficient at every frequency of a region-correct FluxMonitor.  While the monitor's DFT planes are still
+    resident on the device (after the advance() that filled them, before the next one) the plane sums run there
+    (fdtd_mode_overlap: 4 planes of the mode go up, n_freq complex numbers come down); otherwise on the host arrays."""
+    d = flux_monitor.direction
+    sp = flux_monitor._grid.spacing
+    du, dv = [sp[a] for a in range(3) if "xyz"[a] != d][:2]
+    dv = dv if dv else 1.0
+    dev = getattr(flux_monitor, "_b200_device", None)
+    nf = len(flux_monitor._dft_ex)
+    if dev is not None and getattr(dev[0], "ops_epoch", -1) == dev[2] and getattr(dev[0], "_h", None):
+        shape = np.squeeze(flux_monitor._dft_ex[0]).shape
+        fields = [_resize(np.asarray(getattr(mode, c)), shape) for c in _C]
+        box = flux_monitor._dft_ex[0].shape
+        num = dev[0].mode_overlap(dev[1], d, [f.reshape(box) for f in fields])
+        power = mode_power(mode, d, du, dv)
+        return num * du * dv / power if abs(power) > 1e-20 else np.zeros(nf, dtype=np.complex128)
+    return np.array([mode_coefficient_from_dft(flux_monitor, mode, i) for i in range(nf)])
+
+
+def separate_forward_backward(coefficient_left, coefficient_right, neff, distance, wavelength):
+    """Forward / backward amplitudes from two planes a known distance apart (utils/mode_matching.py:228-293):
+    a_L = a_f + a_b,  a_R = a_f e^{i phi} + a_b e^{-i phi},  phi = 2 pi Re(neff) d / lambda."""
+    phi = 2 * np.pi * np.real(neff) / wavelength * distance
+    ep, em = np.exp(1j * phi), np.exp(-1j * phi)
+    det = ep - em
+    if abs(det) > 1e-10:
+        return (coefficient_right - coefficient_left * em) / det, (coefficient_left * ep - coefficient_right) / det
+    return coefficient_right, 0.0
+
+
+def two_port_s_parameters(port1_pair, port2_pair, mode1, mode2, neff1, neff2, distance, wavelengths):
+    """S11 and S21 per frequency from two pairs of region-correct FluxMonitors (left / right plane of each port), port 1
+    excited: S11 = b1 / a1 and S21 = a2 / a1 (analysis/sparameters.py:88-122 with forward / backward mode amplitudes)."""
+    cl1, cr1 = mode_coefficients(port1_pair[0], mode1), mode_coefficients(port1_pair[1], mode1)
+    cl2, cr2 = mode_coefficients(port2_pair[0], mode2), mode_coefficients(port2_pair[1], mode2)
+    s11, s21 = [], []
+    for i, lam in enumerate(wavelengths):
+        a1, b1 = separate_forward_backward(cl1[i], cr1[i], neff1, distance, lam)
+        a2, _ = separate_forward_backward(cl2[i], cr2[i], neff2, distance, lam)
+        s11.append(b1 / a1 if a1 != 0 else complex("nan"))
+        s21.append(a2 / a1 if a1 != 0 else complex("nan"))
+    return np.array(s11), np.array(s21)
+
+
 def s_parameter(coefficient_out: complex, coefficient_in: complex) -> complex:
     """S_ij = a_out / a_in for mode coefficients taken at the output and input port planes."""
     return coefficient_out / coefficient_in if coefficient_in != 0 else complex("nan")

@@ -66,8 +66,27 @@ def main():
             m = [pb.MonitorOp("Ez", (i, 0, 0), (i + 1,) + shape_of("Ez")[1:], False, 2, 0)]
         return s, m
 
+    het = "--het" in sys.argv                    # heterogeneous media + a Drude recursion whose box crosses every cut
+    crng = np.random.default_rng(8)
+    coef = [1 - 0.1 * crng.random(dims), (dt / 8.854187817e-12) / (1 + 11 * crng.random(dims)), 1 - 0.1 * crng.random(dims),
+            np.full(dims, dt / (4e-7 * np.pi)) * (1 + 0.2 * crng.random(dims))]
+    ade_box = ((1, 2, 3), (dims[0] - 2, dims[1] - 3, dims[2] - 4))
+
+    def medium(e, x0, nxl):
+        from prismo_b200.engine import AdeOp
+
+        if not het:
+            return None
+        hi = min(x0 + nxl + 1, dims[0])
+        e.set_coeffs(*[a[x0:hi] for a in coef])
+        a, b = max(ade_box[0][0], x0), min(ade_box[1][0], x0 + e.field_shape("Ex")[0])
+        if b <= a:
+            return None
+        return e.add_ade_op(AdeOp("Ex", 1, (a - x0,) + ade_box[0][1:], (b - x0,) + ade_box[1][1:], 0.3, 0.9)), a, b
+
     x0, nxl = slab_range(dims[0], rank, world)
     eng = pb.Engine(3, (nxl, dims[1], dims[2]), spacing, dt, dtype=dtype, device=local, nx_global=dims[0], x_offset=x0)
+    my_ade = medium(eng, x0, nxl)
     for c in comps:
         eng.upload(c, init[c][x0:x0 + eng.field_shape(c)[0]])
     s_ops, m_ops = ops(x0, nxl, eng.field_shape)
@@ -82,11 +101,13 @@ def main():
     mine = {c: eng.download(c) for c in comps}
     mine["dft"] = eng.dft(ids[0]) if ids else None
     mine["x0"] = x0
+    mine["ade"] = (my_ade[1], my_ade[2], eng.ade_state(my_ade[0], 0)) if my_ade else None
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     ok = True
     if rank == 0:
         whole = pb.Engine(3, dims, spacing, dt, dtype=dtype, device=local)
+        whole_ade = medium(whole, 0, dims[0])
         for c in comps:
             whole.upload(c, init[c])
         s_ops, m_ops = ops(0, dims[0], whole.field_shape)
@@ -104,7 +125,13 @@ def main():
             if g["dft"] is not None and not np.array_equal(g["dft"], whole.dft(wid[0])):
                 ok = False
                 print("MISMATCH dft")
-        print(f"MULTI_GPU_CHECK {'OK' if ok else 'FAILED'} world={world} mode={mode} dtype={dtype} dims={dims}", flush=True)
+            if g["ade"] is not None:
+                a, b, st = g["ade"]
+                want = whole.ade_state(whole_ade[0], 0)[a - ade_box[0][0]:b - ade_box[0][0]]
+                if not (np.abs(st).max() > 0 and np.array_equal(st, want)):
+                    ok = False
+                    print(f"MISMATCH ade state planes [{a},{b})")
+        print(f"MULTI_GPU_CHECK {'OK' if ok else 'FAILED'} world={world} mode={mode} dtype={dtype} dims={dims} het={het}", flush=True)
         whole.close()
     eng.close()
     dist.barrier()
@@ -127,7 +154,7 @@ def sim_check(same):
     dist.init_process_group("gloo" if same else "nccl")
     pb.configure(device=local)
     ok = True
-    names = ["upd3d_vac", "src3d_point", "src3d_plane", "src3d_tfsf", "src3d_mode", "mon3d_field"]
+    names = ["upd3d_vac", "src3d_point", "src3d_plane", "src3d_tfsf", "src3d_mode", "mon3d_field", "upd3d_het", "ade3d"]
     for name in names:
         spec = S.SCENARIOS[name]
         gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))

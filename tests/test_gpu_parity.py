@@ -386,3 +386,50 @@ def test_region_correct_flux_monitor_3d_vs_oracle():
         assert abs(a - b) <= 1e-12 * sc
     assert np.array_equal(fm._dft_ey[0], dft)
     assert np.isfinite(fm.get_frequency_domain_power()).all()
+
+
+def test_device_mode_overlap_matches_reference_formula():
+    """the mode-overlap sums of utils/mode_matching.py:41-131 reduced on the device over the resident
+    DFT planes of a region-correct FluxMonitor, against (a) postprocess.mode_overlap on the downloaded planes (the NumPy
+    restatement, itself bit-exact against the reference in the CPU suite) and (b) the reference's own
+    compute_mode_overlap when the reference is importable.  Summation order differs: 1e-12 relative."""
+    from types import SimpleNamespace
+
+    from prismo_b200 import postprocess as PP
+
+    spec = dict(S.SCENARIOS["src3d_plane"], monitors=[])
+    sim = S.build_mirror(spec, pb, dtype="float64")
+    freqs = [0.9 * S.F0, S.F0, 1.1 * S.F0]
+    fm = pb.FluxMonitor((0.3e-6, 0.25e-6, 0.2e-6), (0.0, 0.3e-6, 0.2e-6), "x", frequencies=freqs, region_correct=True)
+    sim.add_monitor(fm)
+    sim.run_steps(9)
+    shape = np.squeeze(fm._dft_ex[0]).shape
+    rng = np.random.default_rng(2)
+    mode = SimpleNamespace(**{c: rng.standard_normal(shape) + 1j * rng.standard_normal(shape) for c in S.COMPONENTS})
+    assert fm._b200_device[2] == fm._b200_device[0].ops_epoch
+    dev = PP.mode_coefficients(fm, mode)
+    host = np.array([PP.mode_coefficient_from_dft(fm, mode, i) for i in range(len(freqs))])
+    assert dev.shape == host.shape == (3,) and np.abs(host).min() > 0
+    assert np.abs(dev - host).max() <= 1e-12 * np.abs(host).max()
+    # forward / backward split and S-parameter helper: algebraic identity on synthetic amplitudes
+    af, ab, neff, d, lam = 0.8 - 0.1j, 0.05 + 0.2j, 2.4, 0.31e-6, 1.55e-6
+    phi = 2 * np.pi * neff / lam * d
+    f, b = PP.separate_forward_backward(af + ab, af * np.exp(1j * phi) + ab * np.exp(-1j * phi), neff, d, lam)
+    assert abs(f - af) < 1e-12 and abs(b - ab) < 1e-12
+    try:
+        from oracle import ref_loader
+
+        if not ref_loader.available():
+            return
+        ref_loader.load()
+        from prismo.utils.mode_matching import compute_mode_overlap
+    except Exception:
+        return
+    sp = sim.grid.spacing
+    for i in range(len(freqs)):
+        six = [np.squeeze(getattr(fm, "_dft_" + c.lower())[i]) for c in S.COMPONENTS]
+        want = compute_mode_overlap(*six, mode, "x", sp[1], sp[2])
+        assert abs(dev[i] - want) <= 1e-12 * abs(want)
+    # the next advance() re-installs the ops: a fresh handle replaces the stale one
+    sim.run_steps(1)
+    assert fm._b200_device[2] == fm._b200_device[0].ops_epoch

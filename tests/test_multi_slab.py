@@ -231,7 +231,7 @@ def test_two_slabs_on_one_gpu_match_single_engine(dtype):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["p2p", "sim"])
+@pytest.mark.parametrize("mode", ["p2p", "sim", "het"])
 def test_peer_to_peer_slabs_two_processes_one_gpu(mode):
     """The production halo protocol (CUDA IPC mappings, DMA push, release/acquire flags, in-kernel wait) with two
     processes time-slicing one GPU: bitwise equal to a single engine.  Halo waits time out after 5 s."""
@@ -241,7 +241,7 @@ def test_peer_to_peer_slabs_two_processes_one_gpu(mode):
     env = dict(os.environ, FDTD_B200_HALO_TIMEOUT_MS="5000")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(os.path.dirname(__file__), "multi_gpu_check.py"),
-           "--same-device"] + (["--sim"] if mode == "sim" else [])
+           "--same-device"] + {"sim": ["--sim"], "het": ["--het"], "p2p": []}[mode]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     want = "MULTI_GPU_SIM_CHECK OK" if mode == "sim" else "MULTI_GPU_CHECK OK"
     assert want in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
@@ -261,8 +261,6 @@ def test_peer_to_peer_slabs_on_all_gpus(args):
     n = _cuda_devices()
     if n < 2:
         pytest.skip("needs >= 2 CUDA devices")
-    if "--het" in args:
-        pytest.importorskip("prismo_b200")
     env = dict(os.environ, FDTD_B200_HALO_TIMEOUT_MS="20000")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(os.path.dirname(__file__), "multi_gpu_check.py")] + args
