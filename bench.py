@@ -190,69 +190,188 @@ def make_engine(dims, dtype, rank=0, world=1, device=0, flags=0, span=None):
     return eng, dt, spacing, x0, nxl
 
 
-def ridge_box(dims):
-    """(j0, j1, k0, k1) of the Si core of the config-3 ridge waveguide."""
-    nx, ny, nz = dims
-    return ny // 2 - ny // 16, ny // 2 + ny // 16, nz // 2, nz // 2 + nz // 12
+class Medium:
+    """Heterogeneous media of the named configs, x-invariant cross-sections on the (ny, nz) plane.
+      c3  one Si ridge (eps 12.11) on an SiO2 (2.07) half space, air above; one Lorentz pole on the core.
+      c5  directional coupler: two such ridges a gap apart; a gold pad (Drude pole, eps_inf = 1) beside them over the
+          middle quarter of the length.  (The named config's anisotropic cladding is not modelled: the E stage applies
+          one Cb per cell, see DESIGN.md "out of scope".)"""
+
+    def __init__(self, name, dims):
+        self.name, self.dims = name, dims
+        nx, ny, nz = dims
+        w, h = ny // 16, max(nz // 12, 2)
+        if name == "c5":
+            gap = max(w // 2, 2)
+            self.cores = [(ny // 2 - gap // 2 - w, ny // 2 - gap // 2, nz // 2, nz // 2 + h),
+                          (ny // 2 + gap - gap // 2, ny // 2 + gap - gap // 2 + w, nz // 2, nz // 2 + h)]
+            self.pad = ((3 * nx) // 8, (5 * nx) // 8, ny // 2 + ny // 8, ny // 2 + ny // 8 + w, nz // 2, nz // 2 + max(h // 2, 1))
+        else:
+            self.cores = [(ny // 2 - ny // 16, ny // 2 + ny // 16, nz // 2, nz // 2 + h)]
+            self.pad = None
+
+    def eps(self):
+        nx, ny, nz = self.dims
+        eps = np.ones((ny, nz), dtype=np.float64)
+        eps[:, : nz // 2] = 2.07
+        for j0, j1, k0, k1 in self.cores:
+            eps[j0:j1, k0:k1] = 12.11
+        return eps
+
+    def coefficients(self, dt, x_planes, jk=None):
+        """Ca, Cb, Da, Db (lossless: Ca = Da = 1) of x_planes planes, optionally restricted to a (j, k) window."""
+        eps0, mu0 = 8.854187817e-12, 4 * np.pi * 1e-7
+        eps = self.eps()
+        if jk is not None:
+            eps = eps[jk[0]:jk[1], jk[2]:jk[3]]
+        shp = (x_planes,) + eps.shape
+        one = np.ones(shp)
+        return one, np.ascontiguousarray(np.broadcast_to(dt / (eps0 * eps), shp)), one, one * (dt / mu0)
+
+    def mode_profiles(self):
+        """Transverse profile of the mode source: a Gaussian centred on the (first) Si core — it stands in for the solved
+        mode profile a ModeSource injects (sources/mode.py:255-361) — per injected component on its own (ny', nz') grid."""
+        nx, ny, nz = self.dims
+        j0, j1, k0, k1 = self.cores[0]
+        y = (np.arange(ny) - 0.5 * (j0 + j1)) / max(0.5 * (j1 - j0), 1.0)
+        z = (np.arange(nz - 1) - 0.5 * (k0 + k1)) / max(0.5 * (k1 - k0), 1.0)
+        prof = np.exp(-(y[:, None] ** 2) - (z[None, :] ** 2))
+        return {"Ey": prof, "Hz": prof}
+
+    def ade_ops(self, dt, x0=0, nxl=None):
+        """Recursions clipped to planes [x0, x0 + nxl).  c3: one Lorentz pole (resonance at 1.2 um) on the core; c5: the same
+        on both cores plus a Drude pole (gold: omega_p = 1.37e16 rad/s, gamma = 4.05e13 1/s) on the pad — coefficients of
+        materials/dispersion.py:189-231 and :267-286, recursions of materials/ade.py:116-149."""
+        from prismo_b200.engine import AdeOp
+
+        nx, ny, nz = self.dims
+        nxl = nx if nxl is None else nxl
+        w0, de, gam = 2 * np.pi * C0 / 1.2e-6, 1.0, 1e13
+        den = 4.0 + 2 * gam * dt + w0 ** 2 * dt ** 2
+        c0 = 2 * de * w0 ** 2 * dt ** 2 / den
+        c2, c3 = (8.0 - 2 * w0 ** 2 * dt ** 2) / den, -(4.0 - 2 * gam * dt + w0 ** 2 * dt ** 2) / den
+        ops = []
+        shorts = (("Ex", (0, 1, 1)), ("Ey", (1, 0, 1)), ("Ez", (1, 1, 0)))
+
+        def clip(c, short, a, b):
+            planes = nxl - (1 if (short[0] and x0 + nxl == nx) else 0)        # this component's local x extent
+            return max(a - x0, 0), min(b - x0, planes)
+
+        for j0, j1, k0, k1 in self.cores:
+            for c, short in shorts:
+                a, b = clip(c, short, 0, nx)
+                if b > a:
+                    ops.append(AdeOp(c, 0, (a, j0, k0), (b, j1 - short[1], k1 - short[2]), c0, c0, c2, c3))
+        if self.pad is not None:
+            i0, i1, j0, j1, k0, k1 = self.pad
+            e = np.exp(-4.05e13 * dt)
+            d0 = 1.37e16 ** 2 / 4.05e13 * (1.0 - e)
+            for c, short in shorts:
+                a, b = clip(c, short, i0, i1)
+                if b > a:
+                    ops.append(AdeOp(c, 1, (a, j0, k0), (b, j1 - short[1], k1 - short[2]), d0, e))
+        return ops
 
 
-def ridge_eps(dims):
-    """config 3 cross-section: Si ridge (eps 12.11) along x on an SiO2 (2.07) half space, air above."""
-    nx, ny, nz = dims
-    j0, j1, k0, k1 = ridge_box(dims)
-    eps = np.ones((ny, nz), dtype=np.float64)
-    eps[:, : nz // 2] = 2.07
-    eps[j0:j1, k0:k1] = 12.11
-    return eps
+def workload_text(name, dims):
+    if name == "c5":
+        return (f"c5: 3-D {dims[0]}x{dims[1]}x{dims[2]} directional coupler (two Si ridges on SiO2, cell-centred Ca,Cb,Da,Db "
+                "arrays), Lorentz pole on both cores + Au Drude pad (9 recursions), profiled mode-source plane, 2 ports x 2 "
+                "planes x 6 components x 3-frequency DFT + FieldMonitor DFT plane; mode-overlap S-parameters reduced on the "
+                "device (anisotropic cladding of the named config not modelled)")
+    return (f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} Si ridge on SiO2 (cell-centred Ca,Cb,Da,Db arrays), Lorentz pole on "
+            "the core (3 recursions, in-sweep), profiled mode-source plane, FieldMonitor DFT plane (Ey,Hz x 5 freq)")
 
 
-def ridge_coefficients(dims, dt, x_planes, jk=None):
-    """Ca, Cb, Da, Db (lossless: Ca = Da = 1) of x_planes planes, optionally restricted to a (j, k) window."""
-    eps0, mu0 = 8.854187817e-12, 4 * np.pi * 1e-7
-    eps = ridge_eps(dims)
-    if jk is not None:
-        eps = eps[jk[0]:jk[1], jk[2]:jk[3]]
-    shp = (x_planes,) + eps.shape
-    one = np.ones(shp)
-    return one, np.ascontiguousarray(np.broadcast_to(dt / (eps0 * eps), shp)), one, one * (dt / mu0)
-
-
-def set_ridge_coefficients(eng, dims, dt, planes=None):
-    eng.set_coeffs(*ridge_coefficients(dims, dt, dims[0] if planes is None else planes))
-
-
-def ridge_mode_profiles(dims):
-    """Transverse profile of the config-3 mode source: a Gaussian centred on the Si core (stands in for the solved
-    mode profile a ModeSource injects, sources/mode.py:255-361), per injected component, on its own (ny', nz') grid."""
-    nx, ny, nz = dims
-    j0, j1, k0, k1 = ridge_box(dims)
-    out = {}
-    for c in ("Ey", "Hz"):
-        sy, sz = (ny, nz - 1)
-        y = (np.arange(sy) - 0.5 * (j0 + j1)) / max(0.5 * (j1 - j0), 1.0)
-        z = (np.arange(sz) - 0.5 * (k0 + k1)) / max(0.5 * (k1 - k0), 1.0)
-        out[c] = np.exp(-(y[:, None] ** 2) - (z[None, :] ** 2))
-    return out
-
-
-def ridge_ade_ops(dims, dt, x0=0, nxl=None):
-    """One Lorentz pole (Sellmeier-like resonance at 1.2 um) on the Si core, per E component, clipped to planes
-    [x0, x0 + nxl): materials/dispersion.py:189-231 coefficients, materials/ade.py:116-134 recursion."""
-    from prismo_b200.engine import AdeOp
+def port_monitor_ops(dims, x0=0, nxl=None, n_freq=3):
+    """config 5: two ports, two planes each (8 planes apart), all six components on the box common to them, n_freq running
+    DFTs each — what a pair of region-correct FluxMonitors per port lowers to (prismo_b200/lowering.py:_FluxRegionBinder).
+    Returns [(port, which, global plane, [MonitorOp x 6 clipped to the slab or None])]."""
+    import prismo_b200 as pb
 
     nx, ny, nz = dims
     nxl = nx if nxl is None else nxl
-    j0, j1, k0, k1 = ridge_box(dims)
-    w0, de, gam = 2 * np.pi * C0 / 1.2e-6, 1.0, 1e13
-    den = 4.0 + 2 * gam * dt + w0 ** 2 * dt ** 2
-    c0 = 2 * de * w0 ** 2 * dt ** 2 / den
-    c2, c3 = (8.0 - 2 * w0 ** 2 * dt ** 2) / den, -(4.0 - 2 * gam * dt + w0 ** 2 * dt ** 2) / den
-    last = x0 + nxl == nx
-    ops = []
-    for c, short in (("Ex", (0, 1, 1)), ("Ey", (1, 0, 1)), ("Ez", (1, 1, 0))):
-        hi_x = nxl - (1 if (short[0] and last) else 0)
-        ops.append(AdeOp(c, 0, (0, j0, k0), (hi_x, j1 - short[1], k1 - short[2]), c0, c0, c2, c3))
-    return ops
+    planes = [(0, 0, nx // 8), (0, 1, nx // 8 + 8), (1, 0, (7 * nx) // 8 - 8), (1, 1, (7 * nx) // 8)]
+    out = []
+    for port, which, p in planes:
+        ops = None
+        if x0 <= p < x0 + nxl:
+            i = p - x0
+            ops = [pb.MonitorOp(c, (i, 0, 0), (i + 1, ny - 1, nz - 1), False, n_freq, 0) for c in COMPONENTS]
+        out.append((port, which, p, ops))
+    return out
+
+
+def install_workload(eng, name, dims, dt, spacing, args, x0=0, nxl=None):
+    """Coefficients, sources, monitors and recursions of the named workload on this engine (one GPU or one x-slab).
+    Returns a dict: mon_ids (the Ey / Hz DFT plane of the self-check), ports, src_profile, coef_fn, medium, real."""
+    import prismo_b200 as pb
+
+    nx = dims[0]
+    nxl = nx if nxl is None else nxl
+    real = name in ("c3", "c5") and not args.no_ops and not args.physics     # the BASELINE configs as named
+    if real:
+        args.het = True
+    med = Medium(name, dims) if args.het else None
+    if med is not None:
+        eng.set_coeffs(*med.coefficients(dt, min(nxl + 1, nx - x0)))        # + the right neighbour's first plane on a slab
+    src, mon = workload_ops(dims, dt, spacing, x0, nxl)
+    src_profile, ports = None, []
+    if real:
+        src_profile = med.mode_profiles()
+        # (no ghost copies: heterogeneous media step one sweep at a time, which never recomputes a neighbour's planes)
+        src = [pb.SourceOp(o.component, o.lo, o.hi, o.table, src_profile[o.component][None, :, :]) for o in src if not o.ghost]
+        for op in med.ade_ops(dt, x0, nxl):
+            eng.add_ade_op(op)
+    if args.no_ops:
+        src, mon = [], []
+    for op in src:
+        eng.add_source_op(op)
+    mon_ids = [eng.add_monitor_op(op) for op in mon]
+    if real and name == "c5":
+        for port, which, p, ops in port_monitor_ops(dims, x0, nxl):
+            ports.append((port, which, p, None if ops is None else [eng.add_monitor_op(o) for o in ops]))
+    coef_fn = None
+    if med is not None:
+        coef_fn = lambda lo, sd: med.coefficients(dt, sd[0], (lo[1], lo[1] + sd[1], lo[2], lo[2] + sd[2]))  # noqa: E731
+    return {"mon_ids": mon_ids, "mon": mon, "ports": ports, "src_profile": src_profile, "coef_fn": coef_fn, "medium": med,
+            "real": real}
+
+
+def port_s_parameters(eng, ports, med, dims, spacing, gather=None):
+    """2-port S-parameters of config 5 from the four resident DFT planes: mode-overlap sums on the device
+    (fdtd_mode_overlap), forward / backward split between the two planes of a port, S11 = b1/a1, S21 = a2/a1
+    (prismo_b200/postprocess.py; utils/mode_matching.py:41-131, :228-293; analysis/sparameters.py:88-122).
+    gather: callable merging {(port, which): coefficients} over ranks (x-slabs), None on one GPU."""
+    from types import SimpleNamespace
+
+    from prismo_b200 import postprocess as PP
+
+    nx, ny, nz = dims
+    prof = med.mode_profiles()["Ey"][: ny - 1, : nz - 1]
+    zero = np.zeros_like(prof)
+    eta = 377.0 / np.sqrt(12.11)
+    mode = SimpleNamespace(Ex=zero, Ey=prof, Ez=zero, Hx=zero, Hy=zero, Hz=prof / eta)      # +x-going quasi-TE profile
+    power = PP.mode_power(mode, "x", spacing[1], spacing[2])
+    mine = {}
+    for port, which, p, ids in ports:
+        if ids is not None:
+            num = eng.mode_overlap(ids, "x", [getattr(mode, c)[None, :, :] for c in COMPONENTS])
+            mine[(port, which)] = num * spacing[1] * spacing[2] / power
+    coeffs = gather(mine) if gather else mine
+    if coeffs is None or len(coeffs) < 4:
+        return None
+    lams = C0 / (F0 * np.linspace(0.9, 1.1, 5)[:3])
+    s11, s21 = [], []
+    for i, lam in enumerate(lams):
+        a1, b1 = PP.separate_forward_backward(coeffs[(0, 0)][i], coeffs[(0, 1)][i], 2.4, 8 * spacing[0], lam)
+        a2, _ = PP.separate_forward_backward(coeffs[(1, 0)][i], coeffs[(1, 1)][i], 2.4, 8 * spacing[0], lam)
+        s11.append(b1 / a1)
+        s21.append(a2 / a1)
+    fmt = lambda v: [[float(np.real(x)), float(np.imag(x))] for x in v]  # noqa: E731
+    return {"wavelengths_um": [float(x * 1e6) for x in lams], "S11": fmt(s11), "S21": fmt(s21),
+            "note": "mode-overlap sums reduced on the device over resident DFT planes; the reference's update scheme is "
+                    "unstable (SURVEY F4), so the values exercise the extraction path, not a physical device"}
 
 
 def seed_fields(eng, dims, x0=0):
@@ -460,23 +579,8 @@ def main():
 
         thick = int(os.environ.get("FDTD_B200_BENCH_CPML", "10"))       # 0: tuning experiment (no absorbing layer)
         eng.set_cpml(thick, cpml.coefficient_table(dims, spacing, dt, cpml.PMLParams(thickness=max(thick, 1))))
-    real_c3 = name == "c3" and not args.no_ops and not args.physics      # BASELINE config 3 as named: het + ADE + mode source
-    if real_c3:
-        args.het = True
-    if args.het:
-        set_ridge_coefficients(eng, dims, dt)
-    src, mon = workload_ops(dims, dt, spacing)
-    src_profile = None
-    if real_c3:
-        src_profile = ridge_mode_profiles(dims)
-        src = [pb.SourceOp(o.component, o.lo, o.hi, o.table, src_profile[o.component][None, :, :]) for o in src]
-        for op in ridge_ade_ops(dims, dt):
-            eng.add_ade_op(op)
-    if args.no_ops:
-        src, mon = [], []
-    for op in src:
-        eng.add_source_op(op)
-    mon_ids = [eng.add_monitor_op(op) for op in mon]
+    wl = install_workload(eng, name, dims, dt, spacing, args)
+    mon_ids, src_profile, real_c3 = wl["mon_ids"], wl["src_profile"], wl["real"]
     total_steps = args.warmup + args.steps
     amp, ph, _ = tables(total_steps, dt)
     eng.set_tables(total_steps, amp, ph)
@@ -497,6 +601,7 @@ def main():
             prof = eng.run_profiled(args.steps)
     launches = eng.kernel_launches - l0
     timed_sha = fields_sha(eng)                  # state after W + K steps: comparable across N for equal W, K
+    s_params = port_s_parameters(eng, wl["ports"], wl["medium"], dims, spacing) if wl["ports"] else None
     ms = prof["total_ms"]
     value = cells * args.steps / (ms * 1e-3)
 
@@ -539,11 +644,8 @@ def main():
 
     check = None
     if not args.no_check:
-        coef_fn = None
-        if args.het:
-            coef_fn = lambda lo, sd: ridge_coefficients(dims, dt, sd[0], (lo[1], lo[1] + sd[1], lo[2], lo[2] + sd[2]))  # noqa: E731
         check = self_check(eng, dims, dt, spacing, args, mon_ids, do_oracle=not (args.physics or args.no_ops),
-                           coef_fn=coef_fn, src_profile=src_profile)
+                           coef_fn=wl["coef_fn"], src_profile=src_profile)
         check["timed_fields_sha"] = timed_sha
 
     cpu = None
@@ -557,9 +659,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64",
             "data": "synthetic",
-            "config": {"workload": (f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} Si ridge on SiO2 (cell-centred Ca,Cb,Da,Db arrays), "
-                                    f"Lorentz pole on the core (3 recursions, in-sweep), profiled mode-source plane, FieldMonitor "
-                                    f"DFT plane (Ey,Hz x 5 freq)") if real_c3 else
+            "config": {"workload": workload_text(name, dims) if real_c3 else
                                    (f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} " + ("Si ridge on SiO2 (cell-centred coefficient arrays)"
                                     if args.het else "vacuum (uniform coefficients)") + ", TFSF +x "
                                     f"plane source, FieldMonitor DFT plane (Ey,Hz x 5 freq)"),
@@ -571,6 +671,8 @@ def main():
                                          + ("fused one-sweep step" if os.environ.get("FDTD_B200_YEE_FUSED", "2") != "0" else "two-pass"))
                                         if args.physics else "two-pass")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(), "check": check}
+    if s_params is not None:
+        line["s_params"] = s_params
     print(json.dumps(line), flush=True)
     eng.close()
 

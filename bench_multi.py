@@ -35,12 +35,11 @@ def run_multi(args, rank, world, local):
         except ValueError:                       # grid too small for >= 4 planes per rank: equal slabs
             span, balanced = None, False
     eng, dt, spacing, x0, nxl = B.make_engine(dims, args.dtype, rank, world, device=local, span=span)
-    src, mon = B.workload_ops(dims, dt, spacing, x0, nxl)
-    if args.no_ops:
-        src, mon = [], []
-    for op in src:
-        eng.add_source_op(op)
-    mon_ids = [eng.add_monitor_op(op) for op in mon]
+    wl = B.install_workload(eng, name, dims, dt, spacing, args, x0, nxl)
+    mon, mon_ids = wl["mon"], wl["mon_ids"]
+    het = wl["medium"] is not None
+    if het:
+        eng.set_option("tb2", 0)                 # heterogeneous media: one sweep per step on every rank
     total = args.warmup + args.steps
     amp, ph, _ = B.tables(total, dt)
     eng.set_tables(total, amp, ph)
@@ -81,6 +80,17 @@ def run_multi(args, rank, world, local):
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
 
     timed_cs = gather_checksums(eng, rank, world, dist)
+    s_params = None
+    if wl["ports"]:
+        def merge(mine):
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+            out = {}
+            for p in parts:
+                out.update(p)
+            return out
+
+        s_params = B.port_s_parameters(eng, wl["ports"], wl["medium"], dims, spacing, gather=merge)
 
     # e2e: host buffers in / out on every rank, wall clock, max over ranks
     e2e = None
@@ -89,14 +99,15 @@ def run_multi(args, rank, world, local):
 
     check = None
     if not args.no_check:
-        check = self_check_multi(eng, stepper, dims, dt, spacing, args, mon, mon_ids, x0, nxl, rank, world, fence, dist)
+        check = self_check_multi(eng, stepper, dims, dt, spacing, args, mon, mon_ids, x0, nxl, rank, world, fence, dist,
+                                 wl["coef_fn"], wl["src_profile"])
         if rank == 0:
             import bench_check as BC
 
             check["timed_fields_sha"] = BC.sha_of_checksums(timed_cs)
 
     if rank == 0:
-        bpc = B.BYTES_PER_CELL[args.dtype]
+        bpc = B.BYTES_PER_CELL[args.dtype] + (16 if args.dtype == "float32" else 32) * int(het)      # + Ca,Cb,Da,Db reads
         peak, peak_src = B.peaks()
         value = cells * args.steps / (ms * 1e-3)
         achieved = bpc * cells * args.steps / (ms * 1e-3) / 1e9 / world
@@ -105,7 +116,8 @@ def run_multi(args, rank, world, local):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64",
                 "data": "synthetic",
-                "config": {"workload": f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} vacuum (uniform coefficients), TFSF +x "
+                "config": {"workload": B.workload_text(name, dims) if wl["real"] else
+                                       f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} vacuum (uniform coefficients), TFSF +x "
                                        f"plane source, FieldMonitor DFT plane (Ey,Hz x 5 freq)",
                            "l2": "per-rank working set >> 126 MB L2 (no flush needed)",
                            "parallelism": f"x-slabs over {world} GPUs, "
@@ -114,17 +126,21 @@ def run_multi(args, rank, world, local):
                                           + ("NCCL send/recv" if halo == "nccl" else
                                              "DMA push into the neighbour's ghost planes over NVLink (CUDA IPC) + "
                                              "release/acquire flags, in-kernel wait"),
-                           "kernel_path": "temporally blocked fused sweep (2 steps per HBM pass), ping-pong"
-                                          if os.environ.get("FDTD_B200_TB2", "1") != "0" else "fused single sweep, ping-pong"},
+                           "kernel_path": "heterogeneous one-step fused sweep (6 + 4 arrays in, 6 out), ping-pong" if het else
+                                          ("temporally blocked fused sweep (2 steps per HBM pass), ping-pong"
+                                           if os.environ.get("FDTD_B200_TB2", "1") != "0" else "fused single sweep, ping-pong")},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src,
-                             "kernel": ("k_fused3d_tb2 (two steps per launch)" if os.environ.get("FDTD_B200_TB2", "1") != "0"
+                             "kernel": ("k_fused3d_het (one step per launch)" if het else
+                                        "k_fused3d_tb2 (two steps per launch)" if os.environ.get("FDTD_B200_TB2", "1") != "0"
                                         else "k_fused3d (one step per launch)")
                                        + ", per GPU, whole step incl. in-kernel halo wait (max over ranks)",
                              "note": "achieved = 48 B (fp32) per cell-update x global cells / N / step time: the per-GPU "
                                      "share of the single-GPU line's figure; traffic is not re-measured per rank (ncu is "
                                      "single-process: see the 1-GPU line / profiles/)"},
                 "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()), "clocks": clk.summary(), "check": check}
+        if s_params is not None:
+            line["s_params"] = s_params
         print(json.dumps(line), flush=True)
     eng.close()
     dist.destroy_process_group()
@@ -142,7 +158,8 @@ def gather_checksums(eng, rank, world, dist):
     return {c: np.concatenate([p[c] for p in parts], axis=0) for c in B.COMPONENTS}
 
 
-def self_check_multi(eng, stepper, dims, dt, spacing, args, mon, mon_ids, x0, nxl, rank, world, fence, dist):
+def self_check_multi(eng, stepper, dims, dt, spacing, args, mon, mon_ids, x0, nxl, rank, world, fence, dist,
+                     coef_fn=None, src_profile=None):
     """bench_check.run_check over the slab decomposition: boxes are assembled from the ranks that own their planes."""
     import bench as B
     import bench_check as BC
@@ -184,7 +201,7 @@ def self_check_multi(eng, stepper, dims, dt, spacing, args, mon, mon_ids, x0, nx
 
     return BC.run_check(dims, dt, spacing, args.dtype, B.tables, dims[0] // 4, (3 * dims[0]) // 4, reseed, run_steps,
                         fetch_box, fetch_dft, lambda: gather_checksums(eng, rank, world, dist),
-                        do_oracle=not args.no_ops)
+                        do_oracle=not args.no_ops, coef_fn=coef_fn, src_profile=src_profile)
 
 
 def run_e2e_multi(eng, stepper, dims, args, mon_ids, dt, fence, dist, torch):

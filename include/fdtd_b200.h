@@ -86,7 +86,7 @@ typedef struct fdtd_monitor_op {
 } fdtd_monitor_op;
 
 /* One auxiliary-differential-equation recursion of a dispersive medium, cell-local, driven by E[component] after
- * every step (materials/ade.py:116-160 with the coefficients of materials/dispersion.py:189-336):
+ * every step (inside the fused sweeps: on the E values the NEXT step's sweep reads, i.e. the same numbers) (materials/ade.py:116-160 with the coefficients of materials/dispersion.py:189-336):
  *   kind 0 Lorentz  P+ = c0*E + c1*E + c2*P + c3*P_prev     kind 1 Drude  J+ = c0*E + c1*J     kind 2 Debye  P+ = c0*E + c1*P
  * mask (optional, box-shaped bytes) reproduces ADEManager.update_all's "E * mask" (ade.py:291-308).              */
 typedef struct fdtd_ade_op {
@@ -152,9 +152,12 @@ int  fdtd_run(fdtd_engine* e, int32_t n_steps);   /* H pass, E pass, sources, mo
 int  fdtd_update_h(fdtd_engine* e);               /* MaxwellUpdater.update_magnetic_fields :135-149 */
 int  fdtd_update_e(fdtd_engine* e);               /* MaxwellUpdater.update_electric_fields :151-165 */
 int  fdtd_sync(fdtd_engine* e);
-/* tuning switches: "tb2" 0/1 (two-step sweep), "fused_lx" planes per x-segment (0 = auto), "het_fused" 0/1,
+/* switches: "tb2" 0/1 (two-step sweep), "fused_lx" planes per x-segment (0 = auto), "het_fused" 0/1,
  * "yee_fused" 0/1/2 (physics mode: two-pass kernels / fused sweep / TMA-fed fused sweep, the default; set it before the
- * first step of a run) */
+ * first step of a run), "ade_fused" 0/1 (dispersive-medium recursions applied inside the next fused sweep instead of
+ * a kernel of their own; default 1, results identical), "ade_coupled" 0/1 (OPT-IN extension, not the reference's
+ * behaviour: the recursions run at the beginning of each step and their polarisation current is subtracted in the same
+ * E update, E+ -= Cb*eps0*(P+ - P)/dt or Cb*eps0*J+; needs a fused one-step sweep: 3-D, one GPU)                */
 int  fdtd_set_option(fdtd_engine* e, const char* key, int32_t value);
 /* measurement: CUDA events on the engine's own stream (torch.cuda.Event cannot see it).
  * fdtd_run_profiled runs n real steps without a graph and returns summed kernel times in ms:

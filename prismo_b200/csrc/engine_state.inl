@@ -102,6 +102,7 @@ struct fdtd_engine {
     unsigned char* d_plane_flags = nullptr; std::vector<unsigned char> plane_flags_host;
     // staging
     void* d_stage = nullptr; size_t stage_bytes = 0;
+    cudaStream_t xfer2 = nullptr; cudaEvent_t xfer_ev = nullptr;     // second lane of the staged host <-> device copies
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     // x-slab peer-to-peer halo (one process per GPU, CUDA IPC over NVLink)
     struct Slab {

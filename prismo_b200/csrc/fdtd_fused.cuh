@@ -273,6 +273,9 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
       e2z = ldv_pol<T, POL>(pez + po + g.sx, ld_ok);
     P h1x = ldv_pol<T, POL>(phx + po, ld_ok), h1y = ldv_pol<T, POL>(phy + po, ld_ok), h1z = ldv_pol<T, POL>(phz + po, ld_ok);
 
+    unsigned ade_mask = 0;
+    if (ADE) { if (owner) ade_mask = ade_thread_mask<V>(ad, i0, i1, j, k); }
+
     for (int i = i0 - 1; i < i1; ++i) {
         const int par = (i - i0 + 1) & 1;
         po = (long long)(i + 1) * g.sx;                  // plane i+1
@@ -321,11 +324,11 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
             stage_e<T, V, true, AM>(c, g, fo, g.x0 + i, jy1, k, e0x, e0y, e0z, hpx, hpy, hpz, hz_j, hx_j, hpy_n, hpx_n,
                                     hny, hnz, nx_, ny_, nz_);
             if (ADE) {
-                if (owner) {
+                if (ade_mask) {
                     double jx[V], jy[V], jz[V];
 #pragma unroll
                     for (int e = 0; e < V; ++e) jx[e] = jy[e] = jz[e] = 0.0;
-                    ade_in_sweep<T, V>(ad, i, j, k, e0x, e0y, e0z, jx, jy, jz);
+                    ade_in_sweep<T, V>(ad, ade_mask, i, j, k, e0x, e0y, e0z, jx, jy, jz);
                     if (ad.coupled) {
 #pragma unroll
                         for (int e = 0; e < V; ++e) {                  // op boxes lie inside the updated range of their component

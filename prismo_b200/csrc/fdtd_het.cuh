@@ -68,6 +68,8 @@ k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, i
     P da1 = ld8<T, V>(pda + po, ld_ok), db1 = ld8<T, V>(pdb + po, ld_ok);                 // D[i+1]
     P da2 = ld8<T, V>(pda + po + g.sx, ld_ok), db2 = ld8<T, V>(pdb + po + g.sx, ld_ok);   // D[i+2]
     P ca0_j = z_, cb0_j = z_;                                                           // C[i] at j+1
+    unsigned ade_mask = 0;
+    if (ADE) { if (owner) ade_mask = ade_thread_mask<V>(ad, i0, i1, j, k); }
 
     for (int i = i0 - 1; i < i1; ++i) {
         const int par = (i - i0 + 1) & 1;
@@ -137,7 +139,7 @@ k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, i
             double jx[V], jy[V], jz[V];
 #pragma unroll
             for (int e = 0; e < V; ++e) jx[e] = jy[e] = jz[e] = 0.0;
-            if (ADE) { if (owner) ade_in_sweep<T, V>(ad, i, j, k, e0x, e0y, e0z, jx, jy, jz); }
+            if (ADE) { if (ade_mask) ade_in_sweep<T, V>(ad, ade_mask, i, j, k, e0x, e0y, e0z, jx, jy, jz); }
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;

@@ -538,11 +538,32 @@ __global__ void k_ade(const T* const* __restrict__ comp_ptr, const AdeOp* __rest
 //   are in units of eps0 —, with the recursion applied at the BEGINNING of every step (oracle/ade.py: coupled_step).
 struct AdeIn { const AdeOp* ops; int n; void* aux; const unsigned char* mask; int coupled; double kp, kj; };   // kp = eps0/dt, kj = eps0
 
+// Which recursions can ever touch this thread's cells (row j, cells k .. k+V-1, planes [i0, i1))?  A thread's (j, k) is fixed
+// for the whole sweep, so this is evaluated once per kernel: the plane loop of the 97 % of threads outside every box
+// then pays one register test (without it the c3 workload ran 2.4x slower: profiles/r02_tuning.md).
+template <int V>
+__device__ __forceinline__ unsigned ade_thread_mask(const AdeIn& ad, int i0, int i1, int j, int k)
+{
+    unsigned m = 0;
+    const int n = ad.n < 32 ? ad.n : 32;
+    for (int q = 0; q < n; ++q) {
+        const AdeOp& op = ad.ops[q];
+        if ((unsigned)(j - op.lo[1]) < (unsigned)op.n[1] && k + V > op.lo[2] && k < op.lo[2] + op.n[2] &&
+            i1 > op.lo[0] && i0 < op.lo[0] + op.n[0])
+            m |= 1u << q;
+    }
+    if (ad.n > 32) m |= 0x80000000u;            // more than 32 recursions: the tail is tested op by op
+    return m;
+}
+
 template <typename T, int V>
-__device__ __forceinline__ void ade_in_sweep(const AdeIn& ad, int i, int j, int k, const Pack<T, V>& ex, const Pack<T, V>& ey,
-                                             const Pack<T, V>& ez, double (&jx)[V], double (&jy)[V], double (&jz)[V])
+__device__ __forceinline__ void ade_in_sweep(const AdeIn& ad, unsigned mask, int i, int j, int k, const Pack<T, V>& ex,
+                                             const Pack<T, V>& ey, const Pack<T, V>& ez, double (&jx)[V], double (&jy)[V],
+                                             double (&jz)[V])
 {
     for (int q = 0; q < ad.n; ++q) {
+        if (q < 31 && !((mask >> q) & 1u)) continue;
+        if (q >= 31 && !(mask & 0x80000000u)) break;
         const AdeOp& op = ad.ops[q];
         const int a0 = i - op.lo[0], a1 = j - op.lo[1];
         if ((unsigned)a0 >= (unsigned)op.n[0] || (unsigned)a1 >= (unsigned)op.n[1]) continue;

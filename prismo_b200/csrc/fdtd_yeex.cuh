@@ -117,7 +117,17 @@ __device__ __forceinline__ void yee_e_lean(const Coefs<T>& c, const Geom& g,
     }
 }
 
-// ---- psi registers of one stage (E or H) of one thread and plane ------------------------------------------------------------------
+// ---- non-lean bodies: update-range masks + CPML recursion on slab cells (fdtd_yee.cuh:63-89, :106-138) ---------------------------
+// The first version of these bodies spent 726 SASS instructions per H stage, 156 of them floating point: masks, slab
+// indices and psi addresses were re-derived per cell with nested branches (profiles/r02_ncu_yeex.md).  Now
+//   * everything that depends only on the thread's (j, k) is computed ONCE per kernel (YeexThread: mask bits, slab
+//     indices, 32-bit psi offsets), what depends on the plane once per iteration (uniform);
+//   * the three psi families are COMPILE-TIME flags <X, Y, Z>: a warp in a z-slab tile of an interior row on an
+//     interior plane instantiates only the four z recursions, and so on (8 variants per stage, chosen by a warp-
+//     uniform switch);
+//   * cells are updated branch-free: compute, then select by mask bit (a cell outside the update range keeps its field
+//     AND its psi), z coefficients default to the identity (b = a = 0, 1/kappa = 1) outside the slab.
+//
 // The six psi arrays of a stage, in the order of Cpml::psi from `base` (0: E stage, 6: H stage):
 //   base+0 y0 (x-component, d/dy)   base+1 z0 (x-component, d/dz)   base+2 z1 (y-component, d/dz)
 //   base+3 x0 (y-component, d/dx)   base+4 x1 (z-component, d/dx)   base+5 y1 (z-component, d/dy)
@@ -131,170 +141,216 @@ template <typename T, int V> __device__ __forceinline__ Pack<T, V> ldnc8(const T
     return u.r;
 }
 
-// Issue the loads of the psi values that the thread at (plane pl, row j, cells k .. k+V-1) will use.  `ok`: the thread lies
-// inside the arrays (0 <= j < ny, 0 <= k < pz) and 0 <= pl < nx.  The x and y families are row-contiguous like the fields
-// (8-byte vector loads; entries outside the update range exist and stay zero), the z family holds 2t+1 entries per row.
-template <typename T, int V>
-__device__ __forceinline__ void yeex_psi_load(YeexPsi<T, V>& r, const T* const* __restrict__ psi_in, const int base, const Geom& g,
-                                              const SlabGeom& sg, const int tpm, const int pl, const int j, const int k,
-                                              const int syj, const bool ok)
+template <int V> struct YeexThread {
+    int j, k, syj;
+    int szk[V];                 // z-slab index of each cell (-1: none)
+    unsigned off_xy;            // j * sy + k: x family (+ sxp * x_sx) and, with syj in place of j, ...
+    unsigned off_y;             // syj * sy + k: y family (+ plane * y_sx)
+    unsigned off_z[V];          // j * z_pitch + szk: z family (+ plane * ny * z_pitch)
+    unsigned bits;              // bit e: 1 <= k+e <= nz-2 (km); 8+e: k+e < nz-1 (kz1); 16+e: k+e < nz (kz0);
+                                // 24: 1 <= j <= ny-2 (jm); 25: j < ny-1 (jy1); 26: j < ny (jy0)
+    bool ok;                    // inside the arrays: psi may be loaded
+};
+
+template <int V>
+__device__ __forceinline__ YeexThread<V> yeex_thread(const Geom& g, const SlabGeom& sg, int tpm, int j, int k, int syj, bool in_grid)
 {
-    if (!ok || !tpm) return;
-    const int sxp = slab_index(pl, g.nx, tpm);
-    if (sxp >= 0) {
-        const long long oxs = (long long)sxp * sg.x_sx + (long long)j * g.sy + k;
-        r.x0 = ldnc8<T, V>(psi_in[base + 3] + oxs); r.x1 = ldnc8<T, V>(psi_in[base + 4] + oxs);
-    }
-    if (syj >= 0) {
-        const long long oys = (long long)pl * sg.y_sx + (long long)syj * g.sy + k;
-        r.y0 = ldnc8<T, V>(psi_in[base + 0] + oys); r.y1 = ldnc8<T, V>(psi_in[base + 5] + oys);
-    }
+    YeexThread<V> th;
+    th.j = j; th.k = k; th.syj = syj; th.ok = in_grid;
+    th.off_xy = (unsigned)j * (unsigned)g.sy + (unsigned)max(k, 0);
+    th.off_y = (unsigned)max(syj, 0) * (unsigned)g.sy + (unsigned)max(k, 0);
+    unsigned b = 0;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
         const int ke = k + e;
-        const int szk = ke < g.nz ? slab_index(ke, g.nz, tpm) : -1;
-        if (szk >= 0) {
-            const long long ozs = ((long long)pl * g.ny + j) * sg.z_pitch + szk;
-            r.z0.v[e] = __ldg(psi_in[base + 1] + ozs); r.z1.v[e] = __ldg(psi_in[base + 2] + ozs);
-        }
+        th.szk[e] = (tpm && ke >= 0 && ke < g.nz) ? slab_index(ke, g.nz, tpm) : -1;
+        th.off_z[e] = (unsigned)j * (unsigned)sg.z_pitch + (unsigned)max(th.szk[e], 0);
+        if (ke >= 1 && ke <= g.nz - 2) b |= 1u << e;
+        if (ke >= 0 && ke < g.nz - 1) b |= 1u << (8 + e);
+        if (ke >= 0 && ke < g.nz) b |= 1u << (16 + e);
     }
+    if (j >= 1 && j <= g.ny - 2) b |= 1u << 24;
+    if (j < g.ny - 1) b |= 1u << 25;
+    if (j < g.ny) b |= 1u << 26;
+    th.bits = b;
+    return th;
+}
+
+// Issue the loads of the psi values the thread will use at plane pl (runtime family tests: a handful of predicated loads).
+template <typename T, int V>
+__device__ __forceinline__ void yeex_psi_load(YeexPsi<T, V>& r, const T* const* __restrict__ psi_in, const int base, const Geom& g,
+                                              const SlabGeom& sg, const int tpm, const int pl, const YeexThread<V>& th)
+{
+    if (!th.ok || !tpm || pl >= g.nx) return;
+    const int sxp = slab_index(pl, g.nx, tpm);
+    if (sxp >= 0) {
+        const unsigned o = (unsigned)sxp * (unsigned)sg.x_sx + th.off_xy;
+        r.x0 = ldnc8<T, V>(psi_in[base + 3] + o); r.x1 = ldnc8<T, V>(psi_in[base + 4] + o);
+    }
+    if (th.syj >= 0) {
+        const unsigned o = (unsigned)pl * (unsigned)sg.y_sx + th.off_y;
+        r.y0 = ldnc8<T, V>(psi_in[base + 0] + o); r.y1 = ldnc8<T, V>(psi_in[base + 5] + o);
+    }
+    const unsigned zp = (unsigned)pl * (unsigned)(g.ny * sg.z_pitch);
+#pragma unroll
+    for (int e = 0; e < V; ++e)
+        if (th.szk[e] >= 0) { r.z0.v[e] = __ldg(psi_in[base + 1] + zp + th.off_z[e]); r.z1.v[e] = __ldg(psi_in[base + 2] + zp + th.off_z[e]); }
 }
 
 // the same addresses, written to the OTHER psi set (psi is ping-ponged like the fields: rim threads and segment prologues
 // recompute the recursion without storing)
-template <typename T, int V>
+template <typename T, int V, bool X, bool Y, bool Z>
 __device__ __forceinline__ void yeex_psi_store(const YeexPsi<T, V>& r, T* const* __restrict__ psi_out, const int base, const Geom& g,
-                                               const SlabGeom& sg, const int tpm, const int pl, const int j, const int k,
-                                               const int syj)
+                                               const SlabGeom& sg, const int sxp, const int pl, const YeexThread<V>& th)
 {
-    const int sxp = slab_index(pl, g.nx, tpm);
-    if (sxp >= 0) {
-        const long long oxs = (long long)sxp * sg.x_sx + (long long)j * g.sy + k;
-        st8<T, V>(psi_out[base + 3] + oxs, r.x0); st8<T, V>(psi_out[base + 4] + oxs, r.x1);
+    if (X) {
+        const unsigned o = (unsigned)sxp * (unsigned)sg.x_sx + th.off_xy;
+        st8<T, V>(psi_out[base + 3] + o, r.x0); st8<T, V>(psi_out[base + 4] + o, r.x1);
     }
-    if (syj >= 0) {
-        const long long oys = (long long)pl * sg.y_sx + (long long)syj * g.sy + k;
-        st8<T, V>(psi_out[base + 0] + oys, r.y0); st8<T, V>(psi_out[base + 5] + oys, r.y1);
+    if (Y) {
+        const unsigned o = (unsigned)pl * (unsigned)sg.y_sx + th.off_y;
+        st8<T, V>(psi_out[base + 0] + o, r.y0); st8<T, V>(psi_out[base + 5] + o, r.y1);
     }
+    if (Z) {
+        const unsigned zp = (unsigned)pl * (unsigned)(g.ny * sg.z_pitch);
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-        const int ke = k + e;
-        const int szk = ke < g.nz ? slab_index(ke, g.nz, tpm) : -1;
-        if (szk >= 0) {
-            const long long ozs = ((long long)pl * g.ny + j) * sg.z_pitch + szk;
-            psi_out[base + 1][ozs] = r.z0.v[e]; psi_out[base + 2][ozs] = r.z1.v[e];
+        for (int e = 0; e < V; ++e)
+            if (th.szk[e] >= 0) { psi_out[base + 1][zp + th.off_z[e]] = r.z0.v[e]; psi_out[base + 2][zp + th.off_z[e]] = r.z1.v[e]; }
+    }
+}
+
+// CPML coefficients of one stage at this thread's position (v0 = 0: E-derivative positions, 3: H): b, a, 1/kappa
+template <typename T, int V, bool X, bool Y, bool Z> struct YeexCoef { T bx, ax, kx, by, ay, ky; T bz[V], az[V], kz[V]; };
+
+template <typename T, int V, bool X, bool Y, bool Z>
+__device__ __forceinline__ void yeex_coef_load(YeexCoef<T, V, X, Y, Z>& q, const Cpml& pm, const int v0, const int pl,
+                                               const YeexThread<V>& th)
+{
+    if (X) { q.bx = __ldg(cpml_tab<T>(pm.ax[0], v0) + pl); q.ax = __ldg(cpml_tab<T>(pm.ax[0], v0 + 1) + pl); q.kx = __ldg(cpml_tab<T>(pm.ax[0], v0 + 2) + pl); }
+    if (Y) { q.by = __ldg(cpml_tab<T>(pm.ax[1], v0) + th.j); q.ay = __ldg(cpml_tab<T>(pm.ax[1], v0 + 1) + th.j); q.ky = __ldg(cpml_tab<T>(pm.ax[1], v0 + 2) + th.j); }
+    if (Z) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            q.bz[e] = q.az[e] = (T)0; q.kz[e] = (T)1;
+            if (th.szk[e] >= 0) {
+                const int ke = th.k + e;
+                q.bz[e] = __ldg(cpml_tab<T>(pm.ax[2], v0) + ke); q.az[e] = __ldg(cpml_tab<T>(pm.ax[2], v0 + 1) + ke); q.kz[e] = __ldg(cpml_tab<T>(pm.ax[2], v0 + 2) + ke);
+            }
         }
     }
 }
 
-// CPML coefficients of one stage at this thread's position: b, a, 1/kappa along x (plane), y (row), z (per cell)
-template <typename T, int V> struct YeexCoef { T bx, ax, kx, by, ay, ky; T bz[V], az[V], kz[V]; int szk[V]; int sxp; };
-
-template <typename T, int V>
-__device__ __forceinline__ void yeex_coef_load(YeexCoef<T, V>& q, const Cpml& pm, const int v0, const Geom& g, const int pl,
-                                               const int j, const int k, const int syj)
+// one derivative through one recursion: psi' = b psi + a d, d' = d / kappa + psi'; `on` = the cell is in the update range
+template <typename T>
+__device__ __forceinline__ T yeex_cpml(T d, T& psi, T b, T a, T ki, bool on)
 {
-    const int tpm = pm.t;
-    q.sxp = (tpm && pl >= 0 && pl < g.nx) ? slab_index(pl, g.nx, tpm) : -1;
-    q.bx = q.ax = q.by = q.ay = (T)0; q.kx = q.ky = (T)1;
-    if (q.sxp >= 0) {
-        q.bx = __ldg(cpml_tab<T>(pm.ax[0], v0) + pl); q.ax = __ldg(cpml_tab<T>(pm.ax[0], v0 + 1) + pl); q.kx = __ldg(cpml_tab<T>(pm.ax[0], v0 + 2) + pl);
-    }
-    if (syj >= 0) {
-        q.by = __ldg(cpml_tab<T>(pm.ax[1], v0) + j); q.ay = __ldg(cpml_tab<T>(pm.ax[1], v0 + 1) + j); q.ky = __ldg(cpml_tab<T>(pm.ax[1], v0 + 2) + j);
-    }
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-        const int ke = k + e;
-        q.szk[e] = (tpm && ke >= 0 && ke < g.nz) ? slab_index(ke, g.nz, tpm) : -1;
-        q.bz[e] = q.az[e] = (T)0; q.kz[e] = (T)1;
-        if (q.szk[e] >= 0) {
-            q.bz[e] = __ldg(cpml_tab<T>(pm.ax[2], v0) + ke); q.az[e] = __ldg(cpml_tab<T>(pm.ax[2], v0 + 1) + ke); q.kz[e] = __ldg(cpml_tab<T>(pm.ax[2], v0 + 2) + ke);
-        }
-    }
+    const T p = CpmlMath<T>::psi(b, psi, a, d);
+    psi = on ? p : psi;
+    return CpmlMath<T>::eff(ki, d, p);
 }
 
-// ---- full bodies: update-range masks + CPML recursion on slab cells (fdtd_yee.cuh:63-89, :106-138) --------------------------------
-template <typename T, int V>
-__device__ __forceinline__ void yee_h_full(const Coefs<T>& c, const Geom& g, const Cpml& pm, YeexPsi<T, V>& r,
-                                           const int p, const int j, const int k, const int syj,
+template <typename T, int V, bool X, bool Y, bool Z>
+__device__ __forceinline__ void yee_h_full(const Coefs<T>& c, const Geom& g, const Cpml& pm, YeexPsi<T, V>& r, const YeexThread<V>& th,
+                                           const int p,
                                            const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
                                            const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
                                            const Pack<T, V>& ez_jm, const Pack<T, V>& ex_jm, T ey_km, T ex_km,
                                            const Pack<T, V>& ey_im, const Pack<T, V>& ez_im,
                                            Pack<T, V>& ox, Pack<T, V>& oy, Pack<T, V>& oz)
 {
-    YeexCoef<T, V> q;
-    yeex_coef_load<T, V>(q, pm, 3, g, p, j, k, syj);
+    YeexCoef<T, V, X, Y, Z> q;
+    yeex_coef_load<T, V, X, Y, Z>(q, pm, 3, p, th);
     const bool px1 = p < g.nx - 1, pxm = p >= 1 && p <= g.nx - 2;
-    const bool jm = j >= 1 && j <= g.ny - 2, jy1 = j >= 0 && j < g.ny - 1;
-    ox = hx; oy = hy; oz = hz;
+    const bool jm = (th.bits >> 24) & 1u, jy1 = (th.bits >> 25) & 1u;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-        const int ke = k + e;
-        const bool km = ke >= 1 && ke <= g.nz - 2, kz1 = ke >= 0 && ke < g.nz - 1;
+        const bool km = (th.bits >> e) & 1u, kz1 = (th.bits >> (8 + e)) & 1u;
         const T ey_k = e > 0 ? ey.v[(e + V - 1) % V] : ey_km;
         const T ex_k = e > 0 ? ex.v[(e + V - 1) % V] : ex_km;
-        if (px1 && jm && km) {                             // Hx(p+1/2, j, k)
+        {                                                  // Hx(p+1/2, j, k): p < nx-1, 1 <= j <= ny-2, 1 <= k <= nz-2
+            const bool on = px1 && jm && km;
             T dy = Ar<T>::diff(ez.v[e], ez_jm.v[e], g.dy, g.rdy), dz = Ar<T>::diff(ey.v[e], ey_k, g.dz, g.rdz);
-            if (syj >= 0) { r.y0.v[e] = CpmlMath<T>::psi(q.by, r.y0.v[e], q.ay, dy); dy = CpmlMath<T>::eff(q.ky, dy, r.y0.v[e]); }
-            if (q.szk[e] >= 0) { r.z0.v[e] = CpmlMath<T>::psi(q.bz[e], r.z0.v[e], q.az[e], dz); dz = CpmlMath<T>::eff(q.kz[e], dz, r.z0.v[e]); }
-            ox.v[e] = upd_h<T>(c.uda, hx.v[e], c.udb, dy, dz);
+            if (Y) dy = yeex_cpml<T>(dy, r.y0.v[e], q.by, q.ay, q.ky, on);
+            if (Z) dz = yeex_cpml<T>(dz, r.z0.v[e], q.bz[e], q.az[e], q.kz[e], on);
+            const T n = upd_h<T>(c.uda, hx.v[e], c.udb, dy, dz);
+            ox.v[e] = on ? n : hx.v[e];
         }
-        if (pxm && jy1 && km) {                            // Hy(p, j+1/2, k)
+        {                                                  // Hy(p, j+1/2, k): 1 <= p <= nx-2, j < ny-1, 1 <= k <= nz-2
+            const bool on = pxm && jy1 && km;
             T dz = Ar<T>::diff(ex.v[e], ex_k, g.dz, g.rdz), dx = Ar<T>::diff(ez.v[e], ez_im.v[e], g.dx, g.rdx);
-            if (q.szk[e] >= 0) { r.z1.v[e] = CpmlMath<T>::psi(q.bz[e], r.z1.v[e], q.az[e], dz); dz = CpmlMath<T>::eff(q.kz[e], dz, r.z1.v[e]); }
-            if (q.sxp >= 0) { r.x0.v[e] = CpmlMath<T>::psi(q.bx, r.x0.v[e], q.ax, dx); dx = CpmlMath<T>::eff(q.kx, dx, r.x0.v[e]); }
-            oy.v[e] = upd_h<T>(c.uda, hy.v[e], c.udb, dz, dx);
+            if (Z) dz = yeex_cpml<T>(dz, r.z1.v[e], q.bz[e], q.az[e], q.kz[e], on);
+            if (X) dx = yeex_cpml<T>(dx, r.x0.v[e], q.bx, q.ax, q.kx, on);
+            const T n = upd_h<T>(c.uda, hy.v[e], c.udb, dz, dx);
+            oy.v[e] = on ? n : hy.v[e];
         }
-        if (pxm && jm && kz1) {                            // Hz(p, j, k+1/2)
+        {                                                  // Hz(p, j, k+1/2): 1 <= p <= nx-2, 1 <= j <= ny-2, k < nz-1
+            const bool on = pxm && jm && kz1;
             T dx = Ar<T>::diff(ey.v[e], ey_im.v[e], g.dx, g.rdx), dy = Ar<T>::diff(ex.v[e], ex_jm.v[e], g.dy, g.rdy);
-            if (q.sxp >= 0) { r.x1.v[e] = CpmlMath<T>::psi(q.bx, r.x1.v[e], q.ax, dx); dx = CpmlMath<T>::eff(q.kx, dx, r.x1.v[e]); }
-            if (syj >= 0) { r.y1.v[e] = CpmlMath<T>::psi(q.by, r.y1.v[e], q.ay, dy); dy = CpmlMath<T>::eff(q.ky, dy, r.y1.v[e]); }
-            oz.v[e] = upd_h<T>(c.uda, hz.v[e], c.udb, dx, dy);
+            if (X) dx = yeex_cpml<T>(dx, r.x1.v[e], q.bx, q.ax, q.kx, on);
+            if (Y) dy = yeex_cpml<T>(dy, r.y1.v[e], q.by, q.ay, q.ky, on);
+            const T n = upd_h<T>(c.uda, hz.v[e], c.udb, dx, dy);
+            oz.v[e] = on ? n : hz.v[e];
         }
     }
 }
 
-template <typename T, int V>
-__device__ __forceinline__ void yee_e_full(const Coefs<T>& c, const Geom& g, const Cpml& pm, YeexPsi<T, V>& r,
-                                           const int i, const int j, const int k, const int syj,
+template <typename T, int V, bool X, bool Y, bool Z>
+__device__ __forceinline__ void yee_e_full(const Coefs<T>& c, const Geom& g, const Cpml& pm, YeexPsi<T, V>& r, const YeexThread<V>& th,
+                                           const int i,
                                            const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez,
                                            const Pack<T, V>& hx, const Pack<T, V>& hy, const Pack<T, V>& hz,
                                            const Pack<T, V>& hz_jp, const Pack<T, V>& hx_jp, T hy_kp, T hx_kp,
                                            const Pack<T, V>& hy_ip, const Pack<T, V>& hz_ip,
                                            Pack<T, V>& ox, Pack<T, V>& oy, Pack<T, V>& oz)
 {
-    YeexCoef<T, V> q;
-    yeex_coef_load<T, V>(q, pm, 0, g, i, j, k, syj);
-    const bool qx1 = i < g.nx - 1, jy1 = j >= 0 && j < g.ny - 1, jy0 = j >= 0 && j < g.ny;
-    ox = ex; oy = ey; oz = ez;
+    YeexCoef<T, V, X, Y, Z> q;
+    yeex_coef_load<T, V, X, Y, Z>(q, pm, 0, i, th);
+    const bool qx1 = i < g.nx - 1;
+    const bool jy1 = (th.bits >> 25) & 1u, jy0 = (th.bits >> 26) & 1u;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-        const int ke = k + e;
-        const bool kz0 = ke >= 0 && ke < g.nz, kz1 = ke >= 0 && ke < g.nz - 1;
+        const bool kz1 = (th.bits >> (8 + e)) & 1u, kz0 = (th.bits >> (16 + e)) & 1u;
         const T hy_k = (e + 1 < V) ? hy.v[(e + 1) % V] : hy_kp;
         const T hx_k = (e + 1 < V) ? hx.v[(e + 1) % V] : hx_kp;
-        if (jy1 && kz1) {                                  // Ex(i, j+1/2, k+1/2)
+        {                                                  // Ex(i, j+1/2, k+1/2): j < ny-1, k < nz-1
+            const bool on = jy1 && kz1;
             T dy = Ar<T>::diff(hz_jp.v[e], hz.v[e], g.dy, g.rdy), dz = Ar<T>::diff(hy_k, hy.v[e], g.dz, g.rdz);
-            if (syj >= 0) { r.y0.v[e] = CpmlMath<T>::psi(q.by, r.y0.v[e], q.ay, dy); dy = CpmlMath<T>::eff(q.ky, dy, r.y0.v[e]); }
-            if (q.szk[e] >= 0) { r.z0.v[e] = CpmlMath<T>::psi(q.bz[e], r.z0.v[e], q.az[e], dz); dz = CpmlMath<T>::eff(q.kz[e], dz, r.z0.v[e]); }
-            ox.v[e] = upd_e<T>(c.uca, ex.v[e], c.ucb, dy, dz);
+            if (Y) dy = yeex_cpml<T>(dy, r.y0.v[e], q.by, q.ay, q.ky, on);
+            if (Z) dz = yeex_cpml<T>(dz, r.z0.v[e], q.bz[e], q.az[e], q.kz[e], on);
+            const T n = upd_e<T>(c.uca, ex.v[e], c.ucb, dy, dz);
+            ox.v[e] = on ? n : ex.v[e];
         }
-        if (qx1 && kz1 && jy0) {                           // Ey(i+1/2, j, k+1/2)
+        {                                                  // Ey(i+1/2, j, k+1/2): i < nx-1, k < nz-1
+            const bool on = qx1 && kz1 && jy0;
             T dz = Ar<T>::diff(hx_k, hx.v[e], g.dz, g.rdz), dx = Ar<T>::diff(hz_ip.v[e], hz.v[e], g.dx, g.rdx);
-            if (q.szk[e] >= 0) { r.z1.v[e] = CpmlMath<T>::psi(q.bz[e], r.z1.v[e], q.az[e], dz); dz = CpmlMath<T>::eff(q.kz[e], dz, r.z1.v[e]); }
-            if (q.sxp >= 0) { r.x0.v[e] = CpmlMath<T>::psi(q.bx, r.x0.v[e], q.ax, dx); dx = CpmlMath<T>::eff(q.kx, dx, r.x0.v[e]); }
-            oy.v[e] = upd_e<T>(c.uca, ey.v[e], c.ucb, dz, dx);
+            if (Z) dz = yeex_cpml<T>(dz, r.z1.v[e], q.bz[e], q.az[e], q.kz[e], on);
+            if (X) dx = yeex_cpml<T>(dx, r.x0.v[e], q.bx, q.ax, q.kx, on);
+            const T n = upd_e<T>(c.uca, ey.v[e], c.ucb, dz, dx);
+            oy.v[e] = on ? n : ey.v[e];
         }
-        if (qx1 && jy1 && kz0) {                           // Ez(i+1/2, j+1/2, k)
+        {                                                  // Ez(i+1/2, j+1/2, k): i < nx-1, j < ny-1
+            const bool on = qx1 && jy1 && kz0;
             T dx = Ar<T>::diff(hy_ip.v[e], hy.v[e], g.dx, g.rdx), dy = Ar<T>::diff(hx_jp.v[e], hx.v[e], g.dy, g.rdy);
-            if (q.sxp >= 0) { r.x1.v[e] = CpmlMath<T>::psi(q.bx, r.x1.v[e], q.ax, dx); dx = CpmlMath<T>::eff(q.kx, dx, r.x1.v[e]); }
-            if (syj >= 0) { r.y1.v[e] = CpmlMath<T>::psi(q.by, r.y1.v[e], q.ay, dy); dy = CpmlMath<T>::eff(q.ky, dy, r.y1.v[e]); }
-            oz.v[e] = upd_e<T>(c.uca, ez.v[e], c.ucb, dx, dy);
+            if (X) dx = yeex_cpml<T>(dx, r.x1.v[e], q.bx, q.ax, q.kx, on);
+            if (Y) dy = yeex_cpml<T>(dy, r.y1.v[e], q.by, q.ay, q.ky, on);
+            const T n = upd_e<T>(c.uca, ez.v[e], c.ucb, dx, dy);
+            oz.v[e] = on ? n : ez.v[e];
         }
     }
 }
+
+// warp-uniform dispatch of a body templated on the psi families that are active: cls = X | Y << 1 | Z << 2
+#define YEEX_DISPATCH(cls, CALL)                                                                  \
+    switch (cls) {                                                                                \
+    case 0: { constexpr bool X = false, Y = false, Z = false; CALL; } break;                      \
+    case 1: { constexpr bool X = true, Y = false, Z = false; CALL; } break;                       \
+    case 2: { constexpr bool X = false, Y = true, Z = false; CALL; } break;                       \
+    case 3: { constexpr bool X = true, Y = true, Z = false; CALL; } break;                        \
+    case 4: { constexpr bool X = false, Y = false, Z = true; CALL; } break;                       \
+    case 5: { constexpr bool X = true, Y = false, Z = true; CALL; } break;                        \
+    case 6: { constexpr bool X = false, Y = true, Z = true; CALL; } break;                        \
+    default: { constexpr bool X = true, Y = true, Z = true; CALL; } break;                        \
+    }
 
 template <typename T, int R, int AM>
 __global__ void __launch_bounds__(32 * (R + 1), 1)
@@ -373,6 +429,9 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
     const int hl_lo = max(1, tpm), el_lo = tpm, xl_hi = g.nx - 2 - tpm;
     const T* const* psi_in = reinterpret_cast<const T* const*>(pm.psi);
     T* const* psi_out = reinterpret_cast<T* const*>(pout.p);
+    const YeexThread<V> th = yeex_thread<V>(g, sg, tpm, j, k, syj, in_grid);
+    // psi families of this warp that do not depend on the plane: y (row inside a y slab), z (tile touches a z slab)
+    const int cls_yz = (syj >= 0 ? 2 : 0) | (tile_z ? 4 : 0);
 
     P z_;
 #pragma unroll
@@ -388,7 +447,7 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
     hps.x0 = hps.x1 = hps.y0 = hps.y1 = hps.z0 = hps.z1 = z_;
     eps = hps;
     if (!(lean_thread && i0 >= hl_lo && i0 <= xl_hi))
-        yeex_psi_load<T, V>(hps, psi_in, 6, g, sg, tpm, i0, j, k, syj, in_grid && i0 < g.nx);
+        yeex_psi_load<T, V>(hps, psi_in, 6, g, sg, tpm, i0, th);
     // window at it = 0 (i = i0 - 1): E[i] = stage 0 (Ey, Ez feed the x-differences of H+[i0]); H+[i] unused
     mbar_wait(full, 0);
     P eAx = lds8<T, V>(tiles + 0 * ROWS + own_off), eAy = lds8<T, V>(tiles + 1 * ROWS + own_off), eAz = lds8<T, V>(tiles + 2 * ROWS + own_off);
@@ -425,13 +484,15 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
         if (lean_thread && p >= hl_lo && p <= xl_hi)
             yee_h_lean<T, V, AM>(c, g, h1x, h1y, h1z, e1x, e1y, e1z, ez_jm, ex_jm, ey_km, ex_km, e0y, e0z, hnx, hny, hnz);
         else {
-            yee_h_full<T, V>(c, g, pm, hps, p, j, k, syj, h1x, h1y, h1z, e1x, e1y, e1z, ez_jm, ex_jm, ey_km, ex_km, e0y, e0z,
-                             hnx, hny, hnz);
-            if (st_h && tpm) yeex_psi_store<T, V>(hps, psi_out, 6, g, sg, tpm, p, j, k, syj);
+            const int sxp = (tpm && p < g.nx) ? slab_index(p, g.nx, tpm) : -1;
+            YEEX_DISPATCH(cls_yz | (sxp >= 0 ? 1 : 0),
+                          (yee_h_full<T, V, X, Y, Z>(c, g, pm, hps, th, p, h1x, h1y, h1z, e1x, e1y, e1z, ez_jm, ex_jm, ey_km, ex_km,
+                                                     e0y, e0z, hnx, hny, hnz),
+                           st_h ? yeex_psi_store<T, V, X, Y, Z>(hps, psi_out, 6, g, sg, sxp, p, th) : (void)0))
         }
         // psi of the next H stage (plane p + 1): the registers are free now, the loads have a whole iteration to land
         if (more && !(lean_thread && p + 1 >= hl_lo && p + 1 <= xl_hi))
-            yeex_psi_load<T, V>(hps, psi_in, 6, g, sg, tpm, p + 1, j, k, syj, in_grid && p + 1 < g.nx);
+            yeex_psi_load<T, V>(hps, psi_in, 6, g, sg, tpm, p + 1, th);
         // ---- publish Hz+, Hx+ of plane p for the row below (its E+ of the next iteration) ----------------------------------------------
         int xd1 = xd + 1, xph1 = xph;
         if (xd1 == D) { xd1 = 0; xph1 ^= 1; }
@@ -457,9 +518,11 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
             if (lean_thread && i >= el_lo && i <= xl_hi)
                 yee_e_lean<T, V, AM>(c, g, e0x, e0y, e0z, hpx, hpy, hpz, hz_jp, hx_jp, hy_kp, hx_kp, hny, hnz, nx_, ny_, nz_);
             else if (owner) {
-                yee_e_full<T, V>(c, g, pm, eps, i, j, k, syj, e0x, e0y, e0z, hpx, hpy, hpz, hz_jp, hx_jp, hy_kp, hx_kp, hny, hnz,
-                                 nx_, ny_, nz_);
-                if (tpm) yeex_psi_store<T, V>(eps, psi_out, 0, g, sg, tpm, i, j, k, syj);
+                const int sxq = tpm ? slab_index(i, g.nx, tpm) : -1;
+                YEEX_DISPATCH(cls_yz | (sxq >= 0 ? 1 : 0),
+                              (yee_e_full<T, V, X, Y, Z>(c, g, pm, eps, th, i, e0x, e0y, e0z, hpx, hpy, hpz, hz_jp, hx_jp, hy_kp, hx_kp,
+                                                         hny, hnz, nx_, ny_, nz_),
+                               yeex_psi_store<T, V, X, Y, Z>(eps, psi_out, 0, g, sg, sxq, i, th)))
             }
             if (owner) {
                 const unsigned oe = ofs + (unsigned)i * (unsigned)g.sx;
@@ -468,7 +531,7 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
         }
         // psi of the next E stage (plane i + 1 = p)
         if (more && owner && !(lean_thread && p >= el_lo && p <= xl_hi))
-            yeex_psi_load<T, V>(eps, psi_in, 0, g, sg, tpm, p, j, k, syj, p < g.nx);
+            yeex_psi_load<T, V>(eps, psi_in, 0, g, sg, tpm, p, th);
     };
 
     int it = 0;

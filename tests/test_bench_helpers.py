@@ -59,3 +59,37 @@ def test_parse_workload_names():
     assert B.parse_workload("c4")[1] == (1024, 1024, 1024)
     assert B.parse_workload("128x1024x1024")[1] == (128, 1024, 1024)
     assert B.parse_workload("c2")[1] == (121, 121, 121)
+
+
+@pytest.mark.parametrize("name,dims", [("c3", (64, 64, 48)), ("c5", (128, 96, 48))])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_medium_recursions_tile_over_slabs(name, dims, world):
+    """The dispersive-medium boxes every rank builds for its x-slab must tile the single-GPU boxes exactly once."""
+    dt, _ = B.workload_timestep()
+    med = B.Medium(name, dims)
+    whole = med.ade_ops(dt)
+    assert len(whole) == (3 if name == "c3" else 9)
+    cover = {(o.component, o.kind, o.lo[1:], o.hi[1:]): np.zeros(dims[0], dtype=int) for o in whole}
+    for r in range(world):
+        x0, n = slab_range(dims[0], r, world)
+        for o in med.ade_ops(dt, x0, n):
+            assert 0 <= o.lo[0] < o.hi[0] <= n
+            cover[(o.component, o.kind, o.lo[1:], o.hi[1:])][x0 + o.lo[0]:x0 + o.hi[0]] += 1
+    for o in whole:
+        want = np.zeros(dims[0], dtype=int)
+        want[o.lo[0]:o.hi[0]] = 1
+        assert np.array_equal(cover[(o.component, o.kind, o.lo[1:], o.hi[1:])], want), o
+    eps = med.eps()
+    assert eps.shape == dims[1:] and set(np.unique(eps)) == {1.0, 2.07, 12.11}
+    ca, cb, da, db = med.coefficients(dt, 5, (3, 20, 4, 30))
+    assert cb.shape == (5, 17, 26) and np.array_equal(cb[0], dt / (8.854187817e-12 * eps[3:20, 4:30]))
+
+
+def test_port_planes_are_owned_by_exactly_one_slab():
+    dims = (128, 96, 48)
+    for world in (1, 2, 8):
+        seen = []
+        for r in range(world):
+            x0, n = slab_range(dims[0], r, world)
+            seen += [(port, which, p) for port, which, p, ops in B.port_monitor_ops(dims, x0, n) if ops is not None]
+        assert sorted(seen) == [(0, 0, 16), (0, 1, 24), (1, 0, 104), (1, 1, 112)]
