@@ -203,23 +203,45 @@ static int ensure_set_b(fdtd_engine* e)
     return 0;
 }
 
-// one fused sweep over planes [i_begin, i_end): reads the current set, writes the other one
-template <typename T, int TJ> static int launch_fused_tj(fdtd_engine* e, int i_begin, int i_end, cudaStream_t s)
+// Work-item order of a sweep that carries dispersive-medium recursions: the (x-segment, tile) items that meet a recursion
+// box first (they run a few times longer: dispatched last they would be the launch's tail).  Rebuilt when the tiling or
+// the recursion list changes; must be called OUTSIDE stream capture (allocation + synchronous copy).
+static int ensure_ade_order(fdtd_engine* e, const FusedTiling& t, int own_rows, int V)
+{
+    const long long items = (long long)t.nseg * t.ntj * t.ntk;
+    const std::vector<long long> sig = {e->ade_epoch, items, t.nseg, t.ntj, t.ntk, t.lx, t.own_lanes, own_rows, V, t.i_begin, t.i_end};
+    if (e->d_ade_order && sig == e->ade_order_sig) return 0;
+    std::vector<int> first, rest;
+    const int ntiles = t.ntj * t.ntk;
+    for (long long it = 0; it < items; ++it) {
+        const int seg = (int)(it / ntiles), tile = (int)(it - (long long)seg * ntiles);
+        const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
+        const int i0 = t.i_begin + seg * t.lx, i1 = std::min(i0 + t.lx, t.i_end);
+        const int j0 = tj * own_rows, j1 = j0 + own_rows, k0 = tk * t.own_lanes * V, k1 = (tk + 1) * t.own_lanes * V;
+        bool touched = false;
+        for (const AdeOp& op : e->ade)
+            if (j1 > op.lo[1] && j0 < op.lo[1] + op.n[1] && k1 > op.lo[2] && k0 < op.lo[2] + op.n[2] && i1 > op.lo[0] &&
+                i0 < op.lo[0] + op.n[0]) { touched = true; break; }
+        (touched ? first : rest).push_back((int)it);
+    }
+    first.insert(first.end(), rest.begin(), rest.end());
+    if (e->ade_order_items < items) {
+        cudaFree(e->d_ade_order); e->d_ade_order = nullptr; e->ade_order_items = 0;
+        CU(cudaMalloc(&e->d_ade_order, (size_t)items * sizeof(int)));
+        e->ade_order_items = items;
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(e->d_ade_order, first.data(), (size_t)items * sizeof(int), cudaMemcpyHostToDevice));
+    e->ade_order_sig = sig;
+    return 0;
+}
+
+template <typename T, int TJ> static FusedTiling fused_tiling(const fdtd_engine* e, int i_begin, int i_end)
 {
     constexpr int V = VecOf<T>::V;
     const Geom& g = e->g;
-    void** src = cur_fields(e);
-    void** dst = e->cur ? e->fld : e->fldB;
-    CFields<T> in;
-    in.ex = (const T*)src[0]; in.ey = (const T*)src[1]; in.ez = (const T*)src[2];
-    in.hx = (const T*)src[3]; in.hy = (const T*)src[4]; in.hz = (const T*)src[5];
-    Fields<T> out = fields_of<T>(dst);
-    FusedTiling t;
+    FusedTiling t{};
     t.i_begin = i_begin; t.i_end = i_end;
-    t.halo_flag = nullptr; t.halo_need = 0; t.error_word = nullptr; t.timeout_ns = e->slab.timeout_ns;
-    if (e->slab.connected && e->slab.has_right && i_end == g.nx) {
-        t.halo_flag = e->slab.flags; t.halo_need = (int)e->slab.step + 1; t.error_word = e->slab.flags + 2;
-    }
     const int vec_per_row = g.pz / V;
     const int ncols = (vec_per_row + 29) / 30;
     int own = (vec_per_row + ncols - 1) / ncols;
@@ -239,6 +261,46 @@ template <typename T, int TJ> static int launch_fused_tj(fdtd_engine* e, int i_b
     }
     t.lx = std::min(lx, planes);
     t.nseg = (planes + t.lx - 1) / t.lx;
+    return t;
+}
+
+template <typename T> static FusedTiling het_tiling(const fdtd_engine* e)
+{
+    constexpr int R = kHetRows, V = Vec8<T>::V;
+    const Geom& g = e->g;
+    FusedTiling t{};
+    t.i_begin = 0; t.i_end = g.nx;
+    t.own_lanes = kHetOwnLanes;
+    const int vec_per_row = g.pz / V;
+    t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
+    t.ntj = (g.ny + (R - 2) - 1) / (R - 2);
+    int lx = e->fused_lx;
+    if (lx <= 0) {
+        const long long tiles = (long long)t.ntj * t.ntk;
+        long long want = (148ll * 40 + tiles - 1) / tiles;
+        lx = (int)std::max<long long>(32, (g.nx + want - 1) / std::max<long long>(want, 1));
+        while (lx > 8 && tiles * ((g.nx + lx - 1) / lx) < 148 * 2) lx = (lx + 1) / 2;
+    }
+    t.lx = std::min(lx, g.nx);
+    t.nseg = (g.nx + t.lx - 1) / t.lx;
+    return t;
+}
+
+// one fused sweep over planes [i_begin, i_end): reads the current set, writes the other one
+template <typename T, int TJ> static int launch_fused_tj(fdtd_engine* e, int i_begin, int i_end, cudaStream_t s)
+{
+    const Geom& g = e->g;
+    void** src = cur_fields(e);
+    void** dst = e->cur ? e->fld : e->fldB;
+    CFields<T> in;
+    in.ex = (const T*)src[0]; in.ey = (const T*)src[1]; in.ez = (const T*)src[2];
+    in.hx = (const T*)src[3]; in.hy = (const T*)src[4]; in.hz = (const T*)src[5];
+    Fields<T> out = fields_of<T>(dst);
+    FusedTiling t = fused_tiling<T, TJ>(e, i_begin, i_end);
+    t.halo_flag = nullptr; t.halo_need = 0; t.error_word = nullptr; t.timeout_ns = e->slab.timeout_ns;
+    if (e->slab.connected && e->slab.has_right && i_end == g.nx) {
+        t.halo_flag = e->slab.flags; t.halo_need = (int)e->slab.step + 1; t.error_word = e->slab.flags + 2;
+    }
     const size_t smem = fused_smem_bytes<T, TJ>();
     const bool ade = ade_in_this_sweep(e) && e->g.nxg == e->g.nx;
     auto kern = k_fused3d<T, TJ, 0, false>;
@@ -250,7 +312,13 @@ template <typename T, int TJ> static int launch_fused_tj(fdtd_engine* e, int i_b
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, TJ + 1, 1);
     const unsigned items = (unsigned)t.nseg * t.ntj * t.ntk;
-    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, fold_of(e), ade ? ade_in_of(e) : AdeIn{});
+    AdeIn ad{};
+    if (ade) {
+        ad = ade_in_of(e);
+        if (e->ade_order_sig.size() && e->ade_order_sig[0] == e->ade_epoch && e->ade_order_sig[1] == (long long)items)
+            ad.order = e->d_ade_order;                   // prepared by prepare_ade_order for this tiling
+    }
+    kern<<<items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, fold_of(e), ad);
     if (ade && i_end == g.nx) e->ade_deferred = false;
     e->launches++;
     CU(cudaGetLastError());
@@ -336,9 +404,11 @@ template <typename T> static int launch_yeex(fdtd_engine* e, cudaStream_t s)
     t.ntj = (g.ny + (R - 1) - 1) / (R - 1);
     int lx = e->fused_lx;
     if (lx <= 0) {
-        const long long tiles = (long long)t.ntj * t.ntk;
-        long long want = (148ll * 40 + tiles - 1) / tiles;
-        lx = (int)std::max<long long>(32, (g.nx + want - 1) / std::max<long long>(want, 1));
+        // Short segments: measured on 1024^3 (profiles/r02_tuning.md) 64 planes 92.3, 128: 91.4, 205: 87.7, 342: 74.4,
+        // 1024: 62.5 Gcell/s — many short-lived CTAs keep neighbouring tiles on nearby planes, so the rim rows / lanes a
+        // tile re-reads are still in L2, and the slow boundary tiles do not leave a long tail.  Each segment pays one
+        // prologue plane (1.6 % at 64).
+        lx = 64;
     }
     t.lx = std::min(lx, g.nx);
     t.nseg = (g.nx + t.lx - 1) / t.lx;
@@ -371,7 +441,7 @@ static bool use_het_fused(const fdtd_engine* e) { return het_sweep_ok(e) && e->g
 
 template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
 {
-    constexpr int R = kHetRows, V = Vec8<T>::V;
+    constexpr int R = kHetRows;
     const Geom& g = e->g;
     void** src = cur_fields(e);
     void** dst = e->cur ? e->fld : e->fldB;
@@ -379,8 +449,7 @@ template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
     in.ex = (const T*)src[0]; in.ey = (const T*)src[1]; in.ez = (const T*)src[2];
     in.hx = (const T*)src[3]; in.hy = (const T*)src[4]; in.hz = (const T*)src[5];
     Fields<T> out = fields_of<T>(dst);
-    FusedTiling t{};
-    t.i_begin = 0; t.i_end = g.nx;
+    FusedTiling t = het_tiling<T>(e);
     t.timeout_ns = e->slab.timeout_ns;
     if (e->slab.connected && e->slab.has_right) {
         // the last x-segment reads the right neighbour's planes 0 and 1 (same 7 halo planes as the uniform one-step sweep)
@@ -389,26 +458,19 @@ template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
             return fail(FDTD_ESTATE, "x-slab with a right neighbour: fdtd_set_coeffs needs nx + 1 = %d planes", g.nx + 1);
         t.halo_flag = e->slab.flags; t.halo_need = (int)e->slab.step + 1; t.error_word = e->slab.flags + 2;
     }
-    t.own_lanes = kHetOwnLanes;
-    const int vec_per_row = g.pz / V;
-    t.ntk = (vec_per_row + t.own_lanes - 1) / t.own_lanes;
-    t.ntj = (g.ny + (R - 2) - 1) / (R - 2);
-    int lx = e->fused_lx;
-    if (lx <= 0) {
-        const long long tiles = (long long)t.ntj * t.ntk;
-        long long want = (148ll * 40 + tiles - 1) / tiles;
-        lx = (int)std::max<long long>(32, (g.nx + want - 1) / std::max<long long>(want, 1));
-        while (lx > 8 && tiles * ((g.nx + lx - 1) / lx) < 148 * 2) lx = (lx + 1) / 2;
-    }
-    t.lx = std::min(lx, g.nx);
-    t.nseg = (g.nx + t.lx - 1) / t.lx;
     const size_t smem = het_smem_bytes<T, R>();
     const bool ade = ade_in_this_sweep(e);
     auto kern = ade ? k_fused3d_het<T, R, true> : k_fused3d_het<T, R, false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, R, 1);
-    kern<<<(unsigned)t.nseg * t.ntj * t.ntk, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, (int)e->planes_alloc,
-                                                              ade ? ade_in_of(e) : AdeIn{});
+    const long long items = (long long)t.nseg * t.ntj * t.ntk;
+    AdeIn ad{};
+    if (ade) {
+        ad = ade_in_of(e);
+        if (e->ade_order_sig.size() && e->ade_order_sig[0] == e->ade_epoch && e->ade_order_sig[1] == items)
+            ad.order = e->d_ade_order;                   // prepared by prepare_ade_order for this tiling
+    }
+    kern<<<(unsigned)items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, (int)e->planes_alloc, ad);
     e->ade_deferred = false;
     e->launches++;
     CU(cudaGetLastError());
@@ -716,6 +778,15 @@ static bool ade_sweep_capable(const fdtd_engine* e)
     return e->ade_fused && !e->ade.empty() && e->cfg.ndim == 3 && e->g.nxg == e->g.nx && (use_fused(e) || use_het_fused(e));
 }
 
+// before a run (never inside stream capture): the box-first item order of the sweeps that will carry recursions
+template <typename T> static int prepare_ade_order(fdtd_engine* e)
+{
+    if (e->ade.empty() || !(e->ade_coupled || ade_sweep_capable(e))) return 0;
+    if (use_het_fused(e)) return ensure_ade_order(e, het_tiling<T>(e), kHetRows - 2, Vec8<T>::V);
+    if (use_fused(e)) return ensure_ade_order(e, fused_tiling<T, kFusedTJ>(e, 0, e->g.nx), kFusedTJ, VecOf<T>::V);
+    return 0;
+}
+
 template <typename T> static int one_step(fdtd_engine* e, int step_off, int parity, cudaStream_t s, bool defer_ade = false)
 {
     if (e->cfg.ndim == 3) {
@@ -736,6 +807,7 @@ template <typename T> static int run_steps(fdtd_engine* e, int n)
     cudaStream_t s = e->stream;
     if (e->ade_coupled && !e->ade.empty() && !(e->cfg.ndim == 3 && e->g.nxg == e->g.nx && (use_fused(e) || use_het_fused(e))))
         return fail(FDTD_ESTATE, "coupled dispersive media need the fused one-step sweeps (3-D, one GPU, no two-pass / physics flag)");
+    if (int rc = prepare_ade_order<T>(e)) return rc;
     if (use_fused(e) || use_het_fused(e) || use_yee_fused(e)) if (int rc = ensure_set_b(e)) return rc;
     if (e->cfg.ndim == 2) if (int rc = launch_count2d<T>(e, 0, s)) return rc;
     const bool use_graph = !(e->cfg.flags & FDTD_FLAG_NO_GRAPH) && n >= 32;

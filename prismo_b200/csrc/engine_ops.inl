@@ -18,6 +18,7 @@ extern "C" int fdtd_clear_ops(fdtd_engine* e)
     if (!e) return fail(FDTD_EINVAL, "null engine");
     e->src.clear(); e->mon.clear(); e->prof_host.clear(); e->src_ghost.clear();
     e->ade.clear(); e->ade_mask_host.clear(); e->flux.clear();
+    e->ade_epoch++;
     e->ops_dirty = true;
     drop_graph(e);
     return 0;
@@ -126,6 +127,7 @@ extern "C" int fdtd_add_ade_op(fdtd_engine* e, const fdtd_ade_op* op, int32_t* i
     }
     if (id) *id = (int32_t)e->ade.size();
     e->ade.push_back(a);
+    e->ade_epoch++;
     e->ops_dirty = true;
     drop_graph(e);
     return 0;

@@ -42,6 +42,7 @@ extern "C" int fdtd_update_e(fdtd_engine* e) { return e ? single_pass(e, 1) : fa
 template <typename T> static int run_profiled(fdtd_engine* e, int n, double* out_ms)
 {
     cudaStream_t s = e->stream;
+    if (int rc = prepare_ade_order<T>(e)) return rc;
     std::vector<cudaEvent_t> ev((size_t)n * 3 + 1);
     for (auto& x : ev) CU(cudaEventCreate(&x));
     if (e->cfg.ndim == 2) if (int rc = launch_count2d<T>(e, 0, s)) return rc;

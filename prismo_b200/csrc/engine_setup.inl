@@ -108,7 +108,7 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     cudaFree(e->d_src); cudaFree(e->d_mon); cudaFree(e->d_prof); cudaFree(e->d_src_ghost);
     cudaFree(e->d_ade); cudaFree(e->d_aux); cudaFree(e->d_ade_mask);
     cudaFree(e->d_flux); cudaFree(e->d_flux_partial); cudaFree(e->d_flux_out);
-    cudaFree(e->d_cpml_coef); cudaFree(e->d_cpml_coef_f); cudaFree(e->d_plane_flags);
+    cudaFree(e->d_cpml_coef); cudaFree(e->d_cpml_coef_f); cudaFree(e->d_plane_flags); cudaFree(e->d_ade_order);
     for (int q = 0; q < 12; ++q) { cudaFree(e->cpml.psi[q]); cudaFree(e->psiB[q]); }
     cudaFree(e->d_comp_ptr[0]); cudaFree(e->d_comp_ptr[1]);
     cudaFree(e->d_amp); cudaFree(e->d_phasor); cudaFree(e->d_rec); cudaFree(e->d_dft);

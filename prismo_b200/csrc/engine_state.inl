@@ -66,6 +66,8 @@ struct fdtd_engine {
     int ade_fused = 1;              // apply the recursions inside the next fused sweep where one follows (0: always k_ade)
     int ade_coupled = 0;            // OPT-IN, not the reference's behaviour: feed the polarisation current back into E
     bool ade_deferred = false;      // the recursion of the last enqueued step is still to be applied by the next sweep
+    long long ade_epoch = 0;        // bumps whenever the recursion list changes
+    int* d_ade_order = nullptr; long long ade_order_items = 0; std::vector<long long> ade_order_sig;   // box items first
     bool ops_dirty = true;
     Cpml cpml{}; SlabGeom slabg{}; double* d_cpml_coef = nullptr; float* d_cpml_coef_f = nullptr; size_t psi_bytes[12] = {};
     void* psiB[12] = {};            // second psi set: the fused physics sweep ping-pongs psi like the fields

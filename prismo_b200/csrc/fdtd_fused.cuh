@@ -227,9 +227,10 @@ template <typename T, int POL> __device__ __forceinline__ void stv_pol(T* p, con
 // TJ owner rows per CTA; blockDim = (32, TJ + 1);  AM = fp64 arithmetic mode (0 exact, 1 folded).
 // (Rejected by measurement, profiles/r01_tuning.md, and removed: evict-first stores, ld.global.cg loads, 2 CTAs x 8 warps.)
 // ADE: apply the dispersive-medium recursions of the PREVIOUS step on the E stage's input values (ade_in_sweep).
-template <typename T, int TJ, int AM, bool ADE = false>
-__global__ void __launch_bounds__(32 * (TJ + 1), 1)
-k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold fo, AdeIn ad)
+template <typename T, int TJ, int AM, bool ADE>
+__device__ __forceinline__ void
+fused_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const Geom& g, const FusedTiling& t, const Fold& fo,
+            const AdeIn& ad, const int item)
 {
     constexpr int POL = 0;
     constexpr int V = VecOf<T>::V;
@@ -242,7 +243,7 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
 
     const int lane = threadIdx.x, row = threadIdx.y;
     const int ntiles = t.ntj * t.ntk;
-    const int seg = blockIdx.x / ntiles, tile = blockIdx.x - seg * ntiles;
+    const int seg = item / ntiles, tile = item - seg * ntiles;
     const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
     const int j = tj * TJ + row;
     const int k = (tk * t.own_lanes + lane) * V;
@@ -274,7 +275,12 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
     P h1x = ldv_pol<T, POL>(phx + po, ld_ok), h1y = ldv_pol<T, POL>(phy + po, ld_ok), h1z = ldv_pol<T, POL>(phz + po, ld_ok);
 
     unsigned ade_mask = 0;
-    if (ADE) { if (owner) ade_mask = ade_thread_mask<V>(ad, i0, i1, j, k); }
+    __shared__ AdeOp s_ade[ADE ? kAdeSmemOps : 1];
+    if (ADE) {
+        ade_stage_ops(s_ade, ad, threadIdx.y * 32 + threadIdx.x, 32 * (TJ + 1));
+        if (owner) ade_mask = ade_thread_mask<V>(ad, i0, i1, j, k);
+        __syncthreads();
+    }
 
     for (int i = i0 - 1; i < i1; ++i) {
         const int par = (i - i0 + 1) & 1;
@@ -328,7 +334,7 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
                     double jx[V], jy[V], jz[V];
 #pragma unroll
                     for (int e = 0; e < V; ++e) jx[e] = jy[e] = jz[e] = 0.0;
-                    ade_in_sweep<T, V>(ad, ade_mask, i, j, k, e0x, e0y, e0z, jx, jy, jz);
+                    ade_in_sweep<T, V>(ad, s_ade, ade_mask, i, j, k, e0x, e0y, e0z, jx, jy, jz);
                     if (ad.coupled) {
 #pragma unroll
                         for (int e = 0; e < V; ++e) {                  // op boxes lie inside the updated range of their component
@@ -351,6 +357,29 @@ k_fused3d(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, Fold 
         hpx = hnx; hpy = hny; hpz = hnz;
         h1x = n_hx; h1y = n_hy; h1z = n_hz;
     }
+}
+
+template <typename T, int TJ, int AM, bool ADE = false>
+__global__ void __launch_bounds__(32 * (TJ + 1), 1)
+k_fused3d(const __grid_constant__ CFields<T> in, const __grid_constant__ Fields<T> out, const __grid_constant__ Coefs<T> c,
+          const __grid_constant__ Geom g, const __grid_constant__ FusedTiling t, const __grid_constant__ Fold fo,
+          const __grid_constant__ AdeIn ad)
+{
+    if (ADE) {
+        constexpr int V = VecOf<T>::V;
+        const int item = ad.order ? ad.order[blockIdx.x] : (int)blockIdx.x;
+        const int ntiles = t.ntj * t.ntk;
+        const int seg = item / ntiles, tile = item - seg * ntiles;
+        const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
+        const int i0 = t.i_begin + seg * t.lx, i1 = min(i0 + t.lx, t.i_end);
+        if (ade_tile_touched(ad, i0, i1, tj * TJ, tj * TJ + TJ, tk * t.own_lanes * V, (tk + 1) * t.own_lanes * V)) {
+            fused_sweep<T, TJ, AM, true>(in, out, c, g, t, fo, ad, item);
+            return;
+        }
+        fused_sweep<T, TJ, AM, false>(in, out, c, g, t, fo, ad, item);
+        return;
+    }
+    fused_sweep<T, TJ, AM, false>(in, out, c, g, t, fo, ad, (int)blockIdx.x);
 }
 
 }  // namespace fdtd

@@ -21,8 +21,9 @@ template <typename T, int R> constexpr size_t het_smem_bytes() { return 2 * (siz
 
 // ADE: apply the dispersive-medium recursions of the PREVIOUS step on the E stage's input values (ade_in_sweep).
 template <typename T, int R, bool ADE>
-__global__ void __launch_bounds__(32 * R, 1)
-k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, int planes_alloc, AdeIn ad)
+__device__ __forceinline__ void
+het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const Geom& g, const FusedTiling& t, const int planes_alloc,
+          const AdeIn& ad, const int item)
 {
     constexpr int V = Vec8<T>::V;
     typedef Pack<T, V> P;
@@ -33,7 +34,7 @@ k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, i
 
     const int lane = threadIdx.x, row = threadIdx.y;
     const int ntiles = t.ntj * t.ntk;
-    const int seg = blockIdx.x / ntiles, tile = blockIdx.x - seg * ntiles;
+    const int seg = item / ntiles, tile = item - seg * ntiles;
     const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
     const int j = tj * (R - 2) + row;
     const int k = (tk * t.own_lanes + lane) * V;
@@ -69,7 +70,12 @@ k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, i
     P da2 = ld8<T, V>(pda + po + g.sx, ld_ok), db2 = ld8<T, V>(pdb + po + g.sx, ld_ok);   // D[i+2]
     P ca0_j = z_, cb0_j = z_;                                                           // C[i] at j+1
     unsigned ade_mask = 0;
-    if (ADE) { if (owner) ade_mask = ade_thread_mask<V>(ad, i0, i1, j, k); }
+    __shared__ AdeOp s_ade[ADE ? kAdeSmemOps : 1];
+    if (ADE) {
+        ade_stage_ops(s_ade, ad, threadIdx.y * 32 + threadIdx.x, 32 * R);
+        if (owner) ade_mask = ade_thread_mask<V>(ad, i0, i1, j, k);
+        __syncthreads();
+    }
 
     for (int i = i0 - 1; i < i1; ++i) {
         const int par = (i - i0 + 1) & 1;
@@ -139,7 +145,7 @@ k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, i
             double jx[V], jy[V], jz[V];
 #pragma unroll
             for (int e = 0; e < V; ++e) jx[e] = jy[e] = jz[e] = 0.0;
-            if (ADE) { if (ade_mask) ade_in_sweep<T, V>(ad, ade_mask, i, j, k, e0x, e0y, e0z, jx, jy, jz); }
+            if (ADE) { if (ade_mask) ade_in_sweep<T, V>(ad, s_ade, ade_mask, i, j, k, e0x, e0y, e0z, jx, jy, jz); }
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;
@@ -178,6 +184,30 @@ k_fused3d_het(CFields<T> in, Fields<T> out, Coefs<T> c, Geom g, FusedTiling t, i
         ca0_j = ca1_j; cb0_j = cb1_j;
         da1 = da2; db1 = db2; da2 = n_da; db2 = n_db;
     }
+}
+
+template <typename T, int R, bool ADE>
+__global__ void __launch_bounds__(32 * R, 1)
+k_fused3d_het(const __grid_constant__ CFields<T> in, const __grid_constant__ Fields<T> out, const __grid_constant__ Coefs<T> c,
+              const __grid_constant__ Geom g, const __grid_constant__ FusedTiling t, const int planes_alloc,
+              const __grid_constant__ AdeIn ad)
+{
+    if (ADE) {
+        // only the CTAs whose tile and x-segment meet a recursion box run the body that carries the recursion code
+        constexpr int V = Vec8<T>::V;
+        const int item = ad.order ? ad.order[blockIdx.x] : (int)blockIdx.x;
+        const int ntiles = t.ntj * t.ntk;
+        const int seg = item / ntiles, tile = item - seg * ntiles;
+        const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
+        const int i0 = t.i_begin + seg * t.lx, i1 = min(i0 + t.lx, t.i_end);
+        if (ade_tile_touched(ad, i0, i1, tj * (R - 2), tj * (R - 2) + R - 2, tk * t.own_lanes * V, (tk + 1) * t.own_lanes * V)) {
+            het_sweep<T, R, true>(in, out, c, g, t, planes_alloc, ad, item);
+            return;
+        }
+        het_sweep<T, R, false>(in, out, c, g, t, planes_alloc, ad, item);
+        return;
+    }
+    het_sweep<T, R, false>(in, out, c, g, t, planes_alloc, ad, (int)blockIdx.x);
 }
 
 }  // namespace fdtd

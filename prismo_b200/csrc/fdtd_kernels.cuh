@@ -536,7 +536,11 @@ __global__ void k_ade(const T* const* __restrict__ comp_ptr, const AdeOp* __rest
 //   recursion is subtracted in the same E update,  E+ -= Cb * eps0 * (P+ - P) / dt  (Lorentz, Debye)  or
 //   Cb * eps0 * J+  (Drude) — the reference's recursion coefficients (dispersion.py:189-336) carry no eps0, so P and J
 //   are in units of eps0 —, with the recursion applied at the BEGINNING of every step (oracle/ade.py: coupled_step).
-struct AdeIn { const AdeOp* ops; int n; void* aux; const unsigned char* mask; int coupled; double kp, kj; };   // kp = eps0/dt, kj = eps0
+// order: optional permutation of the sweep's work items (x-segment, tile) that dispatches the items which meet a recursion
+// box FIRST — they run a few times longer than the others and would otherwise set the length of the launch's tail.
+struct AdeIn { const AdeOp* ops; int n; void* aux; const unsigned char* mask; int coupled; double kp, kj; const int* order; };   // kp = eps0/dt, kj = eps0
+
+constexpr int kAdeSmemOps = 24;          // recursion descriptors kept in shared memory per CTA (bits 0..23 of the thread mask)
 
 // Which recursions can ever touch this thread's cells (row j, cells k .. k+V-1, planes [i0, i1))?  A thread's (j, k) is fixed
 // for the whole sweep, so this is evaluated once per kernel: the plane loop of the 97 % of threads outside every box
@@ -545,44 +549,136 @@ template <int V>
 __device__ __forceinline__ unsigned ade_thread_mask(const AdeIn& ad, int i0, int i1, int j, int k)
 {
     unsigned m = 0;
-    const int n = ad.n < 32 ? ad.n : 32;
+    const int n = ad.n < kAdeSmemOps ? ad.n : kAdeSmemOps;
     for (int q = 0; q < n; ++q) {
         const AdeOp& op = ad.ops[q];
         if ((unsigned)(j - op.lo[1]) < (unsigned)op.n[1] && k + V > op.lo[2] && k < op.lo[2] + op.n[2] &&
             i1 > op.lo[0] && i0 < op.lo[0] + op.n[0])
             m |= 1u << q;
     }
-    if (ad.n > 32) m |= 0x80000000u;            // more than 32 recursions: the tail is tested op by op
+    if (ad.n > kAdeSmemOps) m |= 0x80000000u;   // more recursions than the shared copy holds: the tail is tested op by op
     return m;
 }
 
-template <typename T, int V>
-__device__ __forceinline__ void ade_in_sweep(const AdeIn& ad, unsigned mask, int i, int j, int k, const Pack<T, V>& ex,
-                                             const Pack<T, V>& ey, const Pack<T, V>& ez, double (&jx)[V], double (&jy)[V],
-                                             double (&jz)[V])
+// CTA-level version of the same test: does any recursion touch the owner cells of a (j, k) tile on planes [i0, i1)?  CTAs
+// that answer no run the sweep body compiled WITHOUT the recursion code (its presence alone costs registers and
+// memory-level parallelism: the c3 sweep ran 2.3x slower with it in every CTA, profiles/r02_tuning.md).
+__device__ __forceinline__ bool ade_tile_touched(const AdeIn& ad, int i0, int i1, int j0, int j1, int k0, int k1)
 {
     for (int q = 0; q < ad.n; ++q) {
-        if (q < 31 && !((mask >> q) & 1u)) continue;
-        if (q >= 31 && !(mask & 0x80000000u)) break;
         const AdeOp& op = ad.ops[q];
+        if (j1 > op.lo[1] && j0 < op.lo[1] + op.n[1] && k1 > op.lo[2] && k0 < op.lo[2] + op.n[2] &&
+            i1 > op.lo[0] && i0 < op.lo[0] + op.n[0])
+            return true;
+    }
+    return false;
+}
+
+// One plane of one thread.  `ops` is the CTA's shared-memory copy of the recursion descriptors (ade_stage_ops): the
+// first version read them from global memory op by op and state by state, a chain of dependent L1 / DRAM latencies in
+// the only warps of the CTA that do this work — every other warp waits for them at the per-plane barrier, and the few
+// CTAs that meet a box set the length of the whole launch (c3: 2.0 ms against 0.87 ms, profiles/r02_tuning.md).  Now the
+// (up to three) recursions that can touch the thread are resolved to static slots, ALL their state loads are issued
+// first, then the arithmetic and the stores follow; further recursions (rare) take the sequential path.
+__device__ __forceinline__ void ade_stage_ops(AdeOp* s_ops, const AdeIn& ad, int tid, int nthreads)
+{
+    const int words = min(ad.n, kAdeSmemOps) * (int)(sizeof(AdeOp) / 4);
+    const unsigned* src = reinterpret_cast<const unsigned*>(ad.ops);
+    unsigned* dst = reinterpret_cast<unsigned*>(s_ops);
+    for (int w = tid; w < words; w += nthreads) dst[w] = src[w];
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void ade_one(const AdeIn& ad, const AdeOp& op, int i, int j, int k, const Pack<T, V>& ex,
+                                        const Pack<T, V>& ey, const Pack<T, V>& ez, double (&jx)[V], double (&jy)[V], double (&jz)[V])
+{
+    const int a0 = i - op.lo[0], a1 = j - op.lo[1];
+    if ((unsigned)a0 >= (unsigned)op.n[0] || (unsigned)a1 >= (unsigned)op.n[1]) return;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const int a2 = k + e - op.lo[2];
+        if ((unsigned)a2 >= (unsigned)op.n[2]) continue;
+        const long long cell = ((long long)a0 * op.n[1] + a1) * op.n[2] + a2;
+        const double ev = (double)(op.comp == 0 ? ex.v[e] : (op.comp == 1 ? ey.v[e] : ez.v[e]));
+        double old;
+        const double nv = ade_update<T>(op, cell, ev, (T*)ad.aux, ad.mask, old);
+        if (ad.coupled) {
+            const double term = op.kind == 1 ? __dmul_rn(nv, ad.kj) : __dmul_rn(__dsub_rn(nv, old), ad.kp);
+            if (op.comp == 0) jx[e] = __dadd_rn(jx[e], term);
+            else if (op.comp == 1) jy[e] = __dadd_rn(jy[e], term);
+            else jz[e] = __dadd_rn(jz[e], term);
+        }
+    }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void ade_in_sweep(const AdeIn& ad, const AdeOp* __restrict__ ops, unsigned mask, int i, int j, int k,
+                                             const Pack<T, V>& ex, const Pack<T, V>& ey, const Pack<T, V>& ez, double (&jx)[V],
+                                             double (&jy)[V], double (&jz)[V])
+{
+    constexpr int K = 3;
+    T* __restrict__ aux = (T*)ad.aux;
+    unsigned mm = mask & 0x7fffffffu;
+    int q[K];
+#pragma unroll
+    for (int m = 0; m < K; ++m) { q[m] = mm ? (int)__ffs(mm) - 1 : -1; mm &= mm - 1u; }
+    // ---- phase 1: which cells, and every state value they need --------------------------------------------------------------
+    unsigned cell[K];                     // a recursion box has fewer than 2^32 cells (array_elems < 2^32 on this path)
+    unsigned em[K];                       // bit e: cell e is inside the box; bit 8+e: its mask byte is zero
+    T cur[K][V], prv[K][V];
+#pragma unroll
+    for (int m = 0; m < K; ++m) {
+        em[m] = 0;
+        if (q[m] < 0) continue;
+        const AdeOp& op = ops[q[m]];
         const int a0 = i - op.lo[0], a1 = j - op.lo[1];
         if ((unsigned)a0 >= (unsigned)op.n[0] || (unsigned)a1 >= (unsigned)op.n[1]) continue;
+        cell[m] = ((unsigned)a0 * (unsigned)op.n[1] + (unsigned)a1) * (unsigned)op.n[2] + (unsigned)(k - op.lo[2]);
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-            const int a2 = k + e - op.lo[2];
-            if ((unsigned)a2 >= (unsigned)op.n[2]) continue;
-            const long long cell = ((long long)a0 * op.n[1] + a1) * op.n[2] + a2;
-            const double ev = (double)(op.comp == 0 ? ex.v[e] : (op.comp == 1 ? ey.v[e] : ez.v[e]));
-            double old;
-            const double nv = ade_update<T>(op, cell, ev, (T*)ad.aux, ad.mask, old);
+            if ((unsigned)(k + e - op.lo[2]) >= (unsigned)op.n[2]) continue;
+            em[m] |= 1u << e;
+            cur[m][e] = aux[op.cur_off + cell[m] + e];
+            prv[m][e] = op.kind == 0 ? aux[op.prev_off + cell[m] + e] : (T)0;
+            if (op.mask_off >= 0 && !ad.mask[op.mask_off + cell[m] + e]) em[m] |= 1u << (8 + e);
+        }
+    }
+    // ---- phase 2: the recursions (same operation order as ade_update / k_ade), stores, feedback terms -----------------------
+#pragma unroll
+    for (int m = 0; m < K; ++m) {
+        if (!em[m]) continue;
+        const AdeOp& op = ops[q[m]];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            if (!((em[m] >> e) & 1u)) continue;
+            double ev = (double)(op.comp == 0 ? ex.v[e] : (op.comp == 1 ? ey.v[e] : ez.v[e]));
+            if (op.mask_off >= 0) ev = __dmul_rn(ev, ((em[m] >> (8 + e)) & 1u) ? 0.0 : 1.0);
+            const double a = (double)cur[m][e];
+            double nv;
+            if (op.kind == 0) {
+                nv = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(op.c0, ev), __dmul_rn(op.c1, ev)), __dmul_rn(op.c2, a)),
+                               __dmul_rn(op.c3, (double)prv[m][e]));
+                aux[op.prev_off + cell[m] + e] = (T)a;
+            } else {
+                nv = __dadd_rn(__dmul_rn(op.c0, ev), __dmul_rn(op.c1, a));
+            }
+            aux[op.cur_off + cell[m] + e] = (T)nv;
             if (ad.coupled) {
-                const double term = op.kind == 1 ? __dmul_rn(nv, ad.kj) : __dmul_rn(__dsub_rn(nv, old), ad.kp);
+                const double term = op.kind == 1 ? __dmul_rn(nv, ad.kj) : __dmul_rn(__dsub_rn(nv, a), ad.kp);
                 if (op.comp == 0) jx[e] = __dadd_rn(jx[e], term);
                 else if (op.comp == 1) jy[e] = __dadd_rn(jy[e], term);
                 else jz[e] = __dadd_rn(jz[e], term);
             }
         }
     }
+    // ---- more than three recursions on this thread, or more descriptors than the shared copy holds: one by one ---------------
+    while (mm) {
+        const int qq = (int)__ffs(mm) - 1;
+        mm &= mm - 1u;
+        ade_one<T, V>(ad, ops[qq], i, j, k, ex, ey, ez, jx, jy, jz);
+    }
+    if (mask & 0x80000000u)
+        for (int qq = kAdeSmemOps; qq < ad.n; ++qq) ade_one<T, V>(ad, ad.ops[qq], i, j, k, ex, ey, ez, jx, jy, jz);
 }
 
 // Region-correct flux (extension): instantaneous power through a box, P = sum (E x H)_n over the

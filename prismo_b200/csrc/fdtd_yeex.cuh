@@ -513,7 +513,7 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
             st8<T, V>(out.hx + oh, hnx); st8<T, V>(out.hy + oh, hny); st8<T, V>(out.hz + oh, hnz);
         }
         // ---- E+[i]: owners only (nobody consumes the E+ of a rim thread) -------------------------------------------------------------------
-        if (it > 0) {
+        if (it > 0 && row <= R - 2) {                         // (the 15th row only provides H+: it has no E stage)
             P nx_ = e0x, ny_ = e0y, nz_ = e0z;
             if (lean_thread && i >= el_lo && i <= xl_hi)
                 yee_e_lean<T, V, AM>(c, g, e0x, e0y, e0z, hpx, hpy, hpz, hz_jp, hx_jp, hy_kp, hx_kp, hny, hnz, nx_, ny_, nz_);
