@@ -638,9 +638,10 @@ __device__ __forceinline__ void ade_in_sweep(const AdeIn& ad, const AdeOp* __res
         for (int e = 0; e < V; ++e) {
             if ((unsigned)(k + e - op.lo[2]) >= (unsigned)op.n[2]) continue;
             em[m] |= 1u << e;
-            cur[m][e] = aux[op.cur_off + cell[m] + e];
-            prv[m][e] = op.kind == 0 ? aux[op.prev_off + cell[m] + e] : (T)0;
-            if (op.mask_off >= 0 && !ad.mask[op.mask_off + cell[m] + e]) em[m] |= 1u << (8 + e);
+            const unsigned ce = cell[m] + (unsigned)e;      // modulo 2^32 on purpose: k - lo may be -1 for the cell before the box
+            cur[m][e] = aux[op.cur_off + ce];
+            prv[m][e] = op.kind == 0 ? aux[op.prev_off + ce] : (T)0;
+            if (op.mask_off >= 0 && !ad.mask[op.mask_off + ce]) em[m] |= 1u << (8 + e);
         }
     }
     // ---- phase 2: the recursions (same operation order as ade_update / k_ade), stores, feedback terms -----------------------
@@ -658,11 +659,11 @@ __device__ __forceinline__ void ade_in_sweep(const AdeIn& ad, const AdeOp* __res
             if (op.kind == 0) {
                 nv = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(op.c0, ev), __dmul_rn(op.c1, ev)), __dmul_rn(op.c2, a)),
                                __dmul_rn(op.c3, (double)prv[m][e]));
-                aux[op.prev_off + cell[m] + e] = (T)a;
+                aux[op.prev_off + (cell[m] + (unsigned)e)] = (T)a;
             } else {
                 nv = __dadd_rn(__dmul_rn(op.c0, ev), __dmul_rn(op.c1, a));
             }
-            aux[op.cur_off + cell[m] + e] = (T)nv;
+            aux[op.cur_off + (cell[m] + (unsigned)e)] = (T)nv;
             if (ad.coupled) {
                 const double term = op.kind == 1 ? __dmul_rn(nv, ad.kj) : __dmul_rn(__dsub_rn(nv, a), ad.kp);
                 if (op.comp == 0) jx[e] = __dadd_rn(jx[e], term);
