@@ -622,17 +622,17 @@ def main():
               else "k_h3d + k_e3d (2 launches/step)")
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        key = f"{name}:{args.dtype}:{'two-step' if tb2 else 'one-step'}"
-        if fused and not args.het and key in tr:
-            traffic = tr[key]["dram_bytes"]          # bytes per launch group, from the committed ncu capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        key = f"{name}:{args.dtype}:" + ("physics" if args.physics else ("two-step" if tb2 else "one-step"))
+        if (fused or args.physics) and not args.het and key in tr:
+            traffic = tr[key]["dram_bytes"]          # bytes per launch, from the committed ncu capture of this kernel
     except (OSError, ValueError):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": kname,
                 "note": ("achieved = ALGORITHMIC bytes (48 B per cell-update, SURVEY 8d) / kernel time; the two-step "
-                         "sweep keeps the intermediate step on chip, so its real DRAM traffic is ~27 B per cell-update "
-                         "(ncu: profiles/) and frac can exceed 1") if tb2 else None,
+                         "sweep keeps the intermediate step on chip, so its real DRAM traffic is 28.2 B per cell-update "
+                         "(ncu: profiles/r02_ncu_summary.md, 84 % of the copy peak) and frac can exceed 1") if tb2 else None,
                 "algorithmic_bytes_per_launch": (2 if tb2 else 1) * bpc * cells if fused else bpc * cells / 2,
                 "odd_last_step": "one-step sweep" if (tb2 and args.steps % 2) else None,
                 "kernel_ms_per_step": kern_ms / args.steps, "post_ms_per_step": prof["post_ms"] / args.steps}

@@ -412,8 +412,6 @@ template <typename T> static int launch_yeex(fdtd_engine* e, cudaStream_t s)
     }
     t.lx = std::min(lx, g.nx);
     t.nseg = (g.nx + t.lx - 1) / t.lx;
-    static const int st_cs = getenv("FDTD_B200_YEEX_STCS") ? atoi(getenv("FDTD_B200_YEEX_STCS")) : 0;
-    t.halo_need = st_cs;
     const int S = e->yeex_stages, D = e->yeex_slots;
     const size_t smem = yeex_smem_bytes<R>(S, D);
     if (smem > 227 * 1024) return fail(FDTD_EINVAL, "physics sweep rings (%d stages, %d slots) need %zu B of shared memory", S, D, smem);

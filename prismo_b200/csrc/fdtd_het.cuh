@@ -11,9 +11,20 @@
 // 8-byte vectors per thread (2 fp32 / 1 fp64 cells) keep the window in registers.  Of R warp rows the first R-2
 // own cells (row R-2 recomputes H+ on the rim, row R-1 only provides raw neighbours); of 32 lanes the first 30.
 #pragma once
+#include <type_traits>
+
 #include "fdtd_tb2.cuh"
 
 namespace fdtd {
+
+// fp64: the divisions by the launch-constant spacings go through the correctly rounded FMA sequence (Ar<double>::div_fast)
+// with ONE range check per stage; a stage whose check fails (inf / nan / denormal quotients) is recomputed with true
+// divisions.  The first version used the per-division fallback (two branches per division): 10 Gcell/s on c3.
+template <typename T, bool SLOW> __device__ __forceinline__ T het_diff(T a1, T a0, double d, Rcp r, unsigned& bad)
+{
+    if (SLOW) return Ar<T>::diff_exact(a1, a0, d, r);
+    return Ar<T>::diff_fast(a1, a0, d, r, bad);
+}
 
 constexpr int kHetRows = 16;
 constexpr int kHetOwnLanes = 30;
@@ -116,22 +127,30 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
         const int gi1 = g.x0 + i + 1;
         const bool ix1 = gi1 < g.nxg - 1, ix2 = gi1 < g.nxg - 2;
         P hnx = h1x, hny = h1y, hnz = h1z;
+        auto h_stage = [&](auto slow) -> unsigned {
+            constexpr bool SLOW = decltype(slow)::value;
+            unsigned bad = 0;
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            const bool kz1 = (k + e) < g.nz - 1, kz2 = (k + e) < g.nz - 2;
-            const T ey_k = (e + 1 < V) ? e1y.v[(e + 1) % V] : ey1_n;
-            const T ex_k = (e + 1 < V) ? e1x.v[(e + 1) % V] : ex1_n;
-            const T da_k = (e + 1 < V) ? da1.v[(e + 1) % V] : da1_n;
-            const T db_k = (e + 1 < V) ? db1.v[(e + 1) % V] : db1_n;
-            T n = upd_h<T>(mean2<T>(da1.v[e], da2.v[e]), h1x.v[e], mean2<T>(db1.v[e], db2.v[e]),
-                           Ar<T>::diff(ez_j.v[e], e1z.v[e], g.dy, g.rdy), Ar<T>::diff(ey_k, e1y.v[e], g.dz, g.rdz));
-            if (ix1 && jy2 && kz2) hnx.v[e] = n;
-            n = upd_h<T>(mean2<T>(da1.v[e], da1_j.v[e]), h1y.v[e], mean2<T>(db1.v[e], db1_j.v[e]),
-                         Ar<T>::diff(ex_k, e1x.v[e], g.dz, g.rdz), Ar<T>::diff(e2z.v[e], e1z.v[e], g.dx, g.rdx));
-            if (ix2 && jy1 && kz2) hny.v[e] = n;
-            n = upd_h<T>(mean2<T>(da1.v[e], da_k), h1z.v[e], mean2<T>(db1.v[e], db_k),
-                         Ar<T>::diff(e2y.v[e], e1y.v[e], g.dx, g.rdx), Ar<T>::diff(ex_j.v[e], e1x.v[e], g.dy, g.rdy));
-            if (ix2 && jy2 && kz1) hnz.v[e] = n;
+            for (int e = 0; e < V; ++e) {
+                const bool kz1 = (k + e) < g.nz - 1, kz2 = (k + e) < g.nz - 2;
+                const T ey_k = (e + 1 < V) ? e1y.v[(e + 1) % V] : ey1_n;
+                const T ex_k = (e + 1 < V) ? e1x.v[(e + 1) % V] : ex1_n;
+                const T da_k = (e + 1 < V) ? da1.v[(e + 1) % V] : da1_n;
+                const T db_k = (e + 1 < V) ? db1.v[(e + 1) % V] : db1_n;
+                T n = upd_h<T>(mean2<T>(da1.v[e], da2.v[e]), h1x.v[e], mean2<T>(db1.v[e], db2.v[e]),
+                               het_diff<T, SLOW>(ez_j.v[e], e1z.v[e], g.dy, g.rdy, bad), het_diff<T, SLOW>(ey_k, e1y.v[e], g.dz, g.rdz, bad));
+                if (ix1 && jy2 && kz2) hnx.v[e] = n;
+                n = upd_h<T>(mean2<T>(da1.v[e], da1_j.v[e]), h1y.v[e], mean2<T>(db1.v[e], db1_j.v[e]),
+                             het_diff<T, SLOW>(ex_k, e1x.v[e], g.dz, g.rdz, bad), het_diff<T, SLOW>(e2z.v[e], e1z.v[e], g.dx, g.rdx, bad));
+                if (ix2 && jy1 && kz2) hny.v[e] = n;
+                n = upd_h<T>(mean2<T>(da1.v[e], da_k), h1z.v[e], mean2<T>(db1.v[e], db_k),
+                             het_diff<T, SLOW>(e2y.v[e], e1y.v[e], g.dx, g.rdx, bad), het_diff<T, SLOW>(ex_j.v[e], e1x.v[e], g.dy, g.rdy, bad));
+                if (ix2 && jy2 && kz1) hnz.v[e] = n;
+            }
+            return bad;
+        };
+        if (h_stage(std::false_type{})) {
+            if (sizeof(T) == 8) { hnx = h1x; hny = h1y; hnz = h1z; h_stage(std::true_type{}); }
         }
         if (owner && i + 1 < i1) {
             const unsigned q = ofs + (unsigned)(i + 1) * (unsigned)g.sx;
@@ -146,6 +165,9 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
 #pragma unroll
             for (int e = 0; e < V; ++e) jx[e] = jy[e] = jz[e] = 0.0;
             if (ADE) { if (ade_mask) ade_in_sweep<T, V>(ad, s_ade, ade_mask, i, j, k, e0x, e0y, e0z, jx, jy, jz); }
+            auto e_stage = [&](auto slow) -> unsigned {
+                constexpr bool SLOW = decltype(slow)::value;
+                unsigned bad = 0;
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 const bool kz0 = (k + e) < g.nz, kz1 = (k + e) < g.nz - 1;
@@ -156,18 +178,23 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
                 const T ca0_jk = (e + 1 < V) ? ca0_j.v[(e + 1) % V] : ca0j_n, cb0_jk = (e + 1 < V) ? cb0_j.v[(e + 1) % V] : cb0j_n;
                 T n = upd_e<T>(mean4<T>(ca0.v[e], ca0_j.v[e], ca0_k, ca0_jk), e0x.v[e],
                                mean4<T>(cb0.v[e], cb0_j.v[e], cb0_k, cb0_jk),
-                               Ar<T>::diff(hz_j.v[e], hpz.v[e], g.dy, g.rdy), Ar<T>::diff(hy_k, hpy.v[e], g.dz, g.rdz));
+                               het_diff<T, SLOW>(hz_j.v[e], hpz.v[e], g.dy, g.rdy, bad), het_diff<T, SLOW>(hy_k, hpy.v[e], g.dz, g.rdz, bad));
                 if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(mean4<T>(cb0.v[e], cb0_j.v[e], cb0_k, cb0_jk), (T)jx[e])); }
                 if (ex0 && jy1 && kz1) ox.v[e] = n;
                 n = upd_e<T>(mean4<T>(ca0.v[e], ca1.v[e], ca0_k, ca1_k), e0y.v[e], mean4<T>(cb0.v[e], cb1.v[e], cb0_k, cb1_k),
-                             Ar<T>::diff(hx_k, hpx.v[e], g.dz, g.rdz), Ar<T>::diff(hnz.v[e], hpz.v[e], g.dx, g.rdx));
+                             het_diff<T, SLOW>(hx_k, hpx.v[e], g.dz, g.rdz, bad), het_diff<T, SLOW>(hnz.v[e], hpz.v[e], g.dx, g.rdx, bad));
                 if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(mean4<T>(cb0.v[e], cb1.v[e], cb0_k, cb1_k), (T)jy[e])); }
                 if (ex1 && kz1) oy.v[e] = n;
                 n = upd_e<T>(mean4<T>(ca0.v[e], ca1.v[e], ca0_j.v[e], ca1_j.v[e]), e0z.v[e],
                              mean4<T>(cb0.v[e], cb1.v[e], cb0_j.v[e], cb1_j.v[e]),
-                             Ar<T>::diff(hny.v[e], hpy.v[e], g.dx, g.rdx), Ar<T>::diff(hx_j.v[e], hpx.v[e], g.dy, g.rdy));
+                             het_diff<T, SLOW>(hny.v[e], hpy.v[e], g.dx, g.rdx, bad), het_diff<T, SLOW>(hx_j.v[e], hpx.v[e], g.dy, g.rdy, bad));
                 if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(mean4<T>(cb0.v[e], cb1.v[e], cb0_j.v[e], cb1_j.v[e]), (T)jz[e])); }
                 if (ex1 && jy1 && kz0) oz.v[e] = n;
+            }
+                return bad;
+            };
+            if (e_stage(std::false_type{})) {
+                if (sizeof(T) == 8) { ox = e0x; oy = e0y; oz = e0z; e_stage(std::true_type{}); }
             }
             if (owner) {
                 const unsigned q = ofs + (unsigned)i * (unsigned)g.sx;

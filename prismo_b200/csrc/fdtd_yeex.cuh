@@ -133,17 +133,7 @@ __device__ __forceinline__ void yee_e_lean(const Coefs<T>& c, const Geom& g,
 //   base+3 x0 (y-component, d/dx)   base+4 x1 (z-component, d/dx)   base+5 y1 (z-component, d/dy)
 template <typename T, int V> struct YeexPsi { Pack<T, V> x0, x1, y0, y1, z0, z1; };
 
-// field stores: st_cs != 0 marks them evict-first (st.global.cs) — the output set is not read again before the next step,
-// so it need not displace the rim lines that neighbouring tiles are about to re-read from L2 (tuning switch)
-template <typename T, int V> __device__ __forceinline__ void st8_pol(T* p, const Pack<T, V>& r, int st_cs)
-{
-    typedef typename Vec8<T>::type VT;
-    union { VT q; Pack<T, V> r; } u;
-    u.r = r;
-    if (st_cs) __stcs(reinterpret_cast<VT*>(p), u.q);
-    else *reinterpret_cast<VT*>(p) = u.q;
-}
-
+// (Evict-first field stores, st.global.cs, were measured and make no difference: 88.0 vs 88.1 Gcell/s, profiles/r02_tuning.md.)
 template <typename T, int V> __device__ __forceinline__ Pack<T, V> ldnc8(const T* p)
 {
     typedef typename Vec8<T>::type VT;
@@ -390,7 +380,6 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
     const int i0 = t.i_begin + seg * t.lx;
     const int i1 = min(i0 + t.lx, t.i_end);
     const int n_it = i1 - i0 + 1;                          // i = i0 - 1 .. i1 - 1
-    const int st_cs = t.halo_need;                         // (no halo on this path: the field carries the store-policy switch)
 
     if (row == R && lane == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full + 8u * s, 1); mbar_init(empty + 8u * s, R); }
@@ -522,7 +511,7 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
         xd = xd1; xph = xph1;
         if (st_h) {
             const unsigned oh = ofs + (unsigned)p * (unsigned)g.sx;
-            st8_pol<T, V>(out.hx + oh, hnx, st_cs); st8_pol<T, V>(out.hy + oh, hny, st_cs); st8_pol<T, V>(out.hz + oh, hnz, st_cs);
+            st8<T, V>(out.hx + oh, hnx); st8<T, V>(out.hy + oh, hny); st8<T, V>(out.hz + oh, hnz);
         }
         // ---- E+[i]: owners only (nobody consumes the E+ of a rim thread) -------------------------------------------------------------------
         if (it > 0 && row <= R - 2) {                         // (the 15th row only provides H+: it has no E stage)
@@ -538,7 +527,7 @@ k_fused3d_yeex(const __grid_constant__ Tb2xMaps maps, const __grid_constant__ Fi
             }
             if (owner) {
                 const unsigned oe = ofs + (unsigned)i * (unsigned)g.sx;
-                st8_pol<T, V>(out.ex + oe, nx_, st_cs); st8_pol<T, V>(out.ey + oe, ny_, st_cs); st8_pol<T, V>(out.ez + oe, nz_, st_cs);
+                st8<T, V>(out.ex + oe, nx_); st8<T, V>(out.ey + oe, ny_); st8<T, V>(out.ez + oe, nz_);
             }
         }
         // psi of the next E stage (plane i + 1 = p)

@@ -140,7 +140,9 @@ class Session:
         from .distributed import SlabExecutor, active_world
 
         rank, world = active_world()
-        self.distributed = bool(_state.get("distributed", True)) and world > 1 and g.is_3d and not physics
+        # (slabs need >= 4 planes each — the two-step sweep ships 4 —: smaller grids run whole on every rank)
+        self.distributed = (bool(_state.get("distributed", True)) and world > 1 and g.is_3d and not physics
+                            and g.dimensions[0] >= 4 * world)
         if self.distributed:
             # one process per GPU under torchrun: this rank owns an x-slab (see distributed.py)
             dev = device if device is not None else rank % max(_device_count(), 1)

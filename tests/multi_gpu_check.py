@@ -162,7 +162,7 @@ def sim_check(same):
         sim._device = local
         sim.run_steps(3)
         sim.run_steps(spec["steps"] - 3)
-        assert sim.solver.updater.session().distributed
+        assert sim.solver.updater.session().distributed == (sim.grid.dimensions[0] >= 4 * world)
         res = S.results_mirror(sim)
         for k in gold.files:
             tol = 1e-14 if name == "src3d_mode" else 0.0
