@@ -433,3 +433,30 @@ def test_device_mode_overlap_matches_reference_formula():
     # the next advance() re-installs the ops: a fresh handle replaces the stale one
     sim.run_steps(1)
     assert fm._b200_device[2] == fm._b200_device[0].ops_epoch
+
+
+def test_box_download_and_plane_checksums():
+    """fdtd_download_box equals a slice of the full download; fdtd_field_checksum equals its NumPy model and is blind to
+    the order of summation (what makes the bench's fields_sha comparable across decompositions)."""
+    dims = (23, 37, 70)
+    for dtype in ("float64", "float32"):
+        eng = pb.Engine(3, dims, (2e-8,) * 3, 1e-17, dtype=dtype)
+        rng = np.random.default_rng(7)
+        for c in S.COMPONENTS:
+            eng.upload(c, rng.standard_normal(eng.field_shape(c)).astype(dtype))
+        eng.run(3)
+        for c, lo, hi in (("Ex", (0, 0, 0), eng.field_shape("Ex")), ("Hz", (5, 9, 11), (17, 30, 69)), ("Ey", (22, 36, 68), (22, 37, 69))):
+            full = eng.download(c)
+            box = eng.download_box(c, lo, hi)
+            assert box.dtype == np.float64 and np.array_equal(box, full[tuple(slice(a, b) for a, b in zip(lo, hi))])
+        with pytest.raises(ValueError, match="outside"):
+            eng.download_box("Ex", (0, 0, 0), (24, 1, 1))
+        for c in S.COMPONENTS:
+            a = eng.download(c).astype(dtype)
+            bits = a.view(np.uint64 if dtype == "float64" else np.uint32).astype(np.uint64).reshape(a.shape[0], -1)
+            w = (np.arange(bits.shape[1], dtype=np.uint64) + np.uint64(1))[None, :]
+            with np.errstate(over="ignore"):
+                want = np.stack([bits.sum(axis=1, dtype=np.uint64), (bits * w).sum(axis=1, dtype=np.uint64)], axis=1)
+            got = eng.plane_checksums(c)
+            assert got.shape == want.shape and np.array_equal(got, want), c
+        eng.close()
