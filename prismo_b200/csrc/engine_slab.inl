@@ -103,6 +103,13 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
     static const int planes2[6] = {4, 4, 4, 3, 3, 3};
     const size_t pbytes = (size_t)e->plane_elems * e->esz;
     CU(cudaEventRecord(sl.post_done, cs));
+    // The planes we push (0..3) are final as soon as the sweep has written them unless a source op of ours touches them:
+    // then the push need not wait for this rank's sources / monitors (on the rank that owns a DFT plane that is 0.1-0.25 ms
+    // per pair, which the left neighbour's ghost-reading segment would otherwise spend spinning: measured at 8 GPUs,
+    // profiles/r02_tuning.md §6).
+    bool early_push = true;
+    for (const HostSrc& h : e->src) if (h.op.lo[0] < 4) early_push = false;
+    std::vector<cudaEvent_t> push_ev;
     int q = 0;
     while (q < n) {
         const bool pair = tb2_ok(e) && q + 2 <= n;        // never for heterogeneous media (tb2_ok needs use_fused)
@@ -110,6 +117,7 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
         const long long st = sl.step;                    // exchange counter, identical on every rank
         if (sl.has_left) {
             CU(cudaStreamWaitEvent(ms, sl.post_done, 0));        // our first planes of the current set are final
+            if (dbg) { push_ev.emplace_back(); cudaEventCreate(&push_ev.back()); cudaEventRecord(push_ev.back(), ms); }
             void** mine = cur_fields(e);
             void** theirs = sl.left_fld[e->cur];
             for (int c = 0; c < 6; ++c)
@@ -120,6 +128,7 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
                 CU(cudaMemcpyAsync(sl.left_flags, sl.seq + (st + 1), sizeof(int), cudaMemcpyDefault, ms));
             else { k_signal<<<1, 1, 0, ms>>>(sl.left_flags, (int)(st + 1)); e->launches++; }
             CU(cudaEventRecord(sl.push_done, ms));
+            if (dbg) { push_ev.emplace_back(); cudaEventCreate(&push_ev.back()); cudaEventRecord(push_ev.back(), ms); }
         }
         if (pair) {
             if (dbg) { dbg_ev.emplace_back(); cudaEventCreate(&dbg_ev.back()); cudaEventRecord(dbg_ev.back(), cs); }
@@ -141,8 +150,9 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
         // the push read the set that is now the output set of the NEXT sweep: it must finish before that sweep
         if (sl.has_left) CU(cudaStreamWaitEvent(cs, sl.push_done, 0));
         q += pair ? 2 : 1;
+        if (early_push) CU(cudaEventRecord(sl.post_done, cs));          // (the event the next push waits for)
         if (has_post(e)) if (int rc = launch_post<T>(e, q - 1, 0, cs)) return rc;
-        CU(cudaEventRecord(sl.post_done, cs));
+        if (!early_push) CU(cudaEventRecord(sl.post_done, cs));
         sl.step++;
     }
     k_bump<<<1, 1, 0, cs>>>(e->d_step, n); e->launches++;
@@ -156,8 +166,13 @@ template <typename T> static int slab_run(fdtd_engine* e, int n)
             cudaEventElapsedTime(&ms, dbg_ev[2 * p], dbg_ev[2 * p + 1]); kern += ms;
             if (p + 1 < np) { cudaEventElapsedTime(&ms, dbg_ev[2 * p], dbg_ev[2 * p + 2]); period += ms; }
         }
-        fprintf(stderr, "[fdtd dbg] dev %d pairs %zu sweep %.4f ms period %.4f ms\n", e->cfg.device, np, kern / np, period / (np - 1));
+        double push = 0;
+        cudaStreamSynchronize(ms);
+        for (size_t p = 0; p + 1 < push_ev.size(); p += 2) { float t = 0; cudaEventElapsedTime(&t, push_ev[p], push_ev[p + 1]); push += t; }
+        fprintf(stderr, "[fdtd dbg] dev %d pairs %zu sweep %.4f ms period %.4f ms push %.4f ms\n", e->cfg.device, np, kern / np,
+                period / (np - 1), push_ev.empty() ? 0.0 : push / (push_ev.size() / 2));
         for (auto ev : dbg_ev) cudaEventDestroy(ev);
+        for (auto ev : push_ev) cudaEventDestroy(ev);
     }
     return 0;
 }

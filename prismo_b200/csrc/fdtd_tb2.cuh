@@ -103,6 +103,12 @@ __device__ __forceinline__ void mid_monitors(const MidOps& m, int comp, int p, i
             if (op.n_freq > 0) {
                 const double d = (double)v.v[e];
                 const double* ph = m.phasors + ((long long)row * m.n_phasor + op.phasor_col) * 2;
+                // The update below is a chain of dependent DRAM round trips (the store of one frequency may alias the load
+                // of the next as far as the compiler knows): request all accumulators of the cell first, so that the chain
+                // runs on L2 hits.  On the rank that owns the DFT plane the chain was 0.2 ms of a 1.6 ms pair of steps
+                // (8 GPUs, profiles/r02_tuning.md §6).
+                for (int fq = 0; fq < op.n_freq; ++fq)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(m.dft + op.dft_off + (long long)fq * op.cells + cell));
                 for (int fq = 0; fq < op.n_freq; ++fq) {
                     double2* a = m.dft + op.dft_off + (long long)fq * op.cells + cell;
                     double2 acc = *a;

@@ -46,15 +46,26 @@ class Program:
     ade_ops: list = field(default_factory=list)
     flux_ops: list = field(default_factory=list)       # (direction, lo, hi): region-correct flux reductions
     _group: int = 0
+    _phasor_cache: dict = field(default_factory=dict)
 
     # -- building blocks ---------------------------------------------------------------------------
     def amp(self, fn: Callable) -> int:
         self.amp_fns.append(fn)
         return len(self.amp_fns) - 1
 
-    def phasors(self, fns) -> int:
+    def phasors(self, fns, keys=None) -> int:
+        """Columns of the phasor table for one monitor's frequency list.  Monitors with the SAME list (keys: one hashable
+        per function, e.g. ("omega", w)) share their columns: the host evaluates each exp(-j w t) once per step instead of
+        once per monitor and component (the per-step Python calls bound the API on small grids)."""
+        if keys is not None:
+            k = tuple(keys)
+            hit = self._phasor_cache.get(k)
+            if hit is not None:
+                return hit
         first = len(self.phasor_fns)
         self.phasor_fns.extend(fns)
+        if keys is not None:
+            self._phasor_cache[k] = first
         return first
 
     def monitor_op(self, comp, box, record, n_freq, phasor_col) -> int:
@@ -314,7 +325,7 @@ class _FieldBinder(_Binder):
         bounds = g.region_bounds(m.center, m.size)
         freqs = list(m.frequencies) if m.frequencies is not None else []
         self.freqs = freqs
-        col = p.phasors([_phasor_scalar(f) for f in freqs]) if freqs else 0
+        col = p.phasors([_phasor_scalar(f) for f in freqs], [("scalar", float(f)) for f in freqs]) if freqs else 0
         self.ids = {c: p.monitor_op(c, _box(g, c, bounds), m.time_domain, len(freqs), col) for c in m.components}
 
     def preload(self, engine):
@@ -351,7 +362,7 @@ class _DFTBinder(_Binder):
         g = p.grid
         self.m = m
         n = len(m.omega)
-        col = p.phasors([_phasor_omega(w) for w in m.omega])
+        col = p.phasors([_phasor_omega(w) for w in m.omega], [("omega", float(w)) for w in m.omega])
         bounds = g.region_bounds(m.center, m.size)
         self.ids = {}
         for c in m.components:
@@ -398,7 +409,7 @@ class _FluxRegionBinder(_Binder):
             raise ValueError("FluxMonitor region is empty on the staggered grid")
         self.shape = tuple(hi - lo for lo, hi in box)
         self.nf = 0 if m.frequencies is None else len(m.omega)
-        col = p.phasors([_phasor_omega(w) for w in m.omega]) if self.nf else 0
+        col = p.phasors([_phasor_omega(w) for w in m.omega], [("omega", float(w)) for w in m.omega]) if self.nf else 0
         self.ids = {c: p.monitor_op(c, box, False, self.nf, col) for c in COMPONENTS} if self.nf else {}
         p.flux_ops.append((m.direction, tuple(lo for lo, _ in box), tuple(hi for _, hi in box)))
         self.flux_id = len(p.flux_ops) - 1
@@ -431,7 +442,7 @@ class _FluxRegionBinder(_Binder):
 class _FluxBinder(_PatchBinder):
     def __init__(self, p: Program, m):
         self.nf = 0 if m.frequencies is None else len(m.omega)
-        col = p.phasors([_phasor_omega(w) for w in m.omega]) if self.nf else 0
+        col = p.phasors([_phasor_omega(w) for w in m.omega], [("omega", float(w)) for w in m.omega]) if self.nf else 0
         super().__init__(p, m, "FluxMonitor", self.nf, col)
 
     def preload(self, engine):
