@@ -385,7 +385,7 @@ static int ensure_ymaps(fdtd_engine* e);
 
 template <typename T> static int launch_yeex(fdtd_engine* e, cudaStream_t s)
 {
-    constexpr int R = kYeexRows, V = Vec8<T>::V;
+    constexpr int R = YeexRows<T>::R, V = Vec8<T>::V;
     if (int rc = ensure_ymaps(e)) return rc;
     const Geom& g = e->g;
     void** dst = e->cur ? e->fld : e->fldB;
@@ -647,7 +647,8 @@ static int ensure_tmaps(fdtd_engine* e)
 static int ensure_ymaps(fdtd_engine* e)
 {
     if (e->ymaps_ok) return 0;
-    if (int rc = encode_maps(e, e->ymaps, kYeexBoxBytes, kYeexBoxRows, getenv("FDTD_B200_YEEX_L2PROMO") ? atoi(getenv("FDTD_B200_YEEX_L2PROMO")) : 3)) return rc;
+    if (int rc = encode_maps(e, e->ymaps, kYeexBoxBytes, e->esz == 4 ? kYeexBoxRowsOf<float> : kYeexBoxRowsOf<double>,
+                             getenv("FDTD_B200_YEEX_L2PROMO") ? atoi(getenv("FDTD_B200_YEEX_L2PROMO")) : 3)) return rc;
     e->ymaps_ok = true;
     return 0;
 }

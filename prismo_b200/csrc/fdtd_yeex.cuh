@@ -31,8 +31,11 @@
 
 namespace fdtd {
 
-constexpr int kYeexRows = kTb2xRows;       // 15 consumer rows + 1 producer warp, as in the two-step sweep
-constexpr int kYeexBoxRows = kYeexRows + 1;
+// consumer rows per CTA (+ 1 producer warp): 15 rows = 512 threads at 128 registers.  Measured alternative for fp32: 19 rows =
+// 640 threads at 96 registers (5 warps per scheduler, 18 of 19 rows own cells) spills 120 B and runs at 78.5 instead of
+// 90.2 Gcell/s (profiles/r02_tuning.md §3).
+template <typename T> struct YeexRows { static constexpr int R = 15; };
+template <typename T> constexpr int kYeexBoxRowsOf = YeexRows<T>::R + 1;
 // TMA box: 272 B x (R + 1) rows.  The first cell a tile CONSUMES is one lane (8 B) left of its first owner lane, i.e. at
 // byte 240 * tk - 8 of the row, but the box origin of cp.async.bulk.tensor must be 16-byte aligned in the innermost
 // dimension (a misaligned origin raises "illegal instruction": measured, gpurun_out/e2_sanitize_memcheck_yee.log), so the

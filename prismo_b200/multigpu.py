@@ -34,8 +34,8 @@ def plane_costs(nx: int, plane_cells: int, source_ops=(), monitor_ops=(), op_pat
     """Cost of every x-plane in units of "one plane of the sweep", for load-balanced slabs.
 
     A plane of the two-step sweep moves ~24 B per cell and step.  A DFT monitor read-modify-writes one complex128
-    per cell, component and frequency each step (32 B): a monitor op adds n_freq * 32 / 24 * (its cells in the
-    plane / plane_cells) plane-equivalents to every plane it covers; a recording op 8 B per cell.  Every plane that
+    per cell, component and frequency each step (32 B, counted twice: see below): a monitor op adds n_freq * 64 / 24 *
+    (its cells in the plane / plane_cells) plane-equivalents to every plane it covers; a recording op 8 B per cell.  Every plane that
     carries any op also puts its x-segment on the op-carrying code path (~9 % slower over ~64 planes):
     `op_path_planes`.  Ops are GLOBAL ops (x in global planes) with .lo / .hi boxes (SourceOp / MonitorOp)."""
     import numpy as np
@@ -50,7 +50,9 @@ def plane_costs(nx: int, plane_cells: int, source_ops=(), monitor_ops=(), op_pat
             continue
         touched[a:b] = True
         frac = (op.hi[1] - op.lo[1]) * (op.hi[2] - op.lo[2]) / float(plane_cells)
-        per_cell = 32.0 * getattr(op, "n_freq", 0) + (8.0 if getattr(op, "record", False) else 0.0)
+        # (measured at 8 GPUs, profiles/r02_tuning.md §6: the in-sweep running-DFT update is a latency chain per cell, worth
+        # about twice its 32 B of read-modify-write traffic per frequency)
+        per_cell = 64.0 * getattr(op, "n_freq", 0) + (8.0 if getattr(op, "record", False) else 0.0)
         cost[a:b] += per_cell / 24.0 * frac
     cost[touched] += op_path_planes
     return cost
