@@ -30,14 +30,14 @@ def slab_range(nx: int, rank: int, world: int):
     return rank * base + min(rank, rem), n
 
 
-def plane_costs(nx: int, plane_cells: int, source_ops=(), monitor_ops=(), op_path_planes: float = 6.0):
+def plane_costs(nx: int, plane_cells: int, source_ops=(), monitor_ops=(), op_path_planes: float = 15.0):
     """Cost of every x-plane in units of "one plane of the sweep", for load-balanced slabs.
 
     A plane of the two-step sweep moves ~24 B per cell and step.  A DFT monitor read-modify-writes one complex128
-    per cell, component and frequency each step (32 B, counted twice: see below): a monitor op adds n_freq * 64 / 24 *
-    (its cells in the plane / plane_cells) plane-equivalents to every plane it covers; a recording op 8 B per cell.  Every plane that
-    carries any op also puts its x-segment on the op-carrying code path (~9 % slower over ~64 planes):
-    `op_path_planes`.  Ops are GLOBAL ops (x in global planes) with .lo / .hi boxes (SourceOp / MonitorOp)."""
+    per cell, component and frequency each step (32 B, counted as 42.5: see below): a monitor op adds n_freq * 42.5 / 24
+    * (its cells in the plane / plane_cells) plane-equivalents to every plane it covers; a recording op 8 B per cell.
+    Every plane that carries any op also puts its x-segment on the op-carrying code path (~10 % slower over ~64 planes,
+    plus the in-sweep injection): `op_path_planes`.  Ops are GLOBAL ops (x in global planes) with .lo / .hi boxes (SourceOp / MonitorOp)."""
     import numpy as np
 
     cost = np.ones(nx, dtype=np.float64)
@@ -50,9 +50,10 @@ def plane_costs(nx: int, plane_cells: int, source_ops=(), monitor_ops=(), op_pat
             continue
         touched[a:b] = True
         frac = (op.hi[1] - op.lo[1]) * (op.hi[2] - op.lo[2]) / float(plane_cells)
-        # (measured at 8 GPUs, profiles/r02_tuning.md §6: the in-sweep running-DFT update is a latency chain per cell, worth
-        # about twice its 32 B of read-modify-write traffic per frequency)
-        per_cell = 64.0 * getattr(op, "n_freq", 0) + (8.0 if getattr(op, "record", False) else 0.0)
+        # (calibrated on two 8-GPU per-rank breakdowns, profiles/r02_tuning.md §6: the rank with the 2 x 5-frequency DFT
+        # plane behaves like 32.7 extra planes, the rank with the source plane like 15: the in-sweep running-DFT update is
+        # a latency chain per cell, worth about 42 B per frequency rather than its 32 B of traffic)
+        per_cell = 42.5 * getattr(op, "n_freq", 0) + (8.0 if getattr(op, "record", False) else 0.0)
         cost[a:b] += per_cell / 24.0 * frac
     cost[touched] += op_path_planes
     return cost

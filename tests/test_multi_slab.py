@@ -176,10 +176,10 @@ def test_balanced_slab_ranges():
     src = [SourceOp("Ey", (256, 0, 0), (257, 1024, 1023), 0), SourceOp("Hz", (256, 0, 0), (257, 1023, 1023), 1)]
     mon = [MonitorOp("Ey", (768, 0, 0), (769, 1024, 1023), False, 5, 0), MonitorOp("Hz", (768, 0, 0), (769, 1023, 1023), False, 5, 0)]
     cost = plane_costs(1024, 1024 * 1024, src, mon)
-    assert cost[0] == 1.0 and 6.9 < cost[256] < 7.1 and 33.0 < cost[768] < 34.4
+    assert cost[0] == 1.0 and 15.9 < cost[256] < 16.1 and 33.0 < cost[768] < 34.4
     spans = balanced_slab_ranges(cost, 8)
     owner = [n for a, n in spans if a <= 768 < a + n][0]
-    assert owner < 110 and max(cost[a:a + n].sum() for a, n in spans) < 137
+    assert owner < 110 and max(cost[a:a + n].sum() for a, n in spans) < 138
 
 
 @pytest.mark.gpu
