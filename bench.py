@@ -194,11 +194,14 @@ class Medium:
     """Heterogeneous media of the named configs, x-invariant cross-sections on the (ny, nz) plane.
       c3  one Si ridge (eps 12.11) on an SiO2 (2.07) half space, air above; one Lorentz pole on the core.
       c5  directional coupler: two such ridges a gap apart; a gold pad (Drude pole, eps_inf = 1) beside them over the
-          middle quarter of the length.  (The named config's anisotropic cladding is not modelled: the E stage applies
-          one Cb per cell, see DESIGN.md "out of scope".)"""
+          middle quarter of the length.
+      aniso: the SiO2 half space becomes a uniaxial cladding, eps = diag(2.07, 2.07, 2.16) (optic axis z) — the named
+          config 5's "anisotropic cladding" — applied as per-component Cb inside the E stage (opt-in extension)."""
 
-    def __init__(self, name, dims):
-        self.name, self.dims = name, dims
+    CLAD = (2.07, 2.07, 2.16)
+
+    def __init__(self, name, dims, aniso=False):
+        self.name, self.dims, self.aniso = name, dims, bool(aniso)
         nx, ny, nz = dims
         w, h = ny // 16, max(nz // 12, 2)
         if name == "c5":
@@ -210,23 +213,48 @@ class Medium:
             self.cores = [(ny // 2 - ny // 16, ny // 2 + ny // 16, nz // 2, nz // 2 + h)]
             self.pad = None
 
-    def eps(self):
+    def eps(self, comp=0):
         nx, ny, nz = self.dims
         eps = np.ones((ny, nz), dtype=np.float64)
-        eps[:, : nz // 2] = 2.07
+        eps[:, : nz // 2] = self.CLAD[comp] if self.aniso else 2.07
         for j0, j1, k0, k1 in self.cores:
             eps[j0:j1, k0:k1] = 12.11
         return eps
 
     def coefficients(self, dt, x_planes, jk=None):
-        """Ca, Cb, Da, Db (lossless: Ca = Da = 1) of x_planes planes, optionally restricted to a (j, k) window."""
+        """Ca, Cb, Da, Db (lossless: Ca = Da = 1) of x_planes planes, optionally restricted to a (j, k) window.  With
+        aniso, Cb is the tuple (Cb_x, Cb_y, Cb_z).  Same operations as core/solver.py:119-130 with sigma = 0."""
         eps0, mu0 = 8.854187817e-12, 4 * np.pi * 1e-7
-        eps = self.eps()
-        if jk is not None:
-            eps = eps[jk[0]:jk[1], jk[2]:jk[3]]
-        shp = (x_planes,) + eps.shape
+
+        def cb(comp):
+            eps = self.eps(comp)
+            if jk is not None:
+                eps = eps[jk[0]:jk[1], jk[2]:jk[3]]
+            shp = (x_planes,) + eps.shape
+            return np.ascontiguousarray(np.broadcast_to((dt / (eps0 * eps)) / (1 + 0.0 * eps), shp)), shp
+
+        cbx, shp = cb(0)
         one = np.ones(shp)
-        return one, np.ascontiguousarray(np.broadcast_to(dt / (eps0 * eps), shp)), one, one * (dt / mu0)
+        Cb = (cbx, cb(1)[0], cb(2)[0]) if self.aniso else cbx
+        return one, Cb, one, one * ((dt / (mu0 * 1.0)) / 1.0)
+
+    def shapes(self, spacing):
+        """The same medium as a SHAPE LIST for the device rasteriser (geometry/shapes.py Box objects on cell coordinates
+        i * d): an index range [a0, a1) becomes a box centred on it with faces a quarter cell beyond the end cells."""
+        from prismo_b200 import geometry as G
+
+        nx, ny, nz = self.dims
+
+        def box(mat, r):
+            c = [0.5 * (a0 + a1 - 1) * d for (a0, a1), d in zip(r, spacing)]
+            size = [(a1 - a0 - 0.5) * d for (a0, a1), d in zip(r, spacing)]
+            return G.Box(mat, c, size)
+
+        clad = G.Material("cladding", self.CLAD if self.aniso else 2.07)
+        out = [box(clad, ((-1, nx + 2), (0, ny), (0, nz // 2)))]
+        for j0, j1, k0, k1 in self.cores:
+            out.append(box(G.Material("Si", 12.11), ((-1, nx + 2), (j0, j1), (k0, k1))))
+        return out
 
     def mode_profiles(self):
         """Transverse profile of the mode source: a Gaussian centred on the (first) Si core — it stands in for the solved
@@ -278,7 +306,7 @@ def workload_text(name, dims):
         return (f"c5: 3-D {dims[0]}x{dims[1]}x{dims[2]} directional coupler (two Si ridges on SiO2, cell-centred Ca,Cb,Da,Db "
                 "arrays), Lorentz pole on both cores + Au Drude pad (9 recursions), profiled mode-source plane, 2 ports x 2 "
                 "planes x 6 components x 3-frequency DFT + FieldMonitor DFT plane; mode-overlap S-parameters reduced on the "
-                "device (anisotropic cladding of the named config not modelled)")
+                "device; uniaxial cladding eps = diag(2.07, 2.07, 2.16) as per-component Cb in the E stage unless --no-aniso")
     return (f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} Si ridge on SiO2 (cell-centred Ca,Cb,Da,Db arrays), Lorentz pole on "
             "the core (3 recursions, in-sweep), profiled mode-source plane, FieldMonitor DFT plane (Ey,Hz x 5 freq)")
 
@@ -312,9 +340,26 @@ def install_workload(eng, name, dims, dt, spacing, args, x0=0, nxl=None):
     real = name in ("c3", "c5") and not args.no_ops and not args.physics     # the BASELINE configs as named
     if real:
         args.het = True
-    med = Medium(name, dims) if args.het else None
+    aniso = bool(args.het and getattr(args, "aniso", False))
+    med = Medium(name, dims, aniso) if args.het else None
+    setup = None
     if med is not None:
-        eng.set_coeffs(*med.coefficients(dt, min(nxl + 1, nx - x0)))        # + the right neighbour's first plane on a slab
+        planes = min(nxl + 1, nx - x0)                                      # + the right neighbour's first plane on a slab
+        t0 = time.perf_counter()
+        if getattr(args, "host_coeffs", False):
+            Ca, Cb, Da, Db = med.coefficients(dt, planes)
+            if aniso:
+                eng.set_coeffs_aniso(Ca, *Cb, Da, Db)
+            else:
+                eng.set_coeffs(Ca, Cb, Da, Db)
+            how = "host-painted fp64 arrays uploaded (fdtd_set_coeffs%s)" % ("_aniso" if aniso else "")
+        else:
+            ax = [np.arange(n) * d for n, d in zip(dims, spacing)]
+            eng.rasterize(med.shapes(spacing), ax[0][x0:x0 + planes], ax[1], ax[2])
+            how = "shape list rasterised on the device (fdtd_rasterize: %d boxes -> %d coefficient arrays)" % (
+                1 + len(med.cores), 6 if aniso else 4)
+        eng.sync()
+        setup = {"coefficients": how, "seconds": time.perf_counter() - t0, "aniso": aniso}
     src, mon = workload_ops(dims, dt, spacing, x0, nxl)
     src_profile, ports = None, []
     if real:
@@ -335,7 +380,7 @@ def install_workload(eng, name, dims, dt, spacing, args, x0=0, nxl=None):
     if med is not None:
         coef_fn = lambda lo, sd: med.coefficients(dt, sd[0], (lo[1], lo[1] + sd[1], lo[2], lo[2] + sd[2]))  # noqa: E731
     return {"mon_ids": mon_ids, "mon": mon, "ports": ports, "src_profile": src_profile, "coef_fn": coef_fn, "medium": med,
-            "real": real}
+            "real": real, "setup": setup, "aniso": aniso}
 
 
 def port_s_parameters(eng, ports, med, dims, spacing, gather=None):
@@ -547,8 +592,15 @@ def main():
                     "(two-pass kernels with slab psi updates; no reference numbers exist for it)")
     ap.add_argument("--no-ops", action="store_true", help="bare field update: no source, no monitor (tuning only)")
     ap.add_argument("--no-check", action="store_true", help="skip the post-run self-check against the oracle")
+    ap.add_argument("--aniso", action="store_true", help="heterogeneous workloads: uniaxial cladding eps = diag(2.07, 2.07, "
+                    "2.16) as per-component Cb inside the E stage (default for c5, whose named config has it)")
+    ap.add_argument("--no-aniso", action="store_true", help="c5 without its anisotropic cladding (one Cb per cell, 64 B/cell)")
+    ap.add_argument("--host-coeffs", action="store_true", help="paint Ca..Db on the host and upload them instead of "
+                    "rasterising the shape list on the device")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload.lower() == "c5" and not args.no_aniso and not args.physics and not args.no_ops:
+        args.aniso = True
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -608,13 +660,14 @@ def main():
     # dominant kernel(s): fused sweep (one launch per step) or H + E pass
     kern_ms = prof["h_or_fused_ms"] + prof["e_ms"]
     peak, peak_src = peaks()
-    bpc = BYTES_PER_CELL[args.dtype] + (16 if args.dtype == "float32" else 32) * int(args.het)   # + Ca,Cb,Da,Db reads
+    n_coef = (6 if wl["aniso"] else 4) * int(args.het)                     # + Ca,Cb,Da,Db (+ Cb_y, Cb_z) reads
+    bpc = BYTES_PER_CELL[args.dtype] + (4 if args.dtype == "float32" else 8) * n_coef
     achieved = bpc * cells * args.steps / (kern_ms * 1e-3) / 1e9
     fused = not (args.two_pass or args.physics)
     tb2 = fused and os.environ.get("FDTD_B200_TB2", "1") != "0" and args.steps >= 2 and not args.het
     kname = ("k_fused3d_tb2x (TMA-fed, 1 launch per TWO steps)" if tb2 else
              ("k_fused3d_het" + ("<ADE> (dispersive recursions applied in-sweep)" if real_c3 else "") + " (1 launch/step, "
-              "6 field + 4 coefficient arrays read, 6 written)") if args.het else "k_fused3d (1 launch/step)") if fused \
+              f"6 field + {n_coef} coefficient arrays read, 6 written)") if args.het else "k_fused3d (1 launch/step)") if fused \
         else ({"2": "k_fused3d_yeex (physics mode: Yee leap-frog + CPML slabs in ONE TMA-fed sweep per step, psi ping-pong)",
                "1": "k_fused3d_yee (physics mode: Yee leap-frog + CPML slabs fused into ONE sweep per step, psi ping-pong)",
                "0": "k_h3d_yee + k_e3d_yee (physics mode: Yee leap-frog + CPML slabs, 2 launches/step)"}[
@@ -673,6 +726,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(), "check": check}
     if s_params is not None:
         line["s_params"] = s_params
+    if wl["setup"] is not None:
+        line["setup"] = wl["setup"]
     print(json.dumps(line), flush=True)
     eng.close()
 

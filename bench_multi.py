@@ -107,7 +107,8 @@ def run_multi(args, rank, world, local):
             check["timed_fields_sha"] = BC.sha_of_checksums(timed_cs)
 
     if rank == 0:
-        bpc = B.BYTES_PER_CELL[args.dtype] + (16 if args.dtype == "float32" else 32) * int(het)      # + Ca,Cb,Da,Db reads
+        n_coef = (6 if wl["aniso"] else 4) * int(het)                        # + Ca,Cb,Da,Db (+ Cb_y, Cb_z) reads
+        bpc = B.BYTES_PER_CELL[args.dtype] + (4 if args.dtype == "float32" else 8) * n_coef
         peak, peak_src = B.peaks()
         value = cells * args.steps / (ms * 1e-3)
         achieved = bpc * cells * args.steps / (ms * 1e-3) / 1e9 / world
@@ -126,7 +127,7 @@ def run_multi(args, rank, world, local):
                                           + ("NCCL send/recv" if halo == "nccl" else
                                              "DMA push into the neighbour's ghost planes over NVLink (CUDA IPC) + "
                                              "release/acquire flags, in-kernel wait"),
-                           "kernel_path": "heterogeneous one-step fused sweep (6 + 4 arrays in, 6 out), ping-pong" if het else
+                           "kernel_path": f"heterogeneous one-step fused sweep (6 + {n_coef} arrays in, 6 out), ping-pong" if het else
                                           ("temporally blocked fused sweep (2 steps per HBM pass), ping-pong"
                                            if os.environ.get("FDTD_B200_TB2", "1") != "0" else "fused single sweep, ping-pong")},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -141,6 +142,8 @@ def run_multi(args, rank, world, local):
                 "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches.item()), "clocks": clk.summary(), "check": check}
         if s_params is not None:
             line["s_params"] = s_params
+        if wl["setup"] is not None:
+            line["setup"] = wl["setup"]
         print(json.dumps(line), flush=True)
     eng.close()
     dist.destroy_process_group()

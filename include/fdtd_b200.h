@@ -99,7 +99,7 @@ typedef struct fdtd_ade_op {
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
 int  fdtd_abi_version(void);
-int  fdtd_struct_size(int32_t which);   /* sizeof: 0 fdtd_config, 1 fdtd_source_op, 2 fdtd_monitor_op, 3 fdtd_ade_op */
+int  fdtd_struct_size(int32_t which);   /* sizeof: 0 fdtd_config, 1 fdtd_source_op, 2 fdtd_monitor_op, 3 fdtd_ade_op, 4 fdtd_shape */
 const char* fdtd_last_error(void);
 int  fdtd_create(const fdtd_config* cfg, fdtd_engine** out);
 int  fdtd_destroy(fdtd_engine* e);
@@ -110,6 +110,42 @@ int  fdtd_set_uniform_coeffs(fdtd_engine* e, double ca, double cb, double da, do
  * neighbour slab exists (the extra plane is the neighbour's first plane).                      */
 int  fdtd_set_coeffs(fdtd_engine* e, const double* ca, const double* cb, const double* da,
                      const double* db, int32_t planes);
+
+/* OPT-IN extension (no counterpart in the reference's solver, which applies one Cb per cell, core/solver.py:458-533):
+ * per-component Cb for a DIAGONAL permittivity tensor — the case AnisotropicUpdater.update_e_from_curl_h handles at
+ * function level (materials/tensor.py:508-514) — applied inside the E stage of the 3-D parity sweeps: Ex averages
+ * cbx over (j, k), Ey averages cby over (i, k), Ez averages cbz over (i, j), exactly as the scalar Cb is averaged.
+ * With cbx == cby == cbz the result is bit-identical to fdtd_set_coeffs.  3-D, not in physics mode.               */
+int  fdtd_set_coeffs_aniso(fdtd_engine* e, const double* ca, const double* cbx, const double* cby,
+                           const double* cbz, const double* da, const double* db, int32_t planes);
+
+/* Geometry rasterisation on the device: shape list -> Ca, Cb, Da, Db in the engine's layout, replacing
+ *   mask = Shape.rasterize(x, y, z)              geometry/shapes.py:71-99 (a 3 x cells fp64 meshgrid on the host)
+ *   eps_rel[mask] = material.epsilon_r ...       user code, in list order (later shapes paint over earlier ones)
+ *   MaxwellUpdater._compute_update_coefficients  core/solver.py:113-133
+ * with the same fp64 operations in the same order (bit-identical masks and coefficients).                         */
+typedef struct fdtd_shape {
+    int32_t kind;           /* 0 Box :125-132, 1 Sphere :155-159, 2 Cylinder :194-214, 3 Polygon :249-283          */
+    int32_t axis;           /* cylinder axis 0/1/2                                                                  */
+    int32_t combine;        /* GeometryGroup :338-378: 0 start a new mask, 1 union, 2 intersection, 3 difference
+                               of the running mask with this shape                                                  */
+    int32_t paint;          /* != 0: cells of the running mask take this entry's material                           */
+    double  center[3];
+    double  a[3];           /* box: size/2; sphere: radius; cylinder: radius, height/2; polygon: z_min, z_max       */
+    int32_t vert_first, vert_count;   /* polygon: its vertices in the (x, y) vertex list                            */
+    double  eps_r[3];       /* eps_xx, eps_yy, eps_zz (all equal for an isotropic material)                         */
+    double  mu_r, sigma_e, sigma_m;
+} fdtd_shape;
+/* x, y, z: host fp64 cell coordinates of length planes (nx, or nx+1 on a slab with a right neighbour), ny, nz
+ * (z == NULL in 2-D: the reference rasterises 2-D grids at z = 0).  background = eps_xx, eps_yy, eps_zz, mu_r,
+ * sigma_e, sigma_m of unpainted cells.  Any entry with unequal eps_r components switches the engine to per-component
+ * Cb (see fdtd_set_coeffs_aniso; such entries need sigma_e == 0).                                                 */
+int  fdtd_rasterize(fdtd_engine* e, const fdtd_shape* shapes, int32_t n_shapes, const double* verts_xy,
+                    int32_t n_verts, const double* x, const double* y, const double* z, int32_t planes,
+                    const double* background);
+/* read-back of a device coefficient array as host fp64 (planes, ny, nz): which = 0 Ca, 1 Cb (Cb_x), 2 Da, 3 Db,
+ * 4 Cb_y, 5 Cb_z                                                                                                   */
+int  fdtd_download_coeffs(fdtd_engine* e, int32_t which, double* host, int32_t planes);
 
 /* Physics mode only: working CPML (the reference's is a stub that is never applied, boundaries/pml.py:259-328).
  * coef = host fp64, axis by axis (x, y, z), 6 vectors of length N_axis each: b, a, 1/kappa at the E-update

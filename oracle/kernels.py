@@ -116,20 +116,26 @@ def update_h_3d(F, Da, Db, spacing):
 
 
 def update_e_3d(F, Ca, Cb, spacing):
-    """solver.py:255-309.  Whole E arrays are written, from the H just produced."""
+    """solver.py:255-309.  Whole E arrays are written, from the H just produced.
+
+    Cb may be a tuple (Cb_x, Cb_y, Cb_z): the OPT-IN per-component extension (diagonal permittivity tensor, the case
+    materials/tensor.py:508-514 handles at function level).  The reference's solver has one Cb per cell; each
+    component's array is averaged exactly as the scalar one is for that component.  PARITY UNPINNED for distinct
+    arrays (no reference numbers exist); with three identical arrays it IS the reference's update."""
     dx, dy, dz = spacing
     Ex, Ey, Ez, Hx, Hy, Hz = (F[c] for c in ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz"))
+    Cbx, Cby, Cbz = Cb if isinstance(Cb, (tuple, list)) else (Cb, Cb, Cb)
 
     ca = _crop(_mean4(Ca, 1, 2), Ex.shape)
-    cb = _crop(_mean4(Cb, 1, 2), Ex.shape)
+    cb = _crop(_mean4(Cbx, 1, 2), Ex.shape)
     Ex[...] = ca * Ex + cb * (_fwd(Hz, 1, dy) - _fwd(Hy, 2, dz))
 
     ca = _crop(_mean4(Ca, 0, 2), Ey.shape)
-    cb = _crop(_mean4(Cb, 0, 2), Ey.shape)
+    cb = _crop(_mean4(Cby, 0, 2), Ey.shape)
     Ey[...] = ca * Ey + cb * (_fwd(Hx, 2, dz) - _fwd(Hz, 0, dx))
 
     ca = _crop(_mean4(Ca, 0, 1), Ez.shape)
-    cb = _crop(_mean4(Cb, 0, 1), Ez.shape)
+    cb = _crop(_mean4(Cbz, 0, 1), Ez.shape)
     Ez[...] = ca * Ez + cb * (_fwd(Hy, 0, dx) - _fwd(Hx, 1, dy))
 
 
@@ -211,6 +217,8 @@ def update_h(F, Da, Db, spacing, is_2d):
 
 def update_e(F, Ca, Cb, spacing, is_2d):
     if is_2d:
+        if isinstance(Cb, (tuple, list)):
+            raise ValueError("per-component Cb is a 3-D extension")
         update_e_2d(F, Ca[:, :, 0] if Ca.ndim == 3 else Ca, Cb[:, :, 0] if Cb.ndim == 3 else Cb, spacing)
     else:
         update_e_3d(F, Ca, Cb, spacing)

@@ -15,10 +15,11 @@ from .monitors import DFTMonitor, FieldMonitor, FluxMonitor, ModeExpansionMonito
 from .materials import (ADESolver, AnisotropicUpdater, DebyeMaterial, DrudeMaterial, LorentzMaterial, LorentzPole,
                         TensorComponents, TensorMaterial, attach_ade, tensor_update)
 from .cpml import PMLParams
+from .geometry import Box, Cylinder, GeometryGroup, Material, Polygon, Shape, Sphere
 from .session import Session, configure
 from .simulation import ElectromagneticFields, FDTDSolver, MaxwellUpdater, Simulation
 from .engine import Engine, MonitorOp, SourceOp
-from .plugin import register
+from .plugin import clear_geometry, register, set_geometry
 
 __version__ = "0.1.0"
 from .sweep import ParameterSweep, SweepParameter

@@ -62,6 +62,9 @@ _PROTOS = {
     "fdtd_destroy": (C.c_int, [_P]),
     "fdtd_set_uniform_coeffs": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double]),
     "fdtd_set_coeffs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32]),
+    "fdtd_set_coeffs_aniso": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32]),
+    "fdtd_rasterize": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, C.c_int32, _P]),
+    "fdtd_download_coeffs": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),
     "fdtd_set_cpml": (C.c_int, [_P, C.c_int32, _P]),
     "fdtd_upload_field": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),
     "fdtd_download_field": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),
@@ -134,7 +137,9 @@ def load() -> C.CDLL:
     got = lib.fdtd_abi_version()
     if got != ABI_VERSION:
         raise OSError(f"{LIB_PATH}: ABI version {got}, binding expects {ABI_VERSION}")
-    for which, st in enumerate((Config, SourceOp, MonitorOp, AdeOp)):
+    from .geometry import ShapeStruct
+
+    for which, st in enumerate((Config, SourceOp, MonitorOp, AdeOp, ShapeStruct)):
         if lib.fdtd_struct_size(which) != C.sizeof(st):
             raise OSError(f"{LIB_PATH}: struct {st.__name__} is {lib.fdtd_struct_size(which)} bytes in C, "
                           f"{C.sizeof(st)} in the binding")

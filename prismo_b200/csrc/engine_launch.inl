@@ -458,9 +458,10 @@ template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
             return fail(FDTD_ESTATE, "x-slab with a right neighbour: fdtd_set_coeffs needs nx + 1 = %d planes", g.nx + 1);
         t.halo_flag = e->slab.flags; t.halo_need = (int)e->slab.step + 1; t.error_word = e->slab.flags + 2;
     }
-    const size_t smem = het_smem_bytes<T, R>();
+    const size_t smem = e->aniso ? het_smem_bytes<T, R, true>() : het_smem_bytes<T, R, false>();
     const bool ade = ade_in_this_sweep(e);
-    auto kern = ade ? k_fused3d_het<T, R, true> : k_fused3d_het<T, R, false>;
+    auto kern = e->aniso ? (ade ? k_fused3d_het<T, R, true, true> : k_fused3d_het<T, R, false, true>)
+                         : (ade ? k_fused3d_het<T, R, true, false> : k_fused3d_het<T, R, false, false>);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, R, 1);
     const long long items = (long long)t.nseg * t.ntj * t.ntk;

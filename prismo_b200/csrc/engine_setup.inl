@@ -9,6 +9,7 @@ extern "C" int fdtd_struct_size(int32_t which)
     case 1: return (int)sizeof(fdtd_source_op);
     case 2: return (int)sizeof(fdtd_monitor_op);
     case 3: return (int)sizeof(fdtd_ade_op);
+    case 4: return (int)sizeof(fdtd_shape);
     default: return -1;
     }
 }
@@ -104,7 +105,7 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     drop_graph(e);
     for (int c = 0; c < 6; ++c) { cudaFree(e->fld[c]); cudaFree(e->fldB[c]); }
-    for (int c = 0; c < 4; ++c) cudaFree(e->coef[c]);
+    for (int c = 0; c < 6; ++c) cudaFree(e->coef[c]);
     cudaFree(e->d_src); cudaFree(e->d_mon); cudaFree(e->d_prof); cudaFree(e->d_src_ghost);
     cudaFree(e->d_ade); cudaFree(e->d_aux); cudaFree(e->d_ade_mask);
     cudaFree(e->d_flux); cudaFree(e->d_flux_partial); cudaFree(e->d_flux_out);
@@ -132,7 +133,8 @@ extern "C" int fdtd_set_uniform_coeffs(fdtd_engine* e, double ca, double cb, dou
     if (!e) return fail(FDTD_EINVAL, "null engine");
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaStreamSynchronize(e->stream));
-    for (int c = 0; c < 4; ++c) { cudaFree(e->coef[c]); e->coef[c] = nullptr; }
+    for (int c = 0; c < 6; ++c) { cudaFree(e->coef[c]); e->coef[c] = nullptr; }
+    e->aniso = false;
     e->het = false;
     e->uni[0] = ca; e->uni[1] = cb; e->uni[2] = da; e->uni[3] = db;
     drop_graph(e);
@@ -241,15 +243,13 @@ static int gather_host(fdtd_engine* e, TH* host, const TD* src, long long c0, in
     return 0;
 }
 
-extern "C" int fdtd_set_coeffs(fdtd_engine* e, const double* ca, const double* cb, const double* da,
-                               const double* db, int32_t planes)
+static int set_coef_arrays(fdtd_engine* e, const double* const* src, int n_arrays, int32_t planes, const char* who)
 {
-    if (!e || !ca || !cb || !da || !db) return fail(FDTD_EINVAL, "fdtd_set_coeffs: null argument");
     if (planes != e->g.nx && planes != e->g.nx + 1)
-        return fail(FDTD_EINVAL, "coefficient arrays must have nx=%d (or nx+1) planes, got %d", e->g.nx, planes);
+        return fail(FDTD_EINVAL, "%s: coefficient arrays must have nx=%d (or nx+1) planes, got %d", who, e->g.nx, planes);
     CU(cudaSetDevice(e->cfg.device));
-    const double* src[4] = {ca, cb, da, db};
-    for (int c = 0; c < 4; ++c) {
+    CU(cudaStreamSynchronize(e->stream));
+    for (int c = 0; c < n_arrays; ++c) {
         if (!e->coef[c]) CU(cudaMalloc(&e->coef[c], e->array_elems * e->esz));
         CU(cudaMemsetAsync(e->coef[c], 0, e->array_elems * e->esz, e->stream));
         int rc;
@@ -258,10 +258,37 @@ extern "C" int fdtd_set_coeffs(fdtd_engine* e, const double* ca, const double* c
         else rc = scatter_host<float, double>(e, (float*)e->coef[c], src[c], planes, c1, c2);
         if (rc) return rc;
     }
+    for (int c = n_arrays; c < 6; ++c) { cudaFree(e->coef[c]); e->coef[c] = nullptr; }
     e->het = true;
+    e->aniso = n_arrays == 6;
     e->coef_planes = planes;
     drop_graph(e);
     return 0;
+}
+
+extern "C" int fdtd_set_coeffs(fdtd_engine* e, const double* ca, const double* cb, const double* da,
+                               const double* db, int32_t planes)
+{
+    if (!e || !ca || !cb || !da || !db) return fail(FDTD_EINVAL, "fdtd_set_coeffs: null argument");
+    const double* src[4] = {ca, cb, da, db};
+    return set_coef_arrays(e, src, 4, planes, "fdtd_set_coeffs");
+}
+
+// per-component Cb: the parity sweeps of 3-D grids only (the physics-mode and 2-D kernels have one Cb per cell)
+static int aniso_supported(const fdtd_engine* e, const char* who)
+{
+    if (e->cfg.ndim != 3) return fail(FDTD_EINVAL, "%s: per-component Cb needs a 3-D grid", who);
+    if (e->cfg.flags & FDTD_FLAG_YEE) return fail(FDTD_EINVAL, "%s: per-component Cb is not available in physics mode", who);
+    return 0;
+}
+
+extern "C" int fdtd_set_coeffs_aniso(fdtd_engine* e, const double* ca, const double* cbx, const double* cby,
+                                     const double* cbz, const double* da, const double* db, int32_t planes)
+{
+    if (!e || !ca || !cbx || !cby || !cbz || !da || !db) return fail(FDTD_EINVAL, "fdtd_set_coeffs_aniso: null argument");
+    if (int rc = aniso_supported(e, "fdtd_set_coeffs_aniso")) return rc;
+    const double* src[6] = {ca, cbx, da, db, cby, cbz};
+    return set_coef_arrays(e, src, 6, planes, "fdtd_set_coeffs_aniso");
 }
 
 // ---- fields ---------------------------------------------------------------------------------------------

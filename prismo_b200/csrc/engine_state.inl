@@ -49,8 +49,9 @@ struct fdtd_engine {
     void* fld[6] = {};              // set A
     void* fldB[6] = {};             // set B (fused ping-pong), allocated lazily
     int cur = 0;                    // which set holds the current fields (fused path)
-    void* coef[4] = {};             // Ca Cb Da Db arrays (T) or null
+    void* coef[6] = {};             // Ca Cb Da Db arrays (T) or null; [4], [5] = Cb of Ey, Ez when aniso (then Cb is Ex's)
     bool het = false;
+    bool aniso = false;             // per-component Cb (diagonal permittivity tensor) in the E stage: OPT-IN extension, 3-D parity sweeps only
     int coef_planes = 0;            // planes of Ca..Db supplied by the caller (nx, or nx + 1 with the right neighbour's first)
     double uni[4] = {1, 0, 1, 0};
     cudaStream_t stream = nullptr;
@@ -150,6 +151,7 @@ template <typename T> static Coefs<T> coefs_of(const fdtd_engine* e)
     Coefs<T> c;
     c.ca = (const T*)e->coef[0]; c.cb = (const T*)e->coef[1];
     c.da = (const T*)e->coef[2]; c.db = (const T*)e->coef[3];
+    c.cby = e->aniso ? (const T*)e->coef[4] : nullptr; c.cbz = e->aniso ? (const T*)e->coef[5] : nullptr;
     c.uca = (T)e->uni[0]; c.ucb = (T)e->uni[1]; c.uda = (T)e->uni[2]; c.udb = (T)e->uni[3];
     return c;
 }

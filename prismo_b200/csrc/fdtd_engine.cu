@@ -14,6 +14,7 @@
 #include "fdtd_yeex.cuh"
 #include "fdtd_het.cuh"
 #include "fdtd_tensor.cuh"
+#include "fdtd_raster.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -31,4 +32,5 @@
 #include "engine_run.inl"   // step loops: fdtd_run (CUDA graph), half steps, profiled run, options, split entry points
 #include "engine_tensor.inl"   // anisotropic tensor update on caller-supplied arrays (row a23)
 #include "engine_slab.inl"   // peer-to-peer x-slabs: CUDA-IPC export / connect, fdtd_slab_run
+#include "engine_raster.inl"   // geometry rasterisation on the device: shape list -> coefficient arrays (row f4)
 #include "engine_readout.inl"   // monitor read-out and introspection

@@ -28,10 +28,14 @@ template <typename T, bool SLOW> __device__ __forceinline__ T het_diff(T a1, T a
 
 constexpr int kHetRows = 16;
 constexpr int kHetOwnLanes = 30;
-template <typename T, int R> constexpr size_t het_smem_bytes() { return 2 * (size_t)R * 8 * 32 * 8; }
+template <typename T, int R, bool ANISO = false> constexpr size_t het_smem_bytes() { return 2 * (size_t)R * (ANISO ? 9 : 8) * 32 * 8; }
 
 // ADE: apply the dispersive-medium recursions of the PREVIOUS step on the E stage's input values (ade_in_sweep).
-template <typename T, int R, bool ADE>
+// ANISO (opt-in extension): per-component Cb — a diagonal permittivity tensor, the case the reference's
+// AnisotropicUpdater handles with one division per component (materials/tensor.py:508-514) — inside the same E stage:
+// Ex averages c.cb (the eps_xx array) over j and k exactly as before, Ey averages c.cby over i and k, Ez averages c.cbz
+// over i and j.  Two more arrays are streamed (72 B per cell-update in fp32), one more smem slot carries Cb_z to row - 1.
+template <typename T, int R, bool ADE, bool ANISO>
 __device__ __forceinline__ void
 het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const Geom& g, const FusedTiling& t, const int planes_alloc,
           const AdeIn& ad, const int item)
@@ -41,7 +45,9 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
     typedef typename Vec8<T>::type VT;
     extern __shared__ __align__(16) unsigned char smem_[];
     // [parity][row][q][lane], q: 0 Ez,1 Ex of plane i+1; 2 Hz+,3 Hx+ of plane i; 4 Da,5 Db of plane i+1; 6 Ca,7 Cb of plane i+1
-    VT (*s_x)[R][8][32] = reinterpret_cast<VT (*)[R][8][32]>(smem_);
+    // (8: Cb_z of plane i+1 when ANISO)
+    constexpr int NQ = ANISO ? 9 : 8;
+    VT (*s_x)[R][NQ][32] = reinterpret_cast<VT (*)[R][NQ][32]>(smem_);
 
     const int lane = threadIdx.x, row = threadIdx.y;
     const int ntiles = t.ntj * t.ntk;
@@ -80,6 +86,13 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
     P da1 = ld8<T, V>(pda + po, ld_ok), db1 = ld8<T, V>(pdb + po, ld_ok);                 // D[i+1]
     P da2 = ld8<T, V>(pda + po + g.sx, ld_ok), db2 = ld8<T, V>(pdb + po + g.sx, ld_ok);   // D[i+2]
     P ca0_j = z_, cb0_j = z_;                                                           // C[i] at j+1
+    // ANISO: Cb_y at planes i, i+1 (k+1 from the next lane), Cb_z at planes i, i+1 and their j+1 neighbours
+    const T* pcby = ANISO ? c.cby + ofs : nullptr; const T* pcbz = ANISO ? c.cbz + ofs : nullptr;
+    P cby0 = z_, cby1 = z_, cbz0 = z_, cbz1 = z_, cbz0_j = z_;
+    if (ANISO) {
+        cby0 = ld8<T, V>(pcby + po - g.sx, pm_ok); cbz0 = ld8<T, V>(pcbz + po - g.sx, pm_ok);
+        cby1 = ld8<T, V>(pcby + po, ld_ok); cbz1 = ld8<T, V>(pcbz + po, ld_ok);
+    }
     unsigned ade_mask = 0;
     __shared__ AdeOp s_ade[ADE ? kAdeSmemOps : 1];
     if (ADE) {
@@ -98,6 +111,8 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
         const P n_hx = ld8<T, V>(phx + pp, p2), n_hy = ld8<T, V>(phy + pp, p2), n_hz = ld8<T, V>(phz + pp, p2);
         const P n_ca = ld8<T, V>(pca + pp, p2), n_cb = ld8<T, V>(pcb + pp, p2);
         const P n_da = ld8<T, V>(pda + pp + g.sx, p3), n_db = ld8<T, V>(pdb + pp + g.sx, p3);
+        P n_cby = z_, n_cbz = z_;
+        if (ANISO) { n_cby = ld8<T, V>(pcby + pp, p2); n_cbz = ld8<T, V>(pcbz + pp, p2); }
         // ---- publish the j+1 inputs ------------------------------------------------------------------------------------
         {
             union { VT q; P r; } u;
@@ -105,6 +120,7 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
             u.r = hpz; s_x[par][row][2][lane] = u.q;  u.r = hpx; s_x[par][row][3][lane] = u.q;
             u.r = da1; s_x[par][row][4][lane] = u.q;  u.r = db1; s_x[par][row][5][lane] = u.q;
             u.r = ca1; s_x[par][row][6][lane] = u.q;  u.r = cb1; s_x[par][row][7][lane] = u.q;
+            if (ANISO) { u.r = cbz1; s_x[par][row][NQ - 1][lane] = u.q; }
         }
         __syncthreads();
         P ez_j, ex_j, hz_j, hx_j, da1_j, db1_j, ca1_j, cb1_j;
@@ -115,6 +131,8 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
             u.q = s_x[par][rown][4][lane]; da1_j = u.r;  u.q = s_x[par][rown][5][lane]; db1_j = u.r;
             u.q = s_x[par][rown][6][lane]; ca1_j = u.r;  u.q = s_x[par][rown][7][lane]; cb1_j = u.r;
         }
+        P cbz1_j = z_;
+        if (ANISO) { union { VT q; P r; } u; u.q = s_x[par][rown][NQ - 1][lane]; cbz1_j = u.r; }
         // ---- k+1 neighbours from the next lane --------------------------------------------------------------------------------
         const T ey1_n = shfl_next<T>(e1y.v[0]), ex1_n = shfl_next<T>(e1x.v[0]);
         const T hpy_n = shfl_next<T>(hpy.v[0]), hpx_n = shfl_next<T>(hpx.v[0]);
@@ -122,6 +140,8 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
         const T ca0_n = shfl_next<T>(ca0.v[0]), cb0_n = shfl_next<T>(cb0.v[0]);
         const T ca1_n = shfl_next<T>(ca1.v[0]), cb1_n = shfl_next<T>(cb1.v[0]);
         const T ca0j_n = shfl_next<T>(ca0_j.v[0]), cb0j_n = shfl_next<T>(cb0_j.v[0]);
+        T cby0_n = (T)0, cby1_n = (T)0;
+        if (ANISO) { cby0_n = shfl_next<T>(cby0.v[0]); cby1_n = shfl_next<T>(cby1.v[0]); }
 
         // ---- H+[i+1] ----------------------------------------------------------------------------------------------------------
         const int gi1 = g.x0 + i + 1;
@@ -176,19 +196,28 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
                 const T ca0_k = (e + 1 < V) ? ca0.v[(e + 1) % V] : ca0_n, cb0_k = (e + 1 < V) ? cb0.v[(e + 1) % V] : cb0_n;
                 const T ca1_k = (e + 1 < V) ? ca1.v[(e + 1) % V] : ca1_n, cb1_k = (e + 1 < V) ? cb1.v[(e + 1) % V] : cb1_n;
                 const T ca0_jk = (e + 1 < V) ? ca0_j.v[(e + 1) % V] : ca0j_n, cb0_jk = (e + 1 < V) ? cb0_j.v[(e + 1) % V] : cb0j_n;
+                // Cb of Ey (mean over i, k) and of Ez (mean over i, j): the component's own array when ANISO
+                T cbm_y, cbm_z;
+                if (ANISO) {
+                    const T cby0_k = (e + 1 < V) ? cby0.v[(e + 1) % V] : cby0_n, cby1_k = (e + 1 < V) ? cby1.v[(e + 1) % V] : cby1_n;
+                    cbm_y = mean4<T>(cby0.v[e], cby1.v[e], cby0_k, cby1_k);
+                    cbm_z = mean4<T>(cbz0.v[e], cbz1.v[e], cbz0_j.v[e], cbz1_j.v[e]);
+                } else {
+                    cbm_y = mean4<T>(cb0.v[e], cb1.v[e], cb0_k, cb1_k);
+                    cbm_z = mean4<T>(cb0.v[e], cb1.v[e], cb0_j.v[e], cb1_j.v[e]);
+                }
                 T n = upd_e<T>(mean4<T>(ca0.v[e], ca0_j.v[e], ca0_k, ca0_jk), e0x.v[e],
                                mean4<T>(cb0.v[e], cb0_j.v[e], cb0_k, cb0_jk),
                                het_diff<T, SLOW>(hz_j.v[e], hpz.v[e], g.dy, g.rdy, bad), het_diff<T, SLOW>(hy_k, hpy.v[e], g.dz, g.rdz, bad));
                 if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(mean4<T>(cb0.v[e], cb0_j.v[e], cb0_k, cb0_jk), (T)jx[e])); }
                 if (ex0 && jy1 && kz1) ox.v[e] = n;
-                n = upd_e<T>(mean4<T>(ca0.v[e], ca1.v[e], ca0_k, ca1_k), e0y.v[e], mean4<T>(cb0.v[e], cb1.v[e], cb0_k, cb1_k),
+                n = upd_e<T>(mean4<T>(ca0.v[e], ca1.v[e], ca0_k, ca1_k), e0y.v[e], cbm_y,
                              het_diff<T, SLOW>(hx_k, hpx.v[e], g.dz, g.rdz, bad), het_diff<T, SLOW>(hnz.v[e], hpz.v[e], g.dx, g.rdx, bad));
-                if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(mean4<T>(cb0.v[e], cb1.v[e], cb0_k, cb1_k), (T)jy[e])); }
+                if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(cbm_y, (T)jy[e])); }
                 if (ex1 && kz1) oy.v[e] = n;
-                n = upd_e<T>(mean4<T>(ca0.v[e], ca1.v[e], ca0_j.v[e], ca1_j.v[e]), e0z.v[e],
-                             mean4<T>(cb0.v[e], cb1.v[e], cb0_j.v[e], cb1_j.v[e]),
+                n = upd_e<T>(mean4<T>(ca0.v[e], ca1.v[e], ca0_j.v[e], ca1_j.v[e]), e0z.v[e], cbm_z,
                              het_diff<T, SLOW>(hny.v[e], hpy.v[e], g.dx, g.rdx, bad), het_diff<T, SLOW>(hx_j.v[e], hpx.v[e], g.dy, g.rdy, bad));
-                if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(mean4<T>(cb0.v[e], cb1.v[e], cb0_j.v[e], cb1_j.v[e]), (T)jz[e])); }
+                if (ADE) { if (ad.coupled) n = Ar<T>::sub(n, Ar<T>::mul(cbm_z, (T)jz[e])); }
                 if (ex1 && jy1 && kz0) oz.v[e] = n;
             }
                 return bad;
@@ -209,11 +238,12 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
         h1x = n_hx; h1y = n_hy; h1z = n_hz;
         ca0 = ca1; cb0 = cb1; ca1 = n_ca; cb1 = n_cb;
         ca0_j = ca1_j; cb0_j = cb1_j;
+        if (ANISO) { cby0 = cby1; cby1 = n_cby; cbz0 = cbz1; cbz1 = n_cbz; cbz0_j = cbz1_j; }
         da1 = da2; db1 = db2; da2 = n_da; db2 = n_db;
     }
 }
 
-template <typename T, int R, bool ADE>
+template <typename T, int R, bool ADE, bool ANISO>
 __global__ void __launch_bounds__(32 * R, 1)
 k_fused3d_het(const __grid_constant__ CFields<T> in, const __grid_constant__ Fields<T> out, const __grid_constant__ Coefs<T> c,
               const __grid_constant__ Geom g, const __grid_constant__ FusedTiling t, const int planes_alloc,
@@ -228,13 +258,13 @@ k_fused3d_het(const __grid_constant__ CFields<T> in, const __grid_constant__ Fie
         const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
         const int i0 = t.i_begin + seg * t.lx, i1 = min(i0 + t.lx, t.i_end);
         if (ade_tile_touched(ad, i0, i1, tj * (R - 2), tj * (R - 2) + R - 2, tk * t.own_lanes * V, (tk + 1) * t.own_lanes * V)) {
-            het_sweep<T, R, true>(in, out, c, g, t, planes_alloc, ad, item);
+            het_sweep<T, R, true, ANISO>(in, out, c, g, t, planes_alloc, ad, item);
             return;
         }
-        het_sweep<T, R, false>(in, out, c, g, t, planes_alloc, ad, item);
+        het_sweep<T, R, false, ANISO>(in, out, c, g, t, planes_alloc, ad, item);
         return;
     }
-    het_sweep<T, R, false>(in, out, c, g, t, planes_alloc, ad, (int)blockIdx.x);
+    het_sweep<T, R, false, ANISO>(in, out, c, g, t, planes_alloc, ad, (int)blockIdx.x);
 }
 
 }  // namespace fdtd

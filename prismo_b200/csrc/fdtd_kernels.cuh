@@ -20,6 +20,7 @@ template <typename T> struct CFields { const T *ex, *ey, *ez, *hx, *hy, *hz; };
 
 template <typename T> struct Coefs {
     const T *ca, *cb, *da, *db;   // cell-centred arrays (field layout) when het != 0
+    const T *cby, *cbz;           // per-component Cb of Ey / Ez (cb is then Ex's); null = isotropic
     T uca, ucb, uda, udb;         // uniform values otherwise
 };
 
@@ -216,6 +217,20 @@ k_e3d(Fields<T> f, Coefs<T> c, Geom g, int i_begin)
         ca_i = ldvp<T>(c.ca + o + g.sx); cb_i = ldvp<T>(c.cb + o + g.sx);
         ca_ij = ldv<T>(c.ca + o + g.sx + g.sy); cb_ij = ldv<T>(c.cb + o + g.sx + g.sy);
     }
+    // per-component Cb (opt-in diagonal anisotropy): Ey averages Cb_y over x and z, Ez averages Cb_z over x and y
+    PackP<T> cby, cby_i;
+    Pack<T, V> cbz, cbz_i, cbz_j, cbz_ij;
+    if (HET) {
+        if (c.cby) {
+            cby = ldvp<T>(c.cby + o); cby_i = ldvp<T>(c.cby + o + g.sx);
+            cbz = ldv<T>(c.cbz + o); cbz_i = ldv<T>(c.cbz + o + g.sx);
+            cbz_j = ldv<T>(c.cbz + o + g.sy); cbz_ij = ldv<T>(c.cbz + o + g.sx + g.sy);
+        } else {
+            cby = cb; cby_i = cb_i; cbz_ij = cb_ij;
+#pragma unroll
+            for (int e = 0; e < V; ++e) { cbz.v[e] = cb.v[e]; cbz_i.v[e] = cb_i.v[e]; cbz_j.v[e] = cb_j.v[e]; }
+        }
+    }
     const int gi = g.x0 + i;
     const bool ix0 = gi < g.nxg, ix1 = gi < g.nxg - 1;
     const bool jy0 = j < g.ny, jy1 = j < g.ny - 1;
@@ -234,7 +249,7 @@ k_e3d(Fields<T> f, Coefs<T> c, Geom g, int i_begin)
         // Ey (:282-292): averaged over x and z
         if (HET) {
             a = mean4<T>(ca.v[e], ca_i.v[e], ca.v[e + 1], ca_i.v[e + 1]);
-            b = mean4<T>(cb.v[e], cb_i.v[e], cb.v[e + 1], cb_i.v[e + 1]);
+            b = mean4<T>(cby.v[e], cby_i.v[e], cby.v[e + 1], cby_i.v[e + 1]);
         }
         n = upd_e<T>(a, ey.v[e], b, Ar<T>::diff(hx.v[e + 1], hx.v[e], g.dz, g.rdz),
                      Ar<T>::diff(hz_i.v[e], hz.v[e], g.dx, g.rdx));
@@ -242,7 +257,7 @@ k_e3d(Fields<T> f, Coefs<T> c, Geom g, int i_begin)
         // Ez (:299-309): averaged over x and y
         if (HET) {
             a = mean4<T>(ca.v[e], ca_i.v[e], ca_j.v[e], ca_ij.v[e]);
-            b = mean4<T>(cb.v[e], cb_i.v[e], cb_j.v[e], cb_ij.v[e]);
+            b = mean4<T>(cbz.v[e], cbz_i.v[e], cbz_j.v[e], cbz_ij.v[e]);
         }
         n = upd_e<T>(a, ez.v[e], b, Ar<T>::diff(hy_i.v[e], hy.v[e], g.dx, g.rdx),
                      Ar<T>::diff(hx_j.v[e], hx.v[e], g.dy, g.rdy));

@@ -74,6 +74,16 @@ class SlabExecutor:
         self._het = True
         self._tb2_ok = False                      # heterogeneous media step one sweep at a time on every rank
 
+    def rasterize(self, shapes, x, y, z=None, background=None):
+        """Global cell coordinates: this rank paints its own planes plus the right neighbour's first one."""
+        hi = min(self.x0 + self.nxl + 1, self.nxg)
+        self.eng.rasterize(shapes, np.asarray(x, dtype=np.float64)[self.x0:hi], y, z, background)
+        self._het = True
+        self._tb2_ok = False
+
+    def download_coeffs(self, which, planes=None):
+        return self.eng.download_coeffs(which, planes)
+
     def _runner_(self):
         if self._runner is None:
             if hasattr(self.eng, "ipc_export"):

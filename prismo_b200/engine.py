@@ -141,6 +141,49 @@ class Engine:
             arrs.append(a)
         _lib.check(self._lib.fdtd_set_coeffs(self._h, *[a.ctypes.data_as(C.c_void_p) for a in arrs], int(planes)))
 
+    def set_coeffs_aniso(self, Ca, Cbx, Cby, Cbz, Da, Db):
+        """OPT-IN extension: per-component Cb (diagonal permittivity tensor) inside the E stage; 3-D, parity sweeps."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (Ca, Cbx, Cby, Cbz, Da, Db)]
+        planes = arrs[0].shape[0]
+        for a in arrs:
+            if a.ndim != 3 or a.shape[1:] != tuple(self.dims[1:]) or a.shape[0] != planes or \
+                    planes not in (self.dims[0], self.dims[0] + 1):
+                raise ValueError(f"coefficient array shape {a.shape} does not match grid {self.dims}")
+        _lib.check(self._lib.fdtd_set_coeffs_aniso(self._h, *[a.ctypes.data_as(C.c_void_p) for a in arrs], int(planes)))
+
+    def rasterize(self, shapes, x, y, z=None, background=None) -> None:
+        """Shape list -> Ca, Cb, Da, Db on the device (geometry/shapes.py:71-99 + core/solver.py:113-133).  x: nx (or nx+1
+        on a slab with a right neighbour) cell coordinates; y, z: ny, nz.  Later shapes paint over earlier ones."""
+        from . import geometry
+
+        arr, n, verts = geometry.lower_shapes(shapes)
+        bg = geometry.background_values(background)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if self.ndim == 3:
+            if z is None:
+                raise ValueError("a 3-D grid needs z coordinates")
+            z = np.ascontiguousarray(z, dtype=np.float64)
+            if z.size != self.dims[2]:
+                raise ValueError(f"z has {z.size} entries, grid has {self.dims[2]}")
+        else:
+            z = None
+        if y.size != self.dims[1]:
+            raise ValueError(f"y has {y.size} entries, grid has {self.dims[1]}")
+        _lib.check(self._lib.fdtd_rasterize(
+            self._h, arr, n, verts.ctypes.data_as(C.c_void_p) if len(verts) else None, len(verts),
+            x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+            z.ctypes.data_as(C.c_void_p) if z is not None else None, int(x.size), bg.ctypes.data_as(C.c_void_p)))
+
+    def download_coeffs(self, which, planes: Optional[int] = None) -> np.ndarray:
+        """Device coefficient array as host fp64: which = 'Ca' | 'Cb' | 'Da' | 'Db' | 'Cby' | 'Cbz' (or 0..5)."""
+        idx = {"Ca": 0, "Cb": 1, "Cbx": 1, "Da": 2, "Db": 3, "Cby": 4, "Cbz": 5}.get(which, which)
+        planes = self.dims[0] if planes is None else int(planes)
+        shape = (planes, self.dims[1], self.dims[2]) if self.ndim == 3 else (planes, self.dims[1])
+        out = np.empty(shape, dtype=np.float64)
+        _lib.check(self._lib.fdtd_download_coeffs(self._h, int(idx), out.ctypes.data_as(C.c_void_p), planes))
+        return out
+
     def set_cpml(self, thickness: int, coef: Optional[np.ndarray]) -> None:
         """Physics mode only.  coef: concatenation over x, y, z of (6, N_axis) arrays (see cpml.py)."""
         if thickness == 0:

@@ -144,6 +144,23 @@ def _session_for(updater) -> "_session.Session":
     return s
 
 
+def set_geometry(sim, shapes, background=None, coords=None) -> None:
+    """Paint a list of the reference's own shape objects (prismo.geometry.shapes Box / Sphere / Cylinder / Polygon /
+    GeometryGroup, material = shape.material) into the update coefficients ON THE DEVICE, for a reference ``Simulation``,
+    ``FDTDSolver`` or ``MaxwellUpdater`` running on the "b200" backend.  Replaces the host pipeline
+    rasterize (geometry/shapes.py:71-99) -> material arrays -> MaxwellUpdater(material_arrays=...) (core/solver.py:79-133);
+    the updater's host Ca..Db stay as they are and are ignored until ``clear_geometry``."""
+    upd = getattr(getattr(sim, "solver", sim), "updater", getattr(sim, "updater", sim))
+    if not _is_b200(upd):
+        raise RuntimeError('set_geometry needs the "b200" backend: prismo.set_backend("b200") before building the Simulation')
+    _session_for(upd).set_geometry(shapes, background, coords)
+
+
+def clear_geometry(sim) -> None:
+    upd = getattr(getattr(sim, "solver", sim), "updater", getattr(sim, "updater", sim))
+    _session_for(upd).clear_geometry()
+
+
 def _advance_sim(sim, n: int) -> None:
     if n <= 0:
         return

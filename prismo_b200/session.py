@@ -168,8 +168,25 @@ class Session:
         self._coef_sig = None
 
     # ---- coefficients ---------------------------------------------------------------------------------
+    def set_geometry(self, shapes, background=None, coords=None) -> None:
+        """Paint a shape list into Ca, Cb, Da, Db ON THE DEVICE (geometry.py; geometry/shapes.py:71-99 +
+        core/solver.py:113-133): nothing of full-grid size is built on the host or crosses PCIe.  background =
+        (eps_r, mu_r, sigma_e, sigma_m) or a Material; coords = (x, y, z) cell coordinates (default: the grid's base
+        coordinates, core/grid.py:194-197).  While a geometry is set, the host coefficient arrays of the updater are
+        ignored (set_coefficients is a no-op) — clear_geometry() returns to them."""
+        from . import geometry
+
+        x, y, z = coords if coords is not None else geometry.cell_coordinates(self.grid)
+        self.engine.rasterize(shapes, x, y, z, background)
+        self._coef_sig = ("geometry",)
+
+    def clear_geometry(self) -> None:
+        self._coef_sig = None
+
     def set_coefficients(self, Ca, Cb, Da, Db) -> None:
         """Cell-centred update coefficients (core/solver.py:113-133); scalars or (nx,ny,nz) arrays."""
+        if self._coef_sig == ("geometry",):
+            return
         if all(np.isscalar(a) for a in (Ca, Cb, Da, Db)):
             sig = ("u", float(Ca), float(Cb), float(Da), float(Db))
             if sig != self._coef_sig:

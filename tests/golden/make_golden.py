@@ -51,7 +51,29 @@ def main_tensor():
     print(f"aniso: {len(res)} arrays, dtypes {sorted({str(a.dtype) for a in res.values()})}, {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def main_raster():
+    """Row f4: Shape.rasterize / GeometryGroup.rasterize masks and MaxwellUpdater's Ca..Db of the real reference on the
+    isotropic scenes of tests/raster_cases.py -> tests/golden/raster.npz."""
+    prismo = ref_loader.load()
+    from tests import raster_cases as R
+
+    res = {}
+    for name in ("scene3d", "scene2d"):
+        masks, coefs = R.reference_scene(name, prismo)
+        res[f"{name}.masks"] = np.packbits(np.stack(masks).astype(np.uint8), axis=None)
+        res[f"{name}.n_masks"] = np.array(len(masks))
+        for k, a in zip(("Ca", "Cb", "Da", "Db"), coefs):
+            res[f"{name}.{k}"] = a
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "raster.npz")
+    np.savez_compressed(path, **res)
+    print(f"raster: {len(res)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
+    if "--raster-only" in sys.argv:
+        main_raster()
+        sys.exit(0)
     if "--tensor-only" not in sys.argv:
         main()
     main_tensor()
+    main_raster()

@@ -72,13 +72,31 @@ def main():
             np.full(dims, dt / (4e-7 * np.pi)) * (1 + 0.2 * crng.random(dims))]
     ade_box = ((1, 2, 3), (dims[0] - 2, dims[1] - 3, dims[2] - 4))
 
+    # --aniso: coefficients painted ON THE DEVICE from a shape list (slab-local x coordinates + the neighbour's first
+    # plane) with an anisotropic slab crossing every cut: per-component Cb in the het sweep, ghost plane of six arrays
+    aniso = "--aniso" in sys.argv
+    het = het or aniso
+    gx, gy, gz = (np.arange(n) * h for n, h in zip(dims, spacing))
+
+    def shapes():
+        from prismo_b200 import geometry as G
+
+        L = [n * h for n, h in zip(dims, spacing)]
+        return [G.Box(G.Material("clad", (2.2, 2.31, 2.4)), (L[0] / 2, L[1] / 2, L[2] / 2), (2 * L[0], L[1] / 2, L[2] / 2)),
+                G.Cylinder(G.Material("core", 12.1), (L[0] / 2, L[1] / 2, L[2] / 2), L[1] / 8, 0.8 * L[0], "x"),
+                G.Sphere(G.Material("pad", 4.0, 1.3, 2e4, 1e3), (L[0] / 3, L[1] / 3, L[2] / 3), L[1] / 5)]
+
     def medium(e, x0, nxl):
         from prismo_b200.engine import AdeOp
 
         if not het:
             return None
         hi = min(x0 + nxl + 1, dims[0])
-        e.set_coeffs(*[a[x0:hi] for a in coef])
+        if aniso:
+            e.rasterize(shapes(), gx[x0:hi], gy, gz, (1.44, 1.0, 0.0, 0.0))
+            assert not np.array_equal(e.download_coeffs("Cby", hi - x0), e.download_coeffs("Cbz", hi - x0))
+        else:
+            e.set_coeffs(*[a[x0:hi] for a in coef])
         a, b = max(ade_box[0][0], x0), min(ade_box[1][0], x0 + e.field_shape("Ex")[0])
         if b <= a:
             return None

@@ -93,3 +93,29 @@ def test_port_planes_are_owned_by_exactly_one_slab():
             x0, n = slab_range(dims[0], r, world)
             seen += [(port, which, p) for port, which, p, ops in B.port_monitor_ops(dims, x0, n) if ops is not None]
         assert sorted(seen) == [(0, 0, 16), (0, 1, 24), (1, 0, 104), (1, 1, 112)]
+
+
+@pytest.mark.parametrize("name,aniso", [("c3", False), ("c5", False), ("c5", True)])
+def test_medium_shape_list_paints_the_same_coefficients_as_the_host_arrays(name, aniso):
+    """bench.py paints the named media on the DEVICE from Medium.shapes(); the self-check's oracle uses Medium.coefficients():
+    both must describe the same medium (checked here with the rasterisation oracle, no GPU)."""
+    import bench as B
+    from oracle import raster
+
+    dims, spacing, dt = (20, 64, 48), (2e-8, 2e-8, 2e-8), 3e-17
+    med = B.Medium(name, dims, aniso)
+    ax = [np.arange(n) * d for n, d in zip(dims, spacing)]
+    shapes = [dict(kind="box", center=tuple(s.center), size=tuple(s.size), eps_r=s.material.epsilon_r) for s in med.shapes(spacing)]
+    got = raster.coefficient_arrays(shapes, ax[0], ax[1], ax[2], dt)
+    want = med.coefficients(dt, dims[0])
+    for k in (0, 2, 3):
+        assert np.array_equal(got[k], want[k]), k
+    if aniso:
+        for c in range(3):
+            assert np.array_equal(got[1][c], want[1][c]), c
+        assert not np.array_equal(want[1][0], want[1][2])
+    else:
+        assert np.array_equal(got[1], want[1])
+    # and on an x-slab: planes [x0, x0 + n)
+    got = raster.coefficient_arrays(shapes, ax[0][7:13], ax[1], ax[2], dt)
+    assert np.array_equal(got[0], want[0][7:13]) and np.array_equal(got[3], want[3][7:13])

@@ -85,3 +85,46 @@ def test_backend_object_is_wired_to_the_library(ref):
         assert isinstance(z, np.ndarray) and z.dtype == np.float64 and not z.any()
     finally:
         ref.set_backend("numpy")
+
+
+def test_plugin_set_geometry_equals_the_reference_rasterise_pipeline(ref):
+    """Row f4: the reference's OWN shape objects painted on the device (pb.set_geometry) against the reference's host
+    pipeline — Shape.rasterize on grid coordinates, eps_rel[mask] = epsilon_r in list order, FDTDSolver(material_arrays)
+    on the stock NumPy backend.  Fields after the run are bit-identical."""
+    from prismo.core.solver import FDTDSolver
+    from prismo.geometry import shapes as RS
+
+    pb.register()
+    spec = S.SCENARIOS["src3d_point"]
+    shapes = [RS.Box(RS.Material("Si", 11.9), (0.3e-6, 0.3e-6, 0.15e-6), (0.4e-6, 2e-6, 0.2e-6)),
+              RS.Sphere(RS.Material("glass", 2.1), (0.2e-6, 0.35e-6, 0.4e-6), 0.17e-6),
+              RS.Cylinder(RS.Material("rod", 4.0, 1.5), (0.4e-6, 0.2e-6, 0.3e-6), 0.1e-6, 0.45e-6, "y"),
+              RS.GeometryGroup([RS.Box(RS.Material("ring", 6.0), (0.1e-6, 0.1e-6, 0.1e-6), (0.3e-6, 0.3e-6, 0.3e-6)),
+                                RS.Sphere(RS.Material("hole", 1.0), (0.1e-6, 0.1e-6, 0.1e-6), 0.1e-6)], "difference")]
+    try:
+        want = S.build_reference(spec, ref, backend="numpy")
+        g = want.grid
+        x, y, z = (g.origin[d] + np.arange(g.dimensions[d]) * g.spacing[d] for d in range(3))
+        eps, mu = np.ones(g.dimensions), np.ones(g.dimensions)
+        for sh in shapes:
+            m = sh.rasterize(x, y, z)
+            mat = sh.shapes[0].material if isinstance(m, tuple) else sh.material
+            m = m[0] if isinstance(m, tuple) else m
+            assert 0 < m.sum() < m.size
+            eps[m], mu[m] = mat.epsilon_r, mat.mu_r
+        want.solver = FDTDSolver(want.grid, want.dt, dict(eps_rel=eps, mu_rel=mu, sigma_e=0 * eps, sigma_m=0 * eps))
+        S.step_reference(want, spec["steps"])
+        got = S.build_reference(spec, ref, backend="b200")
+        pb.set_geometry(got, shapes)
+        got.step()
+        got.run((spec["steps"] - 1 - 0.5) * got.dt)
+        for c in S.COMPONENTS:
+            assert np.array_equal(got.fields[c], want.fields[c]), c
+        sess = got.solver.updater._b200_session
+        assert np.array_equal(sess.engine.download_coeffs("Cb"), want.solver.updater.Cb)
+        pb.clear_geometry(got)                                   # back to the updater's own (vacuum) arrays
+        got.step()
+        with pytest.raises(RuntimeError):                        # vacuum again: uniform coefficients, no arrays on the device
+            sess.engine.download_coeffs("Cb")
+    finally:
+        ref.set_backend("numpy")
