@@ -49,6 +49,20 @@ class Ricker:
     value = __call__
 
 
+class Custom:
+    """amplitude * f(t), f a user callable; phase is the function's business (waveform.py:196-229)."""
+
+    def __init__(self, waveform_func, amplitude=1.0):
+        self.waveform_func, self.amplitude, self.phase = waveform_func, amplitude, 0.0
+
+    def __call__(self, t):
+        if isinstance(t, np.ndarray):
+            return self.amplitude * np.array([self.waveform_func(ti) for ti in t])
+        return self.amplitude * self.waveform_func(t)
+
+    value = __call__
+
+
 def make_waveform(frequency, pulse=True, pulse_width=None, amplitude=1.0, phase=0.0):
     """The pulse/CW switch used by every stock source constructor (e.g. plane_wave.py:73-86)."""
     if pulse:

@@ -65,7 +65,8 @@ extern "C" int fdtd_rasterize(fdtd_engine* e, const fdtd_shape* shapes, int32_t 
         const double* d_v = d_x + n_coord;
         const RasterShape* d_s = (const RasterShape*)(d_buf + bytes_d);
         const long long total = (long long)planes * c1 * c2;
-        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        const long long rows = total / (is3 ? c2 : c1);                      // one CTA per row of the contiguous axis, grid-stride
+        const int blocks = (int)std::max<long long>(1, std::min<long long>(rows, 148 * 8));
         const double eps0 = 8.854187817e-12, mu0 = 4 * 3.141592653589793 * 1e-7;        // core/solver.py:62-63
         if (total > 0) {
 #define RASTER_LAUNCH(T, A)                                                                                                   \

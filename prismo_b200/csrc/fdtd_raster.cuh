@@ -58,9 +58,35 @@ __device__ __forceinline__ bool raster_contains(const RasterShape& s, const doub
 
 struct RasterBg { double eps[3], mu_r, sigma_e, sigma_m; };
 
-// Coefficient arrays of `planes` x c1 x c2 cells from the shape list.  cbx / cby / cbz: per-component Cb (diagonal
-// anisotropy, only written when ANISO); cb always holds the eps_xx one.  Lists of up to kRasterSmemShapes entries are
-// staged in shared memory, longer ones are read from global memory (L1-resident: every thread walks the same list).
+// core/solver.py:119-130 for one material, evaluated left to right in fp64 and rounded once to T:
+// out = Ca, Cb (eps_xx), Da, Db, Cb_y, Cb_z
+template <typename T, bool ANISO>
+__device__ __forceinline__ void raster_coefs(const double* eps3, double mr, double se, double sm, double dt, double eps0, double mu0, T* out)
+{
+    const double sdt = __dmul_rn(se, dt);
+    const double eps = __dmul_rn(eps0, eps3[0]);
+    const double s2e = __ddiv_rn(sdt, __dmul_rn(2.0, eps));
+    out[0] = (T)__ddiv_rn(__dsub_rn(1.0, s2e), __dadd_rn(1.0, s2e));
+    out[1] = (T)__ddiv_rn(__ddiv_rn(dt, eps), __dadd_rn(1.0, s2e));
+    const double mu = __dmul_rn(mu0, mr);
+    const double s2m = __ddiv_rn(__dmul_rn(sm, dt), __dmul_rn(2.0, mu));
+    out[2] = (T)__ddiv_rn(__dsub_rn(1.0, s2m), __dadd_rn(1.0, s2m));
+    out[3] = (T)__ddiv_rn(__ddiv_rn(dt, mu), __dadd_rn(1.0, s2m));
+    if (ANISO) {
+        // per-component Cb (Ca stays the eps_xx one: anisotropic materials are lossless here, the host checks it)
+        const double epy = __dmul_rn(eps0, eps3[1]), epz = __dmul_rn(eps0, eps3[2]);
+        const double s2y = __ddiv_rn(sdt, __dmul_rn(2.0, epy)), s2z = __ddiv_rn(sdt, __dmul_rn(2.0, epz));
+        out[4] = (T)__ddiv_rn(__ddiv_rn(dt, epy), __dadd_rn(1.0, s2y));
+        out[5] = (T)__ddiv_rn(__ddiv_rn(dt, epz), __dadd_rn(1.0, s2z));
+    }
+}
+
+// Coefficient arrays of `planes` x c1 x c2 cells from the shape list.  cby / cbz: per-component Cb (diagonal anisotropy,
+// only written when ANISO); cb always holds the eps_xx one.  The coefficients depend on the MATERIAL only, so a list of up
+// to kRasterSmemShapes entries is staged in shared memory together with one coefficient row per entry (+ the background)
+// computed once per CTA: a cell then costs its containment tests, one table row and 4 (6) stores — the kernel is bound by
+// its 16 (24) B of fp32 stores per cell.  Longer lists are walked in global memory and evaluate the formulas per cell.
+// One CTA works on whole rows of the contiguous axis (k in 3-D, j in 2-D): coalesced stores, one integer division per row.
 constexpr int kRasterSmemShapes = 64;
 
 template <typename T, bool ANISO>
@@ -71,44 +97,48 @@ k_rasterize(T* __restrict__ ca, T* __restrict__ cb, T* __restrict__ da, T* __res
             double eps0, double mu0, long long total, int c1, int c2, Strides3 st)
 {
     __shared__ RasterShape s_sh[kRasterSmemShapes];
+    __shared__ T s_tab[kRasterSmemShapes + 1][6];
     const bool staged = n_shapes <= kRasterSmemShapes;
-    if (staged) for (int q = threadIdx.x; q < n_shapes; q += blockDim.x) s_sh[q] = shapes[q];
+    if (staged) {
+        for (int q = threadIdx.x; q < n_shapes; q += blockDim.x) s_sh[q] = shapes[q];
+        for (int q = threadIdx.x; q <= n_shapes; q += blockDim.x) {
+            if (q < n_shapes) raster_coefs<T, ANISO>(shapes[q].eps, shapes[q].mu_r, shapes[q].sigma_e, shapes[q].sigma_m, dt, eps0, mu0, s_tab[q]);
+            else raster_coefs<T, ANISO>(bg.eps, bg.mu_r, bg.sigma_e, bg.sigma_m, dt, eps0, mu0, s_tab[q]);
+        }
+    }
     __syncthreads();
     const RasterShape* __restrict__ sh = staged ? s_sh : shapes;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(t % c2);
-        const long long r = t / c2;
-        const int j = (int)(r % c1);
-        const long long i = r / c1;
-        const double px = xs[i], py = ys[j], pz = zs ? zs[k] : 0.0;
-        double e0 = bg.eps[0], e1 = bg.eps[1], e2 = bg.eps[2], mr = bg.mu_r, se = bg.sigma_e, sm = bg.sigma_m;
-        bool m = false;
-        for (int q = 0; q < n_shapes; ++q) {
-            const RasterShape& s = sh[q];
-            const bool in = raster_contains(s, verts, px, py, pz);
-            m = s.combine == 0 ? in : s.combine == 1 ? (m || in) : s.combine == 2 ? (m && in) : (m && !in);
-            if (s.paint && m) { e0 = s.eps[0]; e1 = s.eps[1]; e2 = s.eps[2]; mr = s.mu_r; se = s.sigma_e; sm = s.sigma_m; }
+    const bool is3 = zs != nullptr;
+    const int inner = is3 ? c2 : c1;                      // contiguous axis
+    const long long rows = total / inner;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const long long i = is3 ? r / c1 : r;
+        const int jr = is3 ? (int)(r - i * c1) : 0;
+        const double px = xs[i];
+        for (int q = threadIdx.x; q < inner; q += blockDim.x) {
+            const int j = is3 ? jr : q, k = is3 ? q : 0;
+            const double py = ys[j], pz = is3 ? zs[k] : 0.0;
+            int win = n_shapes;                           // the background
+            bool m = false;
+            for (int n = 0; n < n_shapes; ++n) {
+                const RasterShape& s = sh[n];
+                const bool in = raster_contains(s, verts, px, py, pz);
+                m = s.combine == 0 ? in : s.combine == 1 ? (m || in) : s.combine == 2 ? (m && in) : (m && !in);
+                if (s.paint && m) win = n;
+            }
+            T row[6];
+            if (staged) {
+#pragma unroll
+                for (int c = 0; c < (ANISO ? 6 : 4); ++c) row[c] = s_tab[win][c];
+            } else if (win < n_shapes) {
+                raster_coefs<T, ANISO>(sh[win].eps, sh[win].mu_r, sh[win].sigma_e, sh[win].sigma_m, dt, eps0, mu0, row);
+            } else {
+                raster_coefs<T, ANISO>(bg.eps, bg.mu_r, bg.sigma_e, bg.sigma_m, dt, eps0, mu0, row);
+            }
+            const long long o = i * st.s[0] + j * st.s[1] + k * st.s[2];
+            ca[o] = row[0]; cb[o] = row[1]; da[o] = row[2]; db[o] = row[3];
+            if (ANISO) { cby[o] = row[4]; cbz[o] = row[5]; }
         }
-        // core/solver.py:119-130, evaluated left to right
-        const long long o = i * st.s[0] + j * st.s[1] + k * st.s[2];
-        const double sdt = __dmul_rn(se, dt);
-        {
-            const double eps = __dmul_rn(eps0, e0);
-            const double s2e = __ddiv_rn(sdt, __dmul_rn(2.0, eps));
-            ca[o] = (T)__ddiv_rn(__dsub_rn(1.0, s2e), __dadd_rn(1.0, s2e));
-            cb[o] = (T)__ddiv_rn(__ddiv_rn(dt, eps), __dadd_rn(1.0, s2e));
-        }
-        if (ANISO) {
-            // per-component Cb (Ca stays the eps_xx one: the conductivities of anisotropic materials are zero here)
-            const double epy = __dmul_rn(eps0, e1), epz = __dmul_rn(eps0, e2);
-            const double s2y = __ddiv_rn(sdt, __dmul_rn(2.0, epy)), s2z = __ddiv_rn(sdt, __dmul_rn(2.0, epz));
-            cby[o] = (T)__ddiv_rn(__ddiv_rn(dt, epy), __dadd_rn(1.0, s2y));
-            cbz[o] = (T)__ddiv_rn(__ddiv_rn(dt, epz), __dadd_rn(1.0, s2z));
-        }
-        const double mu = __dmul_rn(mu0, mr);
-        const double s2m = __ddiv_rn(__dmul_rn(sm, dt), __dmul_rn(2.0, mu));
-        da[o] = (T)__ddiv_rn(__dsub_rn(1.0, s2m), __dadd_rn(1.0, s2m));
-        db[o] = (T)__ddiv_rn(__ddiv_rn(dt, mu), __dadd_rn(1.0, s2m));
     }
 }
 

@@ -22,6 +22,21 @@ def _wf(kind, **kw):
     return ("waveform", kind, kw)
 
 
+def chirp(t):
+    """User waveform function of the CustomWaveform scenario: a linear chirp under a raised-cosine ramp."""
+    import math
+
+    return math.sin(2 * math.pi * F0 * t * (1.0 + 2.0e13 * t)) * (0.5 - 0.5 * math.cos(min(t * 4e15, math.pi)))
+
+
+_WAVEFORM_FUNCS = {"chirp": chirp}
+
+
+def _wf_kwargs(kw):
+    """Scenario specs name waveform functions by string; resolve them to the callables."""
+    return {k: (_WAVEFORM_FUNCS[v] if k == "waveform_func" else v) for k, v in kw.items()}
+
+
 SCENARIOS = {
     # ---- bare updates ---------------------------------------------------------------------------
     "upd3d_vac": dict(size=(0.9e-6, 0.7e-6, 0.6e-6), resolution=20e6, pml=3, courant=0.9, steps=12),
@@ -45,6 +60,15 @@ SCENARIOS = {
                                                       waveform=_wf("RickerWavelet", frequency=F0))),
                                  ("ElectricDipole", dict(position=(0.3e-6, 0.25e-6, 0.2e-6), polarization="z",
                                                          frequency=F0, pulse=False, amplitude=0.5))]),
+    # row a11: a user-supplied waveform function and the magnetic dipole constructors (sources/waveform.py:196-229,
+    # sources/point.py:142-206), CW and pulsed
+    "src3d_custom": dict(size=(0.6e-6, 0.5e-6, 0.4e-6), resolution=20e6, pml=2, courant=0.5, init="zero", steps=9,
+                         sources=[("PointSource", dict(position=(0.25e-6, 0.2e-6, 0.2e-6), component="Ex",
+                                                       waveform=_wf("CustomWaveform", waveform_func="chirp", amplitude=0.7))),
+                                  ("MagneticDipole", dict(position=(0.3e-6, 0.25e-6, 0.15e-6), polarization="y",
+                                                          frequency=F0, pulse=False, amplitude=2.0, phase=0.4)),
+                                  ("MagneticDipole", dict(position=(0.1e-6, 0.3e-6, 0.25e-6), polarization="z",
+                                                          frequency=F0, pulse=True, pulse_width=2.5e-16))]),
     "src3d_plane": dict(size=(0.6e-6, 0.5e-6, 0.4e-6), resolution=20e6, pml=2, courant=0.5, steps=8,
                         sources=[("PlaneWaveSource", dict(center=(0.2e-6, 0.25e-6, 0.2e-6), size=(0.0, 0.3e-6, 0.2e-6),
                                                           direction="-x", polarization="z", frequency=F0,
@@ -239,12 +263,13 @@ def build_reference(spec, prismo, backend="numpy"):
     if m is not None:
         sim.solver = FDTDSolver(sim.grid, sim.dt, m)
     classes = {"PointSource": prismo.sources.point.PointSource, "ElectricDipole": prismo.sources.point.ElectricDipole,
+               "MagneticDipole": prismo.sources.point.MagneticDipole,
                "PlaneWaveSource": prismo.sources.plane_wave.PlaneWaveSource, "TFSFSource": prismo.sources.tfsf.TFSFSource,
                "GaussianBeamSource": prismo.sources.gaussian.GaussianBeamSource, "ModeSource": prismo.sources.mode.ModeSource,
                "FieldMonitor": prismo.monitors.field.FieldMonitor, "DFTMonitor": prismo.monitors.dft.DFTMonitor,
                "FluxMonitor": prismo.monitors.flux.FluxMonitor,
                "ModeExpansionMonitor": prismo.monitors.mode_monitor.ModeExpansionMonitor}
-    wf = lambda kind, kw: _with_value(getattr(W, kind))(**kw)
+    wf = lambda kind, kw: _with_value(getattr(W, kind))(**_wf_kwargs(kw))
     mf = lambda d: WaveguideMode(**d)
     for kind, kw in spec.get("sources", []):
         sim.add_source(classes[kind](**{k: _resolve(v, wf, mf) for k, v in kw.items()}))
@@ -294,15 +319,15 @@ def build_oracle(spec):
     from oracle import sim as O, waveforms as OW
 
     s = O.OSimulation(spec["size"], spec["resolution"], spec["pml"], spec["courant"], materials=materials(spec))
-    names = {"GaussianPulse": OW.GaussianPulse, "ContinuousWave": OW.CW, "RickerWavelet": OW.Ricker}
-    wf = lambda kind, kw: names[kind](**kw)
+    names = {"GaussianPulse": OW.GaussianPulse, "ContinuousWave": OW.CW, "RickerWavelet": OW.Ricker, "CustomWaveform": OW.Custom}
+    wf = lambda kind, kw: names[kind](**_wf_kwargs(kw))
     mf = lambda d: types.SimpleNamespace(**d)
     for kind, kw in spec.get("sources", []):
         kw = {k: _resolve(v, wf, mf) for k, v in kw.items()}
-        if kind == "ElectricDipole":
+        if kind in ("ElectricDipole", "MagneticDipole"):            # sources/point.py:76-206: a PointSource on E_p / H_p
             w = OW.make_waveform(kw["frequency"], kw.get("pulse", True), kw.get("pulse_width"),
                                  kw.get("amplitude", 1.0), kw.get("phase", 0.0))
-            src = O.PointSource(kw["position"], "E" + kw["polarization"], w)
+            src = O.PointSource(kw["position"], ("E" if kind[0] == "E" else "H") + kw["polarization"], w)
         else:
             src = getattr(O, kind)(**kw)
         s.add_source(src)
@@ -324,7 +349,7 @@ def build_mirror(spec, pb, dtype=None):
     m = materials(spec)
     if m is not None:
         sim.set_materials(m)
-    wf = lambda kind, kw: _with_value(getattr(pb, kind))(**kw)
+    wf = lambda kind, kw: _with_value(getattr(pb, kind))(**_wf_kwargs(kw))
     mf = lambda d: types.SimpleNamespace(**d)
     for kind, kw in spec.get("sources", []):
         sim.add_source(getattr(pb, kind)(**{k: _resolve(v, wf, mf) for k, v in kw.items()}))
