@@ -15,6 +15,28 @@ from prismo_b200.grid import SHORT_AXES
 COMPONENTS = ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")
 
 
+def shape_dict(sh):
+    """A geometry object (mirror or reference class) as the rasterisation oracle's dict."""
+    m = getattr(sh, "material", None)
+    mat = {} if m is None else dict(eps_r=(tuple(m.epsilon_r) if np.ndim(m.epsilon_r) else m.epsilon_r), mu_r=m.mu_r,
+                                    sigma_e=getattr(m, "sigma_e", 0.0), sigma_m=getattr(m, "sigma_m", 0.0))
+    kind = type(sh).__name__
+    if hasattr(sh, "operation"):
+        d = dict(kind="group", operation=sh.operation, shapes=[shape_dict(q) for q in sh.shapes])
+        if m is None:
+            d.update({k: v for k, v in shape_dict(sh.shapes[0]).items() if k in ("eps_r", "mu_r", "sigma_e", "sigma_m")})
+        return dict(d, **mat)
+    if kind == "Box":
+        return dict(kind="box", center=tuple(sh.center), size=tuple(sh.size), **mat)
+    if kind == "Sphere":
+        return dict(kind="sphere", center=tuple(sh.center), radius=sh.radius, **mat)
+    if kind == "Cylinder":
+        return dict(kind="cylinder", center=tuple(sh.center), radius=sh.radius, height=sh.height, axis=sh.axis, **mat)
+    if kind == "Polygon":
+        return dict(kind="polygon", vertices=np.asarray(sh.vertices), z_min=sh.z_min, z_max=sh.z_max, **mat)
+    raise TypeError(kind)
+
+
 class FakeEngine:
     instances = []
 
@@ -48,6 +70,29 @@ class FakeEngine:
     def set_coeffs(self, Ca, Cb, Da, Db):
         self.coeffs = [np.array(a, dtype=np.float64).reshape(self.dims if self.ndim == 3 else self.dims[:2] + (1,))
                        for a in (Ca, Cb, Da, Db)]
+
+    def rasterize(self, shapes, x, y, z=None, background=None):
+        """fdtd_rasterize: the rasterisation oracle stands in for k_rasterize (tests/test_raster.py pins both)."""
+        from oracle import raster
+        from prismo_b200 import geometry as G
+
+        bg = G.background_values(background)
+        bgt = ((bg[0] if bg[0] == bg[1] == bg[2] else tuple(bg[:3])), bg[3], bg[4], bg[5])
+        self._painted = raster.coefficient_arrays([shape_dict(s) for s in shapes], x, y, z, self.dt, bgt)
+        self._set_painted(len(x))
+
+    def _set_painted(self, planes):
+        assert planes == self.dims[0]
+        self.coeffs = list(self._painted)
+
+    def download_coeffs(self, which, planes=None):
+        idx = {"Ca": 0, "Cb": 1, "Cbx": 1, "Da": 2, "Db": 3, "Cby": 4, "Cbz": 5}.get(which, which)
+        Ca, Cb, Da, Db = self.coeffs
+        cb3 = Cb if isinstance(Cb, (tuple, list)) else (Cb, None, None)
+        a = (Ca, cb3[0], Da, Db, cb3[1], cb3[2])[idx]
+        if a is None:
+            raise RuntimeError("coefficient array is not set")
+        return np.array(a[: (planes or self.dims[0])])
 
     def upload(self, comp, a):
         a = np.asarray(a)
@@ -195,6 +240,16 @@ class FakeSlabEngine(FakeEngine):
     def set_uniform_coeffs(self, ca, cb, da, db):
         ed = (self.ext, self.dims[1], self.dims[2])
         self.coeffs = [np.full(ed, float(v)) for v in (ca, cb, da, db)]
+
+    def _set_painted(self, planes):
+        """The real engine holds nx (+1 with a right neighbour) coefficient planes; the extended oracle domain also
+        computes throw-away ghost planes: pad by repeating the last plane supplied."""
+        assert planes == self.dims[0] + (0 if self.last else 1)
+
+        def pad(a):
+            return np.concatenate([a] + [a[-1:]] * (self.ext - a.shape[0]), axis=0) if a.shape[0] < self.ext else a
+
+        self.coeffs = [tuple(pad(c) for c in a) if isinstance(a, tuple) else pad(a) for a in self._painted]
 
     @staticmethod
     def _shape(d, comp):

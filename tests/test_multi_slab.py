@@ -312,3 +312,86 @@ def test_simulation_run_is_slab_decomposed_under_torch_distributed(tmp_path):
                     assert S.rel_l2(got[k], gold[k]) <= 1e-14, (name, r, k)
                 else:
                     assert np.array_equal(got[k], gold[k], equal_nan=True), (name, r, k, S.rel_l2(got[k], gold[k]))
+
+
+# ---- device-painted geometry on slabs: every rank paints its planes + the neighbour's first one ---------------------
+_GEO_SPEC = "src3d_point"
+
+
+def _geo_shapes(G, aniso):
+    return [G.Box(G.Material("clad", (2.2, 2.31, 2.4) if aniso else 2.2), (0.3e-6, 0.3e-6, 0.1e-6), (2e-6, 0.5e-6, 0.25e-6)),
+            G.Sphere(G.Material("ball", 11.9, 1.3, 40.0, 5.0), (0.3e-6, 0.25e-6, 0.35e-6), 0.16e-6),
+            G.GeometryGroup([G.Cylinder(G.Material("rod", 4.0), (0.3e-6, 0.3e-6, 0.3e-6), 0.12e-6, 2e-6, "x"),
+                             G.Box(G.Material("cut", 1.0), (0.3e-6, 0.3e-6, 0.3e-6), (0.2e-6, 1e-6, 1e-6))], "difference")]
+
+
+def _geo_run(pb, aniso):
+    from prismo_b200 import geometry as G
+
+    sim = S.build_mirror(S.SCENARIOS[_GEO_SPEC], pb)
+    sess = sim.solver.updater.session()
+    sess.set_geometry(_geo_shapes(G, aniso))
+    sim.run_steps(3)
+    sim.run_steps(S.SCENARIOS[_GEO_SPEC]["steps"] - 3)
+    return sim, sess
+
+
+def _geo_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    import prismo_b200 as pb
+    import prismo_b200.session as session
+    from tests._fake_engine import FakeSlabEngine
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    session.Engine = FakeSlabEngine
+    for aniso in (False, True):
+        sim, sess = _geo_run(pb, aniso)
+        assert sess.distributed
+        ex = sess.engine
+        planes = ex.nxl + (1 if rank < world - 1 else 0)
+        np.savez(os.path.join(out_dir, f"geo{int(aniso)}_rank{rank}.npz"), x0=ex.x0,
+                 Cb=ex.download_coeffs("Cb", planes), **(dict(Cbz=ex.download_coeffs("Cbz", planes)) if aniso else {}),
+                 **S.results_mirror(sim))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_set_geometry_is_slab_decomposed_under_torch_distributed(tmp_path, monkeypatch):
+    """Session.set_geometry under an initialised process group: each rank rasterises its slice of the x coordinates (+1
+    plane); results equal the single-process run on the whole grid, which equals the oracle on host-painted arrays."""
+    import torch.multiprocessing as mp
+
+    import prismo_b200 as pb
+    import prismo_b200.session as session
+    from oracle import kernels, raster
+    from prismo_b200 import geometry as G
+    from tests._fake_engine import FakeEngine, shape_dict
+
+    world = 2
+    mp.spawn(_geo_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    monkeypatch.setattr(session, "Engine", FakeEngine)
+    for aniso in (False, True):
+        sim, sess = _geo_run(pb, aniso)
+        assert not sess.distributed
+        want = S.results_mirror(sim)
+        whole_cb = sess.engine.download_coeffs("Cb")
+        # the single-process run against the oracle on host-painted arrays
+        o = S.build_oracle(S.SCENARIOS[_GEO_SPEC])
+        x, y, z = G.cell_coordinates(sim.grid)
+        o.coeffs = raster.coefficient_arrays([shape_dict(s) for s in _geo_shapes(G, aniso)], x, y, z, sim.dt)
+        assert isinstance(o.coeffs[1], tuple) == aniso
+        o.run_steps(S.SCENARIOS[_GEO_SPEC]["steps"])
+        oo = S.results_oracle(o)
+        for k in oo:
+            assert np.array_equal(want[k], oo[k]), (aniso, k)
+        assert 0 < (whole_cb != whole_cb.flat[0]).sum() < whole_cb.size
+        for r in range(world):
+            got = np.load(tmp_path / f"geo{int(aniso)}_rank{r}.npz")
+            x0 = int(got["x0"])
+            assert np.array_equal(got["Cb"], whole_cb[x0:x0 + got["Cb"].shape[0]]), (aniso, r)
+            if aniso:
+                assert not np.array_equal(got["Cbz"], got["Cb"])
+            for k in want:
+                assert np.array_equal(got[k], want[k], equal_nan=True), (aniso, r, k)
