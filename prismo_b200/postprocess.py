@@ -132,3 +132,18 @@ def two_port_s_parameters(port1_pair, port2_pair, mode1, mode2, neff1, neff2, di
 def s_parameter(coefficient_out: complex, coefficient_in: complex) -> complex:
     """S_ij = a_out / a_in for mode coefficients taken at the output and input port planes."""
     return coefficient_out / coefficient_in if coefficient_in != 0 else complex("nan")
+
+
+def fill_sparameter_analyzer(analyzer, excitation_port: int, amplitudes: dict) -> None:
+    """Hand device-reduced mode amplitudes to the reference's own ``SParameterAnalyzer`` (analysis/sparameters.py:88-122),
+    whose ``s_matrix`` then feeds its ``export_touchstone`` (:233) unchanged.  amplitudes: port -> (forward, backward)
+    arrays over the analyzer's frequencies, as ``separate_forward_backward`` returns them.  ``add_mode_data`` computes
+    backward / forward for the excited port and, for every other port, "forward" / "backward" of the dict it is given —
+    documented there as transmitted / incident — so port i != j is passed its own forward amplitude over the excited
+    port's forward (incident) amplitude."""
+    inc = np.asarray(amplitudes[excitation_port][0], dtype=np.complex128)
+    for port, (fwd, bwd) in amplitudes.items():
+        if port == excitation_port:
+            analyzer.add_mode_data(port, excitation_port, {"forward": inc, "backward": np.asarray(bwd, dtype=np.complex128)})
+        else:
+            analyzer.add_mode_data(port, excitation_port, {"forward": np.asarray(fwd, dtype=np.complex128), "backward": inc})

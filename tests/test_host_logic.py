@@ -248,3 +248,31 @@ def test_closing_a_session_brings_the_host_up_to_date(fake):
     assert not a.fields._fields.stale
     for c in S.COMPONENTS:
         assert np.array_equal(a.fields._fields._raw(c), b.fields[c])
+
+
+@pytest.mark.reference
+def test_amplitudes_feed_the_reference_sparameter_analyzer_and_touchstone(ref, tmp_path):
+    """Row f2's last hop: forward / backward amplitudes -> the reference's own SParameterAnalyzer.add_mode_data
+    (analysis/sparameters.py:88-122) -> export_touchstone (:233); S11 = b1 / a1, S21 = a2 / a1 as two_port_s_parameters."""
+    from prismo.analysis.sparameters import SParameterAnalyzer, export_touchstone
+
+    from prismo_b200 import postprocess as P
+
+    rng = np.random.default_rng(2)
+    freqs = np.array([1.8e14, 1.9e14, 2.0e14])
+    lam = 299792458.0 / freqs
+    a1, b1, a2 = (rng.standard_normal(3) + 1j * rng.standard_normal(3) for _ in range(3))
+    phi = 2 * np.pi * 2.4 / lam * 0.4e-6
+    left1, right1 = a1 + b1, a1 * np.exp(1j * phi) + b1 * np.exp(-1j * phi)            # what the two planes of port 1 see
+    f1, g1 = zip(*[P.separate_forward_backward(l, r, 2.4, 0.4e-6, w) for l, r, w in zip(left1, right1, lam)])
+    assert np.allclose(f1, a1, rtol=1e-12) and np.allclose(g1, b1, rtol=1e-12)
+    an = SParameterAnalyzer(2, freqs)
+    P.fill_sparameter_analyzer(an, 0, {0: (np.array(f1), np.array(g1)), 1: (a2, np.zeros(3))})
+    assert np.allclose(an.get_s_parameter(0, 0), b1 / a1, rtol=1e-12)
+    assert np.allclose(an.get_s_parameter(1, 0), a2 / a1, rtol=1e-12)
+    path = tmp_path / "coupler.s2p"
+    export_touchstone(path, freqs, an.s_matrix)
+    rows = [ln.split() for ln in open(path) if ln[0] not in "!#"]
+    assert len(rows) == 3 and len(rows[0]) == 1 + 2 * 4
+    s21 = np.array([float(r[5]) + 1j * float(r[6]) for r in rows])                  # row-major: S11, S12, S21, S22
+    assert np.allclose(s21, a2 / a1, rtol=1e-9)
