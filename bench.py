@@ -677,7 +677,9 @@ def main():
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         key = f"{name}:{args.dtype}:" + ("physics" if args.physics else ("two-step" if tb2 else "one-step"))
-        if (fused or args.physics) and not args.het and key in tr:
+        if args.het:
+            key = f"{name}:{args.dtype}:het" + ("-aniso" if wl["aniso"] else "")
+        if (fused or args.physics) and key in tr:
             traffic = tr[key]["dram_bytes"]          # bytes per launch, from the committed ncu capture of this kernel
     except (OSError, ValueError):
         pass
