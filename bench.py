@@ -355,11 +355,13 @@ def install_workload(eng, name, dims, dt, spacing, args, x0=0, nxl=None):
             how = "host-painted fp64 arrays uploaded (fdtd_set_coeffs%s)" % ("_aniso" if aniso else "")
         else:
             ax = [np.arange(n) * d for n, d in zip(dims, spacing)]
+            eng.set_option("het_indexed", int(not getattr(args, "no_indexed", False)))
             eng.rasterize(med.shapes(spacing), ax[0][x0:x0 + planes], ax[1], ax[2])
             how = "shape list rasterised on the device (fdtd_rasterize: %d boxes -> %d coefficient arrays)" % (
                 1 + len(med.cores), 6 if aniso else 4)
         eng.sync()
-        setup = {"coefficients": how, "seconds": time.perf_counter() - t0, "aniso": aniso}
+        setup = {"coefficients": how, "seconds": time.perf_counter() - t0, "aniso": aniso,
+                 "index_coded": not (getattr(args, "no_indexed", False) or getattr(args, "host_coeffs", False))}
     src, mon = workload_ops(dims, dt, spacing, x0, nxl)
     src_profile, ports = None, []
     if real:
@@ -595,6 +597,9 @@ def main():
     ap.add_argument("--aniso", action="store_true", help="heterogeneous workloads: uniaxial cladding eps = diag(2.07, 2.07, "
                     "2.16) as per-component Cb inside the E stage (default for c5, whose named config has it)")
     ap.add_argument("--no-aniso", action="store_true", help="c5 without its anisotropic cladding (one Cb per cell, 64 B/cell)")
+    ap.add_argument("--no-indexed", action="store_true", help="heterogeneous sweep streams the 4 (6) coefficient arrays instead "
+                    "of one material-index byte per cell + a shared-memory material table (the default with device-painted "
+                    "coefficients)")
     ap.add_argument("--host-coeffs", action="store_true", help="paint Ca..Db on the host and upload them instead of "
                     "rasterising the shape list on the device")
     args = ap.parse_args()
@@ -660,6 +665,7 @@ def main():
     # dominant kernel(s): fused sweep (one launch per step) or H + E pass
     kern_ms = prof["h_or_fused_ms"] + prof["e_ms"]
     peak, peak_src = peaks()
+    indexed = bool(wl["setup"] and wl["setup"].get("index_coded"))
     n_coef = (6 if wl["aniso"] else 4) * int(args.het)                     # + Ca,Cb,Da,Db (+ Cb_y, Cb_z) reads
     bpc = BYTES_PER_CELL[args.dtype] + (4 if args.dtype == "float32" else 8) * n_coef
     achieved = bpc * cells * args.steps / (kern_ms * 1e-3) / 1e9
@@ -667,7 +673,8 @@ def main():
     tb2 = fused and os.environ.get("FDTD_B200_TB2", "1") != "0" and args.steps >= 2 and not args.het
     kname = ("k_fused3d_tb2x (TMA-fed, 1 launch per TWO steps)" if tb2 else
              ("k_fused3d_het" + ("<ADE> (dispersive recursions applied in-sweep)" if real_c3 else "") + " (1 launch/step, "
-              f"6 field + {n_coef} coefficient arrays read, 6 written)") if args.het else "k_fused3d (1 launch/step)") if fused \
+              + (f"6 field arrays + 1 material-index byte per cell read (material table of {n_coef} values per entry in shared "
+                 "memory), 6 written)" if indexed else f"6 field + {n_coef} coefficient arrays read, 6 written)")) if args.het else "k_fused3d (1 launch/step)") if fused \
         else ({"2": "k_fused3d_yeex (physics mode: Yee leap-frog + CPML slabs in ONE TMA-fed sweep per step, psi ping-pong)",
                "1": "k_fused3d_yee (physics mode: Yee leap-frog + CPML slabs fused into ONE sweep per step, psi ping-pong)",
                "0": "k_h3d_yee + k_e3d_yee (physics mode: Yee leap-frog + CPML slabs, 2 launches/step)"}[
@@ -678,7 +685,7 @@ def main():
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         key = f"{name}:{args.dtype}:" + ("physics" if args.physics else ("two-step" if tb2 else "one-step"))
         if args.het:
-            key = f"{name}:{args.dtype}:het" + ("-aniso" if wl["aniso"] else "")
+            key = f"{name}:{args.dtype}:het" + ("-aniso" if wl["aniso"] else "") + ("-indexed" if indexed else "")
         if (fused or args.physics) and key in tr:
             traffic = tr[key]["dram_bytes"]          # bytes per launch, from the committed ncu capture of this kernel
     except (OSError, ValueError):
@@ -687,7 +694,11 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "kernel": kname,
                 "note": ("achieved = ALGORITHMIC bytes (48 B per cell-update, SURVEY 8d) / kernel time; the two-step "
                          "sweep keeps the intermediate step on chip, so its real DRAM traffic is 28.2 B per cell-update "
-                         "(ncu: profiles/r02_ncu_summary.md, 84 % of the copy peak) and frac can exceed 1") if tb2 else None,
+                         "(ncu: profiles/r02_ncu_summary.md, 84 % of the copy peak) and frac can exceed 1") if tb2 else
+                        (f"achieved = ALGORITHMIC bytes ({bpc} B per cell-update: fields + the coefficient values the update "
+                         "consumes, SURVEY 8d) / kernel time; with material-index coding the sweep reads one index byte per "
+                         f"cell instead of {n_coef} coefficient values, so its real DRAM traffic is about "
+                         f"{BYTES_PER_CELL[args.dtype] + 1} B per cell-update and frac can exceed the DRAM fraction") if indexed else None,
                 "algorithmic_bytes_per_launch": (2 if tb2 else 1) * bpc * cells if fused else bpc * cells / 2,
                 "odd_last_step": "one-step sweep" if (tb2 and args.steps % 2) else None,
                 "kernel_ms_per_step": kern_ms / args.steps, "post_ms_per_step": prof["post_ms"] / args.steps}

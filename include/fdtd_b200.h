@@ -189,6 +189,10 @@ int  fdtd_update_h(fdtd_engine* e);               /* MaxwellUpdater.update_magne
 int  fdtd_update_e(fdtd_engine* e);               /* MaxwellUpdater.update_electric_fields :151-165 */
 int  fdtd_sync(fdtd_engine* e);
 /* switches: "tb2" 0/1 (two-step sweep), "fused_lx" planes per x-segment (0 = auto), "het_fused" 0/1,
+ * "het_indexed" 0/1 (default 1: after fdtd_rasterize with a list of <= 64 entries the fused heterogeneous sweep reads ONE
+ * material-index byte per cell and looks Ca..Db up in a shared-memory copy of the material table instead of streaming
+ * the 4 (6) coefficient arrays — the same numbers, bit-identical results, 49 instead of 64 (72) B per fp32 cell-update;
+ * host-supplied coefficient arrays always take the array path),
  * "yee_fused" 0/1/2 (physics mode: two-pass kernels / fused sweep / TMA-fed fused sweep, the default; set it before the
  * first step of a run), "ade_fused" 0/1 (dispersive-medium recursions applied inside the next fused sweep instead of
  * a kernel of their own; default 1, results identical), "ade_coupled" 0/1 (OPT-IN extension, not the reference's

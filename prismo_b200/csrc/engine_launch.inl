@@ -460,8 +460,14 @@ template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
     }
     const size_t smem = e->aniso ? het_smem_bytes<T, R, true>() : het_smem_bytes<T, R, false>();
     const bool ade = ade_in_this_sweep(e);
-    auto kern = e->aniso ? (ade ? k_fused3d_het<T, R, true, true> : k_fused3d_het<T, R, false, true>)
-                         : (ade ? k_fused3d_het<T, R, true, false> : k_fused3d_het<T, R, false, false>);
+    const Coefs<T> cf = coefs_of<T>(e);
+    const bool idx = cf.mat != nullptr;         // material-index coding (fdtd_rasterize + option "het_indexed")
+    auto pick = [&](auto aniso_c, auto idx_c) {
+        constexpr bool A = decltype(aniso_c)::value, I = decltype(idx_c)::value;
+        return ade ? k_fused3d_het<T, R, true, A, I> : k_fused3d_het<T, R, false, A, I>;
+    };
+    auto kern = e->aniso ? (idx ? pick(std::true_type{}, std::true_type{}) : pick(std::true_type{}, std::false_type{}))
+                         : (idx ? pick(std::false_type{}, std::true_type{}) : pick(std::false_type{}, std::false_type{}));
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 block(32, R, 1);
     const long long items = (long long)t.nseg * t.ntj * t.ntk;
@@ -471,7 +477,7 @@ template <typename T> static int launch_het(fdtd_engine* e, cudaStream_t s)
         if (e->ade_order_sig.size() && e->ade_order_sig[0] == e->ade_epoch && e->ade_order_sig[1] == items)
             ad.order = e->d_ade_order;                   // prepared by prepare_ade_order for this tiling
     }
-    kern<<<(unsigned)items, block, smem, s>>>(in, out, coefs_of<T>(e), g, t, (int)e->planes_alloc, ad);
+    kern<<<(unsigned)items, block, smem, s>>>(in, out, cf, g, t, (int)e->planes_alloc, ad);
     e->ade_deferred = false;
     e->launches++;
     CU(cudaGetLastError());

@@ -43,6 +43,15 @@ extern "C" int fdtd_rasterize(fdtd_engine* e, const fdtd_shape* shapes, int32_t 
         CU(cudaMemsetAsync(e->coef[c], 0, e->array_elems * e->esz, e->stream));
     }
     for (int c = n_arrays; c < 6; ++c) { cudaFree(e->coef[c]); e->coef[c] = nullptr; }
+    // material-index coding rides along when the list is short enough for the kernel's shared-memory table
+    const bool indexed = n_shapes <= kRasterSmemShapes && n_shapes + 1 <= kMatTabRows && e->cfg.ndim == 3;
+    e->n_mat = 0;
+    if (indexed) {
+        if (!e->mat) CU(cudaMalloc(&e->mat, e->array_elems));
+        if (!e->mat_tab) CU(cudaMalloc(&e->mat_tab, (size_t)kMatTabRows * 6 * e->esz));
+        CU(cudaMemsetAsync(e->mat, 0, e->array_elems, e->stream));
+        CU(cudaMemsetAsync(e->mat_tab, 0, (size_t)kMatTabRows * 6 * e->esz, e->stream));
+    }
     // one small device buffer: coordinates, vertices, shapes
     const int c1 = e->g.ny, c2 = is3 ? e->g.nz : 1;
     const size_t n_coord = (size_t)planes + c1 + (is3 ? c2 : 0);
@@ -72,7 +81,8 @@ extern "C" int fdtd_rasterize(fdtd_engine* e, const fdtd_shape* shapes, int32_t 
 #define RASTER_LAUNCH(T, A)                                                                                                   \
     k_rasterize<T, A><<<blocks, 256, 0, e->stream>>>((T*)e->coef[0], (T*)e->coef[1], (T*)e->coef[2], (T*)e->coef[3],          \
                                                      (T*)e->coef[4], (T*)e->coef[5], d_x, d_y, d_z, d_s, n_shapes, d_v, bg,   \
-                                                     e->cfg.dt, eps0, mu0, total, c1, c2, e->st)
+                                                     e->cfg.dt, eps0, mu0, total, c1, c2, e->st,                             \
+                                                     indexed ? e->mat : nullptr, indexed ? (T*)e->mat_tab : nullptr)
             if (e->cfg.dtype == FDTD_F64) { if (aniso) RASTER_LAUNCH(double, true); else RASTER_LAUNCH(double, false); }
             else { if (aniso) RASTER_LAUNCH(float, true); else RASTER_LAUNCH(float, false); }
 #undef RASTER_LAUNCH
@@ -85,6 +95,7 @@ extern "C" int fdtd_rasterize(fdtd_engine* e, const fdtd_shape* shapes, int32_t 
     if (err != cudaSuccess) return fail(FDTD_ECUDA, "fdtd_rasterize: %s", cudaGetErrorString(err));
     e->het = true;
     e->aniso = aniso;
+    e->n_mat = indexed ? n_shapes + 1 : 0;
     e->coef_planes = planes;
     drop_graph(e);
     return 0;

@@ -132,6 +132,7 @@ extern "C" int fdtd_set_option(fdtd_engine* e, const char* key, int32_t value)
     else if (!strcmp(key, "tb2x_stages")) e->tb2x_stages = std::max(3, (int)value);
     else if (!strcmp(key, "tb2x_slots")) e->tb2x_slots = std::max(2, (int)value);
     else if (!strcmp(key, "het_fused")) e->het_fused = value ? 1 : 0;
+    else if (!strcmp(key, "het_indexed")) e->het_indexed = value ? 1 : 0;
     else if (!strcmp(key, "fused_lx")) e->fused_lx = value;
     else if (!strcmp(key, "ade_fused")) e->ade_fused = value ? 1 : 0;
     else if (!strcmp(key, "ade_coupled")) e->ade_coupled = value ? 1 : 0;

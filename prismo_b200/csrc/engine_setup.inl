@@ -93,6 +93,7 @@ extern "C" int fdtd_create(const fdtd_config* cfg, fdtd_engine** out)
     if (const char* x = getenv("FDTD_B200_YEEX_STAGES")) e->yeex_stages = std::max(2, atoi(x));
     if (const char* x = getenv("FDTD_B200_YEEX_SLOTS")) e->yeex_slots = std::max(2, atoi(x));
     if (const char* hf = getenv("FDTD_B200_HET_FUSED")) e->het_fused = atoi(hf);
+    if (const char* hi = getenv("FDTD_B200_HET_INDEXED")) e->het_indexed = atoi(hi);
     if (const char* af = getenv("FDTD_B200_ADE_FUSED")) e->ade_fused = atoi(af);
     *out = e;
     return 0;
@@ -106,6 +107,7 @@ extern "C" int fdtd_destroy(fdtd_engine* e)
     drop_graph(e);
     for (int c = 0; c < 6; ++c) { cudaFree(e->fld[c]); cudaFree(e->fldB[c]); }
     for (int c = 0; c < 6; ++c) cudaFree(e->coef[c]);
+    cudaFree(e->mat); cudaFree(e->mat_tab);
     cudaFree(e->d_src); cudaFree(e->d_mon); cudaFree(e->d_prof); cudaFree(e->d_src_ghost);
     cudaFree(e->d_ade); cudaFree(e->d_aux); cudaFree(e->d_ade_mask);
     cudaFree(e->d_flux); cudaFree(e->d_flux_partial); cudaFree(e->d_flux_out);
@@ -135,6 +137,7 @@ extern "C" int fdtd_set_uniform_coeffs(fdtd_engine* e, double ca, double cb, dou
     CU(cudaStreamSynchronize(e->stream));
     for (int c = 0; c < 6; ++c) { cudaFree(e->coef[c]); e->coef[c] = nullptr; }
     e->aniso = false;
+    e->n_mat = 0;
     e->het = false;
     e->uni[0] = ca; e->uni[1] = cb; e->uni[2] = da; e->uni[3] = db;
     drop_graph(e);
@@ -261,6 +264,7 @@ static int set_coef_arrays(fdtd_engine* e, const double* const* src, int n_array
     for (int c = n_arrays; c < 6; ++c) { cudaFree(e->coef[c]); e->coef[c] = nullptr; }
     e->het = true;
     e->aniso = n_arrays == 6;
+    e->n_mat = 0;                   // host arrays: no index coding
     e->coef_planes = planes;
     drop_graph(e);
     return 0;

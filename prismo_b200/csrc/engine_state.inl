@@ -51,6 +51,10 @@ struct fdtd_engine {
     int cur = 0;                    // which set holds the current fields (fused path)
     void* coef[6] = {};             // Ca Cb Da Db arrays (T) or null; [4], [5] = Cb of Ey, Ez when aniso (then Cb is Ex's)
     bool het = false;
+    unsigned char* mat = nullptr;   // material-index coding (fdtd_rasterize, lists of <= 64 entries): one byte per cell, field layout
+    void* mat_tab = nullptr;        // [kMatTabRows][6] T
+    int n_mat = 0;                  // > 0: mat / mat_tab describe the same medium as coef[]
+    int het_indexed = 1;            // the fused heterogeneous sweep reads mat (1 B per cell) instead of the coefficient arrays where mat exists
     bool aniso = false;             // per-component Cb (diagonal permittivity tensor) in the E stage: OPT-IN extension, 3-D parity sweeps only
     int coef_planes = 0;            // planes of Ca..Db supplied by the caller (nx, or nx + 1 with the right neighbour's first)
     double uni[4] = {1, 0, 1, 0};
@@ -152,6 +156,8 @@ template <typename T> static Coefs<T> coefs_of(const fdtd_engine* e)
     c.ca = (const T*)e->coef[0]; c.cb = (const T*)e->coef[1];
     c.da = (const T*)e->coef[2]; c.db = (const T*)e->coef[3];
     c.cby = e->aniso ? (const T*)e->coef[4] : nullptr; c.cbz = e->aniso ? (const T*)e->coef[5] : nullptr;
+    const bool idx = e->het && e->het_indexed && e->n_mat > 0;
+    c.mat = idx ? e->mat : nullptr; c.mat_tab = idx ? (const T*)e->mat_tab : nullptr; c.n_mat = idx ? e->n_mat : 0;
     c.uca = (T)e->uni[0]; c.ucb = (T)e->uni[1]; c.uda = (T)e->uni[2]; c.udb = (T)e->uni[3];
     return c;
 }

@@ -35,7 +35,11 @@ template <typename T, int R, bool ANISO = false> constexpr size_t het_smem_bytes
 // AnisotropicUpdater handles with one division per component (materials/tensor.py:508-514) — inside the same E stage:
 // Ex averages c.cb (the eps_xx array) over j and k exactly as before, Ey averages c.cby over i and k, Ez averages c.cbz
 // over i and j.  Two more arrays are streamed (72 B per cell-update in fp32), one more smem slot carries Cb_z to row - 1.
-template <typename T, int R, bool ADE, bool ANISO>
+// IDX (material-index coding): media painted from a shape list hold a handful of distinct materials, so the sweep reads ONE
+// byte per cell (c.mat) instead of 4 (6) coefficient values and looks the values up in a per-CTA shared-memory copy of the
+// material table when an index plane enters the register window: 49 B per cell-update in fp32 instead of 64 (72).  The
+// looked-up values are the very numbers the coefficient arrays hold, so results are bit-identical to the array path.
+template <typename T, int R, bool ADE, bool ANISO, bool IDX>
 __device__ __forceinline__ void
 het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const Geom& g, const FusedTiling& t, const int planes_alloc,
           const AdeIn& ad, const int item)
@@ -69,10 +73,43 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
 
     const T* pex = in.ex + ofs; const T* pey = in.ey + ofs; const T* pez = in.ez + ofs;
     const T* phx = in.hx + ofs; const T* phy = in.hy + ofs; const T* phz = in.hz + ofs;
-    const T* pca = c.ca + ofs; const T* pcb = c.cb + ofs; const T* pda = c.da + ofs; const T* pdb = c.db + ofs;
+    const T* pca = IDX ? nullptr : c.ca + ofs; const T* pcb = IDX ? nullptr : c.cb + ofs;
+    const T* pda = IDX ? nullptr : c.da + ofs; const T* pdb = IDX ? nullptr : c.db + ofs;
     P z_;
 #pragma unroll
     for (int e = 0; e < V; ++e) z_.v[e] = (T)0;
+    // IDX: material table in shared memory; V indices per thread and plane travel packed in one register
+    __shared__ T s_tc[IDX ? kMatTabRows : 1][4];            // Ca, Cb (x), Cb_y, Cb_z
+    __shared__ T s_td[IDX ? kMatTabRows : 1][2];            // Da, Db
+    const unsigned char* pm = IDX ? c.mat + ofs : nullptr;
+    if (IDX) {
+        for (int q = threadIdx.y * 32 + threadIdx.x; q < c.n_mat; q += 32 * R) {
+            const T* r = c.mat_tab + 6 * q;
+            s_tc[q][0] = r[0]; s_tc[q][1] = r[1]; s_tc[q][2] = r[4]; s_tc[q][3] = r[5];
+            s_td[q][0] = r[2]; s_td[q][1] = r[3];
+        }
+        __syncthreads();
+    }
+    auto ldm = [&](unsigned off, bool ok) -> unsigned {
+        if (!ok) return 0u;
+        if (V == 2) return *reinterpret_cast<const unsigned short*>(pm + off);
+        return pm[off];
+    };
+    auto look_c = [&](unsigned m, P& a, P& b, P& by, P& bz) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const unsigned q = (m >> (8 * e)) & 255u;
+            a.v[e] = s_tc[q][0]; b.v[e] = s_tc[q][1];
+            if (ANISO) { by.v[e] = s_tc[q][2]; bz.v[e] = s_tc[q][3]; }
+        }
+    };
+    auto look_d = [&](unsigned m, P& a, P& b) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const unsigned q = (m >> (8 * e)) & 255u;
+            a.v[e] = s_td[q][0]; b.v[e] = s_td[q][1];
+        }
+    };
 
     // window at i = i0 - 1
     unsigned po = (unsigned)i0 * (unsigned)g.sx;
@@ -81,17 +118,29 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
     P e2x = ld8<T, V>(pex + po + g.sx, ld_ok), e2y = ld8<T, V>(pey + po + g.sx, ld_ok), e2z = ld8<T, V>(pez + po + g.sx, ld_ok);
     P h1x = ld8<T, V>(phx + po, ld_ok), h1y = ld8<T, V>(phy + po, ld_ok), h1z = ld8<T, V>(phz + po, ld_ok);            // H[i+1]
     const bool pm_ok = ld_ok && i0 > 0;
-    P ca0 = ld8<T, V>(pca + po - g.sx, pm_ok), cb0 = ld8<T, V>(pcb + po - g.sx, pm_ok);     // C[i]   (unused while i < i0)
-    P ca1 = ld8<T, V>(pca + po, ld_ok), cb1 = ld8<T, V>(pcb + po, ld_ok);                 // C[i+1]
-    P da1 = ld8<T, V>(pda + po, ld_ok), db1 = ld8<T, V>(pdb + po, ld_ok);                 // D[i+1]
-    P da2 = ld8<T, V>(pda + po + g.sx, ld_ok), db2 = ld8<T, V>(pdb + po + g.sx, ld_ok);   // D[i+2]
+    P ca0 = z_, cb0 = z_, ca1 = z_, cb1 = z_, da1 = z_, db1 = z_, da2 = z_, db2 = z_;
     P ca0_j = z_, cb0_j = z_;                                                           // C[i] at j+1
     // ANISO: Cb_y at planes i, i+1 (k+1 from the next lane), Cb_z at planes i, i+1 and their j+1 neighbours
-    const T* pcby = ANISO ? c.cby + ofs : nullptr; const T* pcbz = ANISO ? c.cbz + ofs : nullptr;
+    const T* pcby = (ANISO && !IDX) ? c.cby + ofs : nullptr; const T* pcbz = (ANISO && !IDX) ? c.cbz + ofs : nullptr;
     P cby0 = z_, cby1 = z_, cbz0 = z_, cbz1 = z_, cbz0_j = z_;
-    if (ANISO) {
-        cby0 = ld8<T, V>(pcby + po - g.sx, pm_ok); cbz0 = ld8<T, V>(pcbz + po - g.sx, pm_ok);
-        cby1 = ld8<T, V>(pcby + po, ld_ok); cbz1 = ld8<T, V>(pcbz + po, ld_ok);
+    unsigned m_a = 0, m_b = 0;                                                           // IDX: indices of planes i+2, i+3
+    if (IDX) {
+        look_c(ldm(po - (unsigned)g.sx, pm_ok), ca0, cb0, cby0, cbz0);                   // C[i]   (unused while i < i0)
+        const unsigned m1 = ldm(po, ld_ok);
+        look_c(m1, ca1, cb1, cby1, cbz1);                                                 // C[i+1]
+        look_d(m1, da1, db1);                                                             // D[i+1]
+        m_a = ldm(po + (unsigned)g.sx, ld_ok);
+        look_d(m_a, da2, db2);                                                            // D[i+2]
+        m_b = ldm(po + 2u * (unsigned)g.sx, ld_ok && (i0 + 2 < planes_alloc));
+    } else {
+        ca0 = ld8<T, V>(pca + po - g.sx, pm_ok); cb0 = ld8<T, V>(pcb + po - g.sx, pm_ok);     // C[i]   (unused while i < i0)
+        ca1 = ld8<T, V>(pca + po, ld_ok); cb1 = ld8<T, V>(pcb + po, ld_ok);                 // C[i+1]
+        da1 = ld8<T, V>(pda + po, ld_ok); db1 = ld8<T, V>(pdb + po, ld_ok);                 // D[i+1]
+        da2 = ld8<T, V>(pda + po + g.sx, ld_ok); db2 = ld8<T, V>(pdb + po + g.sx, ld_ok);   // D[i+2]
+        if (ANISO) {
+            cby0 = ld8<T, V>(pcby + po - g.sx, pm_ok); cbz0 = ld8<T, V>(pcbz + po - g.sx, pm_ok);
+            cby1 = ld8<T, V>(pcby + po, ld_ok); cbz1 = ld8<T, V>(pcbz + po, ld_ok);
+        }
     }
     unsigned ade_mask = 0;
     __shared__ AdeOp s_ade[ADE ? kAdeSmemOps : 1];
@@ -109,10 +158,18 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
         const unsigned pp = (unsigned)(i + 2) * (unsigned)g.sx;
         const P n_ex = ld8<T, V>(pex + pp + g.sx, p3), n_ey = ld8<T, V>(pey + pp + g.sx, p3), n_ez = ld8<T, V>(pez + pp + g.sx, p3);
         const P n_hx = ld8<T, V>(phx + pp, p2), n_hy = ld8<T, V>(phy + pp, p2), n_hz = ld8<T, V>(phz + pp, p2);
-        const P n_ca = ld8<T, V>(pca + pp, p2), n_cb = ld8<T, V>(pcb + pp, p2);
-        const P n_da = ld8<T, V>(pda + pp + g.sx, p3), n_db = ld8<T, V>(pdb + pp + g.sx, p3);
-        P n_cby = z_, n_cbz = z_;
-        if (ANISO) { n_cby = ld8<T, V>(pcby + pp, p2); n_cbz = ld8<T, V>(pcbz + pp, p2); }
+        P n_ca = z_, n_cb = z_, n_da = z_, n_db = z_, n_cby = z_, n_cbz = z_;
+        unsigned n_m = 0;
+        if (IDX) {
+            // the index planes i+2 / i+3 arrived one / two iterations ago: their table rows cost no DRAM latency
+            look_c(m_a, n_ca, n_cb, n_cby, n_cbz);
+            look_d(m_b, n_da, n_db);
+            n_m = ldm(pp + 2u * (unsigned)g.sx, more && (i + 4 < planes_alloc));
+        } else {
+            n_ca = ld8<T, V>(pca + pp, p2); n_cb = ld8<T, V>(pcb + pp, p2);
+            n_da = ld8<T, V>(pda + pp + g.sx, p3); n_db = ld8<T, V>(pdb + pp + g.sx, p3);
+            if (ANISO) { n_cby = ld8<T, V>(pcby + pp, p2); n_cbz = ld8<T, V>(pcbz + pp, p2); }
+        }
         // ---- publish the j+1 inputs ------------------------------------------------------------------------------------
         {
             union { VT q; P r; } u;
@@ -239,11 +296,12 @@ het_sweep(const CFields<T>& in, const Fields<T>& out, const Coefs<T>& c, const G
         ca0 = ca1; cb0 = cb1; ca1 = n_ca; cb1 = n_cb;
         ca0_j = ca1_j; cb0_j = cb1_j;
         if (ANISO) { cby0 = cby1; cby1 = n_cby; cbz0 = cbz1; cbz1 = n_cbz; cbz0_j = cbz1_j; }
+        if (IDX) { m_a = m_b; m_b = n_m; }
         da1 = da2; db1 = db2; da2 = n_da; db2 = n_db;
     }
 }
 
-template <typename T, int R, bool ADE, bool ANISO>
+template <typename T, int R, bool ADE, bool ANISO, bool IDX>
 __global__ void __launch_bounds__(32 * R, 1)
 k_fused3d_het(const __grid_constant__ CFields<T> in, const __grid_constant__ Fields<T> out, const __grid_constant__ Coefs<T> c,
               const __grid_constant__ Geom g, const __grid_constant__ FusedTiling t, const int planes_alloc,
@@ -258,13 +316,13 @@ k_fused3d_het(const __grid_constant__ CFields<T> in, const __grid_constant__ Fie
         const int tj = tile / t.ntk, tk = tile - tj * t.ntk;
         const int i0 = t.i_begin + seg * t.lx, i1 = min(i0 + t.lx, t.i_end);
         if (ade_tile_touched(ad, i0, i1, tj * (R - 2), tj * (R - 2) + R - 2, tk * t.own_lanes * V, (tk + 1) * t.own_lanes * V)) {
-            het_sweep<T, R, true, ANISO>(in, out, c, g, t, planes_alloc, ad, item);
+            het_sweep<T, R, true, ANISO, IDX>(in, out, c, g, t, planes_alloc, ad, item);
             return;
         }
-        het_sweep<T, R, false, ANISO>(in, out, c, g, t, planes_alloc, ad, item);
+        het_sweep<T, R, false, ANISO, IDX>(in, out, c, g, t, planes_alloc, ad, item);
         return;
     }
-    het_sweep<T, R, false, ANISO>(in, out, c, g, t, planes_alloc, ad, (int)blockIdx.x);
+    het_sweep<T, R, false, ANISO, IDX>(in, out, c, g, t, planes_alloc, ad, (int)blockIdx.x);
 }
 
 }  // namespace fdtd

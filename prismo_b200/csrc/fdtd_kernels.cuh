@@ -18,9 +18,14 @@ namespace fdtd {
 template <typename T> struct Fields { T *ex, *ey, *ez, *hx, *hy, *hz; };
 template <typename T> struct CFields { const T *ex, *ey, *ez, *hx, *hy, *hz; };
 
+constexpr int kMatTabRows = 72;    // material-index coding: rows of the per-CTA material table (background + <= 64 list entries)
+
 template <typename T> struct Coefs {
     const T *ca, *cb, *da, *db;   // cell-centred arrays (field layout) when het != 0
     const T *cby, *cbz;           // per-component Cb of Ey / Ez (cb is then Ex's); null = isotropic
+    const unsigned char* mat;     // material-index coding (fdtd_rasterize): one byte per cell, field layout; null = off
+    const T* mat_tab;             // [n_mat][6] = Ca, Cb, Da, Db, Cb_y, Cb_z of material m (0 = background)
+    int n_mat;
     T uca, ucb, uda, udb;         // uniform values otherwise
 };
 

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(256)
 k_rasterize(T* __restrict__ ca, T* __restrict__ cb, T* __restrict__ da, T* __restrict__ db, T* __restrict__ cby, T* __restrict__ cbz,
             const double* __restrict__ xs, const double* __restrict__ ys, const double* __restrict__ zs,
             const RasterShape* __restrict__ shapes, int n_shapes, const double* __restrict__ verts, RasterBg bg, double dt,
-            double eps0, double mu0, long long total, int c1, int c2, Strides3 st)
+            double eps0, double mu0, long long total, int c1, int c2, Strides3 st,
+            unsigned char* __restrict__ mat, T* __restrict__ mat_tab)
 {
     __shared__ RasterShape s_sh[kRasterSmemShapes];
     __shared__ T s_tab[kRasterSmemShapes + 1][6];
@@ -107,6 +108,15 @@ k_rasterize(T* __restrict__ ca, T* __restrict__ cb, T* __restrict__ da, T* __res
         }
     }
     __syncthreads();
+    // material-index coding (mat != null, staged lists only): index 0 = background, q + 1 = list entry q; the table goes
+    // to global memory once, in that order, for the sweeps to stage (fdtd_het.cuh IDX)
+    if (mat_tab && blockIdx.x == 0)
+        for (int q = threadIdx.x; q <= n_shapes; q += blockDim.x) {
+            const T* r = s_tab[q == 0 ? n_shapes : q - 1];
+            T* o = mat_tab + 6 * q;
+            o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+            o[4] = ANISO ? r[4] : r[1]; o[5] = ANISO ? r[5] : r[1];
+        }
     const RasterShape* __restrict__ sh = staged ? s_sh : shapes;
     const bool is3 = zs != nullptr;
     const int inner = is3 ? c2 : c1;                      // contiguous axis
@@ -138,6 +148,7 @@ k_rasterize(T* __restrict__ ca, T* __restrict__ cb, T* __restrict__ da, T* __res
             const long long o = i * st.s[0] + j * st.s[1] + k * st.s[2];
             ca[o] = row[0]; cb[o] = row[1]; da[o] = row[2]; db[o] = row[3];
             if (ANISO) { cby[o] = row[4]; cbz[o] = row[5]; }
+            if (mat) mat[o] = (unsigned char)(win == n_shapes ? 0 : win + 1);
         }
     }
 }

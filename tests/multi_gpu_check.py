@@ -93,6 +93,8 @@ def main():
             return None
         hi = min(x0 + nxl + 1, dims[0])
         if aniso:
+            # --indexed: the slabs read material indices, the whole engine the coefficient arrays; else arrays everywhere
+            e.set_option("het_indexed", int("--indexed" in sys.argv and nxl < dims[0]))
             e.rasterize(shapes(), gx[x0:hi], gy, gz, (1.44, 1.0, 0.0, 0.0))
             assert not np.array_equal(e.download_coeffs("Cby", hi - x0), e.download_coeffs("Cbz", hi - x0))
         else:

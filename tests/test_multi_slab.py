@@ -231,7 +231,7 @@ def test_two_slabs_on_one_gpu_match_single_engine(dtype):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["p2p", "sim", "het", "aniso"])
+@pytest.mark.parametrize("mode", ["p2p", "sim", "het", "aniso", "indexed"])
 def test_peer_to_peer_slabs_two_processes_one_gpu(mode):
     """The production halo protocol (CUDA IPC mappings, DMA push, release/acquire flags, in-kernel wait) with two
     processes time-slicing one GPU: bitwise equal to a single engine.  Halo waits time out after 5 s."""
@@ -241,15 +241,16 @@ def test_peer_to_peer_slabs_two_processes_one_gpu(mode):
     env = dict(os.environ, FDTD_B200_HALO_TIMEOUT_MS="5000")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(os.path.dirname(__file__), "multi_gpu_check.py"),
-           "--same-device"] + {"sim": ["--sim"], "het": ["--het"], "aniso": ["--aniso"], "p2p": []}[mode]
+           "--same-device"] + {"sim": ["--sim"], "het": ["--het"], "aniso": ["--aniso"], "indexed": ["--aniso", "--indexed"], "p2p": []}[mode]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     want = "MULTI_GPU_SIM_CHECK OK" if mode == "sim" else "MULTI_GPU_CHECK OK"
     assert want in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("args", [[], ["--f32"], ["--balanced"], ["--sim"], ["--src-offset", "2"], ["--het"], ["--aniso"]],
-                         ids=["p2p", "f32", "balanced", "sim", "ghost-src", "het", "aniso"])
+@pytest.mark.parametrize("args", [[], ["--f32"], ["--balanced"], ["--sim"], ["--src-offset", "2"], ["--het"], ["--aniso"],
+                                  ["--aniso", "--indexed"]],
+                         ids=["p2p", "f32", "balanced", "sim", "ghost-src", "het", "aniso", "indexed"])
 def test_peer_to_peer_slabs_on_all_gpus(args):
     """The same check on REAL separate GPUs (NCCL rendezvous, CUDA-IPC peer mappings over NVLink): one rank per
     device, every device of the box.  Skips on a single-GPU box."""

@@ -337,3 +337,54 @@ def test_session_set_geometry_drives_a_simulation():
     want = S.results_mirror(sim2)
     for k in want:
         assert np.array_equal(got[k], want[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["scene3d", "aniso"])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("ade", [False, True])
+def test_index_coded_sweep_equals_array_sweep(name, dtype, ade):
+    """Material-index coding (option "het_indexed"): the sweep reads one byte per cell and looks Ca..Db up in the material
+    table fdtd_rasterize wrote — the same numbers the coefficient arrays hold, so fields (and recursion state, with a
+    dispersive box applied in-sweep) are bit-identical to the array path in both dtypes; fp64 also equals the oracle."""
+    import prismo_b200 as pb
+    from prismo_b200 import geometry as G
+    from prismo_b200.engine import AdeOp
+
+    dims, sp, org, shapes, bg = R.SCENES[name]
+    x, y, z = R.coords(dims, sp, org)
+    coef = raster.coefficient_arrays(shapes, x, y, z, R.DT, bg)
+    steps = 7
+    with _engine(pb, name, dtype) as a, _engine(pb, name, dtype) as b:
+        a.set_option("het_indexed", 0)
+        b.set_option("het_indexed", 1)
+        ids = []
+        for e in (a, b):
+            e.rasterize(R.build_shapes(shapes, G), x, y, z, bg)
+            if ade:
+                ids.append(e.add_ade_op(AdeOp("Ez", 1, (2, 3, 1), (dims[0] - 3, dims[1] - 2, dims[2] - 4), 0.3, 0.9)))
+        F = _seed(a, dims)
+        _seed(b, dims)
+        a.run(3); a.run(steps - 3)
+        b.run(3); b.run(steps - 3)
+        for c in pb.grid.COMPONENTS:
+            got = b.download(c)
+            assert np.array_equal(got, a.download(c)), (c, np.abs(got - a.download(c)).max())
+        if ade:
+            sa, sb = a.ade_state(ids[0], 0), b.ade_state(ids[1], 0)
+            assert np.abs(sa).max() > 0 and np.array_equal(sa, sb)
+        if dtype == "float64":
+            for _ in range(steps):
+                kernels.step(F, coef, sp, False)
+            for c in pb.grid.COMPONENTS:
+                assert np.array_equal(b.download(c), F[c]), c
+        # host arrays switch the coding off again (nothing describes them as indices)
+        Ca, Cb, Da, Db = coef
+        if isinstance(Cb, tuple):
+            b.set_coeffs_aniso(Ca, *Cb, Da, Db)
+        else:
+            b.set_coeffs(Ca, Cb, Da, Db)
+        b.run(1)
+        a.run(1)
+        for c in pb.grid.COMPONENTS:
+            assert np.array_equal(b.download(c), a.download(c)), c
