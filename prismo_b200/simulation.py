@@ -215,6 +215,12 @@ class Simulation:
         self.solver = FDTDSolver(self.grid, self.dt, material_arrays, dtype=self._dtype, device=self._device,
                                  physics=self._physics)
 
+    def set_geometry(self, shapes, background=None, coords=None) -> None:
+        """Paint a shape list (geometry.Box / Sphere / Cylinder / Polygon / GeometryGroup, or the reference's own shape
+        objects) into the update coefficients on the device instead of building material arrays on the host
+        (geometry/shapes.py:71-99 + core/solver.py:113-133): Session.set_geometry."""
+        self.solver.updater.session().set_geometry(shapes, background, coords)
+
     # ---- stepping -------------------------------------------------------------------------------------
     def run_steps(self, n: int) -> None:
         """n full steps in one device submission (solver, sources, monitors; core/simulation.py:147-164)."""

@@ -276,3 +276,49 @@ def test_amplitudes_feed_the_reference_sparameter_analyzer_and_touchstone(ref, t
     assert len(rows) == 3 and len(rows[0]) == 1 + 2 * 4
     s21 = np.array([float(r[5]) + 1j * float(r[6]) for r in rows])                  # row-major: S11, S12, S21, S22
     assert np.allclose(s21, a2 / a1, rtol=1e-9)
+
+
+@pytest.mark.reference
+def test_plugin_set_geometry_with_reference_shapes(fake, ref):
+    """pb.set_geometry(sim, [reference shape objects]) against the reference's own host pipeline (Shape.rasterize on the
+    grid coordinates, eps_rel[mask] = ..., FDTDSolver(material_arrays)) on the stock NumPy backend; the mirror
+    Simulation.set_geometry with mirror shapes gives the same fields.  (Engine double: the rasterisation oracle paints.)"""
+    from prismo.core.solver import FDTDSolver
+    from prismo.geometry import shapes as RS
+
+    from prismo_b200 import geometry as G
+
+    pb.register()
+    spec = S.SCENARIOS["src3d_point"]
+
+    def shapes(mod):
+        return [mod.Box(mod.Material("Si", 11.9), (0.3e-6, 0.3e-6, 0.15e-6), (0.4e-6, 2e-6, 0.2e-6)),
+                mod.Sphere(mod.Material("glass", 2.1), (0.2e-6, 0.35e-6, 0.4e-6), 0.17e-6),
+                mod.Cylinder(mod.Material("rod", 4.0, 1.5), (0.4e-6, 0.2e-6, 0.3e-6), 0.1e-6, 0.45e-6, "y")]
+
+    try:
+        want = S.build_reference(spec, ref, backend="numpy")
+        g = want.grid
+        x, y, z = (g.origin[d] + np.arange(g.dimensions[d]) * g.spacing[d] for d in range(3))
+        eps, mu = np.ones(g.dimensions), np.ones(g.dimensions)
+        for sh in shapes(RS):
+            m = sh.rasterize(x, y, z)
+            assert 0 < m.sum() < m.size
+            eps[m], mu[m] = sh.material.epsilon_r, sh.material.mu_r
+        want.solver = FDTDSolver(want.grid, want.dt, dict(eps_rel=eps, mu_rel=mu, sigma_e=0 * eps, sigma_m=0 * eps))
+        S.step_reference(want, spec["steps"])
+        got = S.build_reference(spec, ref, backend="b200")
+        pb.set_geometry(got, shapes(RS))
+        got.step()
+        got.run((spec["steps"] - 1 - 0.5) * got.dt)
+        for c in S.COMPONENTS:
+            assert np.array_equal(got.fields[c], want.fields[c]), c
+        with pytest.raises(RuntimeError):
+            pb.set_geometry(want, shapes(RS))              # a NumPy-backend simulation has no device to paint on
+    finally:
+        ref.set_backend("numpy")
+    mirror = S.build_mirror(spec, pb)
+    mirror.set_geometry(shapes(G))
+    mirror.run_steps(spec["steps"])
+    for c in S.COMPONENTS:
+        assert np.array_equal(mirror.fields[c], want.fields[c]), c
