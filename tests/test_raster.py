@@ -388,3 +388,48 @@ def test_index_coded_sweep_equals_array_sweep(name, dtype, ade):
         a.run(1)
         for c in pb.grid.COMPONENTS:
             assert np.array_equal(b.download(c), a.download(c)), c
+
+
+@pytest.mark.reference
+def test_oracle_raster_random_scenes_against_live_reference(ref):
+    """Property-style pinning: random shape lists (all classes, all group operations, degenerate sizes, vertices and faces
+    on cell coordinates) rasterised by the oracle and by the reference's own classes give identical masks, 3-D and 2-D."""
+    from prismo.geometry import shapes as RS
+
+    rng = np.random.default_rng(17)
+    x = np.round(np.linspace(-0.5, 0.5, 12), 3)
+    y = np.round(np.linspace(-0.4, 0.45, 11), 3)
+    z3 = np.round(np.linspace(-0.3, 0.35, 9), 3)
+
+    def rnd_prim():
+        kind = rng.choice(["box", "sphere", "cylinder", "polygon"])
+        c = tuple(float(v) for v in rng.choice(x, 1)) + tuple(float(v) for v in rng.choice(y, 1)) + \
+            tuple(float(v) for v in rng.choice(z3, 1))                       # centres ON cell coordinates
+        if kind == "box":
+            size = tuple(float(v) for v in rng.choice([0.0, 0.1, 0.2, 0.3, 0.55], 3))
+            return dict(kind="box", center=c, size=size)
+        if kind == "sphere":
+            return dict(kind="sphere", center=c, radius=float(rng.choice([0.0, 0.1, 0.25, 0.3])))
+        if kind == "cylinder":
+            return dict(kind="cylinder", center=c, radius=float(rng.choice([0.0, 0.1, 0.2])),
+                        height=float(rng.choice([0.0, 0.2, 0.5])), axis=str(rng.choice(["x", "y", "z"])))
+        n = int(rng.integers(3, 7))
+        v = np.stack([rng.choice(x, n), rng.choice(y, n)], axis=1)              # vertices on cell coordinates, any winding
+        zlo, zhi = sorted(float(q) for q in rng.choice(z3, 2))
+        return dict(kind="polygon", vertices=[tuple(map(float, p)) for p in v], z_min=zlo, z_max=zhi)
+
+    checked = 0
+    for trial in range(40):
+        z = z3 if trial % 3 else None
+        if rng.random() < 0.3:
+            s = dict(kind="group", operation=str(rng.choice(["union", "intersection", "difference"])),
+                     shapes=[rnd_prim() for _ in range(int(rng.integers(2, 4)))])
+        else:
+            s = rnd_prim()
+        obj = R.build_shapes([dict(s, eps_r=2.0)], RS)[0]
+        want = obj.rasterize(x, y, z)
+        want = want[0] if isinstance(want, tuple) else want
+        got = raster.contains(s, x, y, z)
+        assert np.array_equal(got.reshape(want.shape), want), (trial, s)
+        checked += int(want.any())
+    assert checked >= 15
