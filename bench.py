@@ -459,65 +459,91 @@ def self_check(eng, dims, dt, spacing, args, mon_ids, do_oracle, coef_fn=None, s
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_baseline_sample(dims, seconds_budget=20.0, steps=3):
-    """Oracle port of the reference NumPy step (same slicing arithmetic, same per-step temporaries) on a
-    bounded cubic sample of the workload: vacuum + TFSF plane + FieldMonitor DFT plane."""
+def cpu_arm(side):
+    """The CPU implementation of the path on a side^3 sample of the c4 workload (vacuum, TFSF plane, 5-frequency DFT
+    plane): -> (step callable, kind, description).  kind "reference" = the UNMODIFIED rithulkamesh/prismo package on its
+    stock NumPy backend (Simulation.step, core/simulation.py:147-164), imported from oracle/_ref — the staged copy that
+    travels to the GPU box (oracle/stage_reference.py) — or from /root/reference/src in the build container; kind "port" =
+    the oracle restatement (oracle/sim.py: the same NumPy expressions one for one) where no copy of the reference exists.
+    FDTD_B200_CPU_ARM=port forces the port."""
+    res, pml = 50e6, 10
+    size = ((side - 2 * pml - 0.5) / res,) * 3
+    L = size[0]
+    src_kw = dict(center=(L / 2, L / 2, L / 2), size=(L / 2, L / 2, L / 2), direction="+x", polarization="y", frequency=F0,
+                  pulse=False)
+    mon_kw = dict(center=(0.75 * L, L / 2, L / 2), size=(0.0, L, L), components=["Ey", "Hz"], time_domain=False,
+                  frequencies=list(F0 * np.linspace(0.9, 1.1, 5)))
+    why = "forced by FDTD_B200_CPU_ARM=port"
+    if os.environ.get("FDTD_B200_CPU_ARM", "reference") != "port":
+        try:
+            from oracle import ref_loader
+
+            if not ref_loader.available():
+                raise ImportError(f"no reference package at {ref_loader.REF_SRC}")
+            prismo = ref_loader.load()
+            import prismo.monitors.field
+            import prismo.sources.tfsf
+
+            prismo.set_backend("numpy")
+            sim = prismo.Simulation(size=size, resolution=res, pml_layers=pml, courant_factor=0.9)
+            if tuple(sim.grid.dimensions) != (side, side, side):
+                raise ValueError(f"reference grid {sim.grid.dimensions} != {side}^3")
+            sim.add_source(prismo.sources.tfsf.TFSFSource(**src_kw))
+            sim.add_monitor(prismo.monitors.field.FieldMonitor(**mon_kw))
+            return sim.step, "reference", (f"unmodified prismo {getattr(prismo, '__version__', '?')} (NumPy backend, "
+                                           f"Simulation.step) imported from {os.path.relpath(ref_loader.REF_SRC, ROOT)}")
+        except Exception as ex:                 # no staged copy / import problem: the port below
+            why = f"reference not importable ({type(ex).__name__}: {ex})"
     from oracle import sim as O
 
+    s = O.OSimulation(size, res, pml, 0.9)
+    assert s.grid.dims == (side, side, side), s.grid.dims
+    s.add_source(O.TFSFSource(src_kw["center"], src_kw["size"], "+x", "y", F0, pulse=False))
+    s.add_monitor(O.FieldMonitor(mon_kw["center"], mon_kw["size"], components=["Ey", "Hz"], time_domain=False,
+                                 frequencies=mon_kw["frequencies"]))
+    return s.step, "port", f"oracle port of the reference NumPy path (oracle/sim.py); {why}"
+
+
+def cpu_baseline_sample(dims, seconds_budget=20.0, steps=3):
+    """The reference's CPU path (cpu_arm) on a bounded cubic sample of the workload."""
     cells_per_s = 6.0e6                       # survey estimate, only used to size the sample
     side = int(min(min(dims), max(48, round((cells_per_s * seconds_budget / (steps + 1)) ** (1 / 3)))))
     side = min(side, 224)
-    res = 50e6
-    pml = 10
-    size = ((side - 2 * pml - 0.5) / res,) * 3
-    s = O.OSimulation(size, res, pml, 0.9)
-    assert s.grid.dims == (side, side, side), s.grid.dims
-    L = size[0]
-    s.add_source(O.TFSFSource((L / 2, L / 2, L / 2), (L / 2, L / 2, L / 2), "+x", "y", F0, pulse=False))
-    s.add_monitor(O.FieldMonitor((0.75 * L, L / 2, L / 2), (0.0, L, L), components=["Ey", "Hz"], time_domain=False,
-                                 frequencies=list(F0 * np.linspace(0.9, 1.1, 5))))
-    s.step()                                  # warm-up (page faults, first-touch)
+    step, kind, what = cpu_arm(side)
+    step()                                    # warm-up (page faults, first-touch)
     t0 = time.perf_counter()
     for _ in range(steps):
-        s.step()
+        step()
     dt = time.perf_counter() - t0
-    return side ** 3 * steps / dt, side, steps, dt
+    return side ** 3 * steps / dt, side, steps, dt, kind, what
 
 
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and
-    /root/reference does not travel to the GPU box, so this times the oracle port (oracle/sim.py), which
-    reproduces the reference's NumPy expressions one for one (bit-identical results, same temporaries)."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores (cpu_arm): the
+    unmodified package from the staged copy where it exists, the oracle port otherwise.  NumPy's elementwise kernels are
+    single-threaded, so one core is all it can use."""
     if rank != 0:
         return
     name, dims = parse_workload(args.workload)
-    from oracle import sim as O
-
     total = args.steps + args.warmup
     side = int(min(min(dims), max(48, round((6.0e6 * 120.0 / max(total, 1)) ** (1 / 3)))))
     side = min(side, 224)
-    res, pml = 50e6, 10
-    size = ((side - 2 * pml - 0.5) / res,) * 3
-    s = O.OSimulation(size, res, pml, 0.9)
-    L = size[0]
-    s.add_source(O.TFSFSource((L / 2, L / 2, L / 2), (L / 2, L / 2, L / 2), "+x", "y", F0, pulse=False))
-    s.add_monitor(O.FieldMonitor((0.75 * L, L / 2, L / 2), (0.0, L, L), components=["Ey", "Hz"], time_domain=False,
-                                 frequencies=list(F0 * np.linspace(0.9, 1.1, 5))))
+    step, kind, what = cpu_arm(side)
     for _ in range(args.warmup):
-        s.step()
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        s.step()
+        step()
     el = time.perf_counter() - t0
     value = side ** 3 * args.steps / el
     sample = (f"{side}^3 sub-grid of the {name} workload (vacuum, TFSF plane, 5-frequency DFT plane), "
-              f"{args.steps} steps, NumPy {np.__version__}, fp64")
+              f"{args.steps} steps, NumPy {np.__version__}, fp64; {what}")
     line = {"impl": "reference", "metric": "fdtd_cell_updates_per_s", "value": value, "unit": "cell-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{name}: 3-D {dims[0]}x{dims[1]}x{dims[2]} vacuum + TFSF + DFT plane "
                                    f"(timed on a bounded {side}^3 sample)", "l2": "n/a (CPU)"},
-            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample,
+            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": kind, "sample": sample,
                              "host_cores_available": os.cpu_count()},
             "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -716,10 +742,10 @@ def main():
 
     cpu = None
     if not args.no_cpu:
-        v, side, st, el = cpu_baseline_sample(dims)
-        cpu = {"value": v, "unit": "cell-updates/s", "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
-               "sample": f"{side}^3 sub-grid of the workload, {st} steps in {el:.1f} s, oracle port of the reference "
-                         f"NumPy path (single-threaded elementwise ufuncs), fp64"}
+        v, side, st, el, kind, what = cpu_baseline_sample(dims)
+        cpu = {"value": v, "unit": "cell-updates/s", "cores": 1, "kind": kind, "host_cores_available": os.cpu_count(),
+               "sample": f"{side}^3 sub-grid of the workload, {st} steps in {el:.1f} s, {what} (single-threaded "
+                         f"elementwise ufuncs), fp64"}
 
     line = {"metric": "fdtd_cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
